@@ -1,0 +1,213 @@
+/*
+ * rdeic_b200.h — C ABI of librdeic_b200.so, the sm_100a kernel library underneath the
+ * RDEIC relay-diffusion decode path.
+ *
+ * The reference (ShreyasBhaktharam/RDEIC) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §8b); every entry point below therefore names the *Python call site* in the
+ * reference whose arithmetic it replaces.  The Python drop-in classes in rdeic_b200/ keep the
+ * reference signatures and call these symbols through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a CUDA *device* pointer unless the name ends in _host;
+ *   - the caller owns all memory, including workspaces (size queries are provided);
+ *   - `stream` is a cudaStream_t passed as void*; the library never synchronises the device,
+ *     never allocates tensor memory and keeps no mutable global state except the per-thread
+ *     error string and cached function attributes, so it is re-entrant across streams and
+ *     capturable into CUDA graphs;
+ *   - return value: 0 = ok, non-zero = error; the message is in rdeic_last_error().
+ *   - activations inside the network kernels are NHWC bf16 ("pixel-major"); the entropy
+ *     front end and the sampler updates work on the reference's NCHW fp32 tensors directly.
+ */
+#ifndef RDEIC_B200_H
+#define RDEIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rdeic_stream_t;
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* rdeic_last_error(void);
+int rdeic_abi_version(void);
+
+/* ---- entropy-model front end: integer / bit-exact kernels ------------------------------
+ * Tensors are NCHW fp32 exactly as the reference passes them. */
+
+/* utils/ckbd.py:35-45  ckbd_anchor / ckbd_nonanchor.  which: 0 = anchor, 1 = non-anchor. */
+int rdeic_ckbd_mask(const float* y, float* out, int B, int C, int H, int W, int which,
+                    rdeic_stream_t stream);
+/* utils/ckbd.py:6-24  ckbd_split (both halves in one pass). */
+int rdeic_ckbd_split(const float* y, float* anchor, float* nonanchor, int B, int C, int H,
+                     int W, rdeic_stream_t stream);
+/* utils/ckbd.py:26-33  ckbd_merge = anchor + nonanchor. */
+int rdeic_ckbd_merge(const float* anchor, const float* nonanchor, float* out, int64_t numel,
+                     rdeic_stream_t stream);
+/* utils/ckbd.py:47-59  ckbd_{anchor,nonanchor}_sequeeze: [B,C,H,W] -> [B,C,H,W/2]. */
+int rdeic_ckbd_squeeze(const float* y, float* out, int B, int C, int H, int W, int which,
+                       rdeic_stream_t stream);
+/* utils/ckbd.py:61-73  ckbd_{anchor,nonanchor}_unsequeeze: [B,C,H,Wh] -> [B,C,H,2*Wh]. */
+int rdeic_ckbd_unsqueeze(const float* sq, float* out, int B, int C, int H, int Wh, int which,
+                         rdeic_stream_t stream);
+/* compressai 1.2.4 EntropyModel.quantize(x, "symbols", means) as called at
+ * utils/ckbd.py:82,93: sym = int32(rint(x - means)); means may be NULL. */
+int rdeic_quantize_symbols(const float* x, const float* means, int32_t* symbols, int64_t numel,
+                           rdeic_stream_t stream);
+/* utils/ckbd.py:85,96,104,113: x_hat = float(sym) + means. */
+int rdeic_dequantize(const int32_t* symbols, const float* means, float* out, int64_t numel,
+                     rdeic_stream_t stream);
+/* compressai 1.2.4 GaussianConditional.build_indexes as called at utils/ckbd.py:81,92,102,111:
+ * s = max(scale, lower_bound); idx = (levels-1) - #{k < levels-1 : s <= table[k]}.
+ * `table` is the fp32 scale table produced by utils/func.py:10-13 (device pointer). */
+int rdeic_build_indexes(const float* scales, const float* table, int levels, float lower_bound,
+                        int32_t* indexes, int64_t numel, rdeic_stream_t stream);
+/* Fused decode-side hand-off (utils/ckbd.py:99-115 minus the rANS call): squeeze scales and
+ * means of one checkerboard phase and build the CDF indexes in one pass.
+ * scales/means [B,C,H,W] -> means_sq [B,C,H,W/2] fp32, indexes [B,C,H,W/2] int32. */
+int rdeic_ckbd_squeeze_indexes(const float* scales, const float* means, const float* table,
+                               int levels, float lower_bound, float* means_sq,
+                               int32_t* indexes, int B, int C, int H, int W, int which,
+                               rdeic_stream_t stream);
+/* Fused encode-side (utils/ckbd.py:76-97 minus the rANS call): squeeze y/scales/means,
+ * build indexes, quantise symbols, and write y_hat = unsqueeze(sym + means). */
+int rdeic_ckbd_encode_phase(const float* y, const float* scales, const float* means,
+                            const float* table, int levels, float lower_bound,
+                            int32_t* symbols, int32_t* indexes, float* y_hat, int B, int C,
+                            int H, int W, int which, rdeic_stream_t stream);
+/* Fused decode-side second half (utils/ckbd.py:104-105,113-114): y_hat = unsqueeze(float(sym)
+ * + means_sq);  symbols/means_sq [B,C,H,Wh] -> y_hat [B,C,H,2*Wh]. */
+int rdeic_ckbd_decode_phase(const int32_t* symbols, const float* means_sq, float* y_hat, int B,
+                            int C, int H, int Wh, int which, rdeic_stream_t stream);
+/* model/compression_modules.py:309-331 VectorQuantiser.quant: z [B,D,H,W] fp32,
+ * codebook [K,D] fp32 -> idx [B,H,W] int64 (first minimum of |z|^2+|e|^2-2 z.e), zq [B,D,H,W]. */
+int rdeic_vq_quant(const float* z, const float* codebook, int64_t* indices, float* zq, int B,
+                   int D, int HW, int K, rdeic_stream_t stream);
+/* model/compression_modules.py:333-338 get_codebook_entry: idx [B,H,W] -> [B,D,H,W]. */
+int rdeic_vq_lookup(const int64_t* indices, const float* codebook, float* out, int B, int D,
+                    int HW, int K, rdeic_stream_t stream);
+
+/* ---- relay sampler updates (NCHW fp32, elementwise, unfused fp32 rounding order) -------- */
+
+/* ldm/models/diffusion/ddpm.py:357-360 q_sample: out = a*x0 + b*noise. */
+int rdeic_q_sample(const float* x0, const float* noise, float* out, int64_t numel, float a,
+                   float b, rdeic_stream_t stream);
+/* model/spaced_sampler_relay.py:369-384 (p_sample_spaced, cond_fn None):
+ * pred = r*x - rm1*eps; mean = c1*pred + c2*x; out = mean + sigma*noise (sigma = 0 at index 0).
+ * eps_uncond != NULL applies the guidance combine of :281-283 first:
+ * eps = eps_uncond + scale*(eps - eps_uncond). */
+int rdeic_relay_update(const float* x, const float* eps, const float* eps_uncond,
+                       float guidance_scale, const float* noise, float* out, int64_t numel,
+                       float r, float rm1, float c1, float c2, float sigma,
+                       rdeic_stream_t stream);
+/* model/ddim_sampler_relay.py:203-231 (p_sample_ddim): pred_x0 = (x - s1m*e)/sqrt_at;
+ * out = sqrt_aprev*pred_x0 + dir*e + sigma*noise.  pred_x0_out may be NULL. */
+int rdeic_ddim_update(const float* x, const float* eps, const float* eps_uncond,
+                      float guidance_scale, const float* noise, float* out, float* pred_x0_out,
+                      int64_t numel, float sqrt_one_minus_at, float sqrt_at, float sqrt_aprev,
+                      float dir_coef, float sigma, rdeic_stream_t stream);
+
+/* ---- layout / glue kernels ------------------------------------------------------------ */
+
+/* NCHW fp32 -> NHWC bf16 into channel window [c_off, c_off+C) of a [B,H,W,ldc] tensor. */
+int rdeic_nchw_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, int W, int ldc,
+                            int c_off, rdeic_stream_t stream);
+/* NHWC (bf16 or fp32) [B,H,W,ldc] channels [0,C) -> NCHW fp32. */
+int rdeic_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int B, int C, int H,
+                           int W, int ldc, rdeic_stream_t stream);
+/* fp32 -> bf16 copy (weights repack), numel elements. */
+int rdeic_f32_to_bf16(const float* src, void* dst, int64_t numel, rdeic_stream_t stream);
+/* ldm/modules/diffusionmodules/util.py:161-181 timestep_embedding (+ optional SiLU is not
+ * applied here): t [B] int64 -> [B,dim] bf16 (cos | sin). */
+int rdeic_timestep_embedding(const int64_t* t, void* out_bf16, int B, int dim, float max_period,
+                             rdeic_stream_t stream);
+/* y = silu(x) on bf16 or fp32 input, bf16 output. */
+int rdeic_silu_bf16(const void* x, int x_is_f32, void* out, int64_t numel,
+                    rdeic_stream_t stream);
+/* ldm/modules/attention.py:49-56 GEGLU: in [rows, 2F] (value | gate) -> out [rows, F]. */
+int rdeic_geglu(const void* in_bf16, void* out_bf16, int64_t rows, int F,
+                rdeic_stream_t stream);
+/* nearest x2 upsample NHWC bf16 (openaimodel.py:106-113, model.py:63-67). */
+int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
+                          rdeic_stream_t stream);
+/* im2col for the stride-2 pad-1 3x3 Downsample conv (openaimodel.py:150-152):
+ * in NHWC [B,H,W,C] -> out [B*(H/2)*(W/2), 9*Cp] with Cp = C rounded up to 64. */
+int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C,
+                        rdeic_stream_t stream);
+/* row softmax of fp32/bf16 logits with scale, bf16 output: [rows, n]. */
+int rdeic_softmax_rows(const void* in, int in_is_f32, void* out_bf16, int64_t rows, int n,
+                       float scale, rdeic_stream_t stream);
+/* batched transpose bf16 [batch, R, C] -> [batch, C, R]. */
+int rdeic_transpose_bf16(const void* in, void* out, int batch, int R, int C,
+                         rdeic_stream_t stream);
+/* inference.py:85-87: NHWC (fp32) [B,H,W,ldc] rgb in [-1,1] -> uint8 HWC [B,H,W,3]
+ * via ((x+1)/2).clamp(0,1)*255 truncated. */
+int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
+                      rdeic_stream_t stream);
+
+/* ---- normalisation (HBM-bound) --------------------------------------------------------- */
+
+/* GroupNorm(+SiLU) over NHWC bf16, fp32 statistics (util.py:209-226 GroupNorm32,
+ * model.py:48-49 Normalize, rdeic.py:473-485).  The input may be the channel concat of two
+ * tensors x1 [B,HW,C1] and x2 [B,HW,C2] (openaimodel.py:804 `th.cat([h, hs.pop()])`) without
+ * materialising it; x2 may be NULL with C2 = 0.  out [B,HW,C1+C2] bf16.
+ * workspace: rdeic_groupnorm_workspace_bytes(B, HW, C) bytes. */
+int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C);
+int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, const float* gamma,
+                         const float* beta, void* out, int B, int64_t HW, int groups,
+                         float eps, int silu, void* workspace, rdeic_stream_t stream);
+/* LayerNorm over the last dim of [rows, C] bf16 (attention.py:273-275). */
+int rdeic_layernorm(const void* x, const float* gamma, const float* beta, void* out,
+                    int64_t rows, int C, float eps, rdeic_stream_t stream);
+
+/* ---- tensor-core contractions (tcgen05 / TMEM / TMA) ------------------------------------ */
+
+/* One implicit-GEMM descriptor covers conv3x3 (stride 1, pad 1), conv1x1 and Linear:
+ *   out[m, n] = epilogue( sum_{tap, c} A[pixel(m)+tap, c] * Wp[n, tap, c] )
+ * A is NHWC bf16 [a_n, a_h, a_w, a_c] (optionally the channel concat of a and a2);
+ * a Linear over [M, K] is a_n = a_h = 1, a_w = M, a_c = K, taps = 1.
+ * Wp is the packed weight produced by rdeic_pack_conv_weight: bf16 [n_out][taps][cpad] with
+ * cpad = 64*ceil(c/64) per source, source a first then a2.
+ * epilogue: v = acc + bias[n] + row_bias[sample(m)*row_bias_ld + n];  v = act(v);
+ *           v = alpha*v + resid[m, n];  written as bf16 and/or fp32 with row stride ldo.
+ * Batched GEMM (VAE mid attention, model.py:181-205): w_batch_stride != 0 selects a
+ * different weight matrix per a_n index (elements). */
+typedef struct rdeic_conv_params {
+    const void* a;        int a_n, a_h, a_w, a_c;
+    const void* a2;       int a2_c;
+    int taps;             /* 1 (1x1 / linear) or 9 (3x3, pad 1) */
+    const void* w;        /* packed bf16 weights */
+    int64_t w_batch_stride;
+    int n_out;
+    const float* bias;
+    const float* row_bias; int row_bias_ld;
+    const void* resid;    int resid_is_f32; int ld_resid;
+    float alpha;
+    int act;              /* 0 none, 1 SiLU */
+    void* out_bf16;
+    float* out_f32;
+    int ldo;
+    int tile_n_hint;      /* 0 = library picks BLOCK_N */
+} rdeic_conv_params;
+
+int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream);
+/* openaimodel.py:203 etc.: OIHW fp32 [n_out, c1+c2, kh, kw] -> packed bf16 (see above).
+ * dst must hold n_out * taps * (cpad1 + cpad2) bf16. */
+int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, int c2, int kh,
+                           int kw, rdeic_stream_t stream);
+
+/* ---- attention ------------------------------------------------------------------------- */
+
+/* Fused softmax(Q K^T * scale) V (attention.py:171-203).  q [B, Nq, *] with row stride ldq
+ * (elements), heads laid out as consecutive d-wide column groups; k, v [B, Nk, *] likewise;
+ * batch strides in elements.  d in {16, 64}.  out [B, Nq, heads*d] row stride ldo. */
+int rdeic_attention(const void* q, const void* k, const void* v, void* out, int B, int heads,
+                    int Nq, int Nk, int d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                    int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale,
+                    rdeic_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDEIC_B200_H */

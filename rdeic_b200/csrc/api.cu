@@ -1,0 +1,25 @@
+// Library-level entry points: thread-local error string, ABI version.
+#include "common.cuh"
+#include "../../include/rdeic_b200.h"
+
+namespace rdeic {
+
+char* err_buf() {
+    static thread_local char buf[1024] = {0};
+    return buf;
+}
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 1024, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+}  // namespace rdeic
+
+extern "C" {
+const char* rdeic_last_error(void) { return rdeic::err_buf(); }
+int rdeic_abi_version(void) { return 1; }
+}

@@ -1,0 +1,74 @@
+// Shared helpers for librdeic_b200: error reporting, launch checks, small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+namespace rdeic {
+
+// per-thread error string behind rdeic_last_error()
+char* err_buf();
+int set_error(const char* fmt, ...);
+
+#define RDEIC_CHECK_ARG(cond, ...)                          \
+    do {                                                    \
+        if (!(cond)) return ::rdeic::set_error(__VA_ARGS__); \
+    } while (0)
+
+#define RDEIC_CUDA(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::rdeic::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,       \
+                                      cudaGetErrorName(_e), cudaGetErrorString(_e));       \
+    } while (0)
+
+#define RDEIC_LAUNCH_CHECK() RDEIC_CUDA(cudaPeekAtLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid for a grid-stride elementwise kernel: enough CTAs to fill the chip a few times over,
+// in multiples of the SM count.
+static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
+    int64_t blocks = ceil_div64(work_items, threads);
+    int64_t cap = (int64_t)kNumSMs * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+    return __uint_as_float(((uint32_t)b) << 16);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) {
+    lo = __uint_as_float(v << 16);
+    hi = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// streaming 128-bit accesses (read-once / write-once data: keep it out of L1)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+}  // namespace rdeic

@@ -1,0 +1,599 @@
+// Implicit-GEMM convolution / Linear on 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor) stages A and B tiles in 128B-swizzled shared memory,
+//   one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16 x bf16 -> fp32),
+//   the accumulator lives in TMEM and is drained by 4 epilogue warps with tcgen05.ld.
+//
+// conv3x3 (pad 1, stride 1) never materialises im2col: the M tile is a TN x TH x TW box of
+// output pixels and, for filter tap (dy,dx) and 64-channel block cb, the A tile is the same
+// box of the NHWC input shifted by (dy,dx) — one 4-D TMA load whose out-of-bounds rows and
+// columns are zero-filled by the hardware, which *is* the zero padding.  conv1x1 / Linear is
+// the 1-tap case.  The channel concat feeding the UNet decoder blocks (openaimodel.py:804)
+// is read as two K segments from two tensor maps.
+//
+// Reference call sites replaced: torch conv2d / F.linear in
+//   ldm/modules/diffusionmodules/openaimodel.py:203,229,240,106,566,750,
+//   model/rdeic.py:167-172,346,528,554, ldm/modules/attention.py:52,72,162-169,314,328,
+//   ldm/modules/diffusionmodules/model.py:57-61,102-125,160-179,605,647.
+#include "common.cuh"
+#include "../../include/rdeic_b200.h"
+#include <cuda.h>
+#include <mutex>
+
+namespace rdeic {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kNumThreads = 192;            // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+
+struct ConvDev {
+    int a_n, a_h, a_w;
+    int tw_log2, th_log2;          // tile extents (powers of two), TN = 128 >> (tw+th)
+    int tiles_w, tiles_h, tiles_n;
+    int cblk1, cblk2, taps;
+    int n_out;
+    int w_batched;
+    const float* bias;
+    const float* row_bias; int row_bias_ld;
+    const void* resid; int resid_is_f32; int ld_resid;
+    float alpha;
+    int act;
+    __nv_bfloat16* out_bf16;
+    float* out_f32;
+    int ldo;
+};
+
+// ----------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, void* dst, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, void* dst, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+                     "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// Bits: [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4
+//       | [46,48) version=1 (Blackwell) | [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=fp32, A=B=bf16, both K-major, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BN>
+struct TileCfg {
+    static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kATileBytes + kBBytes;
+    static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 2)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                 const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
+    using Cfg = TileCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * kATileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* accum_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // M-tile coordinates
+    const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+    int mt = blockIdx.x;
+    const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
+    const int tih = mt % p.tiles_h; mt /= p.tiles_h;
+    const int tin = mt;
+    const int w0 = tiw * tw, h0 = tih * th;
+    const int n0 = tin * (kBlockM >> (p.tw_log2 + p.th_log2));
+    const int col0 = blockIdx.y * BN;
+    const int cbt = p.cblk1 + p.cblk2;
+    const int num_kb = p.taps * cbt;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        if (p.cblk2) tma_prefetch_desc(&tm_a2);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            const int wz = p.w_batched ? n0 : 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                const int tap = kb / cbt, cb = kb - tap * cbt;
+                int dy = 0, dx = 0;
+                if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                if (cb < p.cblk1)
+                    tma_load_4d(&tm_a, smem_a + s * kATileBytes, &full_bar[s], cb * kBlockK,
+                                w0 + dx, h0 + dy, n0);
+                else
+                    tma_load_4d(&tm_a2, smem_a + s * kATileBytes, &full_bar[s],
+                                (cb - p.cblk1) * kBlockK, w0 + dx, h0 + dy, n0);
+                tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc(BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t da = make_smem_desc(smem_u32(smem_a + s * kATileBytes));
+                const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
+            }
+            umma_commit(accum_bar);           // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int r = quad * 32 + lane;               // row inside the M tile
+        const int rw = r & (tw - 1);
+        const int rh = (r >> p.tw_log2) & (th - 1);
+        const int rn = r >> (p.tw_log2 + p.th_log2);
+        const int gw = w0 + rw, gh = h0 + rh, gn = n0 + rn;
+        const bool row_ok = gw < p.a_w && gh < p.a_h && gn < p.a_n;
+        const int64_t m = ((int64_t)gn * p.a_h + gh) * p.a_w + gw;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const bool vec_ok = (p.ldo % 8 == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t acc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
+            tmem_ld16(taddr, acc);
+            tmem_ld16(taddr + 16, acc + 16);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            const int nbase = col0 + c;
+            if (nbase >= p.n_out) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int n8 = nbase + g * 8;
+                if (n8 >= p.n_out) break;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+                const bool full8 = (n8 + 8 <= p.n_out);
+                if (full8) {
+                    if (p.bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n8 + 4));
+                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                    }
+                    if (p.row_bias) {
+                        const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + n8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += __ldg(rb + j);
+                    }
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+                    }
+                    if (p.resid) {
+                        if (p.resid_is_f32) {
+                            const float* rr = reinterpret_cast<const float*>(p.resid) + m * p.ld_resid + n8;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], rr[j]);
+                        } else if (p.ld_resid % 8 == 0) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(
+                                reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ld_resid + n8);
+                            float f[8];
+                            unpack_bf16x2(rv.x, f[0], f[1]); unpack_bf16x2(rv.y, f[2], f[3]);
+                            unpack_bf16x2(rv.z, f[4], f[5]); unpack_bf16x2(rv.w, f[6], f[7]);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], f[j]);
+                        } else {
+                            const __nv_bfloat16* rr =
+                                reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ld_resid + n8;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], __bfloat162float(rr[j]));
+                        }
+                    } else if (p.alpha != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+                    }
+                    if (p.out_bf16) {
+                        __nv_bfloat16* o = p.out_bf16 + m * p.ldo + n8;
+                        if (vec_ok) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+                            *reinterpret_cast<uint4*>(o) = pk;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* o = p.out_f32 + m * p.ldo + n8;
+                        if (p.ldo % 4 == 0) {
+                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = v[j];
+                        }
+                    }
+                } else {
+                    // ragged tail of the N dimension (e.g. 4 latent / 3 rgb output channels)
+                    for (int j = 0; j < 8 && n8 + j < p.n_out; ++j) {
+                        float x = v[j];
+                        if (p.bias) x += p.bias[n8 + j];
+                        if (p.row_bias) x += p.row_bias[(int64_t)gn * p.row_bias_ld + n8 + j];
+                        if (p.act == 1) x = silu_f(x);
+                        if (p.resid) {
+                            const float rv = p.resid_is_f32
+                                ? reinterpret_cast<const float*>(p.resid)[m * p.ld_resid + n8 + j]
+                                : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[m * p.ld_resid + n8 + j]);
+                            x = fmaf(p.alpha, x, rv);
+                        } else {
+                            x *= p.alpha;
+                        }
+                        if (p.out_bf16) p.out_bf16[m * p.ldo + n8 + j] = __float2bfloat16_rn(x);
+                        if (p.out_f32) p.out_f32[m * p.ldo + n8 + j] = x;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// weight packing: OIHW fp32 -> [n_out][taps][cp1 + cp2] bf16 (zero padded)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int n_out,
+                   int c1, int c2, int taps, int cp1, int cp2) {
+    const int kp = taps * (cp1 + cp2);
+    const int64_t total = (int64_t)n_out * kp;
+    const int cin = c1 + c2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / kp);
+        int k = (int)(i - (int64_t)n * kp);
+        const int tap = k / (cp1 + cp2);
+        k -= tap * (cp1 + cp2);
+        int c = -1;
+        if (k < cp1) { if (k < c1) c = k; }
+        else if (k - cp1 < c2) c = c1 + (k - cp1);
+        float v = 0.f;
+        if (c >= 0) v = w[((int64_t)n * cin + c) * taps + tap];
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                    reinterpret_cast<const cuuint64_t*>(dims),
+                    reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                    reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu)",
+                         what, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                         (unsigned long long)(rank > 2 ? dims[2] : 0),
+                         (unsigned long long)(rank > 3 ? dims[3] : 0));
+    return 0;
+}
+
+// Pick the TN x TH x TW box (powers of two, product 128) that covers the [N,H,W] pixel grid
+// with the fewest tiles; ties go to the widest TW (longest contiguous TMA rows).
+static void pick_m_tile(int N, int H, int W, bool force_tn1, int* tw_o, int* th_o, int* tn_o) {
+    int64_t best = -1;
+    int btw = 128, bth = 1, btn = 1;
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+        for (int th = kBlockM / tw; th >= 1; th >>= 1) {
+            const int tn = kBlockM / (tw * th);
+            if (force_tn1 && tn != 1) continue;
+            const int64_t tiles = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((N + tn - 1) / tn);
+            if (best < 0 || tiles < best) { best = tiles; btw = tw; bth = th; btn = tn; }
+        }
+    }
+    *tw_o = btw; *th_o = bth; *tn_o = btn;
+}
+static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+template <int BN>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+                       const ConvDev& d, int m_tiles, cudaStream_t s) {
+    using Cfg = TileCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid(m_tiles, (d.n_out + BN - 1) / BN);
+    conv_gemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+static int pick_block_n(int n_out, int m_tiles, int hint) {
+    if (hint == 32 || hint == 64 || hint == 128 || hint == 160 || hint == 256) return hint;
+    if (n_out <= 32) return 32;
+    if (n_out <= 64) return 64;
+    const int cands[3] = {256, 160, 128};
+    int best = 128;
+    double best_cost = 1e30;
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        const int nt = (n_out + bn - 1) / bn;
+        const int64_t ctas = (int64_t)m_tiles * nt;
+        const int64_t slots = 2 * kNumSMs;
+        const int64_t waves = (ctas + slots - 1) / slots;
+        // cost ~ waves * per-CTA time; per-CTA time ~ bn (MMA N) + fixed overhead
+        const double cost = (double)waves * (bn + 24);
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+}  // namespace rdeic
+
+using namespace rdeic;
+
+extern "C" {
+
+int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, int c2, int kh,
+                           int kw, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(w_oihw && dst, "rdeic_pack_conv_weight: null pointer");
+    RDEIC_CHECK_ARG(n_out > 0 && c1 > 0 && c2 >= 0, "rdeic_pack_conv_weight: bad channel counts");
+    RDEIC_CHECK_ARG((kh == 1 && kw == 1) || (kh == 3 && kw == 3),
+                    "rdeic_pack_conv_weight: only 1x1 and 3x3 kernels are supported (got %dx%d)", kh, kw);
+    const int taps = kh * kw;
+    const int cp1 = (c1 + 63) / 64 * 64, cp2 = (c2 + 63) / 64 * 64;
+    const int64_t total = (int64_t)n_out * taps * (cp1 + cp2);
+    pack_weight_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        w_oihw, (__nv_bfloat16*)dst, n_out, c1, c2, taps, cp1, cp2);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(p, "rdeic_conv_gemm: null params");
+    RDEIC_CHECK_ARG(p->a && p->w, "rdeic_conv_gemm: null operand");
+    RDEIC_CHECK_ARG(p->out_bf16 || p->out_f32, "rdeic_conv_gemm: no output pointer");
+    RDEIC_CHECK_ARG(p->a_n > 0 && p->a_h > 0 && p->a_w > 0 && p->a_c > 0, "rdeic_conv_gemm: empty A");
+    RDEIC_CHECK_ARG(p->a_c % 8 == 0 && p->a2_c % 8 == 0,
+                    "rdeic_conv_gemm: channel counts (%d, %d) must be multiples of 8 (TMA 16-byte strides)",
+                    p->a_c, p->a2_c);
+    RDEIC_CHECK_ARG(p->a2_c == 0 || p->a2, "rdeic_conv_gemm: a2_c > 0 needs a2");
+    RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9, "rdeic_conv_gemm: taps must be 1 or 9");
+    RDEIC_CHECK_ARG(p->n_out > 0 && p->ldo >= p->n_out, "rdeic_conv_gemm: bad n_out/ldo");
+    RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w) % 16 == 0,
+                    "rdeic_conv_gemm: operands must be 16-byte aligned");
+    RDEIC_CHECK_ARG(((uintptr_t)p->out_bf16 | (uintptr_t)p->out_f32 | (uintptr_t)p->resid |
+                     (uintptr_t)p->bias) % 16 == 0,
+                    "rdeic_conv_gemm: epilogue pointers must be 16-byte aligned");
+    RDEIC_CHECK_ARG(!p->resid || p->ld_resid >= p->n_out, "rdeic_conv_gemm: bad ld_resid");
+    RDEIC_CHECK_ARG(!p->row_bias || p->row_bias_ld >= p->n_out, "rdeic_conv_gemm: bad row_bias_ld");
+
+    ConvDev d;
+    d.a_n = p->a_n; d.a_h = p->a_h; d.a_w = p->a_w;
+    int tw_eff, th_eff, tn;
+    pick_m_tile(p->a_n, p->a_h, p->a_w, p->w_batch_stride != 0, &tw_eff, &th_eff, &tn);
+    d.tw_log2 = ilog2(tw_eff); d.th_log2 = ilog2(th_eff);
+    d.tiles_w = (p->a_w + tw_eff - 1) / tw_eff;
+    d.tiles_h = (p->a_h + th_eff - 1) / th_eff;
+    d.tiles_n = (p->a_n + tn - 1) / tn;
+    const int64_t m_tiles64 = (int64_t)d.tiles_w * d.tiles_h * d.tiles_n;
+    RDEIC_CHECK_ARG(m_tiles64 < (1ll << 31), "rdeic_conv_gemm: too many M tiles");
+    const int m_tiles = (int)m_tiles64;
+    d.cblk1 = (p->a_c + 63) / 64;
+    d.cblk2 = (p->a2_c + 63) / 64;
+    d.taps = p->taps;
+    d.n_out = p->n_out;
+    d.w_batched = p->w_batch_stride != 0;
+    d.bias = p->bias; d.row_bias = p->row_bias; d.row_bias_ld = p->row_bias_ld;
+    d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
+    d.alpha = p->alpha; d.act = p->act;
+    d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
+
+    const int bn = pick_block_n(p->n_out, m_tiles, p->tile_n_hint);
+
+    CUtensorMap ta, ta2, tb;
+    {
+        uint64_t dims[4] = {(uint64_t)p->a_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
+        uint64_t str[3] = {(uint64_t)p->a_c * 2, (uint64_t)p->a_c * 2 * p->a_w,
+                           (uint64_t)p->a_c * 2 * p->a_w * p->a_h};
+        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw_eff, (uint32_t)th_eff, (uint32_t)tn};
+        if (int e = encode_map(&ta, p->a, 4, dims, str, box, "A")) return e;
+        ta2 = ta;
+        if (p->a2_c) {
+            uint64_t dims2[4] = {(uint64_t)p->a2_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
+            uint64_t str2[3] = {(uint64_t)p->a2_c * 2, (uint64_t)p->a2_c * 2 * p->a_w,
+                                (uint64_t)p->a2_c * 2 * p->a_w * p->a_h};
+            if (int e = encode_map(&ta2, p->a2, 4, dims2, str2, box, "A2")) return e;
+        }
+        const uint64_t kp = (uint64_t)p->taps * (d.cblk1 + d.cblk2) * kBlockK;
+        const uint64_t nb = d.w_batched ? (uint64_t)p->a_n : 1;
+        uint64_t dimsb[3] = {kp, (uint64_t)p->n_out, nb};
+        uint64_t strb[2] = {kp * 2, d.w_batched ? (uint64_t)p->w_batch_stride * 2 : kp * 2 * (uint64_t)p->n_out};
+        uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)bn, 1};
+        if (int e = encode_map(&tb, p->w, 3, dimsb, strb, boxb, "W")) return e;
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (bn) {
+        case 32: return launch_conv<32>(ta, ta2, tb, d, m_tiles, s);
+        case 64: return launch_conv<64>(ta, ta2, tb, d, m_tiles, s);
+        case 128: return launch_conv<128>(ta, ta2, tb, d, m_tiles, s);
+        case 160: return launch_conv<160>(ta, ta2, tb, d, m_tiles, s);
+        case 256: return launch_conv<256>(ta, ta2, tb, d, m_tiles, s);
+    }
+    return set_error("rdeic_conv_gemm: unsupported BLOCK_N %d", bn);
+}
+
+}  // extern "C"

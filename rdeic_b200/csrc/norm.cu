@@ -1,0 +1,301 @@
+// GroupNorm(+SiLU) and LayerNorm over pixel-major (NHWC) bf16 activations, fp32 statistics.
+// Both are HBM-bound: every element is read twice (stats pass hits L2 on the second read
+// for UNet-sized tensors) and written once, in 16-byte vectors.
+//
+// Reference semantics: ldm/modules/diffusionmodules/util.py:224 GroupNorm32 (eps 1e-5, fp32
+// compute), ldm/modules/diffusionmodules/model.py:48 Normalize (eps 1e-6),
+// ldm/modules/attention.py:96 Normalize (eps 1e-6), model/rdeic.py:483 GroupNorm_leq32,
+// ldm/modules/attention.py:273-275 nn.LayerNorm (eps 1e-5).
+#include "common.cuh"
+#include "../../include/rdeic_b200.h"
+
+namespace rdeic {
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxChunks = 256;
+constexpr int kGnMaxGroups = 32;
+constexpr int kGnMaxC = 2560;  // widest GN input on the path: concat 1280 + 1280
+
+static inline int gn_num_chunks(int B, int64_t HW) {
+    int64_t want = (4 * kNumSMs + B - 1) / B;   // ~4 CTAs per SM over the whole batch
+    int64_t max_by_rows = HW / 16 > 0 ? HW / 16 : 1;
+    if (want > max_by_rows) want = max_by_rows;
+    if (want > kGnMaxChunks) want = kGnMaxChunks;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+// partial[(b*nchunk + chunk)*G + g] = (sum, sumsq) over the chunk's pixels and the group's
+// channels, reduced in a fixed order (deterministic run to run).
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ x2, int C2,
+                int64_t HW, int G, float2* __restrict__ partial) {
+    __shared__ float s_part[kGnThreads * 16];   // [row][lane][8 sum | 8 sq]
+    __shared__ float s_csum[kGnMaxC];
+    __shared__ float s_csq[kGnMaxC];
+    const int C = C1 + C2;
+    const int VL = C >> 3, VL1 = C1 >> 3, VL2 = C2 >> 3;
+    const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+    const int64_t per = (HW + nchunk - 1) / nchunk;
+    const int64_t p0 = chunk * per;
+    const int64_t p1 = (p0 + per < HW) ? p0 + per : HW;
+    const int lanes_per_pass = VL < kGnThreads ? VL : kGnThreads;
+    const int rows_per_iter = kGnThreads / lanes_per_pass;
+    const int tid = threadIdx.x;
+    const int row = tid / lanes_per_pass, lane_in = tid - row * lanes_per_pass;
+
+    for (int lane_base = 0; lane_base < VL; lane_base += lanes_per_pass) {
+        const int l = lane_base + lane_in;
+        float s[8], q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+        if (row < rows_per_iter && l < VL) {
+            const bool first = l < VL1;
+            const uint4* src = first ? x1 + (int64_t)b * HW * VL1 + l
+                                     : x2 + (int64_t)b * HW * VL2 + (l - VL1);
+            const int64_t stride = first ? VL1 : VL2;
+            for (int64_t p = p0 + row; p < p1; p += rows_per_iter) {
+                const uint4 v = src[p * stride];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a, c;
+                    unpack_bf16x2(w[k], a, c);
+                    s[2 * k] += a;      q[2 * k] = fmaf(a, a, q[2 * k]);
+                    s[2 * k + 1] += c;  q[2 * k + 1] = fmaf(c, c, q[2 * k + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s_part[tid * 16 + k] = s[k];
+            s_part[tid * 16 + 8 + k] = q[k];
+        }
+        __syncthreads();
+        // reduce over rows: one thread per (lane, channel-in-vector)
+        for (int i = tid; i < lanes_per_pass * 8; i += kGnThreads) {
+            const int li = i >> 3, k = i & 7;
+            const int lg = lane_base + li;
+            if (lg < VL) {
+                float a = 0.f, c = 0.f;
+                for (int r = 0; r < rows_per_iter; ++r) {
+                    a += s_part[(r * lanes_per_pass + li) * 16 + k];
+                    c += s_part[(r * lanes_per_pass + li) * 16 + 8 + k];
+                }
+                s_csum[lg * 8 + k] = a;
+                s_csq[lg * 8 + k] = c;
+            }
+        }
+        __syncthreads();
+    }
+    const int cg = C / G;
+    if (tid < G) {
+        float a = 0.f, c = 0.f;
+        for (int k = 0; k < cg; ++k) {
+            a += s_csum[tid * cg + k];
+            c += s_csq[tid * cg + k];
+        }
+        partial[((int64_t)b * nchunk + chunk) * G + tid] = make_float2(a, c);
+    }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ x2, int C2,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
+                const float2* __restrict__ partial, int nchunk) {
+    __shared__ float s_scale[kGnMaxC];
+    __shared__ float s_shift[kGnMaxC];
+    __shared__ float s_mean[kGnMaxGroups];
+    __shared__ float s_rstd[kGnMaxGroups];
+    const int C = C1 + C2;
+    const int VL = C >> 3, VL1 = C1 >> 3, VL2 = C2 >> 3;
+    const int b = blockIdx.y;
+    const int cg = C / G;
+    if (threadIdx.x < G) {
+        double a = 0.0, c = 0.0;
+        for (int k = 0; k < nchunk; ++k) {
+            const float2 v = partial[((int64_t)b * nchunk + k) * G + threadIdx.x];
+            a += (double)v.x;
+            c += (double)v.y;
+        }
+        const double n = (double)HW * cg;
+        const double mean = a / n;
+        double var = c / n - mean * mean;   // biased variance, as nn.GroupNorm
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        const int g = c / cg;
+        const float sc = gamma[c] * s_rstd[g];
+        s_scale[c] = sc;
+        s_shift[c] = beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+    const int64_t total = HW * VL;
+    const uint4* b1 = x1 + (int64_t)b * HW * VL1;
+    const uint4* b2 = x2 ? x2 + (int64_t)b * HW * VL2 : nullptr;
+    uint4* bo = out + (int64_t)b * HW * VL;
+    for (int64_t i = blockIdx.x * (int64_t)kGnThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kGnThreads) {
+        const int64_t p = i / VL;
+        const int l = (int)(i - p * VL);
+        const uint4 v = (l < VL1) ? ld_stream_u4(b1 + p * VL1 + l)
+                                  : ld_stream_u4(b2 + p * VL2 + (l - VL1));
+        const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[l * 8]);
+        const float4 sc1 = *reinterpret_cast<const float4*>(&s_scale[l * 8 + 4]);
+        const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[l * 8]);
+        const float4 sh1 = *reinterpret_cast<const float4*>(&s_shift[l * 8 + 4]);
+        float f[8];
+        unpack_bf16x2(v.x, f[0], f[1]);
+        unpack_bf16x2(v.y, f[2], f[3]);
+        unpack_bf16x2(v.z, f[4], f[5]);
+        unpack_bf16x2(v.w, f[6], f[7]);
+        f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y);
+        f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
+        f[4] = fmaf(f[4], sc1.x, sh1.x); f[5] = fmaf(f[5], sc1.y, sh1.y);
+        f[6] = fmaf(f[6], sc1.z, sh1.z); f[7] = fmaf(f[7], sc1.w, sh1.w);
+        if (silu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        st_stream_u4(bo + i, o);
+    }
+}
+
+// LayerNorm: one warp per row, row held in registers (C <= 8*32*kLnMaxVec)
+constexpr int kLnMaxVec = 5;
+constexpr int kLnWarps = 8;
+
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
+                 float eps) {
+    const int VL = C >> 3;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint4* xr = x + row * VL;
+    float f[kLnMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        const int l = lane + 32 * j;
+        if (l < VL) {
+            const uint4 v = ld_stream_u4(xr + l);
+            unpack_bf16x2(v.x, f[j][0], f[j][1]);
+            unpack_bf16x2(v.y, f[j][2], f[j][3]);
+            unpack_bf16x2(v.z, f[j][4], f[j][5]);
+            unpack_bf16x2(v.w, f[j][6], f[j][7]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += f[j][k];
+        }
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        const int l = lane + 32 * j;
+        if (l < VL) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float d = f[j][k] - mean;
+                sq = fmaf(d, d, sq);
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+        const int l = lane + 32 * j;
+        if (l < VL) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + l * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(gamma + l * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + l * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(beta + l * 8 + 4);
+            float y[8];
+            y[0] = (f[j][0] - mean) * rstd * g0.x + b0.x;
+            y[1] = (f[j][1] - mean) * rstd * g0.y + b0.y;
+            y[2] = (f[j][2] - mean) * rstd * g0.z + b0.z;
+            y[3] = (f[j][3] - mean) * rstd * g0.w + b0.w;
+            y[4] = (f[j][4] - mean) * rstd * g1.x + b1.x;
+            y[5] = (f[j][5] - mean) * rstd * g1.y + b1.y;
+            y[6] = (f[j][6] - mean) * rstd * g1.z + b1.z;
+            y[7] = (f[j][7] - mean) * rstd * g1.w + b1.w;
+            uint4 o;
+            o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+            st_stream_u4(out + row * VL + l, o);
+        }
+    }
+}
+
+}  // namespace rdeic
+
+using namespace rdeic;
+
+extern "C" {
+
+int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C) {
+    (void)HW; (void)C;
+    return (int64_t)B * kGnMaxChunks * kGnMaxGroups * (int64_t)sizeof(float2);
+}
+
+int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, const float* gamma,
+                         const float* beta, void* out, int B, int64_t HW, int groups,
+                         float eps, int silu, void* workspace, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x1 && gamma && beta && out && workspace, "rdeic_groupnorm_nhwc: null pointer");
+    RDEIC_CHECK_ARG(C2 == 0 || x2, "rdeic_groupnorm_nhwc: C2 > 0 needs x2");
+    if (C2 == 0) x2 = nullptr;
+    const int C = C1 + C2;
+    RDEIC_CHECK_ARG(B > 0 && HW > 0, "rdeic_groupnorm_nhwc: empty tensor");
+    RDEIC_CHECK_ARG(B <= 65535, "rdeic_groupnorm_nhwc: B too large");
+    RDEIC_CHECK_ARG(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0,
+                    "rdeic_groupnorm_nhwc: channel counts (%d, %d) must be multiples of 8", C1, C2);
+    RDEIC_CHECK_ARG(C <= kGnMaxC, "rdeic_groupnorm_nhwc: C=%d exceeds %d", C, kGnMaxC);
+    RDEIC_CHECK_ARG(groups > 0 && groups <= kGnMaxGroups && C % groups == 0,
+                    "rdeic_groupnorm_nhwc: groups=%d invalid for C=%d", groups, C);
+    RDEIC_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0,
+                    "rdeic_groupnorm_nhwc: tensors must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    const int nchunk = gn_num_chunks(B, HW);
+    gn_stats_kernel<<<dim3(nchunk, B), kGnThreads, 0, s>>>(
+        (const uint4*)x1, C1, (const uint4*)x2, C2, HW, groups, (float2*)workspace);
+    RDEIC_LAUNCH_CHECK();
+    const int64_t vecs = HW * (C / 8);
+    int64_t blocks = ceil_div64(vecs, (int64_t)kGnThreads * 4);
+    const int64_t cap = (8 * kNumSMs + B - 1) / B;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    gn_apply_kernel<<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
+        (const uint4*)x1, C1, (const uint4*)x2, C2, gamma, beta, (uint4*)out, HW, groups, eps,
+        silu, (const float2*)workspace, nchunk);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_layernorm(const void* x, const float* gamma, const float* beta, void* out,
+                    int64_t rows, int C, float eps, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x && gamma && beta && out, "rdeic_layernorm: null pointer");
+    RDEIC_CHECK_ARG(rows >= 0, "rdeic_layernorm: negative rows");
+    RDEIC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVec,
+                    "rdeic_layernorm: C=%d must be a multiple of 8 and <= %d", C, 8 * 32 * kLnMaxVec);
+    RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0,
+                    "rdeic_layernorm: pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+    const int64_t blocks = ceil_div64(rows, kLnWarps);
+    RDEIC_CHECK_ARG(blocks < (1ll << 31), "rdeic_layernorm: too many rows");
+    layernorm_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(
+        (const uint4*)x, gamma, beta, (uint4*)out, rows, C, eps);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+"""Thin torch-tensor wrappers over the C ABI (include/rdeic_b200.h).
+
+Every function takes CUDA tensors, passes raw pointers + the current torch stream to
+librdeic_b200.so and returns torch tensors.  No arithmetic happens in PyTorch here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, check
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.RdeicLibraryError(
+            f"{name}: expected a CUDA tensor (this path has no CPU fallback), got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# entropy front end
+# ---------------------------------------------------------------------------------------------
+def ckbd_mask(y: torch.Tensor, which: int) -> torch.Tensor:
+    y = _need(y, torch.float32, "ckbd_mask")
+    B, Cc, H, W = y.shape
+    out = torch.empty_like(y)
+    check(_lib.load().rdeic_ckbd_mask(_ptr(y), _ptr(out), B, Cc, H, W, which, _stream()), "rdeic_ckbd_mask")
+    return out
+
+
+def ckbd_split(y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    y = _need(y, torch.float32, "ckbd_split")
+    B, Cc, H, W = y.shape
+    a, n = torch.empty_like(y), torch.empty_like(y)
+    check(_lib.load().rdeic_ckbd_split(_ptr(y), _ptr(a), _ptr(n), B, Cc, H, W, _stream()), "rdeic_ckbd_split")
+    return a, n
+
+
+def ckbd_merge(a: torch.Tensor, n: torch.Tensor) -> torch.Tensor:
+    a = _need(a, torch.float32, "ckbd_merge")
+    n = _need(n, torch.float32, "ckbd_merge")
+    if a.shape != n.shape:
+        raise RuntimeError(f"ckbd_merge: shape mismatch {tuple(a.shape)} vs {tuple(n.shape)}")
+    out = torch.empty_like(a)
+    check(_lib.load().rdeic_ckbd_merge(_ptr(a), _ptr(n), _ptr(out), a.numel(), _stream()), "rdeic_ckbd_merge")
+    return out
+
+
+def ckbd_squeeze(y: torch.Tensor, which: int) -> torch.Tensor:
+    y = _need(y, torch.float32, "ckbd_squeeze")
+    B, Cc, H, W = y.shape
+    out = torch.empty((B, Cc, H, W // 2), dtype=torch.float32, device=y.device)
+    check(_lib.load().rdeic_ckbd_squeeze(_ptr(y), _ptr(out), B, Cc, H, W, which, _stream()), "rdeic_ckbd_squeeze")
+    return out
+
+
+def ckbd_unsqueeze(s: torch.Tensor, which: int) -> torch.Tensor:
+    s = _need(s, torch.float32, "ckbd_unsqueeze")
+    B, Cc, H, Wh = s.shape
+    out = torch.empty((B, Cc, H, Wh * 2), dtype=torch.float32, device=s.device)
+    check(_lib.load().rdeic_ckbd_unsqueeze(_ptr(s), _ptr(out), B, Cc, H, Wh, which, _stream()), "rdeic_ckbd_unsqueeze")
+    return out
+
+
+def quantize_symbols(x: torch.Tensor, means: Optional[torch.Tensor]) -> torch.Tensor:
+    x = _need(x, torch.float32, "quantize_symbols")
+    if means is not None:
+        means = _need(means, torch.float32, "quantize_symbols").expand_as(x).contiguous()
+    out = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    check(_lib.load().rdeic_quantize_symbols(_ptr(x), _ptr(means), _ptr(out), x.numel(), _stream()),
+          "rdeic_quantize_symbols")
+    return out
+
+
+def dequantize(sym: torch.Tensor, means: torch.Tensor) -> torch.Tensor:
+    sym = _need(sym, torch.int32, "dequantize")
+    means = _need(means, torch.float32, "dequantize")
+    out = torch.empty(sym.shape, dtype=torch.float32, device=sym.device)
+    check(_lib.load().rdeic_dequantize(_ptr(sym), _ptr(means), _ptr(out), sym.numel(), _stream()), "rdeic_dequantize")
+    return out
+
+
+def build_indexes(scales: torch.Tensor, table: torch.Tensor, lower_bound: float) -> torch.Tensor:
+    scales = _need(scales, torch.float32, "build_indexes")
+    table = _need(table, torch.float32, "build_indexes")
+    out = torch.empty(scales.shape, dtype=torch.int32, device=scales.device)
+    check(_lib.load().rdeic_build_indexes(_ptr(scales), _ptr(table), table.numel(), lower_bound, _ptr(out),
+                                          scales.numel(), _stream()), "rdeic_build_indexes")
+    return out
+
+
+def ckbd_squeeze_indexes(scales, means, table, lower_bound: float, which: int):
+    scales = _need(scales, torch.float32, "ckbd_squeeze_indexes")
+    means = _need(means, torch.float32, "ckbd_squeeze_indexes")
+    table = _need(table, torch.float32, "ckbd_squeeze_indexes")
+    B, Cc, H, W = scales.shape
+    means_sq = torch.empty((B, Cc, H, W // 2), dtype=torch.float32, device=scales.device)
+    idx = torch.empty((B, Cc, H, W // 2), dtype=torch.int32, device=scales.device)
+    check(_lib.load().rdeic_ckbd_squeeze_indexes(_ptr(scales), _ptr(means), _ptr(table), table.numel(), lower_bound,
+                                                 _ptr(means_sq), _ptr(idx), B, Cc, H, W, which, _stream()),
+          "rdeic_ckbd_squeeze_indexes")
+    return means_sq, idx
+
+
+def ckbd_encode_phase(y, scales, means, table, lower_bound: float, which: int):
+    y = _need(y, torch.float32, "ckbd_encode_phase")
+    scales = _need(scales, torch.float32, "ckbd_encode_phase")
+    means = _need(means, torch.float32, "ckbd_encode_phase")
+    table = _need(table, torch.float32, "ckbd_encode_phase")
+    B, Cc, H, W = y.shape
+    sym = torch.empty((B, Cc, H, W // 2), dtype=torch.int32, device=y.device)
+    idx = torch.empty_like(sym)
+    y_hat = torch.empty_like(y)
+    check(_lib.load().rdeic_ckbd_encode_phase(_ptr(y), _ptr(scales), _ptr(means), _ptr(table), table.numel(),
+                                              lower_bound, _ptr(sym), _ptr(idx), _ptr(y_hat), B, Cc, H, W, which,
+                                              _stream()), "rdeic_ckbd_encode_phase")
+    return sym, idx, y_hat
+
+
+def ckbd_decode_phase(sym: torch.Tensor, means_sq: torch.Tensor, which: int) -> torch.Tensor:
+    sym = _need(sym, torch.int32, "ckbd_decode_phase")
+    means_sq = _need(means_sq, torch.float32, "ckbd_decode_phase")
+    B, Cc, H, Wh = sym.shape
+    out = torch.empty((B, Cc, H, 2 * Wh), dtype=torch.float32, device=sym.device)
+    check(_lib.load().rdeic_ckbd_decode_phase(_ptr(sym), _ptr(means_sq), _ptr(out), B, Cc, H, Wh, which, _stream()),
+          "rdeic_ckbd_decode_phase")
+    return out
+
+
+def vq_quant(z: torch.Tensor, codebook: torch.Tensor):
+    z = _need(z, torch.float32, "vq_quant")
+    codebook = _need(codebook, torch.float32, "vq_quant")
+    B, D, H, W = z.shape
+    K = codebook.shape[0]
+    idx = torch.empty((B, H, W), dtype=torch.int64, device=z.device)
+    zq = torch.empty_like(z)
+    check(_lib.load().rdeic_vq_quant(_ptr(z), _ptr(codebook), _ptr(idx), _ptr(zq), B, D, H * W, K, _stream()),
+          "rdeic_vq_quant")
+    return zq, idx
+
+
+def vq_lookup(idx: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    idx = _need(idx, torch.int64, "vq_lookup")
+    codebook = _need(codebook, torch.float32, "vq_lookup")
+    B, H, W = idx.shape
+    K, D = codebook.shape
+    out = torch.empty((B, D, H, W), dtype=torch.float32, device=idx.device)
+    check(_lib.load().rdeic_vq_lookup(_ptr(idx), _ptr(codebook), _ptr(out), B, D, H * W, K, _stream()), "rdeic_vq_lookup")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler updates
+# ---------------------------------------------------------------------------------------------
+def q_sample(x0, noise, a: float, b: float, out=None):
+    x0 = _need(x0, torch.float32, "q_sample")
+    noise = _need(noise, torch.float32, "q_sample")
+    out = torch.empty_like(x0) if out is None else out
+    check(_lib.load().rdeic_q_sample(_ptr(x0), _ptr(noise), _ptr(out), x0.numel(), a, b, _stream()), "rdeic_q_sample")
+    return out
+
+
+def relay_update(x, eps, noise, r, rm1, c1, c2, sigma, eps_uncond=None, guidance_scale=1.0, out=None):
+    x = _need(x, torch.float32, "relay_update")
+    eps = _need(eps, torch.float32, "relay_update")
+    noise = _need(noise, torch.float32, "relay_update")
+    if eps_uncond is not None:
+        eps_uncond = _need(eps_uncond, torch.float32, "relay_update")
+    out = torch.empty_like(x) if out is None else out
+    check(_lib.load().rdeic_relay_update(_ptr(x), _ptr(eps), _ptr(eps_uncond), guidance_scale, _ptr(noise), _ptr(out),
+                                         x.numel(), r, rm1, c1, c2, sigma, _stream()), "rdeic_relay_update")
+    return out
+
+
+def ddim_update(x, eps, noise, sqrt_one_minus_at, sqrt_at, sqrt_aprev, dir_coef, sigma, eps_uncond=None,
+                guidance_scale=1.0):
+    x = _need(x, torch.float32, "ddim_update")
+    eps = _need(eps, torch.float32, "ddim_update")
+    noise = _need(noise, torch.float32, "ddim_update")
+    if eps_uncond is not None:
+        eps_uncond = _need(eps_uncond, torch.float32, "ddim_update")
+    out = torch.empty_like(x)
+    pred = torch.empty_like(x)
+    check(_lib.load().rdeic_ddim_update(_ptr(x), _ptr(eps), _ptr(eps_uncond), guidance_scale, _ptr(noise), _ptr(out),
+                                        _ptr(pred), x.numel(), sqrt_one_minus_at, sqrt_at, sqrt_aprev, dir_coef, sigma,
+                                        _stream()), "rdeic_ddim_update")
+    return out, pred
+
+
+# ---------------------------------------------------------------------------------------------
+# layout / glue
+# ---------------------------------------------------------------------------------------------
+def nchw_to_nhwc_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, ldc: Optional[int] = None, c_off: int = 0):
+    src = _need(src, torch.float32, "nchw_to_nhwc_bf16")
+    B, Cc, H, W = src.shape
+    if dst is None:
+        ldc = ldc or Cc
+        dst = torch.zeros((B, H, W, ldc), dtype=BF16, device=src.device) if ldc != Cc else \
+            torch.empty((B, H, W, ldc), dtype=BF16, device=src.device)
+    ldc = dst.shape[-1]
+    check(_lib.load().rdeic_nchw_to_nhwc_bf16(_ptr(src), _ptr(dst), B, Cc, H, W, ldc, c_off, _stream()),
+          "rdeic_nchw_to_nhwc_bf16")
+    return dst
+
+
+def nhwc_to_nchw_f32(src: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
+    B, H, W, ldc = src.shape
+    Cc = Cc or ldc
+    is_f32 = 1 if src.dtype == torch.float32 else 0
+    if not is_f32 and src.dtype != BF16:
+        raise TypeError("nhwc_to_nchw_f32: expected bf16 or fp32")
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=src.device)
+    check(_lib.load().rdeic_nhwc_to_nchw_f32(_ptr(src), is_f32, _ptr(out), B, Cc, H, W, ldc, _stream()),
+          "rdeic_nhwc_to_nchw_f32")
+    return out
+
+
+def f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
+    src = _need(src, torch.float32, "f32_to_bf16")
+    out = torch.empty(src.shape, dtype=BF16, device=src.device)
+    check(_lib.load().rdeic_f32_to_bf16(_ptr(src), _ptr(out), src.numel(), _stream()), "rdeic_f32_to_bf16")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    t = _need(t, torch.int64, "timestep_embedding")
+    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    check(_lib.load().rdeic_timestep_embedding(_ptr(t), _ptr(out), t.shape[0], dim, max_period, _stream()),
+          "rdeic_timestep_embedding")
+    return out
+
+
+def silu_bf16(x: torch.Tensor) -> torch.Tensor:
+    is_f32 = 1 if x.dtype == torch.float32 else 0
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_silu_bf16(_ptr(x), is_f32, _ptr(out), x.numel(), _stream()), "rdeic_silu_bf16")
+    return out
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    rows = x.numel() // x.shape[-1]
+    F = x.shape[-1] // 2
+    out = torch.empty((*x.shape[:-1], F), dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_geglu(_ptr(x), _ptr(out), rows, F, _stream()), "rdeic_geglu")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_upsample2x_nhwc(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "rdeic_upsample2x_nhwc")
+    return out
+
+
+def im2col_3x3_s2(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, Cc = x.shape
+    Cp = (Cc + 63) // 64 * 64
+    out = torch.empty((B * (H // 2) * (W // 2), 9 * Cp), dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_im2col_3x3_s2(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "rdeic_im2col_3x3_s2")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
+    n = x.shape[-1]
+    rows = x.numel() // n
+    is_f32 = 1 if x.dtype == torch.float32 else 0
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_softmax_rows(_ptr(x), is_f32, _ptr(out), rows, n, scale, _stream()), "rdeic_softmax_rows")
+    return out
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    batch, R, Cc = x.shape
+    out = torch.empty((batch, Cc, R), dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_transpose_bf16(_ptr(x), _ptr(out), batch, R, Cc, _stream()), "rdeic_transpose_bf16")
+    return out
+
+
+def image_to_u8(x: torch.Tensor) -> torch.Tensor:
+    """x: NHWC fp32 [B,H,W,ldc] in [-1,1] -> uint8 [B,H,W,3] (inference.py:85-87)."""
+    x = _need(x, torch.float32, "image_to_u8")
+    B, H, W, ldc = x.shape
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.load().rdeic_image_to_u8(_ptr(x), _ptr(out), B * H * W, ldc, _stream()), "rdeic_image_to_u8")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------
+_gn_ws = {}
+
+
+def _gn_workspace(B: int, device) -> torch.Tensor:
+    key = (B, str(device))
+    ws = _gn_ws.get(key)
+    if ws is None:
+        nbytes = _lib.load().rdeic_groupnorm_workspace_bytes(B, 1, 8)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+              x2: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x1 [B,H,W,C1] (+ x2 [B,H,W,C2]) bf16 NHWC -> [B,H,W,C1+C2] bf16."""
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[-1]
+    out = torch.empty((B, H, W, C1 + C2), dtype=BF16, device=x1.device)
+    ws = workspace if workspace is not None else _gn_workspace(B, x1.device)
+    check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(out), B, H * W,
+                                           groups, eps, 1 if silu else 0, _ptr(ws), _stream()), "rdeic_groupnorm_nhwc")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty_like(x)
+    check(_lib.load().rdeic_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, Cc, eps, _stream()),
+          "rdeic_layernorm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core contractions
+# ---------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, c1: Optional[int] = None) -> torch.Tensor:
+    """OIHW (or [out,in]) fp32 -> packed bf16 [n_out, taps*(cp1+cp2)].  c1 splits the input
+    channels into two concat sources (c1, cin-c1)."""
+    w = _need(w, torch.float32, "pack_conv_weight")
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    n_out, cin, kh, kw = w.shape
+    c1 = cin if c1 is None else c1
+    c2 = cin - c1
+    cp1, cp2 = (c1 + 63) // 64 * 64, (c2 + 63) // 64 * 64
+    out = torch.empty((n_out, kh * kw * (cp1 + cp2)), dtype=BF16, device=w.device)
+    check(_lib.load().rdeic_pack_conv_weight(_ptr(w.contiguous()), _ptr(out), n_out, c1, c2, kh, kw, _stream()),
+          "rdeic_pack_conv_weight")
+    return out
+
+
+def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *, a2: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
+              resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
+              out: Optional[torch.Tensor] = None, w_batch_stride: int = 0, tile_n: int = 0) -> torch.Tensor:
+    """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out]."""
+    if a.dtype != BF16 or not a.is_contiguous():
+        raise TypeError("conv_gemm: A must be contiguous bf16 NHWC")
+    N, H, W, Cc = a.shape
+    dtype = torch.float32 if out_f32 else BF16
+    if out is None:
+        out = torch.empty((N, H, W, n_out), dtype=dtype, device=a.device)
+    p = ConvParams()
+    p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, H, W, Cc
+    p.a2, p.a2_c = (_ptr(a2), a2.shape[-1]) if a2 is not None else (None, 0)
+    p.taps = taps
+    p.w = _ptr(w_packed)
+    p.w_batch_stride = w_batch_stride
+    p.n_out = n_out
+    p.bias = _ptr(bias)
+    if row_bias is not None:
+        p.row_bias, p.row_bias_ld = _ptr(row_bias), row_bias.stride(0)
+    if resid is not None:
+        p.resid, p.resid_is_f32, p.ld_resid = _ptr(resid), int(resid.dtype == torch.float32), resid.stride(-2)
+    p.alpha = alpha
+    p.act = act
+    if out.dtype == torch.float32:
+        p.out_f32 = _ptr(out)
+    else:
+        p.out_bf16 = _ptr(out)
+    p.ldo = out.stride(-2)
+    p.tile_n_hint = tile_n
+    check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
+    return out
+
+
+def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw) -> torch.Tensor:
+    """x [..., K] bf16 -> [..., n_out] through the same tensor-core kernel (taps = 1)."""
+    K = x.shape[-1]
+    M = x.numel() // K
+    resid = kw.pop("resid", None)
+    if resid is not None:
+        resid = resid.reshape(1, 1, M, resid.shape[-1])
+    out = kw.pop("out", None)
+    if out is not None:
+        out = out.view(1, 1, M, out.shape[-1])
+    y = conv_gemm(x.reshape(1, 1, M, K), w_packed, n_out, 1, resid=resid, out=out, **kw)
+    return y.view(*x.shape[:-1], y.shape[-1])
+
+
+def attention(q, k, v, heads: int, d: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,Nq,>=heads*d], k/v [B,Nk,...] bf16 (may be column slices of a fused projection)."""
+    B, Nq = q.shape[0], q.shape[1]
+    Nk = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Nq, heads * d), dtype=BF16, device=q.device)
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        if t.dtype != BF16 or t.stride(-1) != 1:
+            raise TypeError(f"attention: {name} must be bf16 with unit inner stride")
+    check(_lib.load().rdeic_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, Nq, Nk, d, q.stride(1),
+                                      k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0),
+                                      out.stride(0), scale, _stream()), "rdeic_attention")
+    return out

@@ -1,0 +1,452 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (rdeic_b200.ops ->
+librdeic_b200.so) and compared with the CPU oracle (oracle/) on the same seeded inputs.
+Integer / byte / index work is bit-exact; bf16 tensor-core work states its tolerance."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import entropy as oe
+from oracle import sampler as osamp
+from oracle import nn as onn
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _rand_y(shape, seed, scale=6.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).float()
+
+
+# ------------------------------------------------------------------------------------------
+# entropy front end — bit exact
+# ------------------------------------------------------------------------------------------
+CK_SHAPES = [(1, 8, 32, 32), (2, 16, 7, 10), (1, 3, 5, 6), (3, 64, 32, 48), (1, 1, 1, 2), (1, 2, 9, 4)]
+
+
+@pytest.mark.parametrize("shape", CK_SHAPES)
+def test_ckbd_ops_bit_exact(cuda, shape):
+    from rdeic_b200 import ops
+
+    y = _rand_y(shape, 1)
+    y.view(-1)[0] = float("nan")
+    y.view(-1)[-1] = -0.0
+    yn = y.numpy()
+    yc = y.to(cuda)
+    a, n = ops.ckbd_split(yc)
+    assert np.array_equal(_bits(a.cpu().numpy()), _bits(oe.ckbd_anchor(yn)))
+    assert np.array_equal(_bits(n.cpu().numpy()), _bits(oe.ckbd_nonanchor(yn)))
+    assert np.array_equal(_bits(ops.ckbd_mask(yc, 0).cpu().numpy()), _bits(oe.ckbd_anchor(yn)))
+    assert np.array_equal(_bits(ops.ckbd_mask(yc, 1).cpu().numpy()), _bits(oe.ckbd_nonanchor(yn)))
+    m = ops.ckbd_merge(a, n).cpu().numpy()
+    assert np.array_equal(_bits(m), _bits(oe.ckbd_merge(oe.ckbd_anchor(yn), oe.ckbd_nonanchor(yn))))
+    sa = ops.ckbd_squeeze(yc, 0)
+    sn = ops.ckbd_squeeze(yc, 1)
+    assert np.array_equal(_bits(sa.cpu().numpy()), _bits(oe.ckbd_anchor_sequeeze(yn)))
+    assert np.array_equal(_bits(sn.cpu().numpy()), _bits(oe.ckbd_nonanchor_sequeeze(yn)))
+    ua = ops.ckbd_unsqueeze(sa, 0).cpu().numpy()
+    un = ops.ckbd_unsqueeze(sn, 1).cpu().numpy()
+    assert np.array_equal(_bits(ua), _bits(oe.ckbd_anchor_unsequeeze(oe.ckbd_anchor_sequeeze(yn))))
+    assert np.array_equal(_bits(un), _bits(oe.ckbd_nonanchor_unsequeeze(oe.ckbd_nonanchor_sequeeze(yn))))
+
+
+def test_ckbd_odd_width_raises(cuda):
+    from rdeic_b200 import ops, _lib
+
+    with pytest.raises(_lib.RdeicLibraryError):
+        ops.ckbd_squeeze(torch.zeros(1, 1, 4, 5, device=cuda), 0)
+
+
+def test_ckbd_empty(cuda):
+    from rdeic_b200 import ops
+
+    y = torch.zeros(0, 4, 8, 8, device=cuda)
+    assert ops.ckbd_mask(y, 0).shape == y.shape
+    assert ops.ckbd_squeeze(y, 1).shape == (0, 4, 8, 4)
+
+
+def _entropy_inputs(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(shape, generator=g) * 6.0
+    mu = torch.randn(shape, generator=g) * 2.0
+    lo, hi = math.log(0.05), math.log(300.0)
+    sc = torch.exp(torch.rand(shape, generator=g) * (hi - lo) + lo)
+    # exact .5 ties for round-half-even, table hits, lower-bound edge, NaN scale
+    flat_y, flat_mu, flat_sc = y.view(-1), mu.view(-1), sc.view(-1)
+    n = flat_y.numel()
+    k = min(n // 4, 64)
+    flat_mu[:k] = torch.round(flat_mu[:k] * 4) / 4
+    flat_y[:k] = flat_mu[:k] + (torch.arange(k).float() - k // 2) + 0.5
+    table = torch.from_numpy(oe.get_scale_table())
+    kk = min(n - k, 64)
+    flat_sc[k:k + kk] = table[:kk]
+    if n > k + kk + 4:
+        flat_sc[k + kk] = 0.11
+        flat_sc[k + kk + 1] = 0.0
+        flat_sc[k + kk + 2] = float("nan")
+        flat_sc[k + kk + 3] = 1e9
+    return y.float(), mu.float(), sc.float(), table
+
+
+@pytest.mark.parametrize("numel", [1, 5, 64, 1000, 262144 + 3])
+def test_quantize_dequantize_indexes_bit_exact(cuda, numel):
+    from rdeic_b200 import ops
+
+    y, mu, sc, table = _entropy_inputs((numel,), 3)
+    sym = ops.quantize_symbols(y.to(cuda), mu.to(cuda))
+    ref = oe.quantize_symbols(y.numpy(), mu.numpy())
+    assert np.array_equal(sym.cpu().numpy(), ref)
+    sym0 = ops.quantize_symbols(y.to(cuda), None)
+    assert np.array_equal(sym0.cpu().numpy(), oe.quantize_symbols(y.numpy(), None))
+    deq = ops.dequantize(sym, mu.to(cuda))
+    assert np.array_equal(_bits(deq.cpu().numpy()), _bits(oe.dequantize(ref, mu.numpy())))
+    idx = ops.build_indexes(sc.to(cuda), table.to(cuda), 0.11)
+    assert np.array_equal(idx.cpu().numpy(), oe.build_indexes(sc.numpy(), table.numpy()))
+
+
+def test_build_indexes_unsorted_table_falls_back(cuda):
+    from rdeic_b200 import ops
+
+    table = torch.from_numpy(oe.get_scale_table()).clone()
+    table[[5, 9]] = table[[9, 5]]
+    _, _, sc, _ = _entropy_inputs((4096,), 5)
+    idx = ops.build_indexes(sc.to(cuda), table.to(cuda), 0.11)
+    assert np.array_equal(idx.cpu().numpy(), oe.build_indexes(sc.numpy(), table.numpy()))
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 32, 32), (2, 16, 7, 10), (1, 64, 32, 48), (1, 32, 128, 88)])
+@pytest.mark.parametrize("which", [0, 1])
+def test_fused_phase_kernels_bit_exact(cuda, shape, which):
+    from rdeic_b200 import ops
+
+    y, mu, sc, table = _entropy_inputs(shape, 11)
+    tc = table.to(cuda)
+    sym, idx, yhat = ops.ckbd_encode_phase(y.to(cuda), sc.to(cuda), mu.to(cuda), tc, 0.11, which)
+    rsym, ridx, ryhat = oe.compress_phase(y.numpy(), sc.numpy(), mu.numpy(), table.numpy(), which)
+    assert np.array_equal(sym.cpu().numpy(), rsym)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(_bits(yhat.cpu().numpy()), _bits(ryhat))
+    msq, idx2 = ops.ckbd_squeeze_indexes(sc.to(cuda), mu.to(cuda), tc, 0.11, which)
+    rmsq, ridx2 = oe.decompress_phase_pre(sc.numpy(), mu.numpy(), table.numpy(), which)
+    assert np.array_equal(_bits(msq.cpu().numpy()), _bits(rmsq))
+    assert np.array_equal(idx2.cpu().numpy(), ridx2)
+    # decode side reproduces the encoder's y_hat from (symbols, means): the round trip
+    yhat2 = ops.ckbd_decode_phase(sym, msq, which)
+    assert np.array_equal(_bits(yhat2.cpu().numpy()), _bits(ryhat))
+    assert np.array_equal(_bits(yhat2.cpu().numpy()), _bits(oe.decompress_phase_post(rsym, rmsq, which)))
+
+
+def test_vq_quant_and_lookup(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    K, D = 1024, 256
+    cb = (torch.rand(K, D, generator=g) * 2 - 1).float()
+    cb[17] = cb[900]                       # exact tie -> first index must win
+    pick = torch.randint(0, K, (2 * 3 * 5,), generator=g)
+    pick[0] = 900
+    z = cb[pick] + 0.01 * torch.randn(pick.numel(), D, generator=g)
+    z[0] = cb[900]
+    z = z.reshape(2, 3, 5, D).permute(0, 3, 1, 2).contiguous()
+    zq, idx = ops.vq_quant(z.to(cuda), cb.to(cuda))
+    rzq, ridx = oe.vq_quant(z.numpy(), cb.numpy())
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert idx.view(-1)[0].item() == 17
+    assert np.array_equal(_bits(zq.cpu().numpy()), _bits(rzq))
+    out = ops.vq_lookup(idx, cb.to(cuda))
+    assert np.array_equal(_bits(out.cpu().numpy()), _bits(oe.vq_lookup(ridx, cb.numpy())))
+
+
+def test_vq_full_codebook_size(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(6)
+    K, D = 16384, 256
+    cb = ((torch.rand(K, D, generator=g) * 2 - 1) / 4).float()
+    pick = torch.randint(0, K, (64,), generator=g)
+    z = (cb[pick] + 0.002 * torch.randn(64, D, generator=g)).reshape(1, 8, 8, D).permute(0, 3, 1, 2).contiguous()
+    zq, idx = ops.vq_quant(z.to(cuda), cb.to(cuda))
+    rzq, ridx = oe.vq_quant(z.numpy(), cb.numpy())
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), pick.numpy())
+    assert np.array_equal(_bits(zq.cpu().numpy()), _bits(rzq))
+
+
+# ------------------------------------------------------------------------------------------
+# sampler updates — bit exact (same fp32 op order as the reference)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("steps", [2, 5, 10])
+def test_relay_update_bit_exact(cuda, steps):
+    from rdeic_b200 import ops
+
+    sch = osamp.make_spaced_schedule(steps)
+    g = torch.Generator().manual_seed(9)
+    x, e, n = (torch.randn(2, 4, 16, 24, generator=g) for _ in range(3))
+    for index in range(steps):
+        ref = osamp.relay_update(x, e, n, sch, index)
+        f = lambda v: float(np.float32(v))
+        sigma = 0.0 if index == 0 else float(np.sqrt(np.float32(sch.posterior_variance[index])))
+        out = ops.relay_update(x.to(cuda), e.to(cuda), n.to(cuda), f(sch.sqrt_recip_alphas_cumprod[index]),
+                               f(sch.sqrt_recipm1_alphas_cumprod[index]), f(sch.posterior_mean_coef1[index]),
+                               f(sch.posterior_mean_coef2[index]), sigma)
+        assert np.array_equal(_bits(out.cpu().numpy()), _bits(ref.numpy())), index
+
+
+def test_q_sample_bit_exact(cuda):
+    from rdeic_b200 import ops
+
+    b = osamp.ddpm_buffers()
+    g = torch.Generator().manual_seed(10)
+    x0, n = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    ref = osamp.q_sample(x0, 299, n, b)
+    out = ops.q_sample(x0.to(cuda), n.to(cuda), float(b["sqrt_alphas_cumprod"][299]),
+                       float(b["sqrt_one_minus_alphas_cumprod"][299]))
+    assert np.array_equal(_bits(out.cpu().numpy()), _bits(ref.numpy()))
+
+
+# ------------------------------------------------------------------------------------------
+# glue kernels
+# ------------------------------------------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def test_layout_roundtrip_and_window(cuda):
+    from rdeic_b200 import ops
+
+    x = _rand_y((2, 5, 7, 9), 2, 1.0)
+    nh = ops.nchw_to_nhwc_bf16(x.to(cuda), ldc=8)
+    assert torch.equal(nh[..., :5].float().cpu(), _bf(x).permute(0, 2, 3, 1))
+    assert torch.count_nonzero(nh[..., 5:]) == 0
+    back = ops.nhwc_to_nchw_f32(nh, 5)
+    assert torch.equal(back.cpu(), _bf(x))
+
+
+def test_timestep_embedding(cuda):
+    from rdeic_b200 import ops
+
+    t = torch.tensor([0, 75, 150, 224, 299, 999], dtype=torch.int64)
+    out = ops.timestep_embedding(t.to(cuda), 320).float().cpu()
+    ref = onn.timestep_embedding(t, 320)
+    assert torch.allclose(out, ref, atol=8e-3)  # bf16 output, |v| <= 1
+
+
+def test_geglu_upsample_im2col_transpose_softmax(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    x = _bf(torch.randn(37, 2 * 64, generator=g))
+    a, gate = x.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    out = ops.geglu(x.to(cuda).bfloat16()).float().cpu()
+    assert torch.allclose(out, ref, atol=2e-2, rtol=1e-2)
+
+    u = _bf(torch.randn(2, 3, 5, 16, generator=g))
+    up = ops.upsample2x(u.to(cuda).bfloat16()).float().cpu()
+    ref = F.interpolate(u.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up, ref)
+
+    c = _bf(torch.randn(2, 6, 8, 24, generator=g))
+    col = ops.im2col_3x3_s2(c.to(cuda).bfloat16()).float().cpu()
+    unf = F.unfold(c.permute(0, 3, 1, 2), 3, padding=1, stride=2)          # [B, C*9, L]
+    unf = unf.reshape(2, 24, 9, -1).permute(0, 3, 2, 1)                    # [B, L, tap, C]
+    ref = torch.zeros(2, 12, 9, 64)
+    ref[..., :24] = unf
+    assert torch.equal(col, ref.reshape(24, 9 * 64))
+
+    t = _bf(torch.randn(3, 33, 50, generator=g))
+    assert torch.equal(ops.transpose_bf16(t.to(cuda).bfloat16()).float().cpu(), t.transpose(1, 2))
+
+    s = torch.randn(5, 777, generator=g) * 3
+    sm = ops.softmax_rows(s.to(cuda), 0.7).float().cpu()
+    assert torch.allclose(sm, F.softmax(s * 0.7, dim=-1), atol=2e-3)
+
+
+def test_image_to_u8(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 6, 5, 4, generator=g) * 0.8
+    out = ops.image_to_u8(x.to(cuda)).cpu()
+    ref = onn.to_uint8(x[..., :3].permute(0, 3, 1, 2))
+    assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------------
+# normalisation (bf16 in/out, fp32 statistics): abs tol 3e-2 on O(1) outputs (bf16 eps 2^-8)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C1,C2,silu,eps", [
+    (2, 16, 16, 320, 0, True, 1e-5), (1, 8, 8, 1280, 1280, True, 1e-5), (2, 32, 32, 640, 320, True, 1e-5),
+    (1, 12, 20, 64, 0, False, 1e-6), (1, 64, 64, 128, 0, True, 1e-6), (3, 4, 4, 256, 0, False, 1e-6),
+    (1, 5, 3, 960, 0, True, 1e-5)])
+def test_groupnorm(cuda, B, H, W, C1, C2, silu, eps):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(12)
+    C = C1 + C2
+    x = _bf(torch.randn(B, H, W, C, generator=g) * 2 + 0.5)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    x1 = x[..., :C1].contiguous().to(cuda).bfloat16()
+    x2 = x[..., C1:].contiguous().to(cuda).bfloat16() if C2 else None
+    out = ops.groupnorm(x1, gamma.to(cuda), beta.to(cuda), 32, eps, silu, x2=x2).float().cpu()
+    assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("rows,C", [(77, 320), (4096, 640), (5, 1280), (130, 64), (9, 128), (33, 256)])
+def test_layernorm(cuda, rows, C):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(13)
+    x = _bf(torch.randn(rows, C, generator=g) * 3 - 1)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    out = ops.layernorm(x.to(cuda).bfloat16(), gamma.to(cuda), beta.to(cuda)).float().cpu()
+    assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (out - ref).abs().max()
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core contractions: inputs are exact bf16 values, accumulation fp32 -> fp32 outputs
+# agree with an fp32 conv to 1e-3 relative (summation order only).
+# ------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (256, 320, 320), (77 * 2, 1024, 640), (4096, 1280, 2560),
+                                   (5, 320, 1280), (1000, 96, 4), (128, 2560, 160), (300, 64, 72)])
+def test_linear_tc(cuda, M, K, N):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    x = _bf(torch.randn(M, K, generator=g))
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    ref = F.linear(x, w, b)
+    wp = ops.pack_conv_weight(w.to(cuda))
+    out = ops.linear(x.to(cuda).bfloat16(), wp, N, bias=b.to(cuda), out_f32=True).cpu()
+    assert _rel(out, ref) < 1e-3
+    out16 = ops.linear(x.to(cuda).bfloat16(), wp, N, bias=b.to(cuda)).float().cpu()
+    assert _rel(out16, ref) < 6e-3
+
+
+@pytest.mark.parametrize("tile_n", [32, 64, 128, 160, 256])
+def test_linear_tc_all_tile_widths(cuda, tile_n):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(22)
+    M, K, N = 384, 448, 328
+    x = _bf(torch.randn(M, K, generator=g))
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K))
+    ref = F.linear(x, w)
+    wp = ops.pack_conv_weight(w.to(cuda))
+    out = ops.linear(x.to(cuda).bfloat16(), wp, N, out_f32=True, tile_n=tile_n).cpu()
+    assert _rel(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 64, 64), (2, 16, 16, 320, 320), (8, 8, 8, 128, 256),
+                                            (1, 64, 64, 8, 320), (1, 32, 32, 264, 64), (3, 4, 4, 1280, 640),
+                                            (1, 12, 24, 64, 32), (1, 6, 10, 64, 4), (1, 128, 128, 128, 3),
+                                            (2, 5, 7, 72, 40)])
+def test_conv3x3_tc(cuda, B, H, W, Cin, Cout):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(23)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin))
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    wp = ops.pack_conv_weight(w.to(cuda))
+    out = ops.conv_gemm(a, wp, Cout, 9, bias=b.to(cuda), out_f32=True).cpu()
+    assert _rel(out, ref) < 1e-3
+
+
+def test_conv_two_sources_epilogue(cuda):
+    """concat input as two K segments + per-sample bias + SiLU-free residual/alpha epilogue."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(24)
+    B, H, W, C1, C2, Cout = 2, 16, 16, 640, 320, 320
+    x1 = _bf(torch.randn(B, C1, H, W, generator=g))
+    x2 = _bf(torch.randn(B, C2, H, W, generator=g))
+    for k in (3, 1):
+        w = _bf(torch.randn(Cout, C1 + C2, k, k, generator=g) / math.sqrt(k * k * (C1 + C2)))
+        bias = torch.randn(Cout, generator=g)
+        rb = torch.randn(B, Cout, generator=g)
+        resid = _bf(torch.randn(B, H, W, Cout, generator=g))
+        conv = F.conv2d(torch.cat([x1, x2], 1), w, bias, padding=k // 2) + rb[:, :, None, None]
+        ref = resid + 0.5 * conv.permute(0, 2, 3, 1)
+        wp = ops.pack_conv_weight(w.to(cuda), c1=C1)
+        out = ops.conv_gemm(x1.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16(), wp, Cout, k * k,
+                            a2=x2.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16(), bias=bias.to(cuda),
+                            row_bias=rb.to(cuda), resid=resid.to(cuda).bfloat16(), alpha=0.5, out_f32=True).cpu()
+        assert _rel(out, ref) < 1e-3, k
+
+
+def test_linear_silu_epilogue_and_batched(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(25)
+    x = _bf(torch.randn(8, 320, generator=g))
+    w = _bf(torch.randn(1280, 320, generator=g) / 18)
+    b = torch.randn(1280, generator=g)
+    ref = F.silu(F.linear(x, w, b))
+    out = ops.linear(x.to(cuda).bfloat16(), ops.pack_conv_weight(w.to(cuda)), 1280, bias=b.to(cuda), act=1,
+                     out_f32=True).cpu()
+    assert _rel(out, ref) < 1e-3
+    # batched: S_b = Q_b K_b^T (VAE mid attention, model.py:192)
+    q = _bf(torch.randn(2, 256, 512, generator=g))
+    k = _bf(torch.randn(2, 256, 512, generator=g))
+    ref = torch.bmm(q, k.transpose(1, 2))
+    kc = k.to(cuda).bfloat16().contiguous()
+    out = ops.conv_gemm(q.to(cuda).bfloat16().reshape(2, 1, 256, 512), kc, 256, 1, w_batch_stride=256 * 512,
+                        out_f32=True).cpu().reshape(2, 256, 256)
+    assert _rel(out, ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------
+# attention: bf16 P, fp32 softmax: abs tol 2e-2 on O(1) outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", [(2, 5, 256, 256, 64), (1, 10, 100, 77, 64), (1, 4, 1024, 1024, 16),
+                                             (2, 16, 64, 77, 16), (1, 20, 64, 64, 64), (1, 2, 4096, 4096, 64),
+                                             (1, 3, 70, 130, 16)])
+def test_attention(cuda, B, heads, Nq, Nk, d):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(31)
+    q = _bf(torch.randn(B, Nq, heads * d, generator=g))
+    k = _bf(torch.randn(B, Nk, heads * d, generator=g))
+    v = _bf(torch.randn(B, Nk, heads * d, generator=g))
+    sp = lambda t: t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3)
+    sim = torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * d ** -0.5
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), sp(v)).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    out = ops.attention(q.to(cuda).bfloat16(), k.to(cuda).bfloat16(), v.to(cuda).bfloat16(), heads, d,
+                        d ** -0.5).float().cpu()
+    assert (out - ref).abs().max() < 2e-2
+    assert _rel(out, ref) < 1e-2
+
+
+def test_attention_fused_qkv_slices(cuda):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(32)
+    B, N, heads, d = 2, 128, 5, 64
+    C = heads * d
+    qkv = _bf(torch.randn(B, N, 3 * C, generator=g))
+    q, k, v = qkv.chunk(3, -1)
+    sp = lambda t: t.reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    sim = torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * d ** -0.5
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), sp(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    t = qkv.to(cuda).bfloat16()
+    out = ops.attention(t[..., :C], t[..., C:2 * C], t[..., 2 * C:], heads, d, d ** -0.5).float().cpu()
+    assert (out - ref).abs().max() < 2e-2
