@@ -44,8 +44,13 @@ def test_ckbd_ops_bit_exact(cuda, shape):
     assert np.array_equal(_bits(n.cpu().numpy()), _bits(oe.ckbd_nonanchor(yn)))
     assert np.array_equal(_bits(ops.ckbd_mask(yc, 0).cpu().numpy()), _bits(oe.ckbd_anchor(yn)))
     assert np.array_equal(_bits(ops.ckbd_mask(yc, 1).cpu().numpy()), _bits(oe.ckbd_nonanchor(yn)))
+    # merge is a float add: NaN + 0 yields a NaN whose payload is platform-defined (x86 keeps the
+    # operand's, CUDA returns the canonical 0x7fffffff, as torch's own CUDA add does) -> compare
+    # NaN positions, and bits everywhere else.
     m = ops.ckbd_merge(a, n).cpu().numpy()
-    assert np.array_equal(_bits(m), _bits(oe.ckbd_merge(oe.ckbd_anchor(yn), oe.ckbd_nonanchor(yn))))
+    rm = oe.ckbd_merge(oe.ckbd_anchor(yn), oe.ckbd_nonanchor(yn))
+    assert np.array_equal(np.isnan(m), np.isnan(rm))
+    assert np.array_equal(_bits(m)[~np.isnan(rm)], _bits(rm)[~np.isnan(rm)])
     sa = ops.ckbd_squeeze(yc, 0)
     sn = ops.ckbd_squeeze(yc, 1)
     assert np.array_equal(_bits(sa.cpu().numpy()), _bits(oe.ckbd_anchor_sequeeze(yn)))
