@@ -179,6 +179,8 @@ typedef struct rdeic_conv_params {
     int taps;             /* 1 (1x1 / linear) or 9 (3x3, pad 1) */
     const void* w;        /* packed bf16 weights */
     int64_t w_batch_stride;
+    int w_k, w_ld;        /* 0,0 = packed layout; else true K extent / row stride (elements) of an
+                             activation used as the B operand (Q K^T, P V) */
     int n_out;
     const float* bias;
     const float* row_bias; int row_bias_ld;

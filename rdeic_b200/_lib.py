@@ -28,6 +28,7 @@ class ConvParams(C.Structure):
         ("taps", i32),
         ("w", vp),
         ("w_batch_stride", i64),
+        ("w_k", i32), ("w_ld", i32),
         ("n_out", i32),
         ("bias", vp),
         ("row_bias", vp), ("row_bias_ld", i32),

@@ -540,6 +540,10 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
                     "rdeic_conv_gemm: epilogue pointers must be 16-byte aligned");
     RDEIC_CHECK_ARG(!p->resid || p->ld_resid >= p->n_out, "rdeic_conv_gemm: bad ld_resid");
     RDEIC_CHECK_ARG(!p->row_bias || p->row_bias_ld >= p->n_out, "rdeic_conv_gemm: bad row_bias_ld");
+    RDEIC_CHECK_ARG(p->w_k >= 0 && p->w_ld >= 0 && p->w_k % 8 == 0 && p->w_ld % 8 == 0 &&
+                        (p->w_k == 0 || (p->taps == 1 && p->a2_c == 0 && p->w_k == p->a_c)),
+                    "rdeic_conv_gemm: w_k/w_ld describe an unpacked B operand: taps=1, one source, w_k == a_c, multiples of 8");
+    RDEIC_CHECK_ARG(p->w_batch_stride % 8 == 0, "rdeic_conv_gemm: w_batch_stride must be a multiple of 8");
 
     ConvDev d;
     d.a_n = p->a_n; d.a_h = p->a_h; d.a_w = p->a_w;
@@ -580,8 +584,10 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         }
         const uint64_t kp = (uint64_t)p->taps * (d.cblk1 + d.cblk2) * kBlockK;
         const uint64_t nb = d.w_batched ? (uint64_t)p->a_n : 1;
-        uint64_t dimsb[3] = {kp, (uint64_t)p->n_out, nb};
-        uint64_t strb[2] = {kp * 2, d.w_batched ? (uint64_t)p->w_batch_stride * 2 : kp * 2 * (uint64_t)p->n_out};
+        const uint64_t wk = p->w_k > 0 ? (uint64_t)p->w_k : kp;      // true K extent (OOB -> 0)
+        const uint64_t wld = p->w_ld > 0 ? (uint64_t)p->w_ld : kp;
+        uint64_t dimsb[3] = {wk, (uint64_t)p->n_out, nb};
+        uint64_t strb[2] = {wld * 2, d.w_batched ? (uint64_t)p->w_batch_stride * 2 : wld * 2 * (uint64_t)p->n_out};
         uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)bn, 1};
         if (int e = encode_map(&tb, p->w, 3, dimsb, strb, boxb, "W")) return e;
     }

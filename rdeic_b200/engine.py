@@ -1,0 +1,514 @@
+"""Execution engines for the two networks on the relay decode path, built on the sm_100a kernels.
+
+  * `NoiseEstimatorEngine` — one relay step: SD-2.1 UNet + control adapter run in lock-step with
+    zero-conv cross injection (reference: model/rdeic.py:174-235 over
+    ldm/modules/diffusionmodules/openaimodel.py:421-807 and ldm/modules/attention.py).
+  * `VAEDecoderEngine` — latent -> RGB (reference: ldm/models/diffusion/ddpm.py:835-844,
+    ldm/models/autoencoder.py:97-100, ldm/modules/diffusionmodules/model.py:580-686).
+
+Both consume the reference's flat fp32 `state_dict` unchanged and repack
+it once at load: conv OIHW / linear [out,in] fp32 -> tap-major, 64-channel-padded bf16 operand
+matrices for the TMA/tcgen05 implicit-GEMM kernel; q/k/v projections fused; every ResBlock's
+time-embedding projection concatenated into one GEMM; cross-attention K/V projections of the
+(step-invariant) text context concatenated into one GEMM.
+
+Activations are NHWC bf16 in HBM; accumulation, normalisation statistics and softmax are fp32.
+All arithmetic runs in librdeic_b200.so — this module only sequences launches on the current
+CUDA stream (so a whole step can be captured into a CUDA graph).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+SD = Dict[str, torch.Tensor]
+
+
+def find_denominator(number: int, start: int) -> int:
+    """model/rdeic.py:464-471."""
+    if start >= number:
+        return number
+    while start != 0:
+        if number % start == 0:
+            return start
+        start -= 1
+    return 1
+
+
+# ---------------------------------------------------------------------------------------------
+# prepared weights
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Conv:
+    w: torch.Tensor                 # packed bf16 [n_out, taps*(cp1+cp2)]
+    b: Optional[torch.Tensor]       # fp32 [n_out]
+    n_out: int
+    taps: int
+
+    @staticmethod
+    def load(sd: SD, name: str, dev, c1: Optional[int] = None, scale: float = 1.0) -> "Conv":
+        w = sd[name + ".weight"].to(dev, torch.float32)
+        if scale != 1.0:
+            w = w * scale
+        b = sd.get(name + ".bias")
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        taps = w.shape[2] * w.shape[3]
+        return Conv(ops.pack_conv_weight(w, c1=c1), None if b is None else b.to(dev, torch.float32).contiguous(),
+                    w.shape[0], taps)
+
+    @staticmethod
+    def fused(sd: SD, names: Sequence[str], dev) -> "Conv":
+        """Concatenate several Linear/1x1 weights along the output dim (one GEMM)."""
+        ws = [sd[n + ".weight"].to(dev, torch.float32) for n in names]
+        ws = [w[:, :, None, None] if w.dim() == 2 else w for w in ws]
+        w = torch.cat(ws, 0)
+        bs = [sd.get(n + ".bias") for n in names]
+        b = None
+        if any(x is not None for x in bs):
+            b = torch.cat([torch.zeros(wi.shape[0]) if bi is None else bi.float().cpu() for wi, bi in zip(ws, bs)])
+            b = b.to(dev).contiguous()
+        return Conv(ops.pack_conv_weight(w), b, w.shape[0], 1)
+
+
+@dataclass
+class Norm:
+    g: torch.Tensor
+    b: torch.Tensor
+
+    @staticmethod
+    def load(sd: SD, name: str, dev) -> "Norm":
+        return Norm(sd[name + ".weight"].to(dev, torch.float32).contiguous(),
+                    sd[name + ".bias"].to(dev, torch.float32).contiguous())
+
+
+@dataclass
+class ResBlockW:
+    n_in: Norm
+    conv1: Conv
+    emb_off: int          # column offset of this block's slice in the fused emb projection
+    n_out_norm: Norm
+    conv2: Conv
+    skip: Optional[Conv]
+    cout: int
+    groups_in: int
+    groups_out: int
+
+
+@dataclass
+class TransformerW:
+    norm: Norm
+    proj_in: Conv
+    ln1: Norm
+    qkv: Conv
+    out1: Conv
+    ln2: Norm
+    q2: Conv
+    kv_off: int           # column offset of this block's [K | V] slice in the fused context projection
+    out2: Conv
+    ln3: Norm
+    ff1: Conv
+    ff2: Conv
+    proj_out: Conv
+    heads: int
+    d_head: int
+    ch: int
+    groups: int
+
+
+@dataclass
+class Layer:
+    kind: str             # "conv_in" | "res" | "attn" | "down" | "up"
+    w: object
+
+
+@dataclass
+class UNetW:
+    time0: Conv
+    time2: Conv
+    emb_all: Conv                     # fused emb_layers.1 of every ResBlock
+    kv_all: Conv                      # fused attn2.to_k / to_v of every transformer block
+    input_blocks: List[List[Layer]]
+    middle: List[Layer]
+    output_blocks: List[List[Layer]] = field(default_factory=list)
+    out_norm: Optional[Norm] = None
+    out_conv: Optional[Conv] = None
+
+
+def _load_unet(sd: SD, prefix: str, dev, *, model_channels: int, width: int, in_channels: int, hint_channels: int,
+               channel_mult, num_res_blocks, attention_resolutions, num_head_channels: int, is_control: bool) -> UNetW:
+    """Walk the architecture exactly as UNetModel.__init__ (openaimodel.py:563-751) /
+    ControlModule.__init__ (rdeic.py:343-462) does, binding state_dict tensors as we go."""
+    if isinstance(num_res_blocks, int):
+        num_res_blocks = [num_res_blocks] * len(channel_mult)
+    emb_names: List[str] = []
+    kv_names: List[str] = []
+    emb_cursor = [0]
+    kv_cursor = [0]
+
+    def res(p: str, cin: int, cout: int, split: Optional[int] = None) -> Layer:
+        off = emb_cursor[0]
+        emb_cursor[0] += cout
+        emb_names.append(p + ".emb_layers.1")
+        skip = Conv.load(sd, p + ".skip_connection", dev, c1=split) if (p + ".skip_connection.weight") in sd else None
+        if (cin != cout) != (skip is not None):
+            raise KeyError(f"{p}: skip_connection presence does not match channels {cin}->{cout}")
+        return Layer("res", ResBlockW(Norm.load(sd, p + ".in_layers.0", dev), Conv.load(sd, p + ".in_layers.2", dev, c1=split),
+                                      off, Norm.load(sd, p + ".out_layers.0", dev), Conv.load(sd, p + ".out_layers.3", dev),
+                                      skip, cout, find_denominator(cin, 32), find_denominator(cout, 32)))
+
+    def attn(p: str, ch: int, d_head: int) -> Layer:
+        t = p + ".transformer_blocks.0"
+        off = kv_cursor[0]
+        kv_cursor[0] += 2 * ch
+        kv_names.extend([t + ".attn2.to_k", t + ".attn2.to_v"])
+        return Layer("attn", TransformerW(
+            Norm.load(sd, p + ".norm", dev), Conv.load(sd, p + ".proj_in", dev), Norm.load(sd, t + ".norm1", dev),
+            Conv.fused(sd, [t + ".attn1.to_q", t + ".attn1.to_k", t + ".attn1.to_v"], dev),
+            Conv.load(sd, t + ".attn1.to_out.0", dev), Norm.load(sd, t + ".norm2", dev),
+            Conv.load(sd, t + ".attn2.to_q", dev), off, Conv.load(sd, t + ".attn2.to_out.0", dev),
+            Norm.load(sd, t + ".norm3", dev), Conv.load(sd, t + ".ff.net.0.proj", dev),
+            Conv.load(sd, t + ".ff.net.2", dev), Conv.load(sd, p + ".proj_out", dev), ch // d_head, d_head, ch,
+            find_denominator(ch, 32)))
+
+    def heads_for(ch: int, state: dict) -> int:
+        # openaimodel.py:590-593 vs rdeic.py:371-374 (control re-derives a divisor of ch and keeps it)
+        if is_control:
+            state["nhc"] = find_denominator(ch, num_head_channels)
+            return state["nhc"]
+        return num_head_channels
+
+    st = {"nhc": num_head_channels}
+    P = prefix
+    ib: List[List[Layer]] = []
+    if is_control:
+        ib.append([Layer("conv_in", Conv.load(sd, f"{P}.input_blocks.0.0", dev, c1=in_channels))])
+    else:
+        ib.append([Layer("conv_in", Conv.load(sd, f"{P}.input_blocks.0.0", dev))])
+    chans = [width]
+    ch = width
+    ds = 1
+    idx = 1
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks[level]):
+            blk = [res(f"{P}.input_blocks.{idx}.0", ch, mult * width)]
+            ch = mult * width
+            if ds in attention_resolutions:
+                blk.append(attn(f"{P}.input_blocks.{idx}.1", ch, heads_for(ch, st)))
+            ib.append(blk)
+            chans.append(ch)
+            idx += 1
+        if level != len(channel_mult) - 1:
+            ib.append([Layer("down", Conv.load(sd, f"{P}.input_blocks.{idx}.0.op", dev))])
+            chans.append(ch)
+            idx += 1
+            ds *= 2
+    d_mid = st["nhc"] if is_control else num_head_channels
+    mid = [res(f"{P}.middle_block.0", ch, ch), attn(f"{P}.middle_block.1", ch, d_mid), res(f"{P}.middle_block.2", ch, ch)]
+    net = UNetW(Conv.load(sd, f"{P}.time_embed.0", dev), Conv.load(sd, f"{P}.time_embed.2", dev), None, None, ib, mid)
+    if not is_control:
+        ob: List[List[Layer]] = []
+        oi = 0
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks[level] + 1):
+                ich = chans.pop()
+                blk = [res(f"{P}.output_blocks.{oi}.0", ch + ich, width * mult, split=ch)]
+                ch = width * mult
+                j = 1
+                if ds in attention_resolutions:
+                    blk.append(attn(f"{P}.output_blocks.{oi}.{j}", ch, num_head_channels))
+                    j += 1
+                if level and i == num_res_blocks[level]:
+                    blk.append(Layer("up", Conv.load(sd, f"{P}.output_blocks.{oi}.{j}.conv", dev)))
+                    ds //= 2
+                ob.append(blk)
+                oi += 1
+        net.output_blocks = ob
+        net.out_norm = Norm.load(sd, f"{P}.out.0", dev)
+        net.out_conv = Conv.load(sd, f"{P}.out.2", dev)
+    net.emb_all = Conv.fused(sd, emb_names, dev)
+    net.kv_all = Conv.fused(sd, kv_names, dev)
+    return net
+
+
+# ---------------------------------------------------------------------------------------------
+# UNet + control step
+# ---------------------------------------------------------------------------------------------
+class _Ctx:
+    """Per-call state shared by the block runners of one network."""
+
+    def __init__(self, emb_rows: torch.Tensor, kv: torch.Tensor):
+        self.emb_rows = emb_rows     # fp32 [B, sum(cout)]
+        self.kv = kv                 # bf16 [B, 77, sum(2*ch)]
+
+
+class NoiseEstimatorEngine:
+    def __init__(self, sd: SD, unet_cfg: dict, ctrl_cfg: dict, device="cuda"):
+        dev = torch.device(device)
+        self.device = dev
+        mc = int(unet_cfg["model_channels"])
+        self.model_channels = mc
+        self.in_channels = int(unet_cfg["in_channels"])
+        self.out_channels = int(unet_cfg["out_channels"])
+        self.hint_channels = int(ctrl_cfg["hint_channels"])
+        self.context_dim = int(unet_cfg["context_dim"])
+        self.control_scale = float(ctrl_cfg.get("control_scale", 1.0))
+        if self.hint_channels % 8 != 0 or self.context_dim % 8 != 0:
+            raise ValueError("hint_channels and context_dim must be multiples of 8")
+        common = dict(in_channels=self.in_channels, hint_channels=self.hint_channels)
+        self.base = _load_unet(sd, "model.diffusion_model", dev, model_channels=mc, width=mc,
+                               channel_mult=list(unet_cfg["channel_mult"]), num_res_blocks=unet_cfg["num_res_blocks"],
+                               attention_resolutions=list(unet_cfg["attention_resolutions"]),
+                               num_head_channels=int(unet_cfg["num_head_channels"]), is_control=False, **common)
+        ratio = float(ctrl_cfg.get("control_model_ratio", 1.0))
+        self.ctrl = _load_unet(sd, "control_model.control_model", dev, model_channels=int(ctrl_cfg["model_channels"]),
+                               width=int(int(ctrl_cfg["model_channels"]) * ratio),
+                               channel_mult=list(ctrl_cfg["channel_mult"]), num_res_blocks=ctrl_cfg["num_res_blocks"],
+                               attention_resolutions=list(ctrl_cfg["attention_resolutions"]),
+                               num_head_channels=int(ctrl_cfg["num_head_channels"]), is_control=True, **common)
+        n_enc = len(self.base.input_blocks)
+        self.enc_zero = [Conv.load(sd, f"control_model.enc_zero_convs_out.{i}.0", dev) for i in range(n_enc)]
+        self.mid_zero = Conv.load(sd, "control_model.middle_block_out.0", dev)
+        self.dec_zero = [Conv.load(sd, f"control_model.dec_zero_convs_out.{i}.0", dev)
+                         for i in range(len(self.base.output_blocks))]
+        # rdeic.py:164-165,185: scale_list buffer (already * control_scale) times control_scale again
+        sl = sd["control_model.scale_list"].float().cpu() * self.control_scale
+        self.scales = [float(v) for v in sl]
+        self._cond_key = None
+        self._cond = None
+
+    # ----- step-invariant conditioning --------------------------------------------------------
+    def prepare_cond(self, context: torch.Tensor, guide_hint: Optional[torch.Tensor]):
+        """Text-context K/V for every cross-attention (both networks) and the NHWC bf16 hint are
+        step-invariant: computed once per conditioning."""
+        key = (context.data_ptr(), context._version, tuple(context.shape),
+               None if guide_hint is None else (guide_hint.data_ptr(), guide_hint._version, tuple(guide_hint.shape)))
+        if key == self._cond_key:
+            return self._cond
+        ctx = ops.f32_to_bf16(context.to(self.device, torch.float32).contiguous())
+        kv_base = ops.linear(ctx, self.base.kv_all.w, self.base.kv_all.n_out)
+        kv_ctrl = ops.linear(ctx, self.ctrl.kv_all.w, self.ctrl.kv_all.n_out)
+        hint = None
+        if guide_hint is not None:
+            hint = ops.nchw_to_nhwc_bf16(guide_hint.to(self.device, torch.float32).contiguous())
+        self._cond_key, self._cond = key, (kv_base, kv_ctrl, hint)
+        return self._cond
+
+    def _time_rows(self, net: UNetW, t_emb: torch.Tensor) -> torch.Tensor:
+        # time_embed: Linear, SiLU, Linear (openaimodel.py:539-543); every consumer applies SiLU first
+        # (emb_layers.0, openaimodel.py:216), so SiLU rides in both GEMM epilogues.
+        e = ops.linear(t_emb, net.time0.w, net.time0.n_out, bias=net.time0.b, act=1)
+        e = ops.linear(e, net.time2.w, net.time2.n_out, bias=net.time2.b, act=1)
+        return ops.linear(e, net.emb_all.w, net.emb_all.n_out, bias=net.emb_all.b, out_f32=True)
+
+    # ----- block runners ------------------------------------------------------------------------
+    @staticmethod
+    def _res(w: ResBlockW, x: torch.Tensor, x2: Optional[torch.Tensor], c: _Ctx) -> torch.Tensor:
+        h = ops.groupnorm(x, w.n_in.g, w.n_in.b, w.groups_in, 1e-5, True, x2=x2)
+        rb = c.emb_rows[:, w.emb_off:w.emb_off + w.cout]
+        h = ops.conv_gemm(h, w.conv1.w, w.cout, 9, bias=w.conv1.b, row_bias=rb)
+        h = ops.groupnorm(h, w.n_out_norm.g, w.n_out_norm.b, w.groups_out, 1e-5, True)
+        xs = x
+        if w.skip is not None:
+            xs = ops.conv_gemm(x, w.skip.w, w.cout, 1, a2=x2, bias=w.skip.b)
+        return ops.conv_gemm(h, w.conv2.w, w.cout, 9, bias=w.conv2.b, resid=xs)
+
+    @staticmethod
+    def _attn(w: TransformerW, x: torch.Tensor, c: _Ctx) -> torch.Tensor:
+        B, H, W, C = x.shape
+        scale = w.d_head ** -0.5
+        hn = ops.groupnorm(x, w.norm.g, w.norm.b, w.groups, 1e-6, False)
+        h = ops.linear(hn.view(B, H * W, C), w.proj_in.w, C, bias=w.proj_in.b)
+        n1 = ops.layernorm(h, w.ln1.g, w.ln1.b)
+        qkv = ops.linear(n1, w.qkv.w, 3 * C)
+        a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], w.heads, w.d_head, scale)
+        h = ops.linear(a, w.out1.w, C, bias=w.out1.b, resid=h)
+        n2 = ops.layernorm(h, w.ln2.g, w.ln2.b)
+        q = ops.linear(n2, w.q2.w, C)
+        a = ops.attention(q, c.kv[..., w.kv_off:w.kv_off + C], c.kv[..., w.kv_off + C:w.kv_off + 2 * C], w.heads,
+                          w.d_head, scale)
+        h = ops.linear(a, w.out2.w, C, bias=w.out2.b, resid=h)
+        n3 = ops.layernorm(h, w.ln3.g, w.ln3.b)
+        f = ops.geglu(ops.linear(n3, w.ff1.w, w.ff1.n_out, bias=w.ff1.b))
+        h = ops.linear(f, w.ff2.w, C, bias=w.ff2.b, resid=h)
+        out = ops.linear(h, w.proj_out.w, C, bias=w.proj_out.b, resid=x.view(B, H * W, C))
+        return out.view(B, H, W, C)
+
+    def _run_block(self, layers: List[Layer], x, x2, c: _Ctx, x_in2=None):
+        for L in layers:
+            if L.kind == "res":
+                x = self._res(L.w, x, x2, c)
+                x2 = None
+            elif L.kind == "attn":
+                x = self._attn(L.w, x, c)
+            elif L.kind == "down":
+                B, H, W, C = x.shape
+                col = ops.im2col_3x3_s2(x)
+                y = ops.linear(col, L.w.w, L.w.n_out, bias=L.w.b)
+                x = y.view(B, H // 2, W // 2, L.w.n_out)
+            elif L.kind == "up":
+                x = ops.conv_gemm(ops.upsample2x(x), L.w.w, L.w.n_out, 9, bias=L.w.b)
+            elif L.kind == "conv_in":
+                x = ops.conv_gemm(x, L.w.w, L.w.n_out, 9, a2=x_in2, bias=L.w.b)
+            else:
+                raise RuntimeError(L.kind)
+        return x
+
+    # ----- one relay step -------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor, guide_hint: Optional[torch.Tensor],
+                unconditional: bool = False) -> torch.Tensor:
+        """x [B,4,h,w] fp32 NCHW, t [B] int64, context [B,77,ctx], guide_hint [B,hint,h,w] ->
+        eps [B,4,h,w] fp32 (model/rdeic.py:174-212; :214-235 when `unconditional`)."""
+        if not x.is_cuda:
+            raise ops._lib.RdeicLibraryError("NoiseEstimatorEngine.forward needs CUDA tensors; there is no CPU path")
+        B, Cin, h, w = x.shape
+        kv_base, kv_ctrl, hint = self.prepare_cond(context, None if unconditional else guide_hint)
+        x8 = ops.nchw_to_nhwc_bf16(x.float().contiguous(), ldc=8)          # 4 latent channels padded to 8 (TMA stride)
+        t_emb = ops.timestep_embedding(t.to(self.device, torch.int64).contiguous(), self.model_channels)
+        cb = _Ctx(self._time_rows(self.base, t_emb), kv_base)
+        hb = x8
+        hs_base: List[torch.Tensor] = []
+        if unconditional:
+            for blk in self.base.input_blocks:
+                hb = self._run_block(blk, hb, None, cb)
+                hs_base.append(hb)
+            hb = self._run_block(self.base.middle, hb, None, cb)
+            for blk in self.base.output_blocks:
+                hb = self._run_block(blk, hb, hs_base.pop(), cb)
+        else:
+            cc = _Ctx(self._time_rows(self.ctrl, t_emb), kv_ctrl)
+            hc = x8
+            hs_ctr: List[torch.Tensor] = []
+            si = 0
+            for i, (bb, bc) in enumerate(zip(self.base.input_blocks, self.ctrl.input_blocks)):
+                hb = self._run_block(bb, hb, None, cb)
+                hc = self._run_block(bc, hc, None, cc, x_in2=hint if i == 0 else None)
+                z = self.enc_zero[i]
+                # h_base = h_base + zero_conv(h_ctr) * scale  (rdeic.py:194), fused as a residual epilogue
+                hb = ops.conv_gemm(hc, z.w, z.n_out, 1, bias=z.b, resid=hb, alpha=self.scales[si], out=hb)
+                si += 1
+                hs_base.append(hb)
+                hs_ctr.append(hc)
+            hb = self._run_block(self.base.middle, hb, None, cb)
+            hc = self._run_block(self.ctrl.middle, hc, None, cc)
+            z = self.mid_zero
+            hb = ops.conv_gemm(hc, z.w, z.n_out, 1, bias=z.b, resid=hb, alpha=self.scales[si], out=hb)
+            si += 1
+            for i, blk in enumerate(self.base.output_blocks):
+                z = self.dec_zero[i]
+                hb = ops.conv_gemm(hs_ctr.pop(), z.w, z.n_out, 1, bias=z.b, resid=hb, alpha=self.scales[si], out=hb)
+                si += 1
+                hb = self._run_block(blk, hb, hs_base.pop(), cb)
+        hn = ops.groupnorm(hb, self.base.out_norm.g, self.base.out_norm.b, find_denominator(hb.shape[-1], 32), 1e-5, True)
+        o = ops.conv_gemm(hn, self.base.out_conv.w, self.out_channels, 9, bias=self.base.out_conv.b, out_f32=True)
+        return ops.nhwc_to_nchw_f32(o)
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE decoder
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class VaeRes:
+    n1: Norm
+    c1: Conv
+    n2: Norm
+    c2: Conv
+    nin: Optional[Conv]
+    cout: int
+
+
+class VAEDecoderEngine:
+    def __init__(self, sd: SD, scale_factor: float, device="cuda", prefix: str = "first_stage_model"):
+        dev = torch.device(device)
+        self.device = dev
+        D = prefix + ".decoder"
+        # ddpm.py:843 `1/scale_factor * z` folded into the 1x1 post_quant_conv weights (autoencoder.py:98)
+        self.post_quant = Conv.load(sd, prefix + ".post_quant_conv", dev, scale=1.0 / scale_factor)
+        self.conv_in = Conv.load(sd, D + ".conv_in", dev)
+
+        def rb(p):
+            nin = Conv.load(sd, p + ".nin_shortcut", dev) if (p + ".nin_shortcut.weight") in sd else None
+            c1 = Conv.load(sd, p + ".conv1", dev)
+            return VaeRes(Norm.load(sd, p + ".norm1", dev), c1, Norm.load(sd, p + ".norm2", dev),
+                          Conv.load(sd, p + ".conv2", dev), nin, c1.n_out)
+
+        self.mid1 = rb(D + ".mid.block_1")
+        self.mid2 = rb(D + ".mid.block_2")
+        a = D + ".mid.attn_1"
+        self.attn_norm = Norm.load(sd, a + ".norm", dev)
+        self.attn_q, self.attn_k, self.attn_v = (Conv.load(sd, a + n, dev) for n in (".q", ".k", ".v"))
+        self.attn_out = Conv.load(sd, a + ".proj_out", dev)
+        self.levels = []
+        lvl = 0
+        while any(k.startswith(f"{D}.up.{lvl}.") for k in sd):
+            blocks = []
+            i = 0
+            while (f"{D}.up.{lvl}.block.{i}.conv1.weight") in sd:
+                blocks.append(rb(f"{D}.up.{lvl}.block.{i}"))
+                i += 1
+            up = Conv.load(sd, f"{D}.up.{lvl}.upsample.conv", dev) if (f"{D}.up.{lvl}.upsample.conv.weight") in sd else None
+            self.levels.append((blocks, up))
+            lvl += 1
+        self.norm_out = Norm.load(sd, D + ".norm_out", dev)
+        self.conv_out = Conv.load(sd, D + ".conv_out", dev)
+
+    @staticmethod
+    def _res(w: VaeRes, x):
+        """model.py:128-151 with temb None; GroupNorm eps 1e-6 (model.py:48)."""
+        h = ops.groupnorm(x, w.n1.g, w.n1.b, 32, 1e-6, True)
+        h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b)
+        h = ops.groupnorm(h, w.n2.g, w.n2.b, 32, 1e-6, True)
+        xs = x if w.nin is None else ops.conv_gemm(x, w.nin.w, w.cout, 1, bias=w.nin.b)
+        return ops.conv_gemm(h, w.c2.w, w.cout, 9, bias=w.c2.b, resid=xs)
+
+    def _attn(self, x):
+        """model.py:181-205: single head, d = C = 512; logits fp32, softmax fp32, P bf16."""
+        B, H, W, C = x.shape
+        N = H * W
+        hn = ops.groupnorm(x, self.attn_norm.g, self.attn_norm.b, 32, 1e-6, False).view(B, N, C)
+        q = ops.linear(hn, self.attn_q.w, C, bias=self.attn_q.b)
+        k = ops.linear(hn, self.attn_k.w, C, bias=self.attn_k.b)
+        v = ops.linear(hn, self.attn_v.w, C, bias=self.attn_v.b)
+        s = ops.conv_gemm(q.view(B, 1, N, C), k, N, 1, w_batch_stride=N * C, w_k=C, w_ld=C, out_f32=True)
+        p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
+        vt = ops.transpose_bf16(v)                                   # [B, C, N]: K-major B operand for P V
+        o = ops.conv_gemm(p.view(B, 1, N, N), vt, C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
+        out = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.view(B, N, C))
+        return out.view(B, H, W, C)
+
+    @torch.no_grad()
+    def decode_nhwc(self, z: torch.Tensor) -> torch.Tensor:
+        """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,3] in [-1,1]."""
+        if not z.is_cuda:
+            raise ops._lib.RdeicLibraryError("VAEDecoderEngine needs CUDA tensors; there is no CPU path")
+        z8 = ops.nchw_to_nhwc_bf16(z.float().contiguous(), ldc=8)
+        B, h, w, _ = z8.shape
+        zq = torch.zeros((B, h, w, 8), dtype=BF16, device=z.device)
+        ops.conv_gemm(z8, self.post_quant.w, self.post_quant.n_out, 1, bias=self.post_quant.b, out=zq)
+        x = ops.conv_gemm(zq, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b)
+        x = self._res(self.mid1, x)
+        x = self._attn(x)
+        x = self._res(self.mid2, x)
+        for blocks, up in reversed(self.levels):
+            for b in blocks:
+                x = self._res(b, x)
+            if up is not None:
+                x = ops.conv_gemm(ops.upsample2x(x), up.w, up.n_out, 9, bias=up.b)
+        x = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
+        return ops.conv_gemm(x, self.conv_out.w, self.conv_out.n_out, 9, bias=self.conv_out.b, out_f32=True)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """decode_first_stage contract: [B,3,H,W] fp32 in [-1,1]."""
+        return ops.nhwc_to_nchw_f32(self.decode_nhwc(z))
+
+    @torch.no_grad()
+    def decode_u8(self, z: torch.Tensor) -> torch.Tensor:
+        """Fused caller post-process (inference.py:85-87): uint8 HWC images."""
+        return ops.image_to_u8(self.decode_nhwc(z))

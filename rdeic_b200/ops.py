@@ -360,7 +360,8 @@ def pack_conv_weight(w: torch.Tensor, c1: Optional[int] = None) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *, a2: Optional[torch.Tensor] = None,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
-              out: Optional[torch.Tensor] = None, w_batch_stride: int = 0, tile_n: int = 0) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0,
+              tile_n: int = 0) -> torch.Tensor:
     """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out]."""
     if a.dtype != BF16 or not a.is_contiguous():
         raise TypeError("conv_gemm: A must be contiguous bf16 NHWC")
@@ -374,6 +375,7 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     p.taps = taps
     p.w = _ptr(w_packed)
     p.w_batch_stride = w_batch_stride
+    p.w_k, p.w_ld = w_k, w_ld
     p.n_out = n_out
     p.bias = _ptr(bias)
     if row_bias is not None:

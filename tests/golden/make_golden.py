@@ -1,0 +1,131 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE ITSELF
+(/root/reference, imported through tests/ref_harness.py) on seeded synthetic inputs and the
+seeded synthetic checkpoint of rdeic_b200.synthetic (loaded into the reference modules with
+their own `load_state_dict`, which also proves the checkpoint-layout contract).
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures travel to the GPU box; /root/reference does not.
+
+Files written
+  state_dict_keys.json     decode-path keys + shapes of the reference model (full rdeic.yaml)
+  full_unet_step.npz       reference apply_model / apply_model_unconditional, full width, 256x256
+  full_vae_decode.npz      reference decode_first_stage, full width, 16x16 latent
+  full_sampler.npz         reference SpacedSampler.sample (2 steps) and DDIMSampler.sample (2 steps)
+  small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import ref_harness as rh  # noqa: E402
+from rdeic_b200 import synthetic  # noqa: E402
+
+DECODE_PREFIXES = ("model.diffusion_model.", "control_model.", "first_stage_model.decoder.",
+                   "first_stage_model.post_quant_conv.")
+WEIGHT_SEED = 231
+
+
+def inputs(B, h, w, hint_c, ctx_dim, n_noise):
+    g = lambda s: torch.Generator().manual_seed(s)
+    c_latent = torch.randn(B, 4, h, w, generator=g(7))
+    hint = torch.randn(B, hint_c, h, w, generator=g(8))
+    ctx = torch.randn(B, 77, ctx_dim, generator=g(9))
+    gn = g(231)
+    noises = [torch.randn(B, 4, h, w, generator=gn) for _ in range(n_noise)]
+    return c_latent, hint, ctx, noises
+
+
+def load_synthetic_into_reference(model, params):
+    sd = synthetic.make_state_dict(params, seed=WEIGHT_SEED)
+    ref_keys = {k for k in model.state_dict() if k.startswith(DECODE_PREFIXES)}
+    missing = ref_keys - set(sd)
+    extra = set(sd) - ref_keys
+    assert not missing and not extra, (sorted(missing)[:5], sorted(extra)[:5])
+    for k, v in model.state_dict().items():
+        if k in sd:
+            assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    res = model.load_state_dict(sd, strict=False)
+    assert not [k for k in res.unexpected_keys], res.unexpected_keys
+    return sd
+
+
+def run_config(tag, overrides, unet_hw, vae_hw, samp_hw):
+    model, mods = rh.build_reference_model(overrides)
+    cfg = rh.load_config(overrides)
+    params = cfg["params"]
+    if tag == "full":
+        keys = {k: list(v.shape) for k, v in model.state_dict().items() if k.startswith(DECODE_PREFIXES)}
+        (HERE / "state_dict_keys.json").write_text(json.dumps(keys, indent=0, sort_keys=True))
+    load_synthetic_into_reference(model, params)
+    hint_c = params["control_stage_config"]["params"]["hint_channels"]
+    ctx_dim = params["unet_config"]["params"]["context_dim"]
+
+    with torch.no_grad():
+        # ---- one relay step ----
+        B, (h, w) = 1, unet_hw
+        c_latent, hint, ctx, noises = inputs(B, h, w, hint_c, ctx_dim, 1)
+        x = model.q_sample(c_latent, torch.full((B,), 299, dtype=torch.long), noises[0])
+        cond = {"c_latent": [c_latent], "c_crossattn": [ctx], "guide_hint": hint}
+        t = torch.full((B,), 224, dtype=torch.long)
+        eps = model.apply_model(x, t, cond)
+        eps_u = model.apply_model_unconditional(x, t, cond)
+        np.savez_compressed(HERE / f"{tag}_unet_step.npz", x=x.numpy(), t=t.numpy(), eps=eps.numpy(),
+                            eps_uncond=eps_u.numpy(), hw=np.array([h, w]))
+        print(tag, "unet step", eps.abs().max().item(), eps_u.abs().max().item())
+
+        # ---- VAE decode ----
+        h, w = vae_hw
+        z = torch.randn(1, 4, h, w, generator=torch.Generator().manual_seed(11))
+        img = model.decode_first_stage(z)
+        np.savez_compressed(HERE / f"{tag}_vae_decode.npz", z=z.numpy(), img=img.numpy())
+        print(tag, "vae", img.abs().max().item())
+
+        # ---- samplers (noise injected instead of torch.randn_like / noise_like) ----
+        h, w = samp_hw
+        B = 2 if tag == "small" else 1
+        c_latent, hint, ctx, noises = inputs(B, h, w, hint_c, ctx_dim, 8)
+        cond = {"c_latent": [c_latent], "c_crossattn": [ctx], "guide_hint": hint}
+        x_T = model.q_sample(c_latent, torch.full((B,), model.used_timesteps - 1, dtype=torch.long), noises[0])
+        out = {"x_T": x_T.numpy()}
+        pool = []
+        orig_randn_like = torch.randn_like
+        torch.randn_like = lambda t_, **k: pool.pop(0)
+        try:
+            for steps in (2, 3):
+                pool[:] = [n.clone() for n in noises[1:1 + steps]]
+                s = mods["spaced"].SpacedSampler(model, var_type="fixed_small")
+                out[f"spaced_{steps}"] = s.sample(steps, (B, 4, h, w), cond, x_T=x_T.clone()).numpy()
+            pool[:] = [n.clone() for n in noises[1:3]]
+            s = mods["spaced"].SpacedSampler(model, var_type="fixed_small")
+            out["spaced_2_cfg"] = s.sample(2, (B, 4, h, w), cond, x_T=x_T.clone(),
+                                           unconditional_guidance_scale=1.5).numpy()
+        finally:
+            torch.randn_like = orig_randn_like
+        rh.patch_ddim_register_buffer(mods["ddim"])
+        pool[:] = [n.clone() for n in noises[1:3]]
+        mods["ddim"].noise_like = lambda shape, device, repeat=False: pool.pop(0)
+        d = mods["ddim"].DDIMSampler(model)
+        samples, _ = d.sample(S=2, batch_size=B, shape=(4, h, w), conditioning=cond, x_T=x_T.clone(), eta=0.0,
+                              verbose=False)
+        out["ddim_2"] = samples.numpy()
+        np.savez_compressed(HERE / f"{tag}_sampler.npz", **out)
+        print(tag, "samplers", {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["small", "full"]
+    if "small" in which:
+        run_config("small", rh.SMALL_OVERRIDES, (16, 16), (8, 8), (8, 16))
+    if "full" in which:
+        run_config("full", None, (32, 32), (16, 16), (16, 16))

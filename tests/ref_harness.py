@@ -168,7 +168,7 @@ SMALL_OVERRIDES = {
     "unet_config.params.model_channels": 64,
     "unet_config.params.num_head_channels": 16,
     "control_stage_config.params.model_channels": 64,
-    "control_stage_config.params.num_head_channels": 8,
+    "control_stage_config.params.num_head_channels": 16,
     "control_stage_config.params.control_model_ratio": 0.5,
     "control_stage_config.params.hint_channels": 32,
     "control_stage_config.params.context_dim": 64,

@@ -1,0 +1,160 @@
+"""GPU parity of the assembled decode path (UNet+control step, VAE decoder, relay samplers)
+through the drop-in API, against golden vectors produced by the reference itself
+(tests/golden/, full-width and reduced-width) and against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): per-step UNet output rel-L2 <= 1e-2 in bf16; decoded
+image PSNR >= 40 dB against the reference's fp32 output (peak-to-peak 2.0 for [-1,1] images)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import inputs, psnr, rel_l2
+from rdeic_b200 import configs, synthetic
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+UNET_TOL = 1e-2
+PSNR_MIN = 40.0
+
+
+def _model(params, cuda, graph=True):
+    from rdeic_b200 import RDEIC
+
+    sd = synthetic.make_state_dict(params, seed=231)
+    m = RDEIC.from_config({"params": params}, device=cuda, use_cuda_graph=graph)
+    m.load_state_dict(sd)
+    return m
+
+
+@pytest.fixture(scope="module")
+def small_model(cuda):
+    return _model(configs.small_params(), cuda)
+
+
+@pytest.fixture(scope="module")
+def full_model(cuda):
+    return _model(configs.default_params(), cuda)
+
+
+def _check_unet(model, tag, hint_c, ctx_dim, cuda):
+    gold = np.load(GOLD / f"{tag}_unet_step.npz")
+    h, w = gold["hw"]
+    c_latent, hint, ctx, _ = inputs(1, h, w, hint_c, ctx_dim, 1)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    x, t = torch.from_numpy(gold["x"]).to(cuda), torch.from_numpy(gold["t"]).to(cuda)
+    eps = model.apply_model(x, t, cond).cpu().numpy()
+    eps_u = model.apply_model_unconditional(x, t, cond).cpu().numpy()
+    e1, e2 = rel_l2(eps, gold["eps"]), rel_l2(eps_u, gold["eps_uncond"])
+    print(f"[{tag}] unet step rel-L2 cond {e1:.3e} uncond {e2:.3e}")
+    assert e1 <= UNET_TOL and e2 <= UNET_TOL
+    # second call replays the captured CUDA graph: identical result
+    eps2 = model.apply_model(x, t, cond).cpu().numpy()
+    assert np.array_equal(eps, eps2)
+
+
+def _check_vae(model, tag, cuda):
+    gold = np.load(GOLD / f"{tag}_vae_decode.npz")
+    img = model.decode_first_stage(torch.from_numpy(gold["z"]).to(cuda)).cpu().numpy()
+    p = psnr(img, gold["img"], 2.0)
+    print(f"[{tag}] vae decode PSNR {p:.1f} dB rel-L2 {rel_l2(img, gold['img']):.3e}")
+    assert p >= PSNR_MIN
+    u8 = model.decode_first_stage_u8(torch.from_numpy(gold["z"]).to(cuda)).cpu().numpy()
+    ref_u8 = (((gold["img"] + 1) / 2).clip(0, 1).transpose(0, 2, 3, 1) * 255).clip(0, 255).astype(np.uint8)
+    assert psnr(u8, ref_u8, 255.0) >= PSNR_MIN - 1.0     # +quantisation noise of the uint8 grid
+
+
+def _check_samplers(model, tag, B, h, w, hint_c, ctx_dim, cuda):
+    from rdeic_b200 import SpacedSampler, DDIMSampler
+
+    gold = np.load(GOLD / f"{tag}_sampler.npz")
+    c_latent, hint, ctx, noises = inputs(B, h, w, hint_c, ctx_dim, 8)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    t = torch.full((B,), model.used_timesteps - 1, dtype=torch.long, device=cuda)
+    x_T = model.q_sample(c_latent.to(cuda), t, noises[0].to(cuda))
+    assert np.array_equal(x_T.cpu().numpy(), gold["x_T"])          # elementwise fp32: bit exact
+    for steps in (2, 3):
+        s = SpacedSampler(model, var_type="fixed_small")
+        s.noise_fn = lambda i, like: noises[1 + i]
+        out = s.sample(steps, (B, 4, h, w), cond, x_T=x_T).cpu().numpy()
+        e = rel_l2(out, gold[f"spaced_{steps}"])
+        print(f"[{tag}] spaced {steps} steps rel-L2 {e:.3e}")
+        assert e <= UNET_TOL
+    s = SpacedSampler(model)
+    s.noise_fn = lambda i, like: noises[1 + i]
+    out = s.sample(2, (B, 4, h, w), cond, x_T=x_T, unconditional_guidance_scale=1.5).cpu().numpy()
+    assert rel_l2(out, gold["spaced_2_cfg"]) <= UNET_TOL
+    d = DDIMSampler(model)
+    d.noise_fn = lambda i, like: noises[1 + i]
+    out, inter = d.sample(S=2, batch_size=B, shape=(4, h, w), conditioning=cond, x_T=x_T, eta=0.0, verbose=False)
+    assert rel_l2(out.cpu().numpy(), gold["ddim_2"]) <= UNET_TOL
+    assert set(inter) == {"x_inter", "pred_x0"}
+
+
+def test_small_unet_step_vs_reference_golden(small_model, cuda):
+    _check_unet(small_model, "small", 32, 64, cuda)
+
+
+def test_small_vae_vs_reference_golden(small_model, cuda):
+    _check_vae(small_model, "small", cuda)
+
+
+def test_small_samplers_vs_reference_golden(small_model, cuda):
+    _check_samplers(small_model, "small", 2, 8, 16, 32, 64, cuda)
+
+
+def test_small_step_vs_oracle_batched_odd_shape(small_model, cuda):
+    """Batch > 1 with different per-sample timesteps and a non-square, non-power-of-two latent."""
+    from oracle import nn as onn
+
+    p = configs.small_params()
+    sd = synthetic.make_state_dict(p, seed=231)
+    B, h, w = 3, 8, 24
+    c_latent, hint, ctx, noises = inputs(B, h, w, 32, 64, 1)
+    t = torch.tensor([299, 150, 0], dtype=torch.long)
+    with torch.no_grad():
+        ref = onn.noise_estimator_forward(sd, noises[0], hint, t, ctx, model_channels=64, base_d_head=16, ctrl_d_head=16)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    eps = small_model.apply_model(noises[0].to(cuda), t.to(cuda), cond).cpu().numpy()
+    e = rel_l2(eps, ref.numpy())
+    print(f"[small] B=3 8x24 rel-L2 {e:.3e}")
+    assert e <= UNET_TOL
+
+
+def test_graph_and_eager_agree(small_model, cuda):
+    B, h, w = 1, 16, 16
+    c_latent, hint, ctx, noises = inputs(B, h, w, 32, 64, 1)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    t = torch.full((B,), 75, dtype=torch.long, device=cuda)
+    a = small_model.apply_model(noises[0].to(cuda), t, cond)
+    small_model.use_cuda_graph = False
+    try:
+        b = small_model.apply_model(noises[0].to(cuda), t, cond)
+    finally:
+        small_model.use_cuda_graph = True
+    assert torch.equal(a, b)
+
+
+def test_model_raises_without_weights_and_on_cpu(cuda):
+    from rdeic_b200 import RDEIC, _lib
+
+    m = RDEIC.from_config({"params": configs.small_params()}, device=cuda)
+    with pytest.raises(RuntimeError):
+        m.decode_first_stage(torch.zeros(1, 4, 8, 8, device=cuda))
+    with pytest.raises(_lib.RdeicLibraryError):
+        m.to("cpu")
+    with pytest.raises(KeyError):
+        m.load_state_dict({"model.diffusion_model.time_embed.0.weight": torch.zeros(256, 64)})
+
+
+def test_full_unet_step_vs_reference_golden(full_model, cuda):
+    _check_unet(full_model, "full", 256, 1024, cuda)
+
+
+def test_full_vae_vs_reference_golden(full_model, cuda):
+    _check_vae(full_model, "full", cuda)
+
+
+def test_full_samplers_vs_reference_golden(full_model, cuda):
+    _check_samplers(full_model, "full", 1, 16, 16, 256, 1024, cuda)
