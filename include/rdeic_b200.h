@@ -148,18 +148,20 @@ int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
 
 /* ---- normalisation (HBM-bound) --------------------------------------------------------- */
 
-/* GroupNorm(+SiLU) over NHWC bf16, fp32 statistics (util.py:209-226 GroupNorm32,
+/* GroupNorm(+SiLU) over NHWC bf16 (or, with in_is_f32, the fp32 master copy of a residual
+ * stream), bf16 output, fp32 statistics (util.py:209-226 GroupNorm32,
  * model.py:48-49 Normalize, rdeic.py:473-485).  The input may be the channel concat of two
  * tensors x1 [B,HW,C1] and x2 [B,HW,C2] (openaimodel.py:804 `th.cat([h, hs.pop()])`) without
  * materialising it; x2 may be NULL with C2 = 0.  out [B,HW,C1+C2] bf16.
  * workspace: rdeic_groupnorm_workspace_bytes(B, HW, C) bytes. */
 int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C);
-int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, const float* gamma,
-                         const float* beta, void* out, int B, int64_t HW, int groups,
-                         float eps, int silu, void* workspace, rdeic_stream_t stream);
-/* LayerNorm over the last dim of [rows, C] bf16 (attention.py:273-275). */
-int rdeic_layernorm(const void* x, const float* gamma, const float* beta, void* out,
-                    int64_t rows, int C, float eps, rdeic_stream_t stream);
+int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
+                         const float* gamma, const float* beta, void* out, int B, int64_t HW,
+                         int groups, float eps, int silu, void* workspace,
+                         rdeic_stream_t stream);
+/* LayerNorm over the last dim of [rows, C] bf16 or fp32 -> bf16 (attention.py:273-275). */
+int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const float* beta,
+                    void* out, int64_t rows, int C, float eps, rdeic_stream_t stream);
 
 /* ---- tensor-core contractions (tcgen05 / TMEM / TMA) ------------------------------------ */
 

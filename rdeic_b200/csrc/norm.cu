@@ -25,10 +25,29 @@ static inline int gn_num_chunks(int B, int64_t HW) {
     return (int)want;
 }
 
+// 8 consecutive channels of one pixel as fp32, from a bf16 (16 B) or fp32 (32 B) tensor.
+// `vec_index` counts 8-channel vectors.
+template <bool kF32>
+__device__ __forceinline__ void load8(const void* base, int64_t vec_index, float* f) {
+    if (kF32) {
+        const uint4 a = ld_stream_u4(reinterpret_cast<const uint4*>(base) + 2 * vec_index);
+        const uint4 b = ld_stream_u4(reinterpret_cast<const uint4*>(base) + 2 * vec_index + 1);
+        f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y);
+        f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+        f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y);
+        f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    } else {
+        const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(base) + vec_index);
+        unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+        unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+    }
+}
+
 // partial[(b*nchunk + chunk)*G + g] = (sum, sumsq) over the chunk's pixels and the group's
 // channels, reduced in a fixed order (deterministic run to run).
+template <bool kF32>
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ x2, int C2,
+gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 int64_t HW, int G, float2* __restrict__ partial) {
     __shared__ float s_part[kGnThreads * 16];   // [row][lane][8 sum | 8 sq]
     __shared__ float s_csum[kGnMaxC];
@@ -51,18 +70,16 @@ gn_stats_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ 
         for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
         if (row < rows_per_iter && l < VL) {
             const bool first = l < VL1;
-            const uint4* src = first ? x1 + (int64_t)b * HW * VL1 + l
-                                     : x2 + (int64_t)b * HW * VL2 + (l - VL1);
+            const void* src = first ? x1 : x2;
             const int64_t stride = first ? VL1 : VL2;
+            const int64_t off = (int64_t)b * HW * stride + (first ? l : l - VL1);
             for (int64_t p = p0 + row; p < p1; p += rows_per_iter) {
-                const uint4 v = src[p * stride];
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                float f[8];
+                load8<kF32>(src, off + p * stride, f);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float a, c;
-                    unpack_bf16x2(w[k], a, c);
-                    s[2 * k] += a;      q[2 * k] = fmaf(a, a, q[2 * k]);
-                    s[2 * k + 1] += c;  q[2 * k + 1] = fmaf(c, c, q[2 * k + 1]);
+                for (int k = 0; k < 8; ++k) {
+                    s[k] += f[k];
+                    q[k] = fmaf(f[k], f[k], q[k]);
                 }
             }
         }
@@ -99,8 +116,9 @@ gn_stats_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ 
     }
 }
 
+template <bool kF32>
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ x2, int C2,
+gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
                 const float2* __restrict__ partial, int nchunk) {
@@ -135,24 +153,19 @@ gn_apply_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ 
     }
     __syncthreads();
     const int64_t total = HW * VL;
-    const uint4* b1 = x1 + (int64_t)b * HW * VL1;
-    const uint4* b2 = x2 ? x2 + (int64_t)b * HW * VL2 : nullptr;
+    const int64_t o1 = (int64_t)b * HW * VL1, o2 = (int64_t)b * HW * VL2;
     uint4* bo = out + (int64_t)b * HW * VL;
     for (int64_t i = blockIdx.x * (int64_t)kGnThreads + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * kGnThreads) {
         const int64_t p = i / VL;
         const int l = (int)(i - p * VL);
-        const uint4 v = (l < VL1) ? ld_stream_u4(b1 + p * VL1 + l)
-                                  : ld_stream_u4(b2 + p * VL2 + (l - VL1));
+        float f[8];
+        if (l < VL1) load8<kF32>(x1, o1 + p * VL1 + l, f);
+        else load8<kF32>(x2, o2 + p * VL2 + (l - VL1), f);
         const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[l * 8]);
         const float4 sc1 = *reinterpret_cast<const float4*>(&s_scale[l * 8 + 4]);
         const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[l * 8]);
         const float4 sh1 = *reinterpret_cast<const float4*>(&s_shift[l * 8 + 4]);
-        float f[8];
-        unpack_bf16x2(v.x, f[0], f[1]);
-        unpack_bf16x2(v.y, f[2], f[3]);
-        unpack_bf16x2(v.z, f[4], f[5]);
-        unpack_bf16x2(v.w, f[6], f[7]);
         f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y);
         f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
         f[4] = fmaf(f[4], sc1.x, sh1.x); f[5] = fmaf(f[5], sc1.y, sh1.y);
@@ -172,26 +185,22 @@ gn_apply_kernel(const uint4* __restrict__ x1, int C1, const uint4* __restrict__ 
 constexpr int kLnMaxVec = 5;
 constexpr int kLnWarps = 8;
 
+template <bool kF32>
 __global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
                  float eps) {
     const int VL = C >> 3;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
-    const uint4* xr = x + row * VL;
     float f[kLnMaxVec][8];
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kLnMaxVec; ++j) {
         const int l = lane + 32 * j;
         if (l < VL) {
-            const uint4 v = ld_stream_u4(xr + l);
-            unpack_bf16x2(v.x, f[j][0], f[j][1]);
-            unpack_bf16x2(v.y, f[j][2], f[j][3]);
-            unpack_bf16x2(v.z, f[j][4], f[j][5]);
-            unpack_bf16x2(v.w, f[j][6], f[j][7]);
+            load8<kF32>(x, row * VL + l, f[j]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) sum += f[j][k];
         }
@@ -248,9 +257,10 @@ int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C) {
     return (int64_t)B * kGnMaxChunks * kGnMaxGroups * (int64_t)sizeof(float2);
 }
 
-int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, const float* gamma,
-                         const float* beta, void* out, int B, int64_t HW, int groups,
-                         float eps, int silu, void* workspace, rdeic_stream_t stream) {
+int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
+                         const float* gamma, const float* beta, void* out, int B, int64_t HW,
+                         int groups, float eps, int silu, void* workspace,
+                         rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(x1 && gamma && beta && out && workspace, "rdeic_groupnorm_nhwc: null pointer");
     RDEIC_CHECK_ARG(C2 == 0 || x2, "rdeic_groupnorm_nhwc: C2 > 0 needs x2");
     if (C2 == 0) x2 = nullptr;
@@ -266,23 +276,28 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, const f
                     "rdeic_groupnorm_nhwc: tensors must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
     const int nchunk = gn_num_chunks(B, HW);
-    gn_stats_kernel<<<dim3(nchunk, B), kGnThreads, 0, s>>>(
-        (const uint4*)x1, C1, (const uint4*)x2, C2, HW, groups, (float2*)workspace);
+    if (in_is_f32)
+        gn_stats_kernel<true><<<dim3(nchunk, B), kGnThreads, 0, s>>>(x1, C1, x2, C2, HW, groups, (float2*)workspace);
+    else
+        gn_stats_kernel<false><<<dim3(nchunk, B), kGnThreads, 0, s>>>(x1, C1, x2, C2, HW, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const int64_t vecs = HW * (C / 8);
     int64_t blocks = ceil_div64(vecs, (int64_t)kGnThreads * 4);
     const int64_t cap = (8 * kNumSMs + B - 1) / B;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    gn_apply_kernel<<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
-        (const uint4*)x1, C1, (const uint4*)x2, C2, gamma, beta, (uint4*)out, HW, groups, eps,
-        silu, (const float2*)workspace, nchunk);
+    if (in_is_f32)
+        gn_apply_kernel<true><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk);
+    else
+        gn_apply_kernel<false><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
 
-int rdeic_layernorm(const void* x, const float* gamma, const float* beta, void* out,
-                    int64_t rows, int C, float eps, rdeic_stream_t stream) {
+int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const float* beta,
+                    void* out, int64_t rows, int C, float eps, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(x && gamma && beta && out, "rdeic_layernorm: null pointer");
     RDEIC_CHECK_ARG(rows >= 0, "rdeic_layernorm: negative rows");
     RDEIC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVec,
@@ -292,8 +307,10 @@ int rdeic_layernorm(const void* x, const float* gamma, const float* beta, void* 
     if (rows == 0) return 0;
     const int64_t blocks = ceil_div64(rows, kLnWarps);
     RDEIC_CHECK_ARG(blocks < (1ll << 31), "rdeic_layernorm: too many rows");
-    layernorm_kernel<<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(
-        (const uint4*)x, gamma, beta, (uint4*)out, rows, C, eps);
+    if (in_is_f32)
+        layernorm_kernel<true><<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(x, gamma, beta, (uint4*)out, rows, C, eps);
+    else
+        layernorm_kernel<false><<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(x, gamma, beta, (uint4*)out, rows, C, eps);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -151,7 +151,9 @@ class RDEIC:
                 out = eng.forward(xs, ts, context, hint, unconditional)
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
-            g = (graph, xs, ts, out, context, hint)          # keep cond tensors alive: key uses their pointers
+            # keep alive everything the graph reads: cond tensors (the key uses their pointers) and
+            # the derived K/V + NHWC hint that were computed outside the capture
+            g = (graph, xs, ts, out, context, hint, eng.prepare_cond(context, hint))
             self._graphs[key] = g
         graph, xs, ts, out = g[:4]
         xs.copy_(x)

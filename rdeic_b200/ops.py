@@ -40,6 +40,8 @@ def ckbd_mask(y: torch.Tensor, which: int) -> torch.Tensor:
     y = _need(y, torch.float32, "ckbd_mask")
     B, Cc, H, W = y.shape
     out = torch.empty_like(y)
+    if y.numel() == 0:
+        return out
     check(_lib.load().rdeic_ckbd_mask(_ptr(y), _ptr(out), B, Cc, H, W, which, _stream()), "rdeic_ckbd_mask")
     return out
 
@@ -48,6 +50,8 @@ def ckbd_split(y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     y = _need(y, torch.float32, "ckbd_split")
     B, Cc, H, W = y.shape
     a, n = torch.empty_like(y), torch.empty_like(y)
+    if y.numel() == 0:
+        return a, n
     check(_lib.load().rdeic_ckbd_split(_ptr(y), _ptr(a), _ptr(n), B, Cc, H, W, _stream()), "rdeic_ckbd_split")
     return a, n
 
@@ -66,6 +70,8 @@ def ckbd_squeeze(y: torch.Tensor, which: int) -> torch.Tensor:
     y = _need(y, torch.float32, "ckbd_squeeze")
     B, Cc, H, W = y.shape
     out = torch.empty((B, Cc, H, W // 2), dtype=torch.float32, device=y.device)
+    if W % 2 == 0 and y.numel() == 0:
+        return out
     check(_lib.load().rdeic_ckbd_squeeze(_ptr(y), _ptr(out), B, Cc, H, W, which, _stream()), "rdeic_ckbd_squeeze")
     return out
 
@@ -74,6 +80,8 @@ def ckbd_unsqueeze(s: torch.Tensor, which: int) -> torch.Tensor:
     s = _need(s, torch.float32, "ckbd_unsqueeze")
     B, Cc, H, Wh = s.shape
     out = torch.empty((B, Cc, H, Wh * 2), dtype=torch.float32, device=s.device)
+    if s.numel() == 0:
+        return out
     check(_lib.load().rdeic_ckbd_unsqueeze(_ptr(s), _ptr(out), B, Cc, H, Wh, which, _stream()), "rdeic_ckbd_unsqueeze")
     return out
 
@@ -322,19 +330,22 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     """x1 [B,H,W,C1] (+ x2 [B,H,W,C2]) bf16 NHWC -> [B,H,W,C1+C2] bf16."""
     B, H, W, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[-1]
+    if x2 is not None and x2.dtype != x1.dtype:
+        raise TypeError("groupnorm: both sources must share a dtype")
     out = torch.empty((B, H, W, C1 + C2), dtype=BF16, device=x1.device)
     ws = workspace if workspace is not None else _gn_workspace(B, x1.device)
-    check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(out), B, H * W,
-                                           groups, eps, 1 if silu else 0, _ptr(ws), _stream()), "rdeic_groupnorm_nhwc")
+    check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, int(x1.dtype == torch.float32), _ptr(gamma),
+                                           _ptr(beta), _ptr(out), B, H * W, groups, eps, 1 if silu else 0, _ptr(ws),
+                                           _stream()), "rdeic_groupnorm_nhwc")
     return out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     Cc = x.shape[-1]
     rows = x.numel() // Cc
-    out = torch.empty_like(x)
-    check(_lib.load().rdeic_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, Cc, eps, _stream()),
-          "rdeic_layernorm")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_layernorm(_ptr(x), int(x.dtype == torch.float32), _ptr(gamma), _ptr(beta), _ptr(out), rows,
+                                      Cc, eps, _stream()), "rdeic_layernorm")
     return out
 
 
@@ -360,15 +371,25 @@ def pack_conv_weight(w: torch.Tensor, c1: Optional[int] = None) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *, a2: Optional[torch.Tensor] = None,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
-              out: Optional[torch.Tensor] = None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0,
-              tile_n: int = 0) -> torch.Tensor:
-    """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out]."""
+              dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0):
+    """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out].
+
+    Output selection: bf16 by default, fp32 with `out_f32`, both with `dual` (returns the pair
+    (fp32, bf16): the fp32 master of a residual stream plus its bf16 tensor-core operand copy).
+    `out` may pre-allocate the destination (a tensor, or an (fp32, bf16) pair for `dual`)."""
     if a.dtype != BF16 or not a.is_contiguous():
         raise TypeError("conv_gemm: A must be contiguous bf16 NHWC")
     N, H, W, Cc = a.shape
-    dtype = torch.float32 if out_f32 else BF16
-    if out is None:
-        out = torch.empty((N, H, W, n_out), dtype=dtype, device=a.device)
+    of = oh = None
+    if dual:
+        of, oh = out if out is not None else (torch.empty((N, H, W, n_out), dtype=torch.float32, device=a.device),
+                                              torch.empty((N, H, W, n_out), dtype=BF16, device=a.device))
+    elif out is not None:
+        of, oh = (out, None) if out.dtype == torch.float32 else (None, out)
+    elif out_f32:
+        of = torch.empty((N, H, W, n_out), dtype=torch.float32, device=a.device)
+    else:
+        oh = torch.empty((N, H, W, n_out), dtype=BF16, device=a.device)
     p = ConvParams()
     p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, H, W, Cc
     p.a2, p.a2_c = (_ptr(a2), a2.shape[-1]) if a2 is not None else (None, 0)
@@ -384,17 +405,19 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         p.resid, p.resid_is_f32, p.ld_resid = _ptr(resid), int(resid.dtype == torch.float32), resid.stride(-2)
     p.alpha = alpha
     p.act = act
-    if out.dtype == torch.float32:
-        p.out_f32 = _ptr(out)
-    else:
-        p.out_bf16 = _ptr(out)
-    p.ldo = out.stride(-2)
+    p.out_f32, p.out_bf16 = _ptr(of), _ptr(oh)
+    ref = of if of is not None else oh
+    if of is not None and oh is not None and of.stride(-2) != oh.stride(-2):
+        raise ValueError("conv_gemm: dual outputs must share the row stride")
+    p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
     check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
-    return out
+    if dual:
+        return of, oh
+    return ref
 
 
-def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw) -> torch.Tensor:
+def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw):
     """x [..., K] bf16 -> [..., n_out] through the same tensor-core kernel (taps = 1)."""
     K = x.shape[-1]
     M = x.numel() // K
@@ -403,8 +426,10 @@ def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw) -> torch.T
         resid = resid.reshape(1, 1, M, resid.shape[-1])
     out = kw.pop("out", None)
     if out is not None:
-        out = out.view(1, 1, M, out.shape[-1])
+        out = tuple(o.view(1, 1, M, o.shape[-1]) for o in out) if isinstance(out, tuple) else out.view(1, 1, M, out.shape[-1])
     y = conv_gemm(x.reshape(1, 1, M, K), w_packed, n_out, 1, resid=resid, out=out, **kw)
+    if isinstance(y, tuple):
+        return tuple(t.view(*x.shape[:-1], t.shape[-1]) for t in y)
     return y.view(*x.shape[:-1], y.shape[-1])
 
 

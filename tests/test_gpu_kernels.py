@@ -301,10 +301,11 @@ def test_groupnorm(cuda, B, H, W, C1, C2, silu, eps):
     if silu:
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 3, 1)
-    x1 = x[..., :C1].contiguous().to(cuda).bfloat16()
-    x2 = x[..., C1:].contiguous().to(cuda).bfloat16() if C2 else None
-    out = ops.groupnorm(x1, gamma.to(cuda), beta.to(cuda), 32, eps, silu, x2=x2).float().cpu()
-    assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (out - ref).abs().max()
+    for dt in (torch.bfloat16, torch.float32):      # bf16 activations, or the fp32 residual master
+        x1 = x[..., :C1].contiguous().to(cuda).to(dt)
+        x2 = x[..., C1:].contiguous().to(cuda).to(dt) if C2 else None
+        out = ops.groupnorm(x1, gamma.to(cuda), beta.to(cuda), 32, eps, silu, x2=x2).float().cpu()
+        assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (dt, (out - ref).abs().max())
 
 
 @pytest.mark.parametrize("rows,C", [(77, 320), (4096, 640), (5, 1280), (130, 64), (9, 128), (33, 256)])
@@ -315,8 +316,9 @@ def test_layernorm(cuda, rows, C):
     x = _bf(torch.randn(rows, C, generator=g) * 3 - 1)
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
     ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
-    out = ops.layernorm(x.to(cuda).bfloat16(), gamma.to(cuda), beta.to(cuda)).float().cpu()
-    assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (out - ref).abs().max()
+    for dt in (torch.bfloat16, torch.float32):
+        out = ops.layernorm(x.to(cuda).to(dt), gamma.to(cuda), beta.to(cuda)).float().cpu()
+        assert torch.allclose(out, ref, atol=4e-2, rtol=2e-2), (dt, (out - ref).abs().max())
 
 
 # ------------------------------------------------------------------------------------------
@@ -396,6 +398,12 @@ def test_conv_two_sources_epilogue(cuda):
                             a2=x2.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16(), bias=bias.to(cuda),
                             row_bias=rb.to(cuda), resid=resid.to(cuda).bfloat16(), alpha=0.5, out_f32=True).cpu()
         assert _rel(out, ref) < 1e-3, k
+        # fp32 residual master + dual (fp32, bf16) outputs written by one epilogue
+        of, oh = ops.conv_gemm(x1.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16(), wp, Cout, k * k,
+                               a2=x2.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16(), bias=bias.to(cuda),
+                               row_bias=rb.to(cuda), resid=resid.to(cuda), alpha=0.5, dual=True)
+        assert _rel(of.cpu(), ref) < 1e-3, k
+        assert torch.equal(oh.float().cpu(), of.cpu().bfloat16().float())
 
 
 def test_linear_silu_epilogue_and_batched(cuda):
