@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — decoded images/s of the RDEIC relay decode (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A bench "step" is one pass of the hot path over one batch: BASELINE config[1] — 512x512, batch 8
+per GPU, 5 relay steps (q_sample -> 5 x UNet+control step + posterior update -> VAE decode ->
+uint8), synthetic inputs, seeded random-init weights of the SD-2.1 + adapter + VAE architecture.
+Prints ONE JSON line (rank 0).  `value` is timed with the inputs resident in HBM; `e2e` is the
+same decode through the public API with pinned HOST buffers (H2D of the conditioning and noise,
+D2H of the uint8 images inside the timed region).  `--impl reference` times the CPU oracle port of
+the reference path (oracle/) on the box's host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "decoded images/s @512^2 (5 relay steps)"
+UNIT = "images/s"
+WORKLOAD = "512x512 batch 8 per GPU, 5 relay steps (SpacedSampler), bf16, UNet+control+VAE decode to uint8"
+H = W = 512
+BATCH = 8
+RELAY_STEPS = 5
+HINT_C, CTX_DIM = 256, 1024
+WEIGHT_SEED = 231
+
+
+def make_inputs(batch: int, h: int, w: int, seed_off: int = 0):
+    g = lambda s: torch.Generator().manual_seed(s + seed_off)
+    c_latent = torch.randn(batch, 4, h, w, generator=g(7))
+    hint = torch.randn(batch, HINT_C, h, w, generator=g(8))
+    ctx = torch.randn(batch, 77, CTX_DIM, generator=g(9))
+    gn = g(231)
+    noises = [torch.randn(batch, 4, h, w, generator=gn) for _ in range(RELAY_STEPS + 1)]
+    return c_latent, hint, ctx, noises
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(sd_cpu, steps_to_time: int, warmup: int):
+    """Time the oracle (plain PyTorch fp32 restatement of the reference modules) on ONE 512x512
+    image: `steps_to_time` UNet+control relay steps and one VAE decode; the 5-step decode time is
+    composed as 5 x mean(step) + VAE (every relay step runs the identical network)."""
+    from oracle import nn as onn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c_latent, hint, ctx, noises = make_inputs(1, H // 8, W // 8)
+    t = torch.full((1,), 299, dtype=torch.long)
+    kw = dict(model_channels=320, base_d_head=64, ctrl_d_head=16)
+    step_times = []
+    with torch.no_grad():
+        for i in range(warmup + steps_to_time):
+            t0 = time.perf_counter()
+            onn.noise_estimator_forward(sd_cpu, noises[0], hint, t, ctx, **kw)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                step_times.append(dt)
+        t0 = time.perf_counter()
+        onn.vae_decode(sd_cpu, c_latent)
+        t_vae = time.perf_counter() - t0
+    t_step = float(np.mean(step_times))
+    t_img = RELAY_STEPS * t_step + t_vae
+    return {"value": 1.0 / t_img, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 image 512x512 fp32 on host cores: {steps_to_time} UNet+control step(s) timed "
+                      f"({t_step:.2f} s each) + 1 VAE decode ({t_vae:.2f} s); 5-step decode = 5*step + VAE",
+            "s_per_image": t_img}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rdeic_b200 import configs, synthetic
+
+    sd = synthetic.make_state_dict(configs.default_params(), seed=WEIGHT_SEED, device="cpu")
+    t0 = time.perf_counter()
+    res = cpu_reference_sample(sd, max(1, args.steps), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_image"] * 1e3 * BATCH,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference modules (the reference is pure "
+                                                     "Python and cannot travel to the GPU box); bounded sample"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rdeic_b200 import RDEIC, build, configs, ops, parallel, synthetic
+    from rdeic_b200.pipeline import relay_decode
+
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    params = configs.default_params()
+    spec = [(k, s) for k, s, _ in synthetic.state_dict_spec(params)]
+    sd = synthetic.make_state_dict(params, seed=WEIGHT_SEED, device=dev) if rank == 0 else None
+    sd = parallel.broadcast_state_dict(sd, spec, dev, src=0)          # one-time NCCL weight broadcast
+    model = RDEIC.from_config({"params": params}, device=dev)
+    model.load_state_dict(sd)
+    sd_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    del sd
+    torch.cuda.empty_cache()
+
+    h, w = H // 8, W // 8
+    c_latent, hint, ctx, noises = make_inputs(BATCH, h, w, seed_off=1000 * rank)
+    pin = lambda t: t.contiguous().pin_memory()
+    host = {"c_latent": pin(c_latent), "hint": pin(hint), "ctx": pin(ctx), "noises": [pin(n) for n in noises]}
+    d = {"c_latent": c_latent.to(dev), "hint": hint.to(dev), "ctx": ctx.to(dev), "noises": [n.to(dev) for n in noises]}
+    out_host = torch.empty((BATCH, H, W, 3), dtype=torch.uint8).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in [host["c_latent"], host["hint"], host["ctx"], *host["noises"]])
+    d2h = out_host.numel()
+
+    def decode_device():
+        cond = {"c_latent": [d["c_latent"]], "c_crossattn": [d["ctx"]], "guide_hint": d["hint"]}
+        return relay_decode(model, cond, RELAY_STEPS, sampler="ddpm", start_noise=d["noises"][0],
+                            step_noises=d["noises"][1:])
+
+    # e2e: host -> device copies of this step's inputs, decode, device -> host of the uint8 images
+    e = {"c_latent": torch.empty_like(d["c_latent"]), "hint": torch.empty_like(d["hint"]),
+         "ctx": torch.empty_like(d["ctx"]), "noises": [torch.empty_like(n) for n in d["noises"]]}
+
+    def decode_e2e():
+        e["c_latent"].copy_(host["c_latent"], non_blocking=True)
+        e["hint"].copy_(host["hint"], non_blocking=True)
+        e["ctx"].copy_(host["ctx"], non_blocking=True)
+        for dst, src in zip(e["noises"], host["noises"]):
+            dst.copy_(src, non_blocking=True)
+        cond = {"c_latent": [e["c_latent"]], "c_crossattn": [e["ctx"]], "guide_hint": e["hint"]}
+        img = relay_decode(model, cond, RELAY_STEPS, sampler="ddpm", start_noise=e["noises"][0],
+                           step_noises=e["noises"][1:])
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def timed(fn, k):
+        """K steps between barrier+sync on both sides, CUDA events on the launching stream, MAX over ranks."""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.LAUNCHES
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ops.LAUNCHES - n0
+
+    for _ in range(max(args.warmup, 3)):
+        decode_device()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches = timed(decode_device, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(2):
+        decode_e2e()
+    ms_e2e, _ = timed(decode_e2e, args.steps)
+
+    # UNet-step ms (second half of the BASELINE metric): graph replay of one UNet+control step, B=8
+    cond = {"c_latent": [d["c_latent"]], "c_crossattn": [d["ctx"]], "guide_hint": d["hint"]}
+    tt = torch.full((BATCH,), 224, dtype=torch.long, device=dev)
+    ms_unet, _ = timed(lambda: model.apply_model(d["noises"][0], tt, cond), 10)
+    ms_vae, _ = timed(lambda: model.decode_first_stage_u8(d["c_latent"]), 3)
+
+    # roofline of the dominant kernel (tcgen05 implicit-GEMM conv/linear): per-launch CUDA events
+    # around every launch of one eager decode, on the launching stream
+    model.use_cuda_graph = False
+    decode_device()
+    torch.cuda.synchronize()
+    ops.GEMM_PROFILE = []
+    decode_device()
+    torch.cuda.synchronize()
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    model.use_cuda_graph = True
+    g_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    g_fl = sum(f for _, _, f in prof)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv3x3/conv1x1/linear)", "bound": "tensor",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None, "launches_per_step": len(prof),
+                "flops_per_launch": g_fl / max(len(prof), 1), "ms_per_launch": g_ms / max(len(prof), 1),
+                "share_of_step": g_ms / (ms_dev / args.steps),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
+
+    if rank == 0:
+        n_img = BATCH * world * args.steps
+        line = {"metric": METRIC, "value": n_img / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                           "l2": "no flush needed: per-step working set (1.9 GB bf16 weights + >1 GB activations) "
+                                 "exceeds the 126 MB L2", "sampler": "SpacedSampler fixed_small, CUDA-graphed UNet step"},
+                "unet_step_ms": ms_unet / 10, "vae_decode_ms": ms_vae / 3,
+                "e2e": {"value": n_img / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline}
+        if sd_cpu is not None:
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(sd_cpu, 1, 0).items() if k != "s_per_image"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

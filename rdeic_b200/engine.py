@@ -396,8 +396,15 @@ class NoiseEstimatorEngine:
         eps [B,4,h,w] fp32 (model/rdeic.py:174-212; :214-235 when `unconditional`)."""
         if not x.is_cuda:
             raise ops._lib.RdeicLibraryError("NoiseEstimatorEngine.forward needs CUDA tensors; there is no CPU path")
-        B, Cin, h, w = x.shape
         kv_base, kv_ctrl, hint = self.prepare_cond(context, None if unconditional else guide_hint)
+        return self.forward_prepared(x, t, kv_base, kv_ctrl, hint, unconditional)
+
+    @torch.no_grad()
+    def forward_prepared(self, x: torch.Tensor, t: torch.Tensor, kv_base: torch.Tensor, kv_ctrl: torch.Tensor,
+                         hint: Optional[torch.Tensor], unconditional: bool = False) -> torch.Tensor:
+        """Same as `forward` with the step-invariant conditioning already derived by `prepare_cond`
+        (this is the part that is captured into a CUDA graph)."""
+        B, Cin, h, w = x.shape
         x8 = Act(None, ops.nchw_to_nhwc_bf16(x.float().contiguous(), ldc=8))   # 4 latent channels padded to 8 (TMA stride)
         t_emb = ops.timestep_embedding(t.to(self.device, torch.int64).contiguous(), self.model_channels)
         cb = _Ctx(self._time_rows(self.base, t_emb), kv_base)

@@ -11,9 +11,23 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvParams, check
+from ._lib import ConvParams
+from ._lib import check as _check
 
 BF16 = torch.bfloat16
+
+# Kernel-launch accounting (bench.py's `gpu_launches`) and optional per-GEMM timing hooks.
+LAUNCHES = 0          # kernels launched by this module (graph replays add their node count)
+GEMM_PROFILE = None   # when a list: conv_gemm appends (start_event, end_event, flops)
+
+
+_KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_vq_quant": 3}
+
+
+def check(status: int, what: str) -> None:
+    global LAUNCHES
+    _check(status, what)
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
 
 def _stream() -> int:
@@ -411,7 +425,15 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         raise ValueError("conv_gemm: dual outputs must share the row stride")
     p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
-    check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
+        e1.record()
+        k_true = taps * (Cc + (a2.shape[-1] if a2 is not None else 0))
+        GEMM_PROFILE.append((e0, e1, 2.0 * N * H * W * n_out * k_true))
+    else:
+        check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
     if dual:
         return of, oh
     return ref

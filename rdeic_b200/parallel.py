@@ -1,0 +1,132 @@
+"""Data-parallel plumbing for the relay decode: one process per GPU, weights
+replicated, independent images (or independent latent tiles of one large image) dealt across
+ranks.  There is no collective inside the denoising loop; torch.distributed (NCCL over NVLink on
+the B200 box, gloo in CPU tests) is used for exactly two things: the one-time broadcast of the
+checkpoint from rank 0, and the gather of the decoded uint8 images.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous chunk [lo, hi) of `n_items` owned by `rank`; the first n % world chunks get the
+    extra item, so chunk sizes differ by at most one and concatenation in rank order restores the
+    original order."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_cond(cond: Dict, rank: int, world_size: int) -> Dict:
+    """Slice every batch-first tensor of the reference's cond dict (inference.py:57-61)."""
+    n = cond["guide_hint"].shape[0]
+    lo, hi = shard_range(n, rank, world_size)
+    return {"c_latent": [t[lo:hi] for t in cond["c_latent"]],
+            "c_crossattn": [t[lo:hi] if t.shape[0] == n else t for t in cond["c_crossattn"]],
+            "guide_hint": cond["guide_hint"][lo:hi]}
+
+
+def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], spec: Sequence[Tuple[str, Tuple[int, ...]]],
+                         device, src: int = 0, bucket_bytes: int = 256 << 20) -> Dict[str, torch.Tensor]:
+    """One-time weight broadcast.  Every rank knows (key, shape) from the config; rank `src` holds
+    the tensors.  Tensors are packed into ~256 MB flat fp32 buckets (launch latency, not link count,
+    is what matters on NVSwitch) and broadcast bucket by bucket."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        assert sd is not None
+        return {k: sd[k].to(device) for k, _ in spec}
+    rank = dist.get_rank()
+    out: Dict[str, torch.Tensor] = {}
+    bucket: List[Tuple[str, Tuple[int, ...]]] = []
+    size = 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        numel = sum(int(torch.Size(s).numel()) for _, s in bucket)
+        flat = torch.empty(numel, dtype=torch.float32, device=device)
+        if rank == src:
+            off = 0
+            for k, s in bucket:
+                n = int(torch.Size(s).numel())
+                flat[off:off + n].copy_(sd[k].reshape(-1).to(device, torch.float32))
+                off += n
+        dist.broadcast(flat, src=src)
+        off = 0
+        for k, s in bucket:
+            n = int(torch.Size(s).numel())
+            out[k] = flat[off:off + n].view(*s).clone()
+            off += n
+        bucket, size = [], 0
+
+    for k, s in spec:
+        nbytes = int(torch.Size(s).numel()) * 4
+        if size and size + nbytes > bucket_bytes:
+            flush()
+        bucket.append((k, tuple(s)))
+        size += nbytes
+    flush()
+    return out
+
+
+def gather_images(local: torch.Tensor, counts: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
+    """Gather per-rank uint8 image batches [b_r,H,W,3] to rank `dst` in rank order.  Chunks may
+    differ by one image (shard_range), so every rank pads to the largest chunk first."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    m = max(counts)
+    pad = torch.zeros((m, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    if rank != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
+# ---- overlapping latent tiles of one large image (BASELINE config 4) --------------------------
+def plan_tiles(h: int, w: int, tile: int = 96, overlap: int = 16) -> List[Tuple[int, int, int, int]]:
+    """Cover an h x w latent with tile x tile windows (smaller at the far edge is avoided by
+    shifting the last window back) overlapping by >= `overlap`; returns (y0, x0, th, tw)."""
+    def starts(n):
+        if n <= tile:
+            return [0]
+        step = tile - overlap
+        s = list(range(0, n - tile, step)) + [n - tile]
+        return sorted(set(s))
+    th, tw = min(tile, h), min(tile, w)
+    return [(y, x, th, tw) for y in starts(h) for x in starts(w)]
+
+
+def tile_weights(th: int, tw: int, overlap: int, scale: int, device) -> torch.Tensor:
+    """Separable linear ramp over the overlap band (in pixels = latent * scale) used to blend tiles."""
+    def ramp(n, ov):
+        r = torch.ones(n)
+        if ov > 0:
+            e = torch.linspace(1.0 / (ov + 1), ov / (ov + 1.0), ov)
+            r[:ov] = e
+            r[-ov:] = e.flip(0)
+        return r
+    wy, wx = ramp(th * scale, overlap * scale), ramp(tw * scale, overlap * scale)
+    return (wy[:, None] * wx[None, :]).to(device)
+
+
+def blend_tiles(tiles: Sequence[torch.Tensor], plan: Sequence[Tuple[int, int, int, int]], h: int, w: int,
+                overlap: int, scale: int = 8) -> torch.Tensor:
+    """Weighted average of decoded float tiles [3, th*scale, tw*scale] into one [3, h*scale, w*scale]."""
+    dev = tiles[0].device
+    acc = torch.zeros((3, h * scale, w * scale), dtype=torch.float32, device=dev)
+    wsum = torch.zeros((1, h * scale, w * scale), dtype=torch.float32, device=dev)
+    for t, (y0, x0, th, tw) in zip(tiles, plan):
+        wgt = tile_weights(th, tw, overlap, scale, dev)
+        ys, xs = y0 * scale, x0 * scale
+        acc[:, ys:ys + th * scale, xs:xs + tw * scale] += t.float() * wgt
+        wsum[:, ys:ys + th * scale, xs:xs + tw * scale] += wgt
+    return acc / wsum
