@@ -188,11 +188,14 @@ typedef struct rdeic_conv_params {
     const float* row_bias; int row_bias_ld;
     const void* resid;    int resid_is_f32; int ld_resid;
     float alpha;
-    int act;              /* 0 none, 1 SiLU */
+    int act;              /* 0 none, 1 SiLU, 2 GEGLU: weight rows interleaved in blocks of
+                             16 values | 16 gates (rdeic_b200/engine.py), writes n_out/2 columns */
     void* out_bf16;
     float* out_f32;
     int ldo;
     int tile_n_hint;      /* 0 = library picks BLOCK_N */
+    void* workspace;      /* optional split-K scratch (fp32 partials); NULL disables split-K */
+    int64_t workspace_bytes;
 } rdeic_conv_params;
 
 int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream);

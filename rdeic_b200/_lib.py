@@ -39,6 +39,8 @@ class ConvParams(C.Structure):
         ("out_f32", vp),
         ("ldo", i32),
         ("tile_n_hint", i32),
+        ("workspace", vp),
+        ("workspace_bytes", i64),
     ]
 
 

@@ -42,7 +42,61 @@ struct ConvDev {
     __nv_bfloat16* out_bf16;
     float* out_f32;
     int ldo;
+    float* partial;                // split-K: raw fp32 accumulators [split][M][n_out]
+    int kb_per_split;              // k-blocks per blockIdx.z slice (0 = no split)
+    int64_t m_total;
 };
+
+// Epilogue math shared by the GEMM kernel (phase B) and the split-K reduce kernel: 4 consecutive
+// output columns of one row.  v already holds act(acc + bias + row_bias).
+struct EpiOut {
+    const void* resid; int resid_is_f32; int ld_resid; float alpha;
+    __nv_bfloat16* out_bf16; float* out_f32; int ldo; int n_cols;   // n_cols = valid output columns
+};
+
+__device__ __forceinline__ void epi_store4(const EpiOut& e, int64_t m, int n, float4 v) {
+    const bool full = (n + 4 <= e.n_cols);
+    if (full && (e.ldo & 3) == 0 && (!e.resid || (e.ld_resid & 3) == 0)) {
+        if (e.resid) {
+            float4 r;
+            if (e.resid_is_f32) {
+                r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.resid) + m * e.ld_resid + n);
+            } else {
+                const uint2 rv = *reinterpret_cast<const uint2*>(
+                    reinterpret_cast<const __nv_bfloat16*>(e.resid) + m * e.ld_resid + n);
+                unpack_bf16x2(rv.x, r.x, r.y);
+                unpack_bf16x2(rv.y, r.z, r.w);
+            }
+            v.x = fmaf(e.alpha, v.x, r.x); v.y = fmaf(e.alpha, v.y, r.y);
+            v.z = fmaf(e.alpha, v.z, r.z); v.w = fmaf(e.alpha, v.w, r.w);
+        } else if (e.alpha != 1.0f) {
+            v.x *= e.alpha; v.y *= e.alpha; v.z *= e.alpha; v.w *= e.alpha;
+        }
+        if (e.out_f32) *reinterpret_cast<float4*>(e.out_f32 + m * e.ldo + n) = v;
+        if (e.out_bf16)
+            *reinterpret_cast<uint2*>(e.out_bf16 + m * e.ldo + n) =
+                make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 4 && n + j < e.n_cols; ++j) {
+            float x = vv[j];
+            if (e.resid) {
+                const float rv = e.resid_is_f32
+                    ? reinterpret_cast<const float*>(e.resid)[m * e.ld_resid + n + j]
+                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.resid)[m * e.ld_resid + n + j]);
+                x = fmaf(e.alpha, x, rv);
+            } else {
+                x *= e.alpha;
+            }
+            if (e.out_f32) e.out_f32[m * e.ldo + n + j] = x;
+            if (e.out_bf16) e.out_bf16[m * e.ldo + n + j] = __float2bfloat16_rn(x);
+        }
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
 
 // ----------------------------------------------------------------------------------------
 // PTX wrappers
@@ -200,7 +254,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int n0 = tin * (kBlockM >> (p.tw_log2 + p.th_log2));
     const int col0 = blockIdx.y * BN;
     const int cbt = p.cblk1 + p.cblk2;
-    const int num_kb = p.taps * cbt;
+    const int total_kb = p.taps * cbt;
+    const int kb_begin = p.kb_per_split ? blockIdx.z * p.kb_per_split : 0;
+    const int kb_end = p.kb_per_split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+    const int num_kb = kb_end - kb_begin;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_a);
@@ -224,9 +281,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (lane == 0) {
             // ===== TMA producer =====
             const int wz = p.w_batched ? n0 : 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
+            for (int it = 0; it < num_kb; ++it) {
+                const int kb = kb_begin + it;
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
                 const int tap = kb / cbt, cb = kb - tap * cbt;
@@ -262,117 +320,105 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             umma_commit(accum_bar);           // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced global =====
+        // Phase A: each thread owns one accumulator row (TMEM lane) and 32 columns per chunk; it
+        // adds bias / per-sample bias, applies the activation and parks the row in shared memory
+        // (16-byte chunks XOR-swizzled by row: conflict-free STS.128).  Phase B: the warp re-reads
+        // its 32x32 sub-tile so that 8 lanes cover 128 contiguous bytes of one output row, adds
+        // the residual (read with the same coalesced mapping) and writes fp32 and/or bf16.
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;               // row inside the M tile
         const int rw = r & (tw - 1);
         const int rh = (r >> p.tw_log2) & (th - 1);
         const int rn = r >> (p.tw_log2 + p.th_log2);
         const int gw = w0 + rw, gh = h0 + rh, gn = n0 + rn;
-        const bool row_ok = gw < p.a_w && gh < p.a_h && gn < p.a_n;
-        const int64_t m = ((int64_t)gn * p.a_h + gh) * p.a_w + gw;
+        const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
+        const int m_own = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
+        const bool geglu = (p.act == 2);
+        const bool partial = (p.partial != nullptr);
+        EpiOut eo;
+        eo.resid = partial ? nullptr : p.resid; eo.resid_is_f32 = p.resid_is_f32; eo.ld_resid = p.ld_resid;
+        eo.alpha = partial ? 1.0f : p.alpha;
+        eo.out_bf16 = partial ? nullptr : p.out_bf16;
+        eo.out_f32 = partial ? p.partial + (int64_t)blockIdx.z * p.m_total * p.n_out : p.out_f32;
+        eo.ldo = partial ? p.n_out : p.ldo;
+        eo.n_cols = geglu ? (p.n_out >> 1) : p.n_out;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const bool vec_ok = (p.ldo % 8 == 0);
+        // all MMAs have retired, so every pipeline stage is idle: stage 0's A buffer is the staging area
+        float4* stg = reinterpret_cast<float4*>(smem_a) + (warp & 3) * 256;   // 32 rows x 8 chunks
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
+            const int nbase = col0 + c;
+            if (nbase >= p.n_out) break;                                      // warp-uniform
             uint32_t acc[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
             tmem_ld16(taddr, acc);
             tmem_ld16(taddr + 16, acc + 16);
             tmem_ld_wait();
-            if (!row_ok) continue;
-            const int nbase = col0 + c;
-            if (nbase >= p.n_out) continue;
+            float v[32];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int n8 = nbase + g * 8;
-                if (n8 >= p.n_out) break;
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-                const bool full8 = (n8 + 8 <= p.n_out);
-                if (full8) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+            if (!partial) {
+                if (nbase + 32 <= p.n_out) {
                     if (p.bias) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n8 + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (p.row_bias) {
-                        const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + n8;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] += __ldg(rb + j);
-                    }
-                    if (p.act == 1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-                    }
-                    if (p.resid) {
-                        if (p.resid_is_f32) {
-                            const float* rr = reinterpret_cast<const float*>(p.resid) + m * p.ld_resid + n8;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], rr[j]);
-                        } else if (p.ld_resid % 8 == 0) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(
-                                reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ld_resid + n8);
-                            float f[8];
-                            unpack_bf16x2(rv.x, f[0], f[1]); unpack_bf16x2(rv.y, f[2], f[3]);
-                            unpack_bf16x2(rv.z, f[4], f[5]); unpack_bf16x2(rv.w, f[6], f[7]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], f[j]);
-                        } else {
-                            const __nv_bfloat16* rr =
-                                reinterpret_cast<const __nv_bfloat16*>(p.resid) + m * p.ld_resid + n8;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaf(p.alpha, v[j], __bfloat162float(rr[j]));
-                        }
-                    } else if (p.alpha != 1.0f) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
-                    }
-                    if (p.out_bf16) {
-                        __nv_bfloat16* o = p.out_bf16 + m * p.ldo + n8;
-                        if (vec_ok) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-                            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-                            *reinterpret_cast<uint4*>(o) = pk;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                         }
                     }
-                    if (p.out_f32) {
-                        float* o = p.out_f32 + m * p.ldo + n8;
-                        if (p.ldo % 4 == 0) {
-                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
+                    if (p.row_bias && row_ok) {
+                        const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + nbase;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = v[j];
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] += __ldg(rb + j);
                     }
                 } else {
-                    // ragged tail of the N dimension (e.g. 4 latent / 3 rgb output channels)
-                    for (int j = 0; j < 8 && n8 + j < p.n_out; ++j) {
-                        float x = v[j];
-                        if (p.bias) x += p.bias[n8 + j];
-                        if (p.row_bias) x += p.row_bias[(int64_t)gn * p.row_bias_ld + n8 + j];
-                        if (p.act == 1) x = silu_f(x);
-                        if (p.resid) {
-                            const float rv = p.resid_is_f32
-                                ? reinterpret_cast<const float*>(p.resid)[m * p.ld_resid + n8 + j]
-                                : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[m * p.ld_resid + n8 + j]);
-                            x = fmaf(p.alpha, x, rv);
-                        } else {
-                            x *= p.alpha;
+                    for (int j = 0; j < 32; ++j) {
+                        if (nbase + j < p.n_out) {
+                            if (p.bias) v[j] += p.bias[nbase + j];
+                            if (p.row_bias && row_ok) v[j] += p.row_bias[(int64_t)gn * p.row_bias_ld + nbase + j];
                         }
-                        if (p.out_bf16) p.out_bf16[m * p.ldo + n8 + j] = __float2bfloat16_rn(x);
-                        if (p.out_f32) p.out_f32[m * p.ldo + n8 + j] = x;
                     }
                 }
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                } else if (geglu) {
+                    // columns [0,16) of the chunk are values, [16,32) their gates (weights are
+                    // interleaved that way at load): attention.py:54-56  x * gelu(gate)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf(v[16 + j]);
+                }
             }
+            const int nchunks = geglu ? 4 : 8;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < nchunks)
+                    stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            if (!geglu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + (lane >> 3), q = lane & 7;
+                    const float4 val = stg[row * 8 + (q ^ (row & 7))];
+                    const int m_row = __shfl_sync(0xffffffffu, m_own, row);
+                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                    const int n = nbase + 4 * q;
+                    if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 8 * i + (lane & 7), q = lane >> 3;
+                    const float4 val = stg[row * 8 + (q ^ (row & 7))];
+                    const int m_row = __shfl_sync(0xffffffffu, m_own, row);
+                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                    const int n = (nbase >> 1) + 4 * q;
+                    if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
+                }
+            }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -380,6 +426,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// split-K second pass: sum the fp32 partials in a fixed order (deterministic), then the same
+// epilogue as the fused path.  One thread per 4 output columns.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_total, int n_out,
+                     int rows_per_sample, const float* __restrict__ bias,
+                     const float* __restrict__ row_bias, int row_bias_ld, int act, EpiOut eo) {
+    const int n4 = (n_out + 3) >> 2;
+    const int64_t total = m_total * n4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / n4;
+        const int n = (int)(i - m * n4) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int z = 0; z < splits; ++z) {
+            const float* src = partial + ((int64_t)z * m_total + m) * n_out + n;
+            if (n + 4 <= n_out && (n_out & 3) == 0) {
+                const float4 t = *reinterpret_cast<const float4*>(src);
+                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+            } else {
+                for (int j = 0; j < 4 && n + j < n_out; ++j) v[j] += src[j];
+            }
+        }
+        const int64_t gn = m / rows_per_sample;
+        for (int j = 0; j < 4 && n + j < n_out; ++j) {
+            if (bias) v[j] += bias[n + j];
+            if (row_bias) v[j] += row_bias[gn * row_bias_ld + n + j];
+            if (act == 1) v[j] = silu_f(v[j]);
+        }
+        epi_store4(eo, m, n, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -466,7 +544,7 @@ static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 template <int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
-                       const ConvDev& d, int m_tiles, cudaStream_t s) {
+                       const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -475,7 +553,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                                         Cfg::kSmemBytes));
         attr_set = true;
     }
-    dim3 grid(m_tiles, (d.n_out + BN - 1) / BN);
+    dim3 grid(m_tiles, (d.n_out + BN - 1) / BN, splits);
     conv_gemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -532,7 +610,8 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
                     p->a_c, p->a2_c);
     RDEIC_CHECK_ARG(p->a2_c == 0 || p->a2, "rdeic_conv_gemm: a2_c > 0 needs a2");
     RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9, "rdeic_conv_gemm: taps must be 1 or 9");
-    RDEIC_CHECK_ARG(p->n_out > 0 && p->ldo >= p->n_out, "rdeic_conv_gemm: bad n_out/ldo");
+    RDEIC_CHECK_ARG(p->n_out > 0 && p->ldo > 0, "rdeic_conv_gemm: bad n_out/ldo");
+    RDEIC_CHECK_ARG(p->act >= 0 && p->act <= 2, "rdeic_conv_gemm: act must be 0 (none), 1 (SiLU) or 2 (GEGLU)");
     RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w) % 16 == 0,
                     "rdeic_conv_gemm: operands must be 16-byte aligned");
     RDEIC_CHECK_ARG(((uintptr_t)p->out_bf16 | (uintptr_t)p->out_f32 | (uintptr_t)p->resid |
@@ -565,6 +644,14 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
     d.alpha = p->alpha; d.act = p->act;
     d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
+    d.partial = nullptr; d.kb_per_split = 0;
+    d.m_total = (int64_t)p->a_n * p->a_h * p->a_w;
+    if (p->act == 2) {
+        RDEIC_CHECK_ARG(p->n_out % 32 == 0 && !p->resid && p->ldo >= p->n_out / 2,
+                        "rdeic_conv_gemm: GEGLU epilogue needs n_out %% 32 == 0, no residual, ldo >= n_out/2");
+    } else {
+        RDEIC_CHECK_ARG(p->ldo >= p->n_out, "rdeic_conv_gemm: bad n_out/ldo");
+    }
 
     const int bn = pick_block_n(p->n_out, m_tiles, p->tile_n_hint);
 
@@ -592,14 +679,46 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         if (int e = encode_map(&tb, p->w, 3, dimsb, strb, boxb, "W")) return e;
     }
     cudaStream_t s = as_stream(stream);
-    switch (bn) {
-        case 32: return launch_conv<32>(ta, ta2, tb, d, m_tiles, s);
-        case 64: return launch_conv<64>(ta, ta2, tb, d, m_tiles, s);
-        case 128: return launch_conv<128>(ta, ta2, tb, d, m_tiles, s);
-        case 160: return launch_conv<160>(ta, ta2, tb, d, m_tiles, s);
-        case 256: return launch_conv<256>(ta, ta2, tb, d, m_tiles, s);
+    // split-K: layers with few output tiles but a long reduction (UNet levels 2/3: M = 512..2048,
+    // K up to 23040) would leave most of the 148 SMs idle; slice K across blockIdx.z, write fp32
+    // partials to the caller's workspace and finish with a deterministic reduce + epilogue pass.
+    int splits = 1;
+    const int total_kb = p->taps * (d.cblk1 + d.cblk2);
+    const int n_tiles = (p->n_out + bn - 1) / bn;
+    const int64_t tiles = (int64_t)m_tiles * n_tiles;
+    if (p->act != 2 && p->workspace && tiles <= kNumSMs && total_kb >= 8) {
+        int want = (int)((2 * kNumSMs) / tiles);
+        if (want > total_kb / 4) want = total_kb / 4;
+        if (want > 16) want = 16;
+        const int64_t per_split = d.m_total * p->n_out * (int64_t)sizeof(float);
+        while (want > 1 && want * per_split > p->workspace_bytes) --want;
+        if (want >= 2) {
+            d.kb_per_split = (total_kb + want - 1) / want;
+            splits = (total_kb + d.kb_per_split - 1) / d.kb_per_split;
+            d.partial = reinterpret_cast<float*>(p->workspace);
+        }
     }
-    return set_error("rdeic_conv_gemm: unsupported BLOCK_N %d", bn);
+    int rc;
+    switch (bn) {
+        case 32: rc = launch_conv<32>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        case 64: rc = launch_conv<64>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        case 128: rc = launch_conv<128>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        case 160: rc = launch_conv<160>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        case 256: rc = launch_conv<256>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        default: return set_error("rdeic_conv_gemm: unsupported BLOCK_N %d", bn);
+    }
+    if (rc) return rc;
+    if (splits > 1) {
+        EpiOut eo;
+        eo.resid = p->resid; eo.resid_is_f32 = p->resid_is_f32; eo.ld_resid = p->ld_resid; eo.alpha = p->alpha;
+        eo.out_bf16 = (__nv_bfloat16*)p->out_bf16; eo.out_f32 = p->out_f32; eo.ldo = p->ldo; eo.n_cols = p->n_out;
+        const int64_t work = d.m_total * ((p->n_out + 3) / 4);
+        splitk_reduce_kernel<<<grid_for(work, 256), 256, 0, s>>>(
+            d.partial, splits, d.m_total, p->n_out, p->a_h * p->a_w, p->bias, p->row_bias, p->row_bias_ld,
+            p->act, eo);
+        RDEIC_LAUNCH_CHECK();
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -51,11 +51,22 @@ class Conv:
     taps: int
 
     @staticmethod
-    def load(sd: SD, name: str, dev, c1: Optional[int] = None, scale: float = 1.0) -> "Conv":
+    def load(sd: SD, name: str, dev, c1: Optional[int] = None, scale: float = 1.0, geglu: bool = False) -> "Conv":
         w = sd[name + ".weight"].to(dev, torch.float32)
         if scale != 1.0:
             w = w * scale
         b = sd.get(name + ".bias")
+        if geglu:
+            # GEGLU projection (attention.py:52-56): rows [0,F) are values, [F,2F) gates.  Interleave
+            # them in blocks of 16 so each 32-column chunk of the GEMM tile holds 16 values and
+            # their 16 gates, and x * gelu(gate) can run in the epilogue (act = 2).
+            F = w.shape[0] // 2
+            assert F % 16 == 0, "GEGLU inner width must be a multiple of 16"
+            idx = torch.arange(F, device=w.device).view(F // 16, 1, 16)
+            perm = torch.cat([idx, idx + F], 1).reshape(-1)
+            w = w[perm]
+            if b is not None:
+                b = b.to(w.device)[perm]
         if w.dim() == 2:
             w = w[:, :, None, None]
         taps = w.shape[2] * w.shape[3]
@@ -172,7 +183,7 @@ def _load_unet(sd: SD, prefix: str, dev, *, model_channels: int, width: int, in_
             Conv.fused(sd, [t + ".attn1.to_q", t + ".attn1.to_k", t + ".attn1.to_v"], dev),
             Conv.load(sd, t + ".attn1.to_out.0", dev), Norm.load(sd, t + ".norm2", dev),
             Conv.load(sd, t + ".attn2.to_q", dev), off, Conv.load(sd, t + ".attn2.to_out.0", dev),
-            Norm.load(sd, t + ".norm3", dev), Conv.load(sd, t + ".ff.net.0.proj", dev),
+            Norm.load(sd, t + ".norm3", dev), Conv.load(sd, t + ".ff.net.0.proj", dev, geglu=True),
             Conv.load(sd, t + ".ff.net.2", dev), Conv.load(sd, p + ".proj_out", dev), ch // d_head, d_head, ch,
             find_denominator(ch, 32)))
 
@@ -357,7 +368,7 @@ class NoiseEstimatorEngine:
                           w.d_head, scale)
         h = ops.linear(a, w.out2.w, C, bias=w.out2.b, resid=h, out_f32=True)
         n3 = ops.layernorm(h, w.ln3.g, w.ln3.b)
-        f = ops.geglu(ops.linear(n3, w.ff1.w, w.ff1.n_out, bias=w.ff1.b))
+        f = ops.linear(n3, w.ff1.w, w.ff1.n_out, bias=w.ff1.b, act=2)       # GEGLU fused in the epilogue
         hb = ops.linear(f, w.ff2.w, C, bias=w.ff2.b, resid=h)                 # only consumer is proj_out's A operand
         of, oh = ops.linear(hb, w.proj_out.w, C, bias=w.proj_out.b, resid=x.f.view(B, H * W, C), dual=True)
         return Act(of.view(B, H, W, C), oh.view(B, H, W, C))

@@ -366,6 +366,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 # ---------------------------------------------------------------------------------------------
 # tensor-core contractions
 # ---------------------------------------------------------------------------------------------
+_splitk_ws = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    """Caller-owned split-K scratch (the library never allocates): 64 MB per device."""
+    ws = _splitk_ws.get(str(device))
+    if ws is None:
+        ws = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+        _splitk_ws[str(device)] = ws
+    return ws
+
+
 def pack_conv_weight(w: torch.Tensor, c1: Optional[int] = None) -> torch.Tensor:
     """OIHW (or [out,in]) fp32 -> packed bf16 [n_out, taps*(cp1+cp2)].  c1 splits the input
     channels into two concat sources (c1, cin-c1)."""
@@ -385,7 +397,8 @@ def pack_conv_weight(w: torch.Tensor, c1: Optional[int] = None) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *, a2: Optional[torch.Tensor] = None,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
-              dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0):
+              dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0,
+              split_k: bool = True):
     """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out].
 
     Output selection: bf16 by default, fp32 with `out_f32`, both with `dual` (returns the pair
@@ -394,16 +407,17 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     if a.dtype != BF16 or not a.is_contiguous():
         raise TypeError("conv_gemm: A must be contiguous bf16 NHWC")
     N, H, W, Cc = a.shape
+    n_cols = n_out // 2 if act == 2 else n_out
     of = oh = None
     if dual:
-        of, oh = out if out is not None else (torch.empty((N, H, W, n_out), dtype=torch.float32, device=a.device),
-                                              torch.empty((N, H, W, n_out), dtype=BF16, device=a.device))
+        of, oh = out if out is not None else (torch.empty((N, H, W, n_cols), dtype=torch.float32, device=a.device),
+                                              torch.empty((N, H, W, n_cols), dtype=BF16, device=a.device))
     elif out is not None:
         of, oh = (out, None) if out.dtype == torch.float32 else (None, out)
     elif out_f32:
-        of = torch.empty((N, H, W, n_out), dtype=torch.float32, device=a.device)
+        of = torch.empty((N, H, W, n_cols), dtype=torch.float32, device=a.device)
     else:
-        oh = torch.empty((N, H, W, n_out), dtype=BF16, device=a.device)
+        oh = torch.empty((N, H, W, n_cols), dtype=BF16, device=a.device)
     p = ConvParams()
     p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, H, W, Cc
     p.a2, p.a2_c = (_ptr(a2), a2.shape[-1]) if a2 is not None else (None, 0)
@@ -425,6 +439,9 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         raise ValueError("conv_gemm: dual outputs must share the row stride")
     p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
+    if split_k:
+        ws = _splitk_workspace(a.device)
+        p.workspace, p.workspace_bytes = _ptr(ws), ws.numel()
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -427,6 +427,46 @@ def test_linear_silu_epilogue_and_batched(cuda):
     assert _rel(out, ref) < 1e-3
 
 
+@pytest.mark.parametrize("M,C", [(4096, 320), (300, 64), (77, 1280)])
+def test_linear_geglu_epilogue(cuda, M, C):
+    """ff.net.0.proj + GEGLU (attention.py:49-56) fused: interleaved weight rows, act = 2."""
+    from rdeic_b200 import ops
+    from rdeic_b200.engine import Conv
+
+    g = torch.Generator().manual_seed(26)
+    F_ = 4 * C
+    x = _bf(torch.randn(M, C, generator=g))
+    w = _bf(torch.randn(2 * F_, C, generator=g) / math.sqrt(C))
+    b = torch.randn(2 * F_, generator=g) * 0.5
+    a, gate = F.linear(x, w, b).chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    conv = Conv.load({"p.weight": w, "p.bias": b}, "p", cuda, geglu=True)
+    out = ops.linear(x.to(cuda).bfloat16(), conv.w, conv.n_out, bias=conv.b, act=2).float().cpu()
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,K,N", [(512, 11520, 1280), (64, 4096, 256), (2048, 2560, 640)])
+def test_split_k_matches_single_pass(cuda, M, K, N):
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(27)
+    x = _bf(torch.randn(M, K, generator=g))
+    w = _bf(torch.randn(N, K, generator=g) / math.sqrt(K))
+    b = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g)
+    ref = resid + 0.75 * F.silu(F.linear(x, w, b))
+    wp = ops.pack_conv_weight(w.to(cuda))
+    kw = dict(bias=b.to(cuda), resid=resid.to(cuda), alpha=0.75, act=1, dual=True)
+    of, oh = ops.linear(x.to(cuda).bfloat16(), wp, N, **kw)
+    of1, _ = ops.linear(x.to(cuda).bfloat16(), wp, N, split_k=False, **kw)
+    assert _rel(of.cpu(), ref) < 1e-3 and _rel(of1.cpu(), ref) < 1e-3
+    assert torch.equal(oh.float().cpu(), of.cpu().bfloat16().float())
+    # deterministic: a second split-K run is bit-identical
+    of2, _ = ops.linear(x.to(cuda).bfloat16(), wp, N, **kw)
+    assert torch.equal(of, of2)
+
+
 # ------------------------------------------------------------------------------------------
 # attention: bf16 P, fp32 softmax: abs tol 2e-2 on O(1) outputs
 # ------------------------------------------------------------------------------------------
