@@ -25,7 +25,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
-constexpr int kNumThreads = 192;            // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;   // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..9 epilogue
 
 struct ConvDev {
     int a_n, a_h, a_w;
@@ -43,7 +44,8 @@ struct ConvDev {
     float* out_f32;
     int ldo;
     float* partial;                // split-K: raw fp32 accumulators [split][M][n_out]
-    int kb_per_split;              // k-blocks per blockIdx.z slice (0 = no split)
+    int kb_per_split;              // k-blocks per k-split slice (= all of them without split-K)
+    int splits, n_tiles;
     int64_t m_total;
 };
 
@@ -111,6 +113,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -219,15 +224,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 
 template <int BN>
 struct TileCfg {
-    static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kATileBytes + kBBytes;
-    static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kStagingBytes = kNumEpiWarps * 4096;          // 32 rows x 128 B per epilogue warp
+    static constexpr int kMaxSmem = 227 * 1024;
+    static constexpr int kStagesRaw = (kMaxSmem - kStagingBytes - 1024 - 256) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns per buffer
+    static constexpr int kTmemCols = 2 * kAccStride;                   // double-buffered accumulator
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Persistent, warp-specialised kernel: one CTA per SM loops over (m-tile, n-tile, k-split) work
+// items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
+// Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
+// the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
 template <int BN>
-__global__ void __launch_bounds__(kNumThreads, 2)
+__global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
     using Cfg = TileCfg<BN>;
@@ -237,27 +250,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                                ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kATileBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
     uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* accum_bar = empty_bar + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + kStages;        // [2]
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // M-tile coordinates
     const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
-    int mt = blockIdx.x;
-    const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
-    const int tih = mt % p.tiles_h; mt /= p.tiles_h;
-    const int tin = mt;
-    const int w0 = tiw * tw, h0 = tih * th;
-    const int n0 = tin * (kBlockM >> (p.tw_log2 + p.th_log2));
-    const int col0 = blockIdx.y * BN;
     const int cbt = p.cblk1 + p.cblk2;
     const int total_kb = p.taps * cbt;
-    const int kb_begin = p.kb_per_split ? blockIdx.z * p.kb_per_split : 0;
-    const int kb_end = p.kb_per_split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
-    const int num_kb = kb_end - kb_begin;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int mn_tiles = m_tiles * p.n_tiles;
+    const int num_items = mn_tiles * p.splits;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_a);
@@ -267,7 +273,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], kNumEpiWarps);
+        }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -280,44 +289,67 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            const int wz = p.w_batched ? n0 : 0;
-            for (int it = 0; it < num_kb; ++it) {
-                const int kb = kb_begin + it;
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                const int tap = kb / cbt, cb = kb - tap * cbt;
-                int dy = 0, dx = 0;
-                if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-                if (cb < p.cblk1)
-                    tma_load_4d(&tm_a, smem_a + s * kATileBytes, &full_bar[s], cb * kBlockK,
-                                w0 + dx, h0 + dy, n0);
-                else
-                    tma_load_4d(&tm_a2, smem_a + s * kATileBytes, &full_bar[s],
-                                (cb - p.cblk1) * kBlockK, w0 + dx, h0 + dy, n0);
-                tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int z = item / mn_tiles;
+                int rem = item - z * mn_tiles;
+                const int nt = rem / m_tiles;
+                int mt = rem - nt * m_tiles;
+                const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int tih = mt % p.tiles_h; mt /= p.tiles_h;
+                const int w0 = tiw * tw, h0 = tih * th;
+                const int n0 = mt * (kBlockM >> (p.tw_log2 + p.th_log2));
+                const int col0 = nt * BN;
+                const int wz = p.w_batched ? n0 : 0;
+                const int kb_begin = z * p.kb_per_split;
+                const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                    const int tap = kb / cbt, cb = kb - tap * cbt;
+                    int dy = 0, dx = 0;
+                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                    if (cb < p.cblk1)
+                        tma_load_4d(&tm_a, smem_a + s * kATileBytes, &full_bar[s], cb * kBlockK,
+                                    w0 + dx, h0 + dy, n0);
+                    else
+                        tma_load_4d(&tm_a2, smem_a + s * kATileBytes, &full_bar[s],
+                                    (cb - p.cblk1) * kBlockK, w0 + dx, h0 + dy, n0);
+                    tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc(BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, t = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
+                const int z = item / mn_tiles;
+                const int kb_begin = z * p.kb_per_split;
+                const int num_kb = min(total_kb, kb_begin + p.kb_per_split) - kb_begin;
+                const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t da = make_smem_desc(smem_u32(smem_a + s * kATileBytes));
-                const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
+                const uint32_t tmem_d = tmem_base + buf * Cfg::kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(smem_u32(smem_a + s * kATileBytes));
+                    const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
+                umma_commit(&acc_full[buf]);      // accumulator complete
             }
-            umma_commit(accum_bar);           // accumulator complete
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced global =====
@@ -325,100 +357,167 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // adds bias / per-sample bias, applies the activation and parks the row in shared memory
         // (16-byte chunks XOR-swizzled by row: conflict-free STS.128).  Phase B: the warp re-reads
         // its 32x32 sub-tile so that 8 lanes cover 128 contiguous bytes of one output row, adds
-        // the residual (read with the same coalesced mapping) and writes fp32 and/or bf16.
+        // the residual (prefetched with the same coalesced mapping) and writes fp32 and/or bf16.
+        // Two warps share each TMEM lane quadrant and take alternate 32-column chunks.
+        const int ew = warp - 2;                      // 0..7
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;                     // which alternate chunks
         const int r = quad * 32 + lane;               // row inside the M tile
         const int rw = r & (tw - 1);
         const int rh = (r >> p.tw_log2) & (th - 1);
         const int rn = r >> (p.tw_log2 + p.th_log2);
-        const int gw = w0 + rw, gh = h0 + rh, gn = n0 + rn;
-        const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
-        const int m_own = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
         const bool geglu = (p.act == 2);
         const bool partial = (p.partial != nullptr);
-        EpiOut eo;
-        eo.resid = partial ? nullptr : p.resid; eo.resid_is_f32 = p.resid_is_f32; eo.ld_resid = p.ld_resid;
-        eo.alpha = partial ? 1.0f : p.alpha;
-        eo.out_bf16 = partial ? nullptr : p.out_bf16;
-        eo.out_f32 = partial ? p.partial + (int64_t)blockIdx.z * p.m_total * p.n_out : p.out_f32;
-        eo.ldo = partial ? p.n_out : p.ldo;
-        eo.n_cols = geglu ? (p.n_out >> 1) : p.n_out;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        // all MMAs have retired, so every pipeline stage is idle: stage 0's A buffer is the staging area
-        float4* stg = reinterpret_cast<float4*>(smem_a) + (warp & 3) * 256;   // 32 rows x 8 chunks
+        float4* stg = reinterpret_cast<float4*>(smem_stg) + ew * 256;   // 32 rows x 8 chunks
+        uint32_t t = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
+            const int z = item / mn_tiles;
+            int rem = item - z * mn_tiles;
+            const int nt = rem / m_tiles;
+            int mt = rem - nt * m_tiles;
+            const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int tih = mt % p.tiles_h; mt /= p.tiles_h;
+            const int gw = tiw * tw + rw, gh = tih * th + rh;
+            const int gn = mt * (kBlockM >> (p.tw_log2 + p.th_log2)) + rn;
+            const int col0 = nt * BN;
+            const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
+            const int m_own = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
+            EpiOut eo;
+            eo.resid = partial ? nullptr : p.resid; eo.resid_is_f32 = p.resid_is_f32; eo.ld_resid = p.ld_resid;
+            eo.alpha = partial ? 1.0f : p.alpha;
+            eo.out_bf16 = partial ? nullptr : p.out_bf16;
+            eo.out_f32 = partial ? p.partial + (int64_t)z * p.m_total * p.n_out : p.out_f32;
+            eo.ldo = partial ? p.n_out : p.ldo;
+            eo.n_cols = geglu ? (p.n_out >> 1) : p.n_out;
+            const bool vec_io = (eo.ldo & 3) == 0 && (!eo.resid || (eo.ld_resid & 3) == 0);
+            const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
+            constexpr int kChunks = BN / 32;
+            // chunks this warp owns: half, half+2, ...
+            int last_c = -1;
+            for (int ci = half; ci < kChunks; ci += 2)
+                if (col0 + ci * 32 < p.n_out) last_c = ci;
+            if (last_c < 0) {                       // nothing to read: release the buffer right away
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            const int nbase = col0 + c;
-            if (nbase >= p.n_out) break;                                      // warp-uniform
-            uint32_t acc[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
-            tmem_ld16(taddr, acc);
-            tmem_ld16(taddr + 16, acc + 16);
-            tmem_ld_wait();
-            float v[32];
+            for (int ci = half; ci < kChunks; ci += 2) {
+                const int c = ci * 32;
+                const int nbase = col0 + c;
+                if (nbase >= p.n_out) break;                                      // warp-uniform
+                uint32_t acc[32];
+                tmem_ld16(tmem_acc + (uint32_t)c, acc);
+                tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
+                tmem_ld_wait();
+                if (ci == last_c) {                  // all TMEM reads of this tile by this warp are done
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-            if (!partial) {
-                if (nbase + 32 <= p.n_out) {
-                    if (p.bias) {
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                if (!partial) {
+                    if (nbase + 32 <= p.n_out) {
+                        if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        }
+                        if (p.row_bias && row_ok) {
+                            const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + nbase;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __ldg(rb + j);
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) {
+                            if (nbase + j < p.n_out) {
+                                if (p.bias) v[j] += p.bias[nbase + j];
+                                if (p.row_bias && row_ok) v[j] += p.row_bias[(int64_t)gn * p.row_bias_ld + nbase + j];
+                            }
                         }
                     }
-                    if (p.row_bias && row_ok) {
-                        const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + nbase;
+                    if (p.act == 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += __ldg(rb + j);
+                        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                    } else if (geglu) {
+                        // columns [0,16) of the chunk are values, [16,32) their gates (weights are
+                        // interleaved that way at load): attention.py:54-56  x * gelu(gate)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf(v[16 + j]);
+                    }
+                }
+                const int nchunks = geglu ? 4 : 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < nchunks)
+                        stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                if (!geglu) {
+                    if (vec_io && nbase + 32 <= eo.n_cols) {
+                        // fast path: prefetch the 8 residual vectors first (memory-level parallelism),
+                        // then blend and store
+                        int mrow[8], okr[8];
+                        float4 rv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + (lane >> 3);
+                            mrow[i] = __shfl_sync(0xffffffffu, m_own, row);
+                            okr[i] = __shfl_sync(0xffffffffu, row_ok, row);
+                            rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (eo.resid && okr[i]) {
+                                const int64_t off = (int64_t)mrow[i] * eo.ld_resid + nbase + 4 * (lane & 7);
+                                if (eo.resid_is_f32) {
+                                    rv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eo.resid) + off);
+                                } else {
+                                    const uint2 u = *reinterpret_cast<const uint2*>(
+                                        reinterpret_cast<const __nv_bfloat16*>(eo.resid) + off);
+                                    unpack_bf16x2(u.x, rv[i].x, rv[i].y);
+                                    unpack_bf16x2(u.y, rv[i].z, rv[i].w);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + (lane >> 3), q = lane & 7;
+                            float4 val = stg[row * 8 + (q ^ (row & 7))];
+                            if (!okr[i]) continue;
+                            val.x = fmaf(eo.alpha, val.x, rv[i].x); val.y = fmaf(eo.alpha, val.y, rv[i].y);
+                            val.z = fmaf(eo.alpha, val.z, rv[i].z); val.w = fmaf(eo.alpha, val.w, rv[i].w);
+                            const int64_t off = (int64_t)mrow[i] * eo.ldo + nbase + 4 * q;
+                            if (eo.out_f32) *reinterpret_cast<float4*>(eo.out_f32 + off) = val;
+                            if (eo.out_bf16)
+                                *reinterpret_cast<uint2*>(eo.out_bf16 + off) =
+                                    make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + (lane >> 3), q = lane & 7;
+                            const float4 val = stg[row * 8 + (q ^ (row & 7))];
+                            const int m_row = __shfl_sync(0xffffffffu, m_own, row);
+                            const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                            const int n = nbase + 4 * q;
+                            if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
+                        }
                     }
                 } else {
-                    for (int j = 0; j < 32; ++j) {
-                        if (nbase + j < p.n_out) {
-                            if (p.bias) v[j] += p.bias[nbase + j];
-                            if (p.row_bias && row_ok) v[j] += p.row_bias[(int64_t)gn * p.row_bias_ld + nbase + j];
-                        }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = 8 * i + (lane & 7), q = lane >> 3;
+                        const float4 val = stg[row * 8 + (q ^ (row & 7))];
+                        const int m_row = __shfl_sync(0xffffffffu, m_own, row);
+                        const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                        const int n = (nbase >> 1) + 4 * q;
+                        if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
                     }
                 }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                } else if (geglu) {
-                    // columns [0,16) of the chunk are values, [16,32) their gates (weights are
-                    // interleaved that way at load): attention.py:54-56  x * gelu(gate)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf(v[16 + j]);
-                }
+                __syncwarp();
             }
-            const int nchunks = geglu ? 4 : 8;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q < nchunks)
-                    stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            __syncwarp();
-            if (!geglu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = 4 * i + (lane >> 3), q = lane & 7;
-                    const float4 val = stg[row * 8 + (q ^ (row & 7))];
-                    const int m_row = __shfl_sync(0xffffffffu, m_own, row);
-                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
-                    const int n = nbase + 4 * q;
-                    if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = 8 * i + (lane & 7), q = lane >> 3;
-                    const float4 val = stg[row * 8 + (q ^ (row & 7))];
-                    const int m_row = __shfl_sync(0xffffffffu, m_own, row);
-                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
-                    const int n = (nbase >> 1) + 4 * q;
-                    if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
-                }
-            }
-            __syncwarp();
         }
     }
     tc_fence_before();
@@ -546,6 +645,7 @@ template <int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN>;
+    static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
         RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>,
@@ -553,7 +653,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                                         Cfg::kSmemBytes));
         attr_set = true;
     }
-    dim3 grid(m_tiles, (d.n_out + BN - 1) / BN, splits);
+    const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
+    dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
     conv_gemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -569,11 +670,10 @@ static int pick_block_n(int n_out, int m_tiles, int hint) {
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const int nt = (n_out + bn - 1) / bn;
-        const int64_t ctas = (int64_t)m_tiles * nt;
-        const int64_t slots = 2 * kNumSMs;
-        const int64_t waves = (ctas + slots - 1) / slots;
-        // cost ~ waves * per-CTA time; per-CTA time ~ bn (MMA N) + fixed overhead
-        const double cost = (double)waves * (bn + 24);
+        const int64_t tiles = (int64_t)m_tiles * nt;
+        const int64_t per_sm = (tiles + kNumSMs - 1) / kNumSMs;      // persistent: tiles each CTA walks
+        // cost ~ tiles per SM * per-tile time; per-tile time ~ bn (MMA N) + fixed overhead
+        const double cost = (double)per_sm * (bn + 16);
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
     return best;
@@ -644,7 +744,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
     d.alpha = p->alpha; d.act = p->act;
     d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
-    d.partial = nullptr; d.kb_per_split = 0;
+    d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0;
     d.m_total = (int64_t)p->a_n * p->a_h * p->a_w;
     if (p->act == 2) {
         RDEIC_CHECK_ARG(p->n_out % 32 == 0 && !p->resid && p->ldo >= p->n_out / 2,
@@ -685,9 +785,11 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     int splits = 1;
     const int total_kb = p->taps * (d.cblk1 + d.cblk2);
     const int n_tiles = (p->n_out + bn - 1) / bn;
+    d.n_tiles = n_tiles;
+    d.kb_per_split = total_kb;
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
-    if (p->act != 2 && p->workspace && tiles <= kNumSMs && total_kb >= 8) {
-        int want = (int)((2 * kNumSMs) / tiles);
+    if (p->act != 2 && p->workspace && tiles <= kNumSMs / 2 && total_kb >= 8) {
+        int want = (int)(kNumSMs / tiles);
         if (want > total_kb / 4) want = total_kb / 4;
         if (want > 16) want = 16;
         const int64_t per_split = d.m_total * p->n_out * (int64_t)sizeof(float);
@@ -696,6 +798,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
             d.kb_per_split = (total_kb + want - 1) / want;
             splits = (total_kb + d.kb_per_split - 1) / d.kb_per_split;
             d.partial = reinterpret_cast<float*>(p->workspace);
+            d.splits = splits;
         }
     }
     int rc;
