@@ -10,7 +10,10 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "librdeic_b200.so"
+import os as _os
+
+# RDEIC_B200_LIB selects an alternative build of the same ABI (kernel A/B experiments)
+LIB_PATH = Path(_os.environ.get("RDEIC_B200_LIB", _HERE / "librdeic_b200.so"))
 
 c_f32p = C.c_void_p
 vp = C.c_void_p

@@ -39,6 +39,25 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
+def build_variant(csrc_dir: Path, out: Path, extra_flags=()) -> Path:
+    """Compile another checkout of csrc/ (or the same one with extra -D flags) into `out`."""
+    nvcc = _nvcc()
+    tmp = BUILD / ("variant_" + out.stem)
+    tmp.mkdir(parents=True, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = tmp / (src + ".o")
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *extra_flags, "-I", str(HERE.parent / "include"), "-c",
+                            str(csrc_dir / src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-o", str(out), *map(str, objs), "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ and link the shared library. Returns its path."""
     deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "rdeic_b200.h"]

@@ -96,8 +96,23 @@ __device__ __forceinline__ void epi_store4(const EpiOut& e, int64_t m, int n, fl
     }
 }
 
+// Exact-erf GELU (torch F.gelu default) with a branch-free erf: Abramowitz & Stegun 7.1.26,
+// |error| <= 1.5e-7, two MUFU ops + a short Horner chain, so 16 instances interleave freely in
+// the epilogue (libdevice erff is a branchy call that serialises them).
 __device__ __forceinline__ float gelu_erf(float x) {
+#ifdef RDEIC_GELU_ERFF
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+#endif
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    const float erf_abs = fmaf(-p * t, e, 1.0f);                 // erf(|x|/sqrt2)
+    return 0.5f * x + 0.5f * fabsf(x) * erf_abs;                 // 0.5 x (1 + sign(x) erf|.|)
 }
 
 // ----------------------------------------------------------------------------------------
@@ -239,7 +254,7 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN>
+template <int BN, bool kPrefetchResid>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
@@ -391,14 +406,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             eo.n_cols = geglu ? (p.n_out >> 1) : p.n_out;
             const bool vec_io = (eo.ldo & 3) == 0 && (!eo.resid || (eo.ld_resid & 3) == 0);
             const uint32_t buf = t & 1, aph = (t >> 1) & 1;
-            mbar_wait(&acc_full[buf], aph);
-            tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
             constexpr int kChunks = BN / 32;
             // chunks this warp owns: half, half+2, ...
             int last_c = -1;
             for (int ci = half; ci < kChunks; ci += 2)
                 if (col0 + ci * 32 < p.n_out) last_c = ci;
+            // phase-B row mapping: row = 4*i + lane/8; its global row index / validity come from the
+            // lane that owns that accumulator row (a shuffle is cheaper than 16 live registers here:
+            // with 10 warps per CTA one SM sub-partition hosts 3 warps, capping threads at 168 regs)
+            // bf16 residuals (VAE stream) are prefetched two chunks deep: the loads of chunk c+1 are in
+            // flight while chunk c is drained, and the first chunk's are issued before we even wait
+            // for the accumulator (they do not depend on it).  fp32 residuals (UNet stream) are loaded
+            // at the top of phase B instead: 64 more live registers cost more than the latency they
+            // hide (measured: +0.9 ms per UNet step), with the 168-register cap of a 10-warp CTA.
+            auto fast_chunk = [&](int ci) -> bool {
+                return !geglu && vec_io && ci <= last_c && col0 + ci * 32 + 32 <= eo.n_cols;
+            };
+            // (kPrefetchResid is a template flag so the fp32 instantiation carries no prefetch state)
+            const bool pre_bf16 = kPrefetchResid && eo.resid && !eo.resid_is_f32;
+            auto prefetch = [&](int ci, uint2* dst) {
+                if (!pre_bf16 || !fast_chunk(ci)) return;
+                const int n = col0 + ci * 32 + 4 * (lane & 7);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + (lane >> 3);
+                    const int mr = __shfl_sync(0xffffffffu, m_own, row);
+                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                    dst[i] = make_uint2(0u, 0u);
+                    if (ok)
+                        dst[i] = *reinterpret_cast<const uint2*>(
+                            reinterpret_cast<const __nv_bfloat16*>(eo.resid) + (int64_t)mr * eo.ld_resid + n);
+                }
+            };
+            uint2 rcur[kPrefetchResid ? 8 : 1], rnext[kPrefetchResid ? 8 : 1];
+            if (kPrefetchResid) prefetch(half, rcur);
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
             if (last_c < 0) {                       // nothing to read: release the buffer right away
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -408,9 +452,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int c = ci * 32;
                 const int nbase = col0 + c;
                 if (nbase >= p.n_out) break;                                      // warp-uniform
+                if (kPrefetchResid) prefetch(ci + 2, rnext);
                 uint32_t acc[32];
                 tmem_ld16(tmem_acc + (uint32_t)c, acc);
                 tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
+                const bool full32 = nbase + 32 <= p.n_out;
                 tmem_ld_wait();
                 if (ci == last_c) {                  // all TMEM reads of this tile by this warp are done
                     tc_fence_before();
@@ -420,18 +466,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
                 if (!partial) {
-                    if (nbase + 32 <= p.n_out) {
+                    if (full32) {
                         if (p.bias) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + j);
+                                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
                             }
                         }
                         if (p.row_bias && row_ok) {
                             const float* rb = p.row_bias + (int64_t)gn * p.row_bias_ld + nbase;
+#ifdef RDEIC_ROWBIAS_SCALAR
+                            if (false) {
+#else
+                            if (((p.row_bias_ld | nbase) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.row_bias) & 15) == 0) {
+#endif
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += __ldg(rb + j);
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb) + j);
+                                    v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += __ldg(rb + j);
+                            }
                         }
                     } else {
                         for (int j = 0; j < 32; ++j) {
@@ -458,19 +516,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (!geglu) {
-                    if (vec_io && nbase + 32 <= eo.n_cols) {
-                        // fast path: prefetch the 8 residual vectors first (memory-level parallelism),
-                        // then blend and store
-                        int mrow[8], okr[8];
+                    if (fast_chunk(ci)) {
+                        int mr[8], okr[8];
                         float4 rv[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = 4 * i + (lane >> 3);
-                            mrow[i] = __shfl_sync(0xffffffffu, m_own, row);
+                            mr[i] = __shfl_sync(0xffffffffu, m_own, row);
                             okr[i] = __shfl_sync(0xffffffffu, row_ok, row);
                             rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (eo.resid && okr[i]) {
-                                const int64_t off = (int64_t)mrow[i] * eo.ld_resid + nbase + 4 * (lane & 7);
+                            if (eo.resid && okr[i] && !(kPrefetchResid && pre_bf16)) {
+                                const int64_t off = (int64_t)mr[i] * eo.ld_resid + nbase + 4 * (lane & 7);
                                 if (eo.resid_is_f32) {
                                     rv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eo.resid) + off);
                                 } else {
@@ -486,9 +542,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             const int row = 4 * i + (lane >> 3), q = lane & 7;
                             float4 val = stg[row * 8 + (q ^ (row & 7))];
                             if (!okr[i]) continue;
-                            val.x = fmaf(eo.alpha, val.x, rv[i].x); val.y = fmaf(eo.alpha, val.y, rv[i].y);
-                            val.z = fmaf(eo.alpha, val.z, rv[i].z); val.w = fmaf(eo.alpha, val.w, rv[i].w);
-                            const int64_t off = (int64_t)mrow[i] * eo.ldo + nbase + 4 * q;
+                            if (kPrefetchResid && pre_bf16) {
+                                unpack_bf16x2(rcur[kPrefetchResid ? i : 0].x, rv[i].x, rv[i].y);
+                                unpack_bf16x2(rcur[kPrefetchResid ? i : 0].y, rv[i].z, rv[i].w);
+                            }
+                            if (eo.resid) {
+                                val.x = fmaf(eo.alpha, val.x, rv[i].x); val.y = fmaf(eo.alpha, val.y, rv[i].y);
+                                val.z = fmaf(eo.alpha, val.z, rv[i].z); val.w = fmaf(eo.alpha, val.w, rv[i].w);
+                            } else if (eo.alpha != 1.0f) {
+                                val.x *= eo.alpha; val.y *= eo.alpha; val.z *= eo.alpha; val.w *= eo.alpha;
+                            }
+                            const int64_t off = (int64_t)mr[i] * eo.ldo + nbase + 4 * q;
                             if (eo.out_f32) *reinterpret_cast<float4*>(eo.out_f32 + off) = val;
                             if (eo.out_bf16)
                                 *reinterpret_cast<uint2*>(eo.out_bf16 + off) =
@@ -515,6 +579,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const int n = (nbase >> 1) + 4 * q;
                         if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
                     }
+                }
+                if (kPrefetchResid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rcur[kPrefetchResid ? i : 0] = rnext[kPrefetchResid ? i : 0];
                 }
                 __syncwarp();
             }
@@ -641,23 +709,31 @@ static void pick_m_tile(int N, int H, int W, bool force_tn1, int* tw_o, int* th_
 }
 static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
-template <int BN>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
-                       const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
+template <int BN, bool kPre>
+static int launch_conv2(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    conv_gemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
+    conv_gemm_kernel<BN, kPre><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+                       const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
+    // bf16 residual streams (VAE) take the instantiation that prefetches the residual ahead
+    if (d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, true>(ta, ta2, tb, d, m_tiles, splits, s);
+    return launch_conv2<BN, false>(ta, ta2, tb, d, m_tiles, splits, s);
 }
 
 static int pick_block_n(int n_out, int m_tiles, int hint) {

@@ -499,7 +499,15 @@ class VAEDecoderEngine:
             self.levels.append((blocks, up))
             lvl += 1
         self.norm_out = Norm.load(sd, D + ".norm_out", dev)
-        self.conv_out = Conv.load(sd, D + ".conv_out", dev)
+        # conv_out has 3 output channels; pad to 4 (zero weights) so every output row is one aligned
+        # 16-byte vector and the epilogue takes its coalesced path (12-byte rows cannot).
+        wo, bo = sd[D + ".conv_out.weight"].float(), sd[D + ".conv_out.bias"].float()
+        self.out_ch = wo.shape[0]
+        pad = (-self.out_ch) % 4
+        if pad:
+            wo = torch.cat([wo, torch.zeros(pad, *wo.shape[1:], device=wo.device)], 0)
+            bo = torch.cat([bo, torch.zeros(pad, device=bo.device)], 0)
+        self.conv_out = Conv.load({"w.weight": wo, "w.bias": bo}, "w", dev)
 
     @staticmethod
     def _res(w: VaeRes, x):
@@ -527,7 +535,7 @@ class VAEDecoderEngine:
 
     @torch.no_grad()
     def decode_nhwc(self, z: torch.Tensor) -> torch.Tensor:
-        """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,3] in [-1,1]."""
+        """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,4] in [-1,1] (channel 3 is padding)."""
         if not z.is_cuda:
             raise ops._lib.RdeicLibraryError("VAEDecoderEngine needs CUDA tensors; there is no CPU path")
         z8 = ops.nchw_to_nhwc_bf16(z.float().contiguous(), ldc=8)
@@ -549,7 +557,7 @@ class VAEDecoderEngine:
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         """decode_first_stage contract: [B,3,H,W] fp32 in [-1,1]."""
-        return ops.nhwc_to_nchw_f32(self.decode_nhwc(z))
+        return ops.nhwc_to_nchw_f32(self.decode_nhwc(z), self.out_ch)
 
     @torch.no_grad()
     def decode_u8(self, z: torch.Tensor) -> torch.Tensor:
