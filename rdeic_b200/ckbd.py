@@ -1,0 +1,158 @@
+"""Drop-in for the reference's `utils/ckbd.py`: checkerboard split / merge / squeeze / unsqueeze and
+the quantise -> symbols / CDF-index glue around the (host) rANS coder, on CUDA tensors, bit-exact.
+
+Function names keep the reference's spelling (`sequeeze`).  The four `(de)compress_*` helpers keep
+the reference signatures (utils/ckbd.py:76-115) but run each phase as ONE fused kernel and hand
+symbols / indexes to the coder as int32 numpy views of pinned host buffers instead of
+`.reshape(-1).tolist()` Python lists built from a synchronous D2H copy per tensor (ckbd.py:83-84,103).
+The byte coder itself (compressai rANS, torchac) stays in the host library: out of scope.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+ANCHOR, NONANCHOR = 0, 1
+
+
+def ckbd_split(y):
+    """utils/ckbd.py:6-24."""
+    return ops.ckbd_split(y)
+
+
+def ckbd_merge(anchor, nonanchor):
+    """utils/ckbd.py:26-33."""
+    return ops.ckbd_merge(anchor, nonanchor)
+
+
+def ckbd_anchor(y):
+    """utils/ckbd.py:35-39."""
+    return ops.ckbd_mask(y, ANCHOR)
+
+
+def ckbd_nonanchor(y):
+    """utils/ckbd.py:41-45."""
+    return ops.ckbd_mask(y, NONANCHOR)
+
+
+def ckbd_anchor_sequeeze(y):
+    """utils/ckbd.py:47-52."""
+    return ops.ckbd_squeeze(y, ANCHOR)
+
+
+def ckbd_nonanchor_sequeeze(y):
+    """utils/ckbd.py:54-59."""
+    return ops.ckbd_squeeze(y, NONANCHOR)
+
+
+def ckbd_anchor_unsequeeze(anchor):
+    """utils/ckbd.py:61-66."""
+    return ops.ckbd_unsqueeze(anchor, ANCHOR)
+
+
+def ckbd_nonanchor_unsequeeze(nonanchor):
+    """utils/ckbd.py:68-73."""
+    return ops.ckbd_unsqueeze(nonanchor, NONANCHOR)
+
+
+def get_scale_table(min=0.11, max=256, levels=64):  # noqa: A002  (reference argument names)
+    """utils/func.py:10-13 — evaluated by torch on the host so the fp32 table is the reference's."""
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+class GaussianConditional:
+    """The two arithmetic entry points of compressai 1.2.4 `GaussianConditional` the decode path uses
+    (`build_indexes`, `quantize`), over CUDA tensors.  `scale_bound` is compressai's LowerBound(0.11)."""
+
+    def __init__(self, scale_table: Optional[torch.Tensor] = None, scale_bound: float = 0.11, device="cuda"):
+        table = get_scale_table() if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
+        self.scale_table = table.to(device, torch.float32).contiguous()
+        self.scale_bound = float(scale_bound)
+
+    def update_scale_table(self, scale_table, force=False):
+        self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32).to(self.scale_table.device).contiguous()
+        return True
+
+    def build_indexes(self, scales: torch.Tensor) -> torch.Tensor:
+        return ops.build_indexes(scales, self.scale_table, self.scale_bound)
+
+    def quantize(self, inputs: torch.Tensor, mode: str, means: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if mode == "symbols":
+            return ops.quantize_symbols(inputs, means)
+        if mode == "dequantize":
+            sym = ops.quantize_symbols(inputs, means)
+            zeros = means if means is not None else torch.zeros_like(inputs)
+            return ops.dequantize(sym, zeros.expand_as(inputs).contiguous())
+        raise ValueError(f'Invalid quantization mode: "{mode}"')
+
+    def dequantize(self, inputs: torch.Tensor, means: Optional[torch.Tensor] = None) -> torch.Tensor:
+        means = torch.zeros(inputs.shape, dtype=torch.float32, device=inputs.device) if means is None else means
+        return ops.dequantize(inputs.to(torch.int32), means.expand(inputs.shape).contiguous())
+
+
+class _Pinned:
+    """Reusable pinned int32 staging buffers for the symbol hand-off."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def to_host(self, t: torch.Tensor, slot: str) -> np.ndarray:
+        n = t.numel()
+        b = self.buf.get(slot)
+        if b is None or b.numel() < n:
+            b = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
+            self.buf[slot] = b
+        b[:n].copy_(t.reshape(-1), non_blocking=True)
+        return b[:n]
+
+    def sync(self):
+        torch.cuda.current_stream().synchronize()
+
+
+_pinned = _Pinned()
+
+
+def _phase(gc: GaussianConditional, y, scales, means, symbols_list, indexes_list, which: int):
+    sym, idx, y_hat = ops.ckbd_encode_phase(y, scales, means, gc.scale_table, gc.scale_bound, which)
+    hs, hi = _pinned.to_host(sym, "sym"), _pinned.to_host(idx, "idx")
+    _pinned.sync()
+    symbols_list.extend(hs.tolist())
+    indexes_list.extend(hi.tolist())
+    return y_hat
+
+
+def compress_anchor(gaussian_conditional, anchor, scales_anchor, means_anchor, symbols_list, indexes_list):
+    """utils/ckbd.py:76-86."""
+    return _phase(gaussian_conditional, anchor, scales_anchor, means_anchor, symbols_list, indexes_list, ANCHOR)
+
+
+def compress_nonanchor(gaussian_conditional, nonanchor, scales_nonanchor, means_nonanchor, symbols_list, indexes_list):
+    """utils/ckbd.py:88-97."""
+    return _phase(gaussian_conditional, nonanchor, scales_nonanchor, means_nonanchor, symbols_list, indexes_list,
+                  NONANCHOR)
+
+
+def _dephase(gc: GaussianConditional, scales, means, decoder, cdf, cdf_lengths, offsets, which: int):
+    means_sq, idx = ops.ckbd_squeeze_indexes(scales, means, gc.scale_table, gc.scale_bound, which)
+    hi = _pinned.to_host(idx, "idx")
+    _pinned.sync()
+    symbols = decoder.decode_stream(hi.tolist(), cdf, cdf_lengths, offsets)
+    sym = torch.as_tensor(np.asarray(symbols, dtype=np.int32)).reshape(means_sq.shape).to(means_sq.device,
+                                                                                        non_blocking=True)
+    return ops.ckbd_decode_phase(sym, means_sq, which)
+
+
+def decompress_anchor(gaussian_conditional, scales_anchor, means_anchor, decoder, cdf, cdf_lengths, offsets):
+    """utils/ckbd.py:99-106."""
+    return _dephase(gaussian_conditional, scales_anchor, means_anchor, decoder, cdf, cdf_lengths, offsets, ANCHOR)
+
+
+def decompress_nonanchor(gaussian_conditional, scales_nonanchor, means_nonanchor, decoder, cdf, cdf_lengths, offsets):
+    """utils/ckbd.py:108-115."""
+    return _dephase(gaussian_conditional, scales_nonanchor, means_nonanchor, decoder, cdf, cdf_lengths, offsets,
+                    NONANCHOR)

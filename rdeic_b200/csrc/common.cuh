@@ -43,6 +43,23 @@ static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
     return (int)blocks;
 }
 
+// Division by a launch-invariant 32-bit divisor without the ~50-instruction integer divide
+// (Granlund-Montgomery): q = (umulhi(n, mul) + n) >> shr, exact for n < 2^31.
+struct FastDiv {
+    uint32_t d, mul, shr;
+    FastDiv() : d(1), mul(0), shr(0) {}
+    explicit FastDiv(uint32_t div) : d(div) {
+        shr = 0;
+        while ((1ull << shr) < div) ++shr;
+        mul = (uint32_t)(((1ull << 32) * ((1ull << shr) - div)) / div + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, mul) + n) >> shr; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {

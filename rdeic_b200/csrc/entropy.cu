@@ -14,20 +14,41 @@ namespace rdeic {
 
 constexpr int kThreads = 256;
 
+// Flat index -> (row, column-in-row, h = row % H) without integer divides on the fast path.
+struct RowMap {
+    FastDiv per_row, per_h;
+    int fast;          // 1 when every flat index fits the 31-bit fast divider
+    int cols, H;
+    RowMap(int64_t total, int cols_, int H_) : per_row((uint32_t)(cols_ > 0 ? cols_ : 1)), per_h((uint32_t)(H_ > 0 ? H_ : 1)),
+                                              fast(total < (1ll << 31)), cols(cols_), H(H_) {}
+    __device__ __forceinline__ void map(int64_t i, int64_t& r, int& col, int& h) const {
+        if (fast) {
+            uint32_t rq, cq, hq, dummy;
+            per_row.divmod((uint32_t)i, rq, cq);
+            per_h.divmod(rq, dummy, hq);
+            r = rq; col = (int)cq; h = (int)hq;
+        } else {
+            r = i / cols;
+            col = (int)(i - r * cols);
+            h = (int)(r % H);
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // ckbd mask / split
 // ------------------------------------------------------------------------------------------
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads)
 ckbd_mask_kernel(const uint32_t* __restrict__ y, uint32_t* __restrict__ out_a,
-                 uint32_t* __restrict__ out_n, int64_t rows, int H, int W, int which) {
+                 uint32_t* __restrict__ out_n, int64_t rows, int H, int W, int which, RowMap rm) {
     // vector path: W % 4 == 0, one uint4 per thread-iteration
     const int wv = W >> 2;
     const int64_t total = rows * wv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / wv;
-        const int h = (int)(r % H);
+        int64_t r; int col, h;
+        rm.map(i, r, col, h);
         uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(y) + i);
         // column index of v.x is a multiple of 4 -> parity of (h + w) for lanes x,y,z,w is
         // h, h+1, h, h+1.
@@ -97,18 +118,21 @@ ckbd_merge_kernel(const float* __restrict__ a, const float* __restrict__ n,
 //   anchor: even row -> 1, odd row -> 0 ; non-anchor: even row -> 0, odd row -> 1
 __device__ __forceinline__ int pair_offset(int h, int which) { return (h & 1) ^ (which == 0); }
 
+// Log-domain guess for a sorted table (the reference's is exp(linspace(ln .11, ln 256, 64)),
+// utils/func.py:10-13): tab[L + 1] / tab[L + 2] hold ln(tab[0]) and L / (ln tab[L] - ln tab[0]).
+// The guess only seeds the search; the two fix-up loops compare against the table itself, so the
+// result is exactly  first k with s <= tab[k]  (L if none) for ANY sorted table and any s, NaN included.
 __device__ __forceinline__ int scale_index(float scale, const float* __restrict__ tab, int L,
                                            float lower_bound, bool sorted) {
     // compressai LowerBound = torch.max(x, bound): NaN propagates.
     const float s = (scale != scale) ? scale : fmaxf(scale, lower_bound);
     if (sorted) {
         // idx = L - #{k<L : s <= tab[k]} = first k with s <= tab[k] (L if none)
-        int lo = 0, hi = L;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s <= tab[mid]) hi = mid; else lo = mid + 1;
-        }
-        return lo;
+        float g = ceilf((__logf(s) - tab[L + 1]) * tab[L + 2]);
+        int k = (g >= 0.f) ? ((g <= (float)L) ? (int)g : L) : 0;       // NaN -> 0
+        while (k > 0 && s <= tab[k - 1]) --k;
+        while (k < L && !(s <= tab[k])) ++k;
+        return k;
     }
     int idx = L;
     for (int k = 0; k < L; ++k) idx -= (s <= tab[k]) ? 1 : 0;
@@ -123,11 +147,17 @@ __device__ __forceinline__ bool load_table(const float* __restrict__ table, int 
     __syncthreads();
     for (int k = threadIdx.x; k + 1 < levels - 1; k += blockDim.x)
         if (!(s_tab[k] <= s_tab[k + 1])) *s_flag = 0;  // benign race: all writers store 0
+    if (threadIdx.x == 0) {                            // seeds of the log-domain guess (see scale_index)
+        const int L = levels - 1;
+        const float l0 = logf(s_tab[0]), l1 = logf(s_tab[L]);
+        s_tab[L + 1] = l0;
+        s_tab[L + 2] = (l1 > l0) ? (float)L / (l1 - l0) : 0.f;
+    }
     __syncthreads();
-    return *s_flag != 0;
+    return *s_flag != 0 && s_tab[0] > 0.f;
 }
 
-constexpr int kMaxLevels = 256;
+constexpr int kMaxLevels = 256;   // s_tab holds levels + 2 floats
 
 // mode 0: squeeze only (out_f)                      [ckbd.py:47-59]
 // mode 1: squeeze scales+means -> means_sq, indexes [ckbd.py:99-103,108-112]
@@ -136,7 +166,7 @@ ckbd_squeeze_kernel(const uint32_t* __restrict__ y, const float* __restrict__ sc
                     const float* __restrict__ table, int levels, float lower_bound,
                     uint32_t* __restrict__ out_f, int32_t* __restrict__ out_idx, int64_t rows,
                     int H, int W, int which, int mode) {
-    __shared__ float s_tab[kMaxLevels];
+    __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     bool sorted = false;
     if (mode == 1) sorted = load_table(table, levels, s_tab, &s_flag);
@@ -159,8 +189,8 @@ __global__ void __launch_bounds__(kThreads)
 ckbd_squeeze_vec_kernel(const uint32_t* __restrict__ y, const float* __restrict__ scales,
                         const float* __restrict__ table, int levels, float lower_bound,
                         uint32_t* __restrict__ out_f, int32_t* __restrict__ out_idx,
-                        int64_t rows, int H, int W, int which, int mode) {
-    __shared__ float s_tab[kMaxLevels];
+                        int64_t rows, int H, int W, int which, int mode, RowMap rm) {
+    __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     bool sorted = false;
     if (mode == 1) sorted = load_table(table, levels, s_tab, &s_flag);
@@ -168,8 +198,8 @@ ckbd_squeeze_vec_kernel(const uint32_t* __restrict__ y, const float* __restrict_
     const int64_t total = rows * Wq;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / Wq;
-        const int h = (int)(r % H);
+        int64_t r; int col, h;
+        rm.map(i, r, col, h);
         const int off = pair_offset(h, which);
         const uint4 lo = ld_stream_u4(reinterpret_cast<const uint4*>(y) + 2 * i);
         const uint4 hi = ld_stream_u4(reinterpret_cast<const uint4*>(y) + 2 * i + 1);
@@ -211,23 +241,41 @@ ckbd_unsqueeze_kernel(const uint32_t* __restrict__ sq, const int32_t* __restrict
     }
 }
 
+// vector variant of the raw unsqueeze: 4 inputs -> 8 outputs per thread (Wh % 4 == 0)
+__global__ void __launch_bounds__(kThreads)
+ckbd_unsqueeze_vec_kernel(const uint4* __restrict__ sq, uint4* __restrict__ out, int64_t rows, int H,
+                          int Wh, int which, RowMap rm) {
+    const int wq = Wh >> 2;
+    const int64_t total = rows * wq;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r; int col, h;
+        rm.map(i, r, col, h);
+        const int off = pair_offset(h, which);
+        const uint4 v = ld_stream_u4(sq + i);
+        const uint4 lo = off ? make_uint4(0u, v.x, 0u, v.y) : make_uint4(v.x, 0u, v.y, 0u);
+        const uint4 hi = off ? make_uint4(0u, v.z, 0u, v.w) : make_uint4(v.z, 0u, v.w, 0u);
+        st_stream_u4(out + 2 * i, lo);
+        st_stream_u4(out + 2 * i + 1, hi);
+    }
+}
+
 // encode-side fused phase [ckbd.py:76-97]: one thread per kept element
 __global__ void __launch_bounds__(kThreads)
 ckbd_encode_phase_kernel(const float* __restrict__ y, const float* __restrict__ scales,
                          const float* __restrict__ means, const float* __restrict__ table,
                          int levels, float lower_bound, int32_t* __restrict__ symbols,
                          int32_t* __restrict__ indexes, float* __restrict__ y_hat,
-                         int64_t rows, int H, int W, int which) {
-    __shared__ float s_tab[kMaxLevels];
+                         int64_t rows, int H, int W, int which, RowMap rm) {
+    __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     const bool sorted = load_table(table, levels, s_tab, &s_flag);
     const int Wh = W >> 1;
     const int64_t total = rows * Wh;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / Wh;
-        const int j = (int)(i - r * Wh);
-        const int h = (int)(r % H);
+        int64_t r; int j, h;
+        rm.map(i, r, j, h);
         const int off = pair_offset(h, which);
         const int64_t src = r * W + 2 * j + off;
         const float m = means[src];
@@ -297,7 +345,7 @@ dequantize_kernel(const int32_t* __restrict__ sym, const float* __restrict__ mea
 __global__ void __launch_bounds__(kThreads)
 build_indexes_kernel(const float* __restrict__ scales, const float* __restrict__ table,
                      int levels, float lower_bound, int32_t* __restrict__ idx, int64_t numel) {
-    __shared__ float s_tab[kMaxLevels];
+    __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     const bool sorted = load_table(table, levels, s_tab, &s_flag);
     const int L = levels - 1;
@@ -457,7 +505,7 @@ int rdeic_ckbd_mask(const float* y, float* out, int B, int C, int H, int W, int 
     const bool vec = (W % 4 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out % 16 == 0);
     if (vec)
         ckbd_mask_kernel<false><<<grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
-            (const uint32_t*)y, (uint32_t*)out, nullptr, rows, H, W, which);
+            (const uint32_t*)y, (uint32_t*)out, nullptr, rows, H, W, which, RowMap(rows * (W / 4), W / 4, H));
     else
         ckbd_mask_scalar_kernel<false><<<grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream)>>>(
             (const uint32_t*)y, (uint32_t*)out, nullptr, rows, H, W, which);
@@ -475,7 +523,7 @@ int rdeic_ckbd_split(const float* y, float* anchor, float* nonanchor, int B, int
                      ((uintptr_t)nonanchor % 16 == 0);
     if (vec)
         ckbd_mask_kernel<true><<<grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
-            (const uint32_t*)y, (uint32_t*)anchor, (uint32_t*)nonanchor, rows, H, W, 0);
+            (const uint32_t*)y, (uint32_t*)anchor, (uint32_t*)nonanchor, rows, H, W, 0, RowMap(rows * (W / 4), W / 4, H));
     else
         ckbd_mask_scalar_kernel<true><<<grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream)>>>(
             (const uint32_t*)y, (uint32_t*)anchor, (uint32_t*)nonanchor, rows, H, W, 0);
@@ -511,7 +559,7 @@ static int launch_squeeze(const float* y, const float* scales, const float* tabl
     if (vec)
         ckbd_squeeze_vec_kernel<<<grid_for(rows * (W / 8), kThreads), kThreads, 0, as_stream(stream)>>>(
             (const uint32_t*)y, scales, table, levels, lower_bound, (uint32_t*)out_f, out_idx,
-            rows, H, W, which, mode);
+            rows, H, W, which, mode, RowMap(rows * (W / 8), W / 8, H));
     else
         ckbd_squeeze_kernel<<<grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream)>>>(
             (const uint32_t*)y, scales, table, levels, lower_bound, (uint32_t*)out_f, out_idx,
@@ -545,8 +593,12 @@ int rdeic_ckbd_unsqueeze(const float* sq, float* out, int B, int C, int H, int W
     const int64_t rows = (int64_t)B * C * H;
     if (rows == 0 || Wh == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)out % 8 == 0, "rdeic_ckbd_unsqueeze: out must be 8-byte aligned");
-    ckbd_unsqueeze_kernel<<<grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream)>>>(
-        (const uint32_t*)sq, nullptr, nullptr, (uint32_t*)out, rows, H, Wh, which, 0);
+    if (Wh % 4 == 0 && (uintptr_t)sq % 16 == 0 && (uintptr_t)out % 16 == 0)
+        ckbd_unsqueeze_vec_kernel<<<grid_for(rows * (Wh / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
+            (const uint4*)sq, (uint4*)out, rows, H, Wh, which, RowMap(rows * (Wh / 4), Wh / 4, H));
+    else
+        ckbd_unsqueeze_kernel<<<grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream)>>>(
+            (const uint32_t*)sq, nullptr, nullptr, (uint32_t*)out, rows, H, Wh, which, 0);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -579,7 +631,8 @@ int rdeic_ckbd_encode_phase(const float* y, const float* scales, const float* me
     if (rows == 0 || W == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)y_hat % 8 == 0, "rdeic_ckbd_encode_phase: y_hat must be 8-byte aligned");
     ckbd_encode_phase_kernel<<<grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream)>>>(
-        y, scales, means, table, levels, lower_bound, symbols, indexes, y_hat, rows, H, W, which);
+        y, scales, means, table, levels, lower_bound, symbols, indexes, y_hat, rows, H, W, which,
+        RowMap(rows * (W / 2), W / 2, H));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

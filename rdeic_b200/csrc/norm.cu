@@ -17,8 +17,8 @@ constexpr int kGnMaxGroups = 32;
 constexpr int kGnMaxC = 2560;  // widest GN input on the path: concat 1280 + 1280
 
 static inline int gn_num_chunks(int B, int64_t HW) {
-    int64_t want = (4 * kNumSMs + B - 1) / B;   // ~4 CTAs per SM over the whole batch
-    int64_t max_by_rows = HW / 16 > 0 ? HW / 16 : 1;
+    int64_t want = (8 * kNumSMs + B - 1) / B;   // ~8 CTAs per SM over the whole batch
+    int64_t max_by_rows = HW / 32 > 0 ? HW / 32 : 1;
     if (want > max_by_rows) want = max_by_rows;
     if (want > kGnMaxChunks) want = kGnMaxChunks;
     if (want < 1) want = 1;
@@ -73,7 +73,22 @@ gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
             const void* src = first ? x1 : x2;
             const int64_t stride = first ? VL1 : VL2;
             const int64_t off = (int64_t)b * HW * stride + (first ? l : l - VL1);
-            for (int64_t p = p0 + row; p < p1; p += rows_per_iter) {
+            int64_t p = p0 + row;
+            // four independent 16/32-byte loads in flight per thread (memory-level parallelism)
+            for (; p + 3 * (int64_t)rows_per_iter < p1; p += 4 * (int64_t)rows_per_iter) {
+                float f[4][8];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) load8<kF32>(src, off + (p + u * (int64_t)rows_per_iter) * stride, f[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        s[k] += f[u][k];
+                        q[k] = fmaf(f[u][k], f[u][k], q[k]);
+                    }
+                }
+            }
+            for (; p < p1; p += rows_per_iter) {
                 float f[8];
                 load8<kF32>(src, off + p * stride, f);
 #pragma unroll
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
-                const float2* __restrict__ partial, int nchunk) {
+                const float2* __restrict__ partial, int nchunk, FastDiv div_vl) {
     __shared__ float s_scale[kGnMaxC];
     __shared__ float s_shift[kGnMaxC];
     __shared__ float s_mean[kGnMaxGroups];
@@ -157,8 +172,10 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     uint4* bo = out + (int64_t)b * HW * VL;
     for (int64_t i = blockIdx.x * (int64_t)kGnThreads + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * kGnThreads) {
-        const int64_t p = i / VL;
-        const int l = (int)(i - p * VL);
+        uint32_t pq, lq;
+        div_vl.divmod((uint32_t)i, pq, lq);          // host guarantees HW * VL < 2^31
+        const int64_t p = pq;
+        const int l = (int)lq;
         float f[8];
         if (l < VL1) load8<kF32>(x1, o1 + p * VL1 + l, f);
         else load8<kF32>(x2, o2 + p * VL2 + (l - VL1), f);
@@ -181,11 +198,13 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
 }
 
-// LayerNorm: one warp per row, row held in registers (C <= 8*32*kLnMaxVec)
-constexpr int kLnMaxVec = 5;
+// LayerNorm: one warp per row, row held in registers (C <= 8*32*kLnMaxVec); kLnMaxVec is a template
+// parameter so narrow rows keep few registers live and the SM holds enough warps (= bytes in
+// flight) to cover HBM latency.
+constexpr int kLnMaxVecLimit = 5;
 constexpr int kLnWarps = 8;
 
-template <bool kF32>
+template <bool kF32, int kLnMaxVec>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
@@ -282,16 +301,18 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
         gn_stats_kernel<false><<<dim3(nchunk, B), kGnThreads, 0, s>>>(x1, C1, x2, C2, HW, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const int64_t vecs = HW * (C / 8);
+    RDEIC_CHECK_ARG(vecs < (1ll << 31), "rdeic_groupnorm_nhwc: per-sample tensor too large (HW*C/8 must be < 2^31)");
+    const FastDiv div_vl((uint32_t)(C / 8));
     int64_t blocks = ceil_div64(vecs, (int64_t)kGnThreads * 4);
     const int64_t cap = (8 * kNumSMs + B - 1) / B;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (in_is_f32)
         gn_apply_kernel<true><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
-            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk);
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     else
         gn_apply_kernel<false><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
-            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk);
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -300,17 +321,22 @@ int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const floa
                     void* out, int64_t rows, int C, float eps, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(x && gamma && beta && out, "rdeic_layernorm: null pointer");
     RDEIC_CHECK_ARG(rows >= 0, "rdeic_layernorm: negative rows");
-    RDEIC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVec,
-                    "rdeic_layernorm: C=%d must be a multiple of 8 and <= %d", C, 8 * 32 * kLnMaxVec);
+    RDEIC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVecLimit,
+                    "rdeic_layernorm: C=%d must be a multiple of 8 and <= %d", C, 8 * 32 * kLnMaxVecLimit);
     RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0,
                     "rdeic_layernorm: pointers must be 16-byte aligned");
     if (rows == 0) return 0;
     const int64_t blocks = ceil_div64(rows, kLnWarps);
     RDEIC_CHECK_ARG(blocks < (1ll << 31), "rdeic_layernorm: too many rows");
-    if (in_is_f32)
-        layernorm_kernel<true><<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(x, gamma, beta, (uint4*)out, rows, C, eps);
-    else
-        layernorm_kernel<false><<<(unsigned)blocks, kLnWarps * 32, 0, as_stream(stream)>>>(x, gamma, beta, (uint4*)out, rows, C, eps);
+    const int nv = (C / 8 + 31) / 32;   // 16-byte vectors per lane
+    cudaStream_t s = as_stream(stream);
+#define RDEIC_LN(F32, NV) layernorm_kernel<F32, NV><<<(unsigned)blocks, kLnWarps * 32, 0, s>>>(x, gamma, beta, (uint4*)out, rows, C, eps)
+    if (in_is_f32) {
+        if (nv <= 1) RDEIC_LN(true, 1); else if (nv == 2) RDEIC_LN(true, 2); else if (nv == 3) RDEIC_LN(true, 3); else RDEIC_LN(true, 5);
+    } else {
+        if (nv <= 1) RDEIC_LN(false, 1); else if (nv == 2) RDEIC_LN(false, 2); else if (nv == 3) RDEIC_LN(false, 3); else RDEIC_LN(false, 5);
+    }
+#undef RDEIC_LN
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -307,24 +307,29 @@ class NoiseEstimatorEngine:
         """Text-context K/V for every cross-attention (both networks) and the NHWC bf16 hint are
         step-invariant: computed once per conditioning tensor.  The returned
         tensors must be kept alive by whoever captured them into a CUDA graph."""
-        ck = (context.data_ptr(), context._version, tuple(context.shape))
-        kv = self._ctx_cache.get(ck)
-        if kv is None:
+        # Cache identity = (object id, in-place version) with a strong reference held in the entry: a
+        # (data_ptr, version) key alone can collide when a freed conditioning tensor's memory is
+        # handed to a new one by the caching allocator.
+        ck = (id(context), context._version)
+        ent = self._ctx_cache.get(ck)
+        if ent is None or ent[0] is not context:
             ctx = ops.f32_to_bf16(context.to(self.device, torch.float32).contiguous())
-            kv = (ops.linear(ctx, self.base.kv_all.w, self.base.kv_all.n_out),
-                  ops.linear(ctx, self.ctrl.kv_all.w, self.ctrl.kv_all.n_out))
+            ent = (context, ops.linear(ctx, self.base.kv_all.w, self.base.kv_all.n_out),
+                   ops.linear(ctx, self.ctrl.kv_all.w, self.ctrl.kv_all.n_out))
             if len(self._ctx_cache) >= 4:
                 self._ctx_cache.pop(next(iter(self._ctx_cache)))
-            self._ctx_cache[ck] = kv
+            self._ctx_cache[ck] = ent
+        kv = ent[1:]
         hint = None
         if guide_hint is not None:
-            hk = (guide_hint.data_ptr(), guide_hint._version, tuple(guide_hint.shape))
-            hint = self._hint_cache.get(hk)
-            if hint is None:
-                hint = ops.nchw_to_nhwc_bf16(guide_hint.to(self.device, torch.float32).contiguous())
+            hk = (id(guide_hint), guide_hint._version)
+            hent = self._hint_cache.get(hk)
+            if hent is None or hent[0] is not guide_hint:
+                hent = (guide_hint, ops.nchw_to_nhwc_bf16(guide_hint.to(self.device, torch.float32).contiguous()))
                 if len(self._hint_cache) >= 4:
                     self._hint_cache.pop(next(iter(self._hint_cache)))
-                self._hint_cache[hk] = hint
+                self._hint_cache[hk] = hent
+            hint = hent[1]
         return kv[0], kv[1], hint
 
     def _time_rows(self, net: UNetW, t_emb: torch.Tensor) -> torch.Tensor:

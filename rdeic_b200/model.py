@@ -140,12 +140,14 @@ class RDEIC:
         static buffers that are refreshed, outside the graph, whenever the cond tensors change."""
         eng = self.control_model
         key = (tuple(x.shape), unconditional, tuple(context.shape), None if hint is None else tuple(hint.shape))
-        cond_id = (context.data_ptr(), context._version, None if hint is None else (hint.data_ptr(), hint._version))
+        # identity of the conditioning the static buffers currently hold: object identity + in-place
+        # version, with the objects kept alive in the entry (see NoiseEstimatorEngine.prepare_cond)
+        cond_id = (id(context), context._version, None if hint is None else (id(hint), hint._version))
         g = self._graphs.get(key)
         if g is None:
             kvb, kvc, hn = eng.prepare_cond(context, hint)
             st = {"x": x.clone(), "t": t.clone(), "kvb": kvb.clone(), "kvc": kvc.clone(),
-                  "hint": None if hn is None else hn.clone(), "cond_id": cond_id}
+                  "hint": None if hn is None else hn.clone(), "cond_id": cond_id, "cond_refs": (context, hint)}
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):                       # warm-up: lazy inits, workspaces
@@ -167,7 +169,7 @@ class RDEIC:
             g["kvc"].copy_(kvc)
             if hn is not None:
                 g["hint"].copy_(hn)
-            g["cond_id"] = cond_id
+            g["cond_id"], g["cond_refs"] = cond_id, (context, hint)
         g["x"].copy_(x)
         g["t"].copy_(t)
         g["graph"].replay()

@@ -130,3 +130,46 @@ def blend_tiles(tiles: Sequence[torch.Tensor], plan: Sequence[Tuple[int, int, in
         acc[:, ys:ys + th * scale, xs:xs + tw * scale] += t.float() * wgt
         wsum[:, ys:ys + th * scale, xs:xs + tw * scale] += wgt
     return acc / wsum
+
+
+def crop_cond(cond: Dict, y0: int, x0: int, th: int, tw: int) -> Dict:
+    """Latent-space crop of the reference cond dict (c_latent / guide_hint are at H/8)."""
+    sl = (slice(None), slice(None), slice(y0, y0 + th), slice(x0, x0 + tw))
+    return {"c_latent": [t[sl].contiguous() for t in cond["c_latent"]], "c_crossattn": cond["c_crossattn"],
+            "guide_hint": cond["guide_hint"][sl].contiguous()}
+
+
+def decode_tiled(decode_fn, cond: Dict, tile: int = 96, overlap: int = 16, scale: int = 8,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, dst: int = 0):
+    """Decode ONE large image (batch 1) as overlapping latent tiles dealt round-robin across ranks
+    (BASELINE config 4: 2048x1365 -> latent 256x176).  `decode_fn(cond_tile, tile_index) ->
+    float tensor [1,3,th*scale,tw*scale]` is the per-tile relay decode (each tile is an independent
+    decode unit: GroupNorm / attention statistics are per tile, so the result is NOT the full-frame
+    decode — the reference never tiles).  Returns the blended image on `dst`."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    lat = cond["c_latent"][0]
+    assert lat.shape[0] == 1, "decode_tiled handles one image at a time"
+    h, w = lat.shape[-2:]
+    plan = plan_tiles(h, w, tile, overlap)
+    mine = list(range(rank, len(plan), world_size))
+    outs = [decode_fn(crop_cond(cond, *plan[i]), i)[0].float() for i in mine]
+    th, tw = plan[0][2], plan[0][3]
+    dev = lat.device
+    if world_size == 1:
+        return blend_tiles(outs, plan, h, w, overlap, scale)
+    per = (len(plan) + world_size - 1) // world_size
+    buf = torch.zeros((per, 3, th * scale, tw * scale), dtype=torch.float32, device=dev)
+    for j, o in enumerate(outs):
+        buf[j] = o
+    gathered = [torch.empty_like(buf) for _ in range(world_size)]
+    dist.all_gather(gathered, buf)
+    if rank != dst:
+        return None
+    tiles = [None] * len(plan)
+    for r in range(world_size):
+        for j, i in enumerate(range(r, len(plan), world_size)):
+            tiles[i] = gathered[r][j]
+    return blend_tiles(tiles, plan, h, w, overlap, scale)

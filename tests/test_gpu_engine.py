@@ -158,3 +158,45 @@ def test_full_vae_vs_reference_golden(full_model, cuda):
 
 def test_full_samplers_vs_reference_golden(full_model, cuda):
     _check_samplers(full_model, "full", 1, 16, 16, 256, 1024, cuda)
+
+
+def test_tiled_decode_matches_per_tile_oracle(small_model, cuda):
+    """BASELINE config 4 in miniature: one large latent decoded as overlapping tiles.  The oracle is
+    the reference arithmetic applied per tile + the identical blend (the reference never tiles and
+    a full-frame decode differs by construction: GroupNorm/attention are global — SURVEY.md §5)."""
+    from oracle import nn as onn
+    from oracle import sampler as osamp
+    from rdeic_b200 import parallel
+    from rdeic_b200.pipeline import relay_decode
+
+    p = configs.small_params()
+    sd = synthetic.make_state_dict(p, seed=231)
+    h, w, tile, ov = 24, 40, 16, 8
+    c_latent, hint, ctx, noises = inputs(1, h, w, 32, 64, 3)
+    plan = parallel.plan_tiles(h, w, tile, ov)
+    assert len(plan) > 2
+    kw = dict(model_channels=64, base_d_head=16, ctrl_d_head=16)
+    crop = lambda t, y0, x0, th, tw: t[:, :, y0:y0 + th, x0:x0 + tw].contiguous()
+
+    ref_tiles = []
+    with torch.no_grad():
+        for (y0, x0, th, tw) in plan:
+            cl, hn = crop(c_latent, y0, x0, th, tw), crop(hint, y0, x0, th, tw)
+            ns = [crop(n, y0, x0, th, tw) for n in noises]
+            x_T = osamp.q_sample(cl, 299, ns[0])
+            z = osamp.spaced_sample(lambda x, t: onn.noise_estimator_forward(sd, x, hn, t, ctx, **kw), x_T, 2, ns[1:])
+            ref_tiles.append(onn.vae_decode(sd, z)[0])
+    ref = parallel.blend_tiles(ref_tiles, plan, h, w, ov, 8)
+
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    dn = [n.to(cuda) for n in noises]
+
+    def decode_fn(c, i):
+        y0, x0, th, tw = plan[i]
+        ns = [crop(n, y0, x0, th, tw) for n in dn]
+        return relay_decode(small_model, c, 2, start_noise=ns[0], step_noises=ns[1:], as_uint8=False)
+
+    img = parallel.decode_tiled(decode_fn, cond, tile=tile, overlap=ov).cpu()
+    pq = psnr(img.numpy(), ref.numpy(), 2.0)
+    print(f"[small] tiled decode ({len(plan)} tiles) PSNR vs per-tile oracle {pq:.1f} dB")
+    assert pq >= PSNR_MIN

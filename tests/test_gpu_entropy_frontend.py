@@ -1,0 +1,123 @@
+"""GPU parity of the drop-in entropy front end (rdeic_b200.ckbd / compression_modules /
+compression) against the CPU oracle: symbols, CDF indexes and reconstructed latents bit-exact,
+full compress -> loopback coder -> decompress round trip over the 10 reference slices."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import compression as ocomp
+from oracle import entropy as oe
+
+pytestmark = pytest.mark.gpu
+SLICE_CH = [8, 8, 8, 8, 16, 16, 32, 32, 64, 64]        # configs/model/rdeic.yaml:110
+
+
+def _bits(t):
+    a = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _param_fns():
+    """Deterministic stand-ins for the learned conv stacks: exactly reproducible on CPU and GPU
+    (only IEEE fp32 mul/add/abs on gathered channels), covering scales below the 0.11 bound, across
+    all 64 table bins and above 256."""
+    def ep(k):
+        def f(x):
+            c = SLICE_CH[k]
+            base = x[:, :c] if x.shape[1] >= c else x.repeat(1, (c + x.shape[1] - 1) // x.shape[1], 1, 1)[:, :c]
+            tail = x[:, -c:]
+            scales = (base.abs() * 40.0 + 0.01) * (tail.abs() + 0.05)
+            means = base * 1.5 - tail * 0.25
+            return torch.cat([scales, means], 1)
+        return f
+
+    def local(k):
+        return lambda a: torch.cat([a * 0.5, a.abs() * 0.25], 1)
+
+    def chan(k):
+        c = SLICE_CH[k]
+        return lambda yh: (yh[:, :c] * 0.125 + yh[:, -c:] * 0.0625).repeat(1, 2, 1, 1)
+
+    n = len(SLICE_CH)
+    return ([ep(k) for k in range(n)], [ep(k) for k in range(n)], [local(k) for k in range(n)],
+            [None] + [chan(k) for k in range(1, n)])
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 32, 32), (2, 16, 24), (1, 8, 6)])
+def test_slice_compress_decompress_roundtrip(cuda, B, H, W):
+    from rdeic_b200 import ckbd
+    from rdeic_b200.compression import SliceCoder
+
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(B, sum(SLICE_CH), H, W, generator=g) * 6
+    hyper = torch.randn(B, 64, H, W, generator=g)
+    fns = _param_fns()
+    table = oe.get_scale_table()
+    # oracle
+    rsym, rind, ryhat = ocomp.compress(y, hyper, SLICE_CH, fns, table)
+    assert len(set(rind)) > 40, "test inputs must exercise most of the 64 scale bins"
+    coder = ocomp.LoopbackCoder()
+    coder.encode_with_indexes(rsym, rind)
+    ryhat2 = ocomp.decompress(hyper, SLICE_CH, fns, table, coder)
+    assert np.array_equal(_bits(ryhat), _bits(ryhat2))
+    # CUDA drop-in
+    gc = ckbd.GaussianConditional(device=cuda)
+    sc = SliceCoder(SLICE_CH, gc, *fns)
+    sym, ind, yhat = sc.compress(y.to(cuda), hyper.to(cuda))
+    assert sym == rsym
+    assert ind == rind
+    assert np.array_equal(_bits(yhat), _bits(ryhat))
+    coder2 = ocomp.LoopbackCoder()
+    coder2.encode_with_indexes(sym, ind)
+    yhat2 = sc.decompress(hyper.to(cuda), coder2, None, None, None)      # raises if indexes diverge
+    assert np.array_equal(_bits(yhat2), _bits(ryhat))
+    assert coder2.pos == len(sym) == B * sum(SLICE_CH) * H * W
+
+
+def test_ckbd_dropin_names_and_gaussian_conditional(cuda):
+    from rdeic_b200 import ckbd
+
+    g = torch.Generator().manual_seed(4)
+    y = torch.randn(2, 8, 6, 10, generator=g) * 5
+    yc = y.to(cuda)
+    yn = y.numpy()
+    a, n = ckbd.ckbd_split(yc)
+    assert np.array_equal(_bits(a), _bits(oe.ckbd_anchor(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_anchor(yc)), _bits(oe.ckbd_anchor(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_nonanchor(yc)), _bits(oe.ckbd_nonanchor(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_merge(a, n)), _bits(yn))
+    assert np.array_equal(_bits(ckbd.ckbd_anchor_sequeeze(yc)), _bits(oe.ckbd_anchor_sequeeze(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_nonanchor_sequeeze(yc)), _bits(oe.ckbd_nonanchor_sequeeze(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_anchor_unsequeeze(ckbd.ckbd_anchor_sequeeze(yc))), _bits(oe.ckbd_anchor(yn)))
+    assert np.array_equal(_bits(ckbd.ckbd_nonanchor_unsequeeze(ckbd.ckbd_nonanchor_sequeeze(yc))),
+                          _bits(oe.ckbd_nonanchor(yn)))
+    gc = ckbd.GaussianConditional(device=cuda)
+    assert np.array_equal(gc.scale_table.cpu().numpy(), oe.get_scale_table())
+    sc = torch.exp(torch.rand(2, 8, 6, 10, generator=g) * 9 - 3)
+    mu = torch.randn(2, 8, 6, 10, generator=g)
+    assert np.array_equal(gc.build_indexes(sc.to(cuda)).cpu().numpy(), oe.build_indexes(sc.numpy(), oe.get_scale_table()))
+    sym = gc.quantize(yc, "symbols", mu.to(cuda))
+    assert np.array_equal(sym.cpu().numpy(), oe.quantize_symbols(yn, mu.numpy()))
+    deq = gc.quantize(yc, "dequantize", mu.to(cuda))
+    assert np.array_equal(_bits(deq), _bits(oe.dequantize(oe.quantize_symbols(yn, mu.numpy()), mu.numpy())))
+    with pytest.raises(ValueError):
+        gc.quantize(yc, "noise")
+
+
+def test_vector_quantiser_dropin(cuda):
+    from rdeic_b200.compression_modules import VectorQuantiser
+
+    g = torch.Generator().manual_seed(5)
+    K, D = 16384, 256
+    cb = ((torch.rand(K, D, generator=g) * 2 - 1) / 8).float()
+    vq = VectorQuantiser(K, D, device=cuda).load_state_dict({"embedding.weight": cb, "embed_prob": torch.zeros(K)})
+    pick = torch.randint(0, K, (2 * 8 * 12,), generator=g)
+    z = (cb[pick] + 0.001 * torch.randn(pick.numel(), D, generator=g)).reshape(2, 8, 12, D).permute(0, 3, 1, 2).contiguous()
+    zq, idx = vq.quant(z.to(cuda))
+    rzq, ridx = oe.vq_quant(z.numpy(), cb.numpy())
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (2, 8, 12)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+    assert np.array_equal(_bits(zq), _bits(rzq))
+    assert np.array_equal(_bits(vq.get_codebook_entry(idx)), _bits(oe.vq_lookup(ridx, cb.numpy())))
+    with pytest.raises(IndexError):
+        vq.get_codebook_entry(torch.full((1, 1, 1), K, dtype=torch.int64))

@@ -1,0 +1,103 @@
+"""CPU tests of the data-parallel plumbing: world_size-2 gloo process groups
+exercise the weight broadcast, the batch sharding + image gather and the tile sharding + blend."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rdeic_b200 import parallel
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            chunks = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert chunks[0][0] == 0 and chunks[-1][1] == n
+            for (a, b), (c, d) in zip(chunks, chunks[1:]):
+                assert b == c
+            sizes = [b - a for a, b in chunks]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def test_plan_tiles_cover_and_overlap():
+    for h, w in ((256, 176), (64, 64), (96, 200), (97, 131)):
+        plan = parallel.plan_tiles(h, w, tile=96, overlap=16)
+        cover = np.zeros((h, w), int)
+        for y0, x0, th, tw in plan:
+            assert 0 <= y0 and y0 + th <= h and 0 <= x0 and x0 + tw <= w
+            cover[y0:y0 + th, x0:x0 + tw] += 1
+        assert cover.min() >= 1
+        ys = sorted({p[0] for p in plan})
+        for a, b in zip(ys, ys[1:]):
+            assert a + min(96, h) - b >= 16          # neighbouring rows of tiles overlap by >= 16
+
+
+def test_blend_of_consistent_tiles_is_identity():
+    h, w, s = 40, 56, 2
+    full = torch.randn(3, h * s, w * s)
+    plan = parallel.plan_tiles(h, w, tile=24, overlap=8)
+    tiles = [full[:, y0 * s:(y0 + th) * s, x0 * s:(x0 + tw) * s] for y0, x0, th, tw in plan]
+    out = parallel.blend_tiles(tiles, plan, h, w, overlap=8, scale=s)
+    assert torch.allclose(out, full, atol=1e-5)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. weight broadcast: only rank 0 holds the tensors
+        spec = [("a.weight", (5, 3, 3, 3)), ("a.bias", (5,)), ("b.weight", (7, 5)), ("scale_list", (4,))]
+        g = torch.Generator().manual_seed(0)
+        full = {k: torch.randn(s, generator=g) for k, s in spec}
+        got = parallel.broadcast_state_dict(full if rank == 0 else None, spec, "cpu", src=0, bucket_bytes=300)
+        ok_bcast = all(torch.equal(got[k], full[k]) for k, _ in spec)
+        # 2. batch sharding + gather of "decoded images" (uneven: 5 images over 2 ranks)
+        n = 5
+        imgs = torch.arange(n * 4 * 6 * 3, dtype=torch.uint8).reshape(n, 4, 6, 3)
+        cond = {"c_latent": [torch.arange(n).float().view(n, 1, 1, 1)], "c_crossattn": [torch.zeros(n, 77, 8)],
+                "guide_hint": torch.arange(n).float().view(n, 1, 1, 1)}
+        mine = parallel.shard_cond(cond, rank, world)
+        lo, hi = parallel.shard_range(n, rank, world)
+        ok_shard = mine["guide_hint"].flatten().tolist() == list(range(lo, hi)) and \
+            mine["c_crossattn"][0].shape[0] == hi - lo
+        counts = [parallel.shard_range(n, r, world)[1] - parallel.shard_range(n, r, world)[0] for r in range(world)]
+        out = parallel.gather_images(imgs[lo:hi].clone(), counts, dst=0)
+        ok_gather = (out is None) if rank != 0 else torch.equal(out, imgs)
+        # 3. tiles of one large latent dealt across ranks, decoded by a stand-in, blended on rank 0
+        h, w, s = 40, 56, 2
+        lat = torch.randn(1, 4, h, w, generator=torch.Generator().manual_seed(1))
+        big = {"c_latent": [lat], "c_crossattn": [torch.zeros(1, 77, 8)], "guide_hint": torch.zeros(1, 2, h, w)}
+        seen = []
+
+        def fake_decode(c, i):   # "decode" = nearest upsample of the first 3 latent channels
+            seen.append(i)
+            return torch.nn.functional.interpolate(c["c_latent"][0][:, :3], scale_factor=s, mode="nearest")
+
+        img = parallel.decode_tiled(fake_decode, big, tile=24, overlap=8, scale=s)
+        ref = torch.nn.functional.interpolate(lat[:, :3], scale_factor=s, mode="nearest")[0]
+        ok_tiles = (img is None) if rank != 0 else torch.allclose(img, ref, atol=1e-5)
+        ok_deal = all(i % world == rank for i in seen)
+        ret[rank] = (ok_bcast, ok_shard, ok_gather, ok_tiles, ok_deal)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_broadcast_shard_gather_tiles():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] == (True, True, True, True, True), (r, ret[r])
