@@ -12,6 +12,8 @@ Files written
   full_vae_decode.npz      reference decode_first_stage, full width, 16x16 latent
   full_sampler.npz         reference SpacedSampler.sample (2 steps) and DDIMSampler.sample (2 steps)
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
+  entropy_ref.npz          reference utils/ckbd.py checkerboard ops, utils/func.py scale table and
+                           model/compression_modules.py VectorQuantiser.quant / get_codebook_entry
 """
 from __future__ import annotations
 
@@ -122,9 +124,54 @@ def run_config(tag, overrides, unet_hw, vae_hw, samp_hw):
         print(tag, "samplers", {k: float(np.abs(v).max()) for k, v in out.items()})
 
 
+def entropy_inputs():
+    g = torch.Generator().manual_seed(41)
+    y = torch.randn(2, 8, 6, 10, generator=g) * 6
+    y.view(-1)[3] = -0.0
+    K, D = 512, 256
+    cb = (torch.rand(K, D, generator=g) * 2 - 1) / K
+    cb[7] = cb[300]                                      # exact tie: first index wins
+    pick = torch.randint(0, K, (2 * 3 * 5,), generator=g)
+    pick[0] = 300
+    z = cb[pick] + 1e-5 * torch.randn(pick.numel(), D, generator=g)
+    z[0] = cb[300]
+    z = z.reshape(2, 3, 5, D).permute(0, 3, 1, 2).contiguous()
+    return y, cb, z
+
+
+def run_entropy():
+    """a9 / a11: run the reference's own utils/ckbd.py checkerboard ops and
+    model/compression_modules.py VectorQuantiser on seeded inputs."""
+    import importlib
+
+    rh.import_reference()
+    ck = importlib.import_module("utils.ckbd")
+    cm = importlib.import_module("model.compression_modules")
+    func = importlib.import_module("utils.func")
+    y, cb, z = entropy_inputs()
+    out = {"anchor": ck.ckbd_anchor(y), "nonanchor": ck.ckbd_nonanchor(y),
+           "anchor_sq": ck.ckbd_anchor_sequeeze(y), "nonanchor_sq": ck.ckbd_nonanchor_sequeeze(y)}
+    out["anchor_unsq"] = ck.ckbd_anchor_unsequeeze(out["anchor_sq"])
+    out["nonanchor_unsq"] = ck.ckbd_nonanchor_unsequeeze(out["nonanchor_sq"])
+    a, n = ck.ckbd_split(y)
+    out["merge"] = ck.ckbd_merge(a, n)
+    out["scale_table"] = func.get_scale_table()
+    vq = cm.VectorQuantiser(cb.shape[0], cb.shape[1])
+    vq.eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb)
+        zq, idx = vq.quant(z)
+        out["vq_zq"], out["vq_idx"] = zq, idx
+        out["vq_entry"] = vq.get_codebook_entry(idx)
+    np.savez_compressed(HERE / "entropy_ref.npz", **{k: v.numpy() for k, v in out.items()})
+    print("entropy goldens", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["small", "full"]
+    which = sys.argv[1:] or ["entropy", "small", "full"]
+    if "entropy" in which:
+        run_entropy()
     if "small" in which:
         run_config("small", rh.SMALL_OVERRIDES, (16, 16), (8, 8), (8, 16))
     if "full" in which:

@@ -121,3 +121,31 @@ def test_vector_quantiser_dropin(cuda):
     assert np.array_equal(_bits(vq.get_codebook_entry(idx)), _bits(oe.vq_lookup(ridx, cb.numpy())))
     with pytest.raises(IndexError):
         vq.get_codebook_entry(torch.full((1, 1, 1), K, dtype=torch.int64))
+
+
+def test_kernels_match_reference_golden(cuda):
+    """CUDA kernels vs the reference's own utils/ckbd.py / VectorQuantiser outputs (golden)."""
+    from pathlib import Path
+
+    from helpers import entropy_golden_inputs
+    from rdeic_b200 import ckbd
+    from rdeic_b200.compression_modules import VectorQuantiser
+
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "entropy_ref.npz")
+    y, cb, z = entropy_golden_inputs()
+    yc = y.to(cuda)
+    assert np.array_equal(_bits(ckbd.ckbd_anchor(yc)), _bits(gold["anchor"]))
+    assert np.array_equal(_bits(ckbd.ckbd_nonanchor(yc)), _bits(gold["nonanchor"]))
+    a, n = ckbd.ckbd_split(yc)
+    assert np.array_equal(_bits(a), _bits(gold["anchor"])) and np.array_equal(_bits(n), _bits(gold["nonanchor"]))
+    assert np.array_equal(_bits(ckbd.ckbd_merge(a, n)), _bits(gold["merge"]))
+    sa, sn = ckbd.ckbd_anchor_sequeeze(yc), ckbd.ckbd_nonanchor_sequeeze(yc)
+    assert np.array_equal(_bits(sa), _bits(gold["anchor_sq"])) and np.array_equal(_bits(sn), _bits(gold["nonanchor_sq"]))
+    assert np.array_equal(_bits(ckbd.ckbd_anchor_unsequeeze(sa)), _bits(gold["anchor_unsq"]))
+    assert np.array_equal(_bits(ckbd.ckbd_nonanchor_unsequeeze(sn)), _bits(gold["nonanchor_unsq"]))
+    assert np.array_equal(_bits(ckbd.GaussianConditional(device=cuda).scale_table), _bits(gold["scale_table"]))
+    vq = VectorQuantiser(cb.shape[0], cb.shape[1], device=cuda).load_state_dict({"embedding.weight": cb})
+    zq, idx = vq.quant(z.to(cuda))
+    assert np.array_equal(idx.cpu().numpy(), gold["vq_idx"])
+    assert np.array_equal(_bits(zq), _bits(gold["vq_zq"]))
+    assert np.array_equal(_bits(vq.get_codebook_entry(idx)), _bits(gold["vq_entry"]))

@@ -204,3 +204,26 @@ def test_product_does_not_import_oracle():
     for py in (ROOT / "rdeic_b200").glob("*.py"):
         src = py.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), py
+
+
+def test_entropy_oracle_matches_reference_golden():
+    """a9 / a11 pinned: oracle/entropy.py vs outputs of the reference's own utils/ckbd.py,
+    utils/func.py and VectorQuantiser (tests/golden/entropy_ref.npz), bit for bit."""
+    from helpers import entropy_golden_inputs
+
+    gold = np.load(GOLD / "entropy_ref.npz")
+    y, cb, z = entropy_golden_inputs()
+    yn = y.numpy()
+    b = lambda a: np.ascontiguousarray(a).view(np.uint32)
+    assert np.array_equal(b(oe.ckbd_anchor(yn)), b(gold["anchor"]))
+    assert np.array_equal(b(oe.ckbd_nonanchor(yn)), b(gold["nonanchor"]))
+    assert np.array_equal(b(oe.ckbd_anchor_sequeeze(yn)), b(gold["anchor_sq"]))
+    assert np.array_equal(b(oe.ckbd_nonanchor_sequeeze(yn)), b(gold["nonanchor_sq"]))
+    assert np.array_equal(b(oe.ckbd_anchor_unsequeeze(gold["anchor_sq"])), b(gold["anchor_unsq"]))
+    assert np.array_equal(b(oe.ckbd_nonanchor_unsequeeze(gold["nonanchor_sq"])), b(gold["nonanchor_unsq"]))
+    assert np.array_equal(b(oe.ckbd_merge(*oe.ckbd_split(yn))), b(gold["merge"]))
+    assert np.array_equal(b(oe.get_scale_table()), b(gold["scale_table"]))
+    zq, idx = oe.vq_quant(z.numpy(), cb.numpy())
+    assert np.array_equal(idx, gold["vq_idx"]) and idx.reshape(-1)[0] == 7
+    assert np.array_equal(b(zq), b(gold["vq_zq"]))
+    assert np.array_equal(b(oe.vq_lookup(idx, cb.numpy())), b(gold["vq_entry"]))
