@@ -7,6 +7,7 @@
 // Two head widths are instantiated: 64 (SD-2.1 UNet) and 16 (control adapter, rdeic.yaml:45).
 // Cross-attention (Nk = 77 text tokens) runs through the same kernel with a masked tail.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/rdeic_b200.h"
 
 namespace rdeic {
@@ -196,6 +197,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     }
 }
 
+// tcgen05 / TMEM path (attention_tc.cu)
+bool attention_tc_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                            int64_t q_bs, int64_t k_bs, int64_t v_bs, const void* q, const void* k, const void* v,
+                            const void* out);
+int launch_attention_tc(const void* q, const void* k, const void* v, void* out, int B, int heads, int Nq, int Nk,
+                        int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
+                        int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream);
+
 }  // namespace rdeic
 
 using namespace rdeic;
@@ -213,6 +222,10 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
                     "rdeic_attention: strides must keep 16-byte row alignment");
     RDEIC_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) % 16 == 0 && (uintptr_t)out % 4 == 0,
                     "rdeic_attention: pointers must be 16-byte aligned");
+    if (attention_tc_supported(d, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, q, k, v, out) &&
+        !getenv("RDEIC_ATTN_MMA_SYNC"))
+        return launch_attention_tc(q, k, v, out, B, heads, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs,
+                                   scale, as_stream(stream));
     const float scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Nq + kQTile - 1) / kQTile, heads, B);
     if (d == 64)

@@ -1,0 +1,291 @@
+// Flash-style attention forward on 5th-gen tensor cores (sm_100a) for head dim 64:
+//   S = Q K^T and O_tile = P V are tcgen05.mma instructions issued by one thread, S and O tiles live
+//   in TMEM (two buffers each), Q/K/V tiles arrive by TMA into 128B-swizzled shared memory, and
+//   four softmax warps (one query row per thread) turn S into P with an online softmax in fp32
+//   (exp2 domain).  P goes back to shared memory in the K-major swizzled layout the MMA reads;
+//   V is consumed as an MN-major B operand straight from its row-major TMA tile (no transpose).
+//   O_tile is never accumulated in TMEM: each thread adds it to its 64 fp32 registers and applies
+//   the running-max correction there, so there is no TMEM read-modify-write on the critical path.
+//
+// Replaces `CrossAttention.forward` (ldm/modules/attention.py:171-203) for the SD-2.1 self-attention
+// shapes (d = 64, token counts that are multiples of 128).  Ragged shapes (text keys, Nk = 77) and
+// the control adapter's d = 16 heads stay on the mma.sync kernel in attention.cu.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "../../include/rdeic_b200.h"
+
+namespace rdeic {
+
+constexpr int kAD = 64;                       // head dim
+constexpr int kAQ = 128;                      // query rows per CTA (= TMEM lanes)
+constexpr int kAK = 128;                      // keys per tile
+constexpr int kAStages = 3;                   // K/V ring
+constexpr int kATile = kAK * kAD * 2;         // 16 KB: one Q, K or V tile
+constexpr int kAPBytes = kAQ * kAK * 2;       // 32 KB: one P buffer (two 64-key panels)
+constexpr int kAThreads = 192;                // warp0 TMA, warp1 MMA, warps 2-5 softmax
+constexpr int kASmem = kATile * (1 + 2 * kAStages) + 2 * kAPBytes + 1024 + 256;
+constexpr uint32_t kColS = 0, kColO = 256;    // TMEM columns: S0,S1 at 0/128 ; O0,O1 at 256/320
+
+struct AttDev {
+    int tiles_k;
+    float scale_log2;
+    __nv_bfloat16* out;
+    int64_t ldo, o_bs;
+};
+
+// MN-major, 128-byte swizzled B operand (V tile: rows = keys (K), 64 contiguous d (N) per row):
+// SBO = 1024 B between groups of 8 K-rows, LBO unused for a single 64-wide MN atom.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(kATile >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kAThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_q = smem;
+    uint8_t* s_k = s_q + kATile;
+    uint8_t* s_v = s_k + kAStages * kATile;
+    uint8_t* s_p = s_v + kAStages * kATile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAPBytes);
+    uint64_t* q_full = bars;                  // [1]
+    uint64_t* kv_full = bars + 1;             // [kAStages]
+    uint64_t* kv_empty = kv_full + kAStages;  // [kAStages]
+    uint64_t* s_full = kv_empty + kAStages;   // [2]
+    uint64_t* p_full = s_full + 2;            // [2]
+    uint64_t* o_full = p_full + 2;            // [2]
+    uint64_t* o_empty = o_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int T = p.tiles_k;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_empty[i], 4);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(q_full, kATile);
+            tma_load_3d(&tm_q, s_q, q_full, head * kAD, qt * kAQ, b);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % kAStages;
+                mbar_wait(&kv_empty[s], ((j / kAStages) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], 2 * kATile);
+                tma_load_3d(&tm_k, s_k + s * kATile, &kv_full[s], head * kAD, j * kAK, b);
+                tma_load_3d(&tm_v, s_v + s * kATile, &kv_full[s], head * kAD, j * kAK, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc_s = make_idesc_mn(kAQ, kAK, false);   // S  = Q K^T : N = 128 keys
+            constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);    // O  = P V   : N = 64, V MN-major
+            const uint64_t dq = make_smem_desc(smem_u32(s_q));
+            auto issue_pv = [&](int i) {
+                const uint32_t bf = i & 1, ph = (i >> 1) & 1;
+                mbar_wait(&p_full[bf], ph);
+                mbar_wait(&o_empty[bf], ph ^ 1);
+                tc_fence_after();
+                const uint32_t pb = smem_u32(s_p + bf * kAPBytes);
+                const uint64_t dv = make_smem_desc_mn(smem_u32(s_v + (i % kAStages) * kATile));
+#pragma unroll
+                for (int ks = 0; ks < kAK / 16; ++ks) {
+                    const uint64_t dp = make_smem_desc(pb + (ks >> 2) * (kAQ * 128) + (ks & 3) * 32);
+                    umma_bf16(tmem_base + kColO + bf * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o, ks != 0);
+                }
+                umma_commit(&o_full[bf]);
+                umma_commit(&kv_empty[i % kAStages]);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % kAStages;
+                mbar_wait(&kv_full[s], (j / kAStages) & 1);
+                tc_fence_after();
+                const uint64_t dk = make_smem_desc(smem_u32(s_k + s * kATile));
+#pragma unroll
+                for (int k = 0; k < kAD / 16; ++k)
+                    umma_bf16(tmem_base + kColS + (j & 1) * kAK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[j & 1]);
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(T - 1);
+        }
+    } else {
+        // ===== softmax / correction / epilogue: one query row per thread =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float sc = p.scale_log2;
+        float o[kAD];
+#pragma unroll
+        for (int i = 0; i < kAD; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+
+        auto add_o = [&](int i) {
+            const uint32_t bf = i & 1;
+            mbar_wait(&o_full[bf], (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < kAD / 32; ++h) {
+                uint32_t r[32];
+                const uint32_t ta = tmem_base + lane_addr + kColO + bf * kAD + h * 32;
+                tmem_ld16(ta, r);
+                tmem_ld16(ta + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[h * 32 + c] += __uint_as_float(r[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[bf]);
+        };
+
+        for (int j = 0; j < T; ++j) {
+            const uint32_t bf = j & 1;
+            mbar_wait(&s_full[bf], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ts = tmem_base + lane_addr + kColS + bf * kAK;
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c4 = 0; c4 < kAK / 32; ++c4) {
+                uint32_t r[32];
+                tmem_ld16(ts + c4 * 32, r);
+                tmem_ld16(ts + c4 * 32 + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+            }
+            const float m_new = fmaxf(m_run, mx * sc);
+            const float corr = ex2_approx(m_run - m_new);
+            // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled K-major smem (A operand of P V)
+            float rowsum = 0.f;
+            uint8_t* prow = s_p + bf * kAPBytes + row * 128;
+#pragma unroll
+            for (int c4 = 0; c4 < kAK / 32; ++c4) {
+                uint32_t r[32];
+                tmem_ld16(ts + c4 * 32, r);
+                tmem_ld16(ts + c4 * 32 + 16, r + 16);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * c]), sc, -m_new));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * c + 1]), sc, -m_new));
+                    rowsum += p0 + p1;
+                    pk[c] = pack_bf16x2(p0, p1);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = c4 * 4 + q;                 // 16-byte chunk = 8 keys
+                    uint8_t* dst = prow + (chunk >> 3) * (kAQ * 128) + (((chunk & 7) ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l_run = fmaf(l_run, corr, rowsum);
+            m_run = m_new;
+            tc_fence_before();        // S reads done before the MMA warp may overwrite this S buffer
+            fence_proxy_async();      // P stores visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[bf]);
+            // fold in the previous tile's O while the tensor core works on this one
+            if (j > 0) add_o(j - 1);
+#pragma unroll
+            for (int i = 0; i < kAD; ++i) o[i] *= corr;
+        }
+        add_o(T - 1);
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(qt * kAQ + row) * p.ldo + head * kAD;
+#pragma unroll
+        for (int v8 = 0; v8 < kAD / 8; ++v8) {
+            uint4 w;
+            w.x = pack_bf16x2(o[8 * v8] * inv, o[8 * v8 + 1] * inv);
+            w.y = pack_bf16x2(o[8 * v8 + 2] * inv, o[8 * v8 + 3] * inv);
+            w.z = pack_bf16x2(o[8 * v8 + 4] * inv, o[8 * v8 + 5] * inv);
+            w.w = pack_bf16x2(o[8 * v8 + 6] * inv, o[8 * v8 + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + 8 * v8) = w;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// host: true when the tcgen05 kernel can take the problem
+bool attention_tc_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                            int64_t q_bs, int64_t k_bs, int64_t v_bs, const void* q, const void* k, const void* v,
+                            const void* out) {
+    return d == kAD && Nq % kAQ == 0 && Nk % kAK == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+           ldo % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 &&
+           (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0;
+}
+
+int launch_attention_tc(const void* q, const void* k, const void* v, void* out, int B, int heads, int Nq, int Nk,
+                        int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
+                        int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream) {
+    CUtensorMap tq, tk, tv;
+    const uint32_t box[3] = {(uint32_t)kAD, (uint32_t)kAQ, 1};
+    auto mk = [&](CUtensorMap* m, const void* ptr, int N, int64_t ld, int64_t bs, const char* what) -> int {
+        // with B == 1 the batch stride is never used; TMA still wants a 16-byte multiple >= row extent
+        const uint64_t bstride = (B > 1 ? (uint64_t)bs : (uint64_t)ld * N) * 2;
+        uint64_t dims[3] = {(uint64_t)heads * kAD, (uint64_t)N, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)ld * 2, bstride};
+        return encode_map(m, ptr, 3, dims, str, box, what);
+    };
+    if (int e = mk(&tq, q, Nq, ldq, q_bs, "attn Q")) return e;
+    if (int e = mk(&tk, k, Nk, ldk, k_bs, "attn K")) return e;
+    if (int e = mk(&tv, v, Nk, ldv, v_bs, "attn V")) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDEIC_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmem));
+        attr_set = true;
+    }
+    AttDev d;
+    d.tiles_k = Nk / kAK;
+    d.scale_log2 = scale * 1.4426950408889634f;
+    d.out = (__nv_bfloat16*)out;
+    d.ldo = ldo;
+    d.o_bs = o_bs;
+    dim3 grid(Nq / kAQ, heads, B);
+    attention_tc_kernel<<<grid, kAThreads, kASmem, stream>>>(tq, tk, tv, d);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rdeic
