@@ -1,5 +1,6 @@
 // Library-level entry points: thread-local error string, ABI version.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/rdeic_b200.h"
 
 namespace rdeic {
@@ -7,6 +8,11 @@ namespace rdeic {
 char* err_buf() {
     static thread_local char buf[1024] = {0};
     return buf;
+}
+
+bool pdl_enabled() {
+    static const bool on = getenv("RDEIC_NO_PDL") == nullptr;
+    return on;
 }
 
 int set_error(const char* fmt, ...) {

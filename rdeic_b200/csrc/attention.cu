@@ -45,6 +45,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
                  const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int Nq,
                  int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs,
                  int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kPitch = D + 8;                 // bf16 elements per smem row (bank spread)
     constexpr int kVecPerRow = D / 8;             // 16-byte vectors per K/V row
     constexpr int kKSteps = D / 16;               // k-steps of the QK^T mma
@@ -229,11 +231,11 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
     const float scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Nq + kQTile - 1) / kQTile, heads, B);
     if (d == 64)
-        attention_kernel<64><<<grid, kAttnWarps * 32, 0, as_stream(stream)>>>(
+        launch_k(attention_kernel<64>, grid, kAttnWarps * 32, 0, as_stream(stream), 
             (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
             (__nv_bfloat16*)out, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, scale_log2);
     else
-        attention_kernel<16><<<grid, kAttnWarps * 32, 0, as_stream(stream)>>>(
+        launch_k(attention_kernel<16>, grid, kAttnWarps * 32, 0, as_stream(stream), 
             (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
             (__nv_bfloat16*)out, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, scale_log2);
     RDEIC_LAUNCH_CHECK();

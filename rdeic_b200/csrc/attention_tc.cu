@@ -54,6 +54,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kAThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_q = smem;
@@ -94,6 +95,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // prologue above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -283,7 +285,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
     d.ldo = ldo;
     d.o_bs = o_bs;
     dim3 grid(Nq / kAQ, heads, B);
-    attention_tc_kernel<<<grid, kAThreads, kASmem, stream>>>(tq, tk, tv, d);
+    launch_k(attention_tc_kernel, grid, kAThreads, kASmem, stream, tq, tk, tv, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -27,6 +27,30 @@ int set_error(const char* fmt, ...);
 
 #define RDEIC_LAUNCH_CHECK() RDEIC_CUDA(cudaPeekAtLastError())
 
+// Programmatic dependent launch (PDL): every kernel of the library is launched with
+// programmaticStreamSerialization, calls pdl_trigger() on entry (the next kernel in the stream may
+// start launching: its launch latency and prologue overlap our execution) and pdl_wait() before
+// its first global-memory access (blocks until the preceding grid has completed and flushed).
+// ~660 dependent launches per UNet step make launch gaps a first-order cost.  RDEIC_NO_PDL=1
+// falls back to plain stream order.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200
@@ -59,6 +83,9 @@ struct FastDiv {
         r = n - q * d;
     }
 };
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 

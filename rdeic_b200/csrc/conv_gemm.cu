@@ -16,6 +16,7 @@
 //   ldm/modules/diffusionmodules/model.py:57-61,102-125,160-179,605,647.
 #include "common.cuh"
 #include "sm100.cuh"
+#include <stdlib.h>
 #include "../../include/rdeic_b200.h"
 
 namespace rdeic {
@@ -131,12 +132,17 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN, bool kPrefetchResid>
+template <int BN, int kResidMode>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
+    pdl_trigger();
     using Cfg = TileCfg<BN>;
     constexpr int kStages = Cfg::kStages;
+    // residual handling in the epilogue: 0 = loaded at the top of phase B, 1 = bf16 residual
+    // prefetched two chunks deep, 2 = fp32 residual prefetched one phase ahead (single buffer)
+    constexpr bool kPrefetchResid = (kResidMode == 1);
+    constexpr bool kAheadF32 = (kResidMode == 2);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~(uintptr_t)1023);
@@ -177,6 +183,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, descriptor prefetch, TMEM allocation) overlapped the previous
+    // kernel's tail; from here on we touch memory it may still be writing
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -317,6 +326,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             };
             uint2 rcur[kPrefetchResid ? 8 : 1], rnext[kPrefetchResid ? 8 : 1];
             if (kPrefetchResid) prefetch(half, rcur);
+            float4 rf[kAheadF32 ? 8 : 1];
+            const bool ahead_f32 = kAheadF32 && eo.resid && eo.resid_is_f32;
+            auto prefetch_f32 = [&](int ci) {
+                if (!ahead_f32 || !fast_chunk(ci)) return;
+                const int n = col0 + ci * 32 + 4 * (lane & 7);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + (lane >> 3);
+                    const int mr = __shfl_sync(0xffffffffu, m_own, row);
+                    const int ok = __shfl_sync(0xffffffffu, row_ok, row);
+                    rf[kAheadF32 ? i : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok)
+                        rf[kAheadF32 ? i : 0] = *reinterpret_cast<const float4*>(
+                            reinterpret_cast<const float*>(eo.resid) + (int64_t)mr * eo.ld_resid + n);
+                }
+            };
+            if (kAheadF32) prefetch_f32(half);
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
@@ -402,7 +428,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             mr[i] = __shfl_sync(0xffffffffu, m_own, row);
                             okr[i] = __shfl_sync(0xffffffffu, row_ok, row);
                             rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (eo.resid && okr[i] && !(kPrefetchResid && pre_bf16)) {
+                            if (kAheadF32 && ahead_f32) {
+                                rv[i] = rf[kAheadF32 ? i : 0];
+                            } else if (eo.resid && okr[i] && !(kPrefetchResid && pre_bf16)) {
                                 const int64_t off = (int64_t)mr[i] * eo.ld_resid + nbase + 4 * (lane & 7);
                                 if (eo.resid_is_f32) {
                                     rv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eo.resid) + off);
@@ -461,6 +489,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 8; ++i) rcur[kPrefetchResid ? i : 0] = rnext[kPrefetchResid ? i : 0];
                 }
+                if (kAheadF32) prefetch_f32(ci + 2);     // in flight during the next chunk's TMEM load + phase A
                 __syncwarp();
             }
         }
@@ -479,6 +508,8 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_total, int n_out,
                      int rows_per_sample, const float* __restrict__ bias,
                      const float* __restrict__ row_bias, int row_bias_ld, int act, EpiOut eo) {
+    pdl_trigger();
+    pdl_wait();
     const int n4 = (n_out + 3) >> 2;
     const int64_t total = m_total * n4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -511,6 +542,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_to
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int n_out,
                    int c1, int c2, int taps, int cp1, int cp2) {
+    pdl_trigger();
+    pdl_wait();
     const int kp = taps * (cp1 + cp2);
     const int64_t total = (int64_t)n_out * kp;
     const int cin = c1 + c2;
@@ -549,7 +582,7 @@ static void pick_m_tile(int N, int H, int W, bool force_tn1, int* tw_o, int* th_
 }
 static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
-template <int BN, bool kPre>
+template <int BN, int kPre>
 static int launch_conv2(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN>;
@@ -563,7 +596,7 @@ static int launch_conv2(const CUtensorMap& ta, const CUtensorMap& ta2, const CUt
     }
     const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    conv_gemm_kernel<BN, kPre><<<grid, kNumThreads, Cfg::kSmemBytes, s>>>(ta, ta2, tb, d);
+    launch_k(conv_gemm_kernel<BN, kPre>, grid, kNumThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -572,8 +605,10 @@ template <int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     // bf16 residual streams (VAE) take the instantiation that prefetches the residual ahead
-    if (d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, true>(ta, ta2, tb, d, m_tiles, splits, s);
-    return launch_conv2<BN, false>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, 1>(ta, ta2, tb, d, m_tiles, splits, s);
+    static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
+    if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv2<BN, 2>(ta, ta2, tb, d, m_tiles, splits, s);
+    return launch_conv2<BN, 0>(ta, ta2, tb, d, m_tiles, splits, s);
 }
 
 static int pick_block_n(int n_out, int m_tiles, int hint) {
@@ -610,7 +645,7 @@ int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, in
     const int taps = kh * kw;
     const int cp1 = (c1 + 63) / 64 * 64, cp2 = (c2 + 63) / 64 * 64;
     const int64_t total = (int64_t)n_out * taps * (cp1 + cp2);
-    pack_weight_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+    launch_k(pack_weight_kernel, grid_for(total, 256), 256, 0, as_stream(stream), 
         w_oihw, (__nv_bfloat16*)dst, n_out, c1, c2, taps, cp1, cp2);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -732,7 +767,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         eo.resid = p->resid; eo.resid_is_f32 = p->resid_is_f32; eo.ld_resid = p->ld_resid; eo.alpha = p->alpha;
         eo.out_bf16 = (__nv_bfloat16*)p->out_bf16; eo.out_f32 = p->out_f32; eo.ldo = p->ldo; eo.n_cols = p->n_out;
         const int64_t work = d.m_total * ((p->n_out + 3) / 4);
-        splitk_reduce_kernel<<<grid_for(work, 256), 256, 0, s>>>(
+        launch_k(splitk_reduce_kernel, grid_for(work, 256), 256, 0, s, 
             d.partial, splits, d.m_total, p->n_out, p->a_h * p->a_w, p->bias, p->row_bias, p->row_bias_ld,
             p->act, eo);
         RDEIC_LAUNCH_CHECK();

@@ -19,6 +19,8 @@ __device__ __forceinline__ float guided_eps(float e, float eu, float scale, bool
 __global__ void __launch_bounds__(kThreads)
 q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                 float* __restrict__ out, int64_t n, float a, float b) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         out[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(b, noise[i]));
@@ -29,6 +31,8 @@ relay_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                     const float* __restrict__ eps_u, float gscale,
                     const float* __restrict__ noise, float* __restrict__ out, int64_t n,
                     float r, float rm1, float c1, float c2, float sigma) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float xv = x[i];
@@ -48,6 +52,8 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                    const float* __restrict__ noise, float* __restrict__ out,
                    float* __restrict__ pred_out, int64_t n, float s1m, float sqrt_at,
                    float sqrt_aprev, float dir, float sigma) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float e = guided_eps(eps[i], eps_u ? eps_u[i] : 0.f, gscale, eps_u != nullptr);
@@ -67,6 +73,8 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C,
                     int64_t HW, int ldc, int c_off) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -90,6 +98,8 @@ template <bool kF32>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int C, int64_t HW,
                     int ldc) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -116,6 +126,8 @@ nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int C
 
 __global__ void __launch_bounds__(kThreads)
 f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = __float2bfloat16_rn(src[i]);
@@ -125,6 +137,8 @@ f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ ds
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t,
                                           __nv_bfloat16* __restrict__ out, int B, int dim,
                                           float max_period) {
+    pdl_trigger();
+    pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * dim) return;
@@ -142,6 +156,8 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t,
 template <bool kF32>
 __global__ void __launch_bounds__(kThreads)
 silu_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float v = kF32 ? reinterpret_cast<const float*>(x)[i]
@@ -153,6 +169,8 @@ silu_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t
 // attention.py:54-56: x, gate = proj(x).chunk(2); x * gelu(gate)   (exact erf GELU)
 __global__ void __launch_bounds__(kThreads)
 geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows, int F) {
+    pdl_trigger();
+    pdl_wait();
     const int fv = F >> 3;  // vectors of 8 bf16
     const int64_t total = rows * fv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -181,6 +199,8 @@ geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows
 __global__ void __launch_bounds__(kThreads)
 upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                   int cv) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)B * (2 * H) * (2 * W) * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -197,6 +217,8 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
 __global__ void __launch_bounds__(kThreads)
 im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                  int C, int Cp) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = H / 2, Wo = W / 2;
     const int cpv = Cp >> 3, cv = C >> 3;
     const int64_t total = (int64_t)B * Ho * Wo * 9 * cpv;
@@ -221,6 +243,8 @@ template <bool kF32>
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const void* __restrict__ in, __nv_bfloat16* __restrict__ out, int n,
                     float scale) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t row = blockIdx.x;
     const float* inf = reinterpret_cast<const float*>(in) + row * n;
     const __nv_bfloat16* inh = reinterpret_cast<const __nv_bfloat16*>(in) + row * n;
@@ -256,6 +280,8 @@ softmax_rows_kernel(const void* __restrict__ in, __nv_bfloat16* __restrict__ out
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                       int R, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __nv_bfloat16 tile[32][34];
     const int64_t base = (int64_t)blockIdx.z * R * C;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -275,6 +301,8 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __res
 __global__ void __launch_bounds__(kThreads)
 image_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t pixels,
                    int ldc) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = pixels * 3;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -299,7 +327,7 @@ int rdeic_q_sample(const float* x0, const float* noise, float* out, int64_t nume
     RDEIC_CHECK_ARG(x0 && noise && out, "rdeic_q_sample: null pointer");
     RDEIC_CHECK_ARG(numel >= 0, "rdeic_q_sample: negative numel");
     if (numel == 0) return 0;
-    q_sample_kernel<<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(x0, noise, out, numel, a, b);
+    launch_k(q_sample_kernel, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), x0, noise, out, numel, a, b);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -311,7 +339,7 @@ int rdeic_relay_update(const float* x, const float* eps, const float* eps_uncond
     RDEIC_CHECK_ARG(x && eps && noise && out, "rdeic_relay_update: null pointer");
     RDEIC_CHECK_ARG(numel >= 0, "rdeic_relay_update: negative numel");
     if (numel == 0) return 0;
-    relay_update_kernel<<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(relay_update_kernel, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), 
         x, eps, eps_uncond, guidance_scale, noise, out, numel, r, rm1, c1, c2, sigma);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -324,7 +352,7 @@ int rdeic_ddim_update(const float* x, const float* eps, const float* eps_uncond,
     RDEIC_CHECK_ARG(x && eps && noise && out, "rdeic_ddim_update: null pointer");
     RDEIC_CHECK_ARG(numel >= 0, "rdeic_ddim_update: negative numel");
     if (numel == 0) return 0;
-    ddim_update_kernel<<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(ddim_update_kernel, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), 
         x, eps, eps_uncond, guidance_scale, noise, out, pred_x0_out, numel, sqrt_one_minus_at,
         sqrt_at, sqrt_aprev, dir_coef, sigma);
     RDEIC_LAUNCH_CHECK();
@@ -338,7 +366,7 @@ int rdeic_nchw_to_nhwc_bf16(const float* src, void* dst, int B, int C, int H, in
                     "rdeic_nchw_to_nhwc_bf16: bad dims");
     const int64_t HW = (int64_t)H * W;
     dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)((C + 31) / 32), (unsigned)B);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, C, HW, ldc, c_off);
+    launch_k(nchw_to_nhwc_kernel, grid, 256, 0, as_stream(stream), src, (__nv_bfloat16*)dst, C, HW, ldc, c_off);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -349,8 +377,8 @@ int rdeic_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int B, i
     RDEIC_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && C <= ldc, "rdeic_nhwc_to_nchw_f32: bad dims");
     const int64_t HW = (int64_t)H * W;
     dim3 grid((unsigned)ceil_div64(HW, 32), (unsigned)((C + 31) / 32), (unsigned)B);
-    if (src_is_f32) nhwc_to_nchw_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ldc);
-    else nhwc_to_nchw_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW, ldc);
+    if (src_is_f32) launch_k(nhwc_to_nchw_kernel<true>, grid, 256, 0, as_stream(stream), src, dst, C, HW, ldc);
+    else launch_k(nhwc_to_nchw_kernel<false>, grid, 256, 0, as_stream(stream), src, dst, C, HW, ldc);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -358,7 +386,7 @@ int rdeic_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int B, i
 int rdeic_f32_to_bf16(const float* src, void* dst, int64_t numel, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(src && dst && numel >= 0, "rdeic_f32_to_bf16: bad args");
     if (numel == 0) return 0;
-    f32_to_bf16_kernel<<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, numel);
+    launch_k(f32_to_bf16_kernel, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), src, (__nv_bfloat16*)dst, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -367,7 +395,7 @@ int rdeic_timestep_embedding(const int64_t* t, void* out_bf16, int B, int dim, f
                              rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(t && out_bf16 && B > 0 && dim > 0, "rdeic_timestep_embedding: bad args");
     const int n = B * dim;
-    timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(
+    launch_k(timestep_embedding_kernel, (n + 255) / 256, 256, 0, as_stream(stream), 
         (const long long*)t, (__nv_bfloat16*)out_bf16, B, dim, max_period);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -377,8 +405,8 @@ int rdeic_silu_bf16(const void* x, int x_is_f32, void* out, int64_t numel,
                     rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(x && out && numel >= 0, "rdeic_silu_bf16: bad args");
     if (numel == 0) return 0;
-    if (x_is_f32) silu_kernel<true><<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)out, numel);
-    else silu_kernel<false><<<grid_for(numel, kThreads), kThreads, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)out, numel);
+    if (x_is_f32) launch_k(silu_kernel<true>, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), x, (__nv_bfloat16*)out, numel);
+    else launch_k(silu_kernel<false>, grid_for(numel, kThreads), kThreads, 0, as_stream(stream), x, (__nv_bfloat16*)out, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -389,7 +417,7 @@ int rdeic_geglu(const void* in_bf16, void* out_bf16, int64_t rows, int F,
     RDEIC_CHECK_ARG(F > 0 && F % 8 == 0, "rdeic_geglu: F=%d must be a multiple of 8", F);
     RDEIC_CHECK_ARG(((uintptr_t)in_bf16 | (uintptr_t)out_bf16) % 16 == 0, "rdeic_geglu: unaligned");
     if (rows == 0) return 0;
-    geglu_kernel<<<grid_for(rows * (F / 8), kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(geglu_kernel, grid_for(rows * (F / 8), kThreads), kThreads, 0, as_stream(stream), 
         (const uint4*)in_bf16, (uint4*)out_bf16, rows, F);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -400,7 +428,7 @@ int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
     RDEIC_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0, "rdeic_upsample2x_nhwc: bad args");
     RDEIC_CHECK_ARG(C > 0 && C % 8 == 0, "rdeic_upsample2x_nhwc: C=%d must be a multiple of 8", C);
     const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_for(total, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(upsample2x_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream), 
         (const uint4*)in, (uint4*)out, B, H, W, C / 8);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -413,7 +441,7 @@ int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C,
     RDEIC_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "rdeic_im2col_3x3_s2: H, W must be even");
     const int Cp = (C + 63) / 64 * 64;
     const int64_t total = (int64_t)B * (H / 2) * (W / 2) * 9 * (Cp / 8);
-    im2col_s2_kernel<<<grid_for(total, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(im2col_s2_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream), 
         (const uint4*)in, (uint4*)out, B, H, W, C, Cp);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -424,8 +452,8 @@ int rdeic_softmax_rows(const void* in, int in_is_f32, void* out_bf16, int64_t ro
     RDEIC_CHECK_ARG(in && out_bf16 && rows >= 0 && n > 0, "rdeic_softmax_rows: bad args");
     RDEIC_CHECK_ARG(rows < (1ll << 31), "rdeic_softmax_rows: too many rows");
     if (rows == 0) return 0;
-    if (in_is_f32) softmax_rows_kernel<true><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out_bf16, n, scale);
-    else softmax_rows_kernel<false><<<(unsigned)rows, 256, 0, as_stream(stream)>>>(in, (__nv_bfloat16*)out_bf16, n, scale);
+    if (in_is_f32) launch_k(softmax_rows_kernel<true>, (unsigned)rows, 256, 0, as_stream(stream), in, (__nv_bfloat16*)out_bf16, n, scale);
+    else launch_k(softmax_rows_kernel<false>, (unsigned)rows, 256, 0, as_stream(stream), in, (__nv_bfloat16*)out_bf16, n, scale);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -434,7 +462,7 @@ int rdeic_transpose_bf16(const void* in, void* out, int batch, int R, int C,
                          rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(in && out && batch > 0 && R > 0 && C > 0, "rdeic_transpose_bf16: bad args");
     dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
-    transpose_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C);
+    launch_k(transpose_bf16_kernel, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -443,7 +471,7 @@ int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
                       rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(in && out && pixels >= 0 && ldc >= 3, "rdeic_image_to_u8: bad args");
     if (pixels == 0) return 0;
-    image_to_u8_kernel<<<grid_for(pixels * 3, kThreads), kThreads, 0, as_stream(stream)>>>(in, out, pixels, ldc);
+    launch_k(image_to_u8_kernel, grid_for(pixels * 3, kThreads), kThreads, 0, as_stream(stream), in, out, pixels, ldc);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -42,6 +42,8 @@ template <bool kSplit>
 __global__ void __launch_bounds__(kThreads)
 ckbd_mask_kernel(const uint32_t* __restrict__ y, uint32_t* __restrict__ out_a,
                  uint32_t* __restrict__ out_n, int64_t rows, int H, int W, int which, RowMap rm) {
+    pdl_trigger();
+    pdl_wait();
     // vector path: W % 4 == 0, one uint4 per thread-iteration
     const int wv = W >> 2;
     const int64_t total = rows * wv;
@@ -75,6 +77,8 @@ template <bool kSplit>
 __global__ void __launch_bounds__(kThreads)
 ckbd_mask_scalar_kernel(const uint32_t* __restrict__ y, uint32_t* __restrict__ out_a,
                         uint32_t* __restrict__ out_n, int64_t rows, int H, int W, int which) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = rows * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -95,6 +99,8 @@ ckbd_mask_scalar_kernel(const uint32_t* __restrict__ y, uint32_t* __restrict__ o
 __global__ void __launch_bounds__(kThreads)
 ckbd_merge_kernel(const float* __restrict__ a, const float* __restrict__ n,
                   float* __restrict__ out, int64_t numel) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t nv = numel >> 2;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -166,6 +172,8 @@ ckbd_squeeze_kernel(const uint32_t* __restrict__ y, const float* __restrict__ sc
                     const float* __restrict__ table, int levels, float lower_bound,
                     uint32_t* __restrict__ out_f, int32_t* __restrict__ out_idx, int64_t rows,
                     int H, int W, int which, int mode) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     bool sorted = false;
@@ -190,6 +198,8 @@ ckbd_squeeze_vec_kernel(const uint32_t* __restrict__ y, const float* __restrict_
                         const float* __restrict__ table, int levels, float lower_bound,
                         uint32_t* __restrict__ out_f, int32_t* __restrict__ out_idx,
                         int64_t rows, int H, int W, int which, int mode, RowMap rm) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     bool sorted = false;
@@ -227,6 +237,8 @@ __global__ void __launch_bounds__(kThreads)
 ckbd_unsqueeze_kernel(const uint32_t* __restrict__ sq, const int32_t* __restrict__ sym,
                       const float* __restrict__ means_sq, uint32_t* __restrict__ out,
                       int64_t rows, int H, int Wh, int which, int mode) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = rows * Wh;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -245,6 +257,8 @@ ckbd_unsqueeze_kernel(const uint32_t* __restrict__ sq, const int32_t* __restrict
 __global__ void __launch_bounds__(kThreads)
 ckbd_unsqueeze_vec_kernel(const uint4* __restrict__ sq, uint4* __restrict__ out, int64_t rows, int H,
                           int Wh, int which, RowMap rm) {
+    pdl_trigger();
+    pdl_wait();
     const int wq = Wh >> 2;
     const int64_t total = rows * wq;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -267,6 +281,8 @@ ckbd_encode_phase_kernel(const float* __restrict__ y, const float* __restrict__ 
                          int levels, float lower_bound, int32_t* __restrict__ symbols,
                          int32_t* __restrict__ indexes, float* __restrict__ y_hat,
                          int64_t rows, int H, int W, int which, RowMap rm) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     const bool sorted = load_table(table, levels, s_tab, &s_flag);
@@ -295,6 +311,8 @@ ckbd_encode_phase_kernel(const float* __restrict__ y, const float* __restrict__ 
 __global__ void __launch_bounds__(kThreads)
 quantize_kernel(const float* __restrict__ x, const float* __restrict__ means,
                 int32_t* __restrict__ sym, int64_t numel) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t nv = numel >> 2;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -325,6 +343,8 @@ quantize_kernel(const float* __restrict__ x, const float* __restrict__ means,
 __global__ void __launch_bounds__(kThreads)
 dequantize_kernel(const int32_t* __restrict__ sym, const float* __restrict__ means,
                   float* __restrict__ out, int64_t numel) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t nv = numel >> 2;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -345,6 +365,8 @@ dequantize_kernel(const int32_t* __restrict__ sym, const float* __restrict__ mea
 __global__ void __launch_bounds__(kThreads)
 build_indexes_kernel(const float* __restrict__ scales, const float* __restrict__ table,
                      int levels, float lower_bound, int32_t* __restrict__ idx, int64_t numel) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_tab[kMaxLevels + 2];
     __shared__ int s_flag;
     const bool sorted = load_table(table, levels, s_tab, &s_flag);
@@ -376,6 +398,8 @@ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
 }
 
 __global__ void vq_init_kernel(unsigned long long* keys, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = ~0ull;
 }
@@ -389,6 +413,8 @@ constexpr int kVqMaxD = 512;
 __global__ void __launch_bounds__(kVqWarps * 32)
 vq_search_kernel(const float* __restrict__ z, const float* __restrict__ codebook,
                  unsigned long long* __restrict__ keys, int nvec, int D, int HW, int K) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_z[kVqVecs][kVqMaxD];
     __shared__ float s_zz[kVqVecs];
     const int v0 = blockIdx.x * kVqVecs;
@@ -461,6 +487,8 @@ vq_search_kernel(const float* __restrict__ z, const float* __restrict__ codebook
 __global__ void __launch_bounds__(128)
 vq_finalize_kernel(unsigned long long* __restrict__ keys, const float* __restrict__ codebook,
                    float* __restrict__ zq, int nvec, int D, int HW) {
+    pdl_trigger();
+    pdl_wait();
     const int v = blockIdx.x;
     __shared__ long long s_idx;
     if (threadIdx.x == 0) s_idx = (long long)(keys[v] & 0xffffffffull);
@@ -478,6 +506,8 @@ vq_finalize_kernel(unsigned long long* __restrict__ keys, const float* __restric
 __global__ void __launch_bounds__(128)
 vq_lookup_kernel(const long long* __restrict__ indices, const float* __restrict__ codebook,
                  float* __restrict__ out, int nvec, int D, int HW, int K, int* __restrict__ bad) {
+    pdl_trigger();
+    pdl_wait();
     const int v = blockIdx.x;
     long long idx = indices[v];
     if (idx < 0 || idx >= K) {  // nn.Embedding raises; we flag and clamp
@@ -504,10 +534,10 @@ int rdeic_ckbd_mask(const float* y, float* out, int B, int C, int H, int W, int 
     if (rows == 0 || W == 0) return 0;
     const bool vec = (W % 4 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out % 16 == 0);
     if (vec)
-        ckbd_mask_kernel<false><<<grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_mask_kernel<false>, grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, (uint32_t*)out, nullptr, rows, H, W, which, RowMap(rows * (W / 4), W / 4, H));
     else
-        ckbd_mask_scalar_kernel<false><<<grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_mask_scalar_kernel<false>, grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, (uint32_t*)out, nullptr, rows, H, W, which);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -522,10 +552,10 @@ int rdeic_ckbd_split(const float* y, float* anchor, float* nonanchor, int B, int
     const bool vec = (W % 4 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)anchor % 16 == 0) &&
                      ((uintptr_t)nonanchor % 16 == 0);
     if (vec)
-        ckbd_mask_kernel<true><<<grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_mask_kernel<true>, grid_for(rows * (W / 4), kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, (uint32_t*)anchor, (uint32_t*)nonanchor, rows, H, W, 0, RowMap(rows * (W / 4), W / 4, H));
     else
-        ckbd_mask_scalar_kernel<true><<<grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_mask_scalar_kernel<true>, grid_for(rows * W, kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, (uint32_t*)anchor, (uint32_t*)nonanchor, rows, H, W, 0);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -538,7 +568,7 @@ int rdeic_ckbd_merge(const float* anchor, const float* nonanchor, float* out, in
     if (numel == 0) return 0;
     RDEIC_CHECK_ARG(((uintptr_t)anchor | (uintptr_t)nonanchor | (uintptr_t)out) % 16 == 0,
                     "rdeic_ckbd_merge: pointers must be 16-byte aligned");
-    ckbd_merge_kernel<<<grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(ckbd_merge_kernel, grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream), 
         anchor, nonanchor, out, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -557,11 +587,11 @@ static int launch_squeeze(const float* y, const float* scales, const float* tabl
     bool vec = (W % 8 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out_f % 16 == 0);
     if (mode == 1) vec = vec && ((uintptr_t)scales % 16 == 0) && ((uintptr_t)out_idx % 16 == 0);
     if (vec)
-        ckbd_squeeze_vec_kernel<<<grid_for(rows * (W / 8), kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_squeeze_vec_kernel, grid_for(rows * (W / 8), kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, scales, table, levels, lower_bound, (uint32_t*)out_f, out_idx,
             rows, H, W, which, mode, RowMap(rows * (W / 8), W / 8, H));
     else
-        ckbd_squeeze_kernel<<<grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_squeeze_kernel, grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, scales, table, levels, lower_bound, (uint32_t*)out_f, out_idx,
             rows, H, W, which, mode);
     RDEIC_LAUNCH_CHECK();
@@ -594,10 +624,10 @@ int rdeic_ckbd_unsqueeze(const float* sq, float* out, int B, int C, int H, int W
     if (rows == 0 || Wh == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)out % 8 == 0, "rdeic_ckbd_unsqueeze: out must be 8-byte aligned");
     if (Wh % 4 == 0 && (uintptr_t)sq % 16 == 0 && (uintptr_t)out % 16 == 0)
-        ckbd_unsqueeze_vec_kernel<<<grid_for(rows * (Wh / 4), kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_unsqueeze_vec_kernel, grid_for(rows * (Wh / 4), kThreads), kThreads, 0, as_stream(stream), 
             (const uint4*)sq, (uint4*)out, rows, H, Wh, which, RowMap(rows * (Wh / 4), Wh / 4, H));
     else
-        ckbd_unsqueeze_kernel<<<grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream)>>>(
+        launch_k(ckbd_unsqueeze_kernel, grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)sq, nullptr, nullptr, (uint32_t*)out, rows, H, Wh, which, 0);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -611,7 +641,7 @@ int rdeic_ckbd_decode_phase(const int32_t* symbols, const float* means_sq, float
     const int64_t rows = (int64_t)B * C * H;
     if (rows == 0 || Wh == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)y_hat % 8 == 0, "rdeic_ckbd_decode_phase: y_hat must be 8-byte aligned");
-    ckbd_unsqueeze_kernel<<<grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(ckbd_unsqueeze_kernel, grid_for(rows * Wh, kThreads), kThreads, 0, as_stream(stream), 
         nullptr, symbols, means_sq, (uint32_t*)y_hat, rows, H, Wh, which, 1);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -630,7 +660,7 @@ int rdeic_ckbd_encode_phase(const float* y, const float* scales, const float* me
     const int64_t rows = (int64_t)B * C * H;
     if (rows == 0 || W == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)y_hat % 8 == 0, "rdeic_ckbd_encode_phase: y_hat must be 8-byte aligned");
-    ckbd_encode_phase_kernel<<<grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(ckbd_encode_phase_kernel, grid_for(rows * (W / 2), kThreads), kThreads, 0, as_stream(stream), 
         y, scales, means, table, levels, lower_bound, symbols, indexes, y_hat, rows, H, W, which,
         RowMap(rows * (W / 2), W / 2, H));
     RDEIC_LAUNCH_CHECK();
@@ -644,7 +674,7 @@ int rdeic_quantize_symbols(const float* x, const float* means, int32_t* symbols,
     if (numel == 0) return 0;
     RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)means | (uintptr_t)symbols) % 16 == 0,
                     "rdeic_quantize_symbols: pointers must be 16-byte aligned");
-    quantize_kernel<<<grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(quantize_kernel, grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream), 
         x, means, symbols, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -657,7 +687,7 @@ int rdeic_dequantize(const int32_t* symbols, const float* means, float* out, int
     if (numel == 0) return 0;
     RDEIC_CHECK_ARG(((uintptr_t)symbols | (uintptr_t)means | (uintptr_t)out) % 16 == 0,
                     "rdeic_dequantize: pointers must be 16-byte aligned");
-    dequantize_kernel<<<grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(dequantize_kernel, grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream), 
         symbols, means, out, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -671,7 +701,7 @@ int rdeic_build_indexes(const float* scales, const float* table, int levels, flo
     if (numel == 0) return 0;
     RDEIC_CHECK_ARG(((uintptr_t)scales | (uintptr_t)indexes) % 16 == 0,
                     "rdeic_build_indexes: pointers must be 16-byte aligned");
-    build_indexes_kernel<<<grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream)>>>(
+    launch_k(build_indexes_kernel, grid_for((numel + 3) / 4, kThreads), kThreads, 0, as_stream(stream), 
         scales, table, levels, lower_bound, indexes, numel);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -687,16 +717,16 @@ int rdeic_vq_quant(const float* z, const float* codebook, int64_t* indices, floa
     const int nvec = B * HW;
     if (nvec == 0) return 0;
     cudaStream_t s = as_stream(stream);
-    vq_init_kernel<<<(nvec + 255) / 256, 256, 0, s>>>((unsigned long long*)indices, nvec);
+    launch_k(vq_init_kernel, (nvec + 255) / 256, 256, 0, s, (unsigned long long*)indices, nvec);
     RDEIC_LAUNCH_CHECK();
     const int vtiles = (nvec + kVqVecs - 1) / kVqVecs;
     int ksplit = (2 * kNumSMs + vtiles - 1) / vtiles;
     ksplit = ksplit < 1 ? 1 : (ksplit > 64 ? 64 : ksplit);
     if (ksplit > K) ksplit = K;
-    vq_search_kernel<<<dim3(vtiles, ksplit), kVqWarps * 32, 0, s>>>(
+    launch_k(vq_search_kernel, dim3(vtiles, ksplit), kVqWarps * 32, 0, s, 
         z, codebook, (unsigned long long*)indices, nvec, D, HW, K);
     RDEIC_LAUNCH_CHECK();
-    vq_finalize_kernel<<<nvec, 128, 0, s>>>((unsigned long long*)indices, codebook, zq, nvec, D, HW);
+    launch_k(vq_finalize_kernel, nvec, 128, 0, s, (unsigned long long*)indices, codebook, zq, nvec, D, HW);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -707,7 +737,7 @@ int rdeic_vq_lookup(const int64_t* indices, const float* codebook, float* out, i
     RDEIC_CHECK_ARG(B >= 0 && HW >= 0 && D > 0 && K > 0, "rdeic_vq_lookup: bad dims");
     const int nvec = B * HW;
     if (nvec == 0) return 0;
-    vq_lookup_kernel<<<nvec, 128, 0, as_stream(stream)>>>((const long long*)indices, codebook, out,
+    launch_k(vq_lookup_kernel, nvec, 128, 0, as_stream(stream), (const long long*)indices, codebook, out,
                                                          nvec, D, HW, K, nullptr);
     RDEIC_LAUNCH_CHECK();
     return 0;

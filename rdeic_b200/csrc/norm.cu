@@ -49,6 +49,8 @@ template <bool kF32>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 int64_t HW, int G, float2* __restrict__ partial) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_part[kGnThreads * 16];   // [row][lane][8 sum | 8 sq]
     __shared__ float s_csum[kGnMaxC];
     __shared__ float s_csq[kGnMaxC];
@@ -137,6 +139,8 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
                 const float2* __restrict__ partial, int nchunk, FastDiv div_vl) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_scale[kGnMaxC];
     __shared__ float s_shift[kGnMaxC];
     __shared__ float s_mean[kGnMaxGroups];
@@ -209,6 +213,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
                  float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int VL = C >> 3;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -296,9 +302,9 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     cudaStream_t s = as_stream(stream);
     const int nchunk = gn_num_chunks(B, HW);
     if (in_is_f32)
-        gn_stats_kernel<true><<<dim3(nchunk, B), kGnThreads, 0, s>>>(x1, C1, x2, C2, HW, groups, (float2*)workspace);
+        launch_k(gn_stats_kernel<true>, dim3(nchunk, B), kGnThreads, 0, s, x1, C1, x2, C2, HW, groups, (float2*)workspace);
     else
-        gn_stats_kernel<false><<<dim3(nchunk, B), kGnThreads, 0, s>>>(x1, C1, x2, C2, HW, groups, (float2*)workspace);
+        launch_k(gn_stats_kernel<false>, dim3(nchunk, B), kGnThreads, 0, s, x1, C1, x2, C2, HW, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const int64_t vecs = HW * (C / 8);
     RDEIC_CHECK_ARG(vecs < (1ll << 31), "rdeic_groupnorm_nhwc: per-sample tensor too large (HW*C/8 must be < 2^31)");
@@ -308,10 +314,10 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (in_is_f32)
-        gn_apply_kernel<true><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     else
-        gn_apply_kernel<false><<<dim3((unsigned)blocks, B), kGnThreads, 0, s>>>(
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -330,7 +336,7 @@ int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const floa
     RDEIC_CHECK_ARG(blocks < (1ll << 31), "rdeic_layernorm: too many rows");
     const int nv = (C / 8 + 31) / 32;   // 16-byte vectors per lane
     cudaStream_t s = as_stream(stream);
-#define RDEIC_LN(F32, NV) layernorm_kernel<F32, NV><<<(unsigned)blocks, kLnWarps * 32, 0, s>>>(x, gamma, beta, (uint4*)out, rows, C, eps)
+#define RDEIC_LN(F32, NV) launch_k(layernorm_kernel<F32, NV>, (unsigned)blocks, kLnWarps * 32, 0, s, x, gamma, beta, (uint4*)out, rows, C, eps)
     if (in_is_f32) {
         if (nv <= 1) RDEIC_LN(true, 1); else if (nv == 2) RDEIC_LN(true, 2); else if (nv == 3) RDEIC_LN(true, 3); else RDEIC_LN(true, 5);
     } else {
