@@ -283,6 +283,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int col0 = nt * BN;
             const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
             const int m_own = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
+            // Common case: the whole tile is in bounds and the 32 rows of this warp's slab are
+            // consecutive output rows -> phase B needs no shuffles, predicates or divergence.
+            const int tn_ = kBlockM >> (p.tw_log2 + p.th_log2);
+            const bool tile_full = (tiw * tw + tw <= p.a_w) && (tih * th + th <= p.a_h) && (mt * tn_ + tn_ <= p.a_n);
+            const bool affine = tile_full && (tw >= 32 || (tw == p.a_w && (tw * th >= 32 || th == p.a_h)));
+            const int m_slab = __shfl_sync(0xffffffffu, m_own, 0);
             EpiOut eo;
             eo.resid = partial ? nullptr : p.resid; eo.resid_is_f32 = p.resid_is_f32; eo.ld_resid = p.ld_resid;
             eo.alpha = partial ? 1.0f : p.alpha;
@@ -419,7 +425,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (!geglu) {
-                    if (fast_chunk(ci)) {
+                    if (affine && fast_chunk(ci) && !(kPrefetchResid && pre_bf16) && !(kAheadF32 && ahead_f32)) {
+                        const int q = lane & 7;
+                        const int64_t m0 = (int64_t)m_slab + (lane >> 3);
+                        float4 rv[8];
+                        if (eo.resid) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int64_t off = (m0 + 4 * i) * eo.ld_resid + nbase + 4 * q;
+                                if (eo.resid_is_f32) {
+                                    rv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eo.resid) + off);
+                                } else {
+                                    const uint2 u = *reinterpret_cast<const uint2*>(
+                                        reinterpret_cast<const __nv_bfloat16*>(eo.resid) + off);
+                                    unpack_bf16x2(u.x, rv[i].x, rv[i].y);
+                                    unpack_bf16x2(u.y, rv[i].z, rv[i].w);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + (lane >> 3);
+                            float4 val = stg[row * 8 + (q ^ (row & 7))];
+                            if (eo.resid) {
+                                val.x = fmaf(eo.alpha, val.x, rv[i].x); val.y = fmaf(eo.alpha, val.y, rv[i].y);
+                                val.z = fmaf(eo.alpha, val.z, rv[i].z); val.w = fmaf(eo.alpha, val.w, rv[i].w);
+                            } else if (eo.alpha != 1.0f) {
+                                val.x *= eo.alpha; val.y *= eo.alpha; val.z *= eo.alpha; val.w *= eo.alpha;
+                            }
+                            const int64_t off = (m0 + 4 * i) * eo.ldo + nbase + 4 * q;
+                            if (eo.out_f32) *reinterpret_cast<float4*>(eo.out_f32 + off) = val;
+                            if (eo.out_bf16)
+                                *reinterpret_cast<uint2*>(eo.out_bf16 + off) =
+                                    make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                        }
+                    } else if (fast_chunk(ci)) {
                         int mr[8], okr[8];
                         float4 rv[8];
 #pragma unroll
