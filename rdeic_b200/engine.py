@@ -18,6 +18,8 @@ CUDA stream (so a whole step can be captured into a CUDA graph).
 """
 from __future__ import annotations
 
+import os
+from contextlib import contextmanager
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -299,6 +301,10 @@ class NoiseEstimatorEngine:
         # rdeic.py:164-165,185: scale_list buffer (already * control_scale) times control_scale again
         sl = sd["control_model.scale_list"].float().cpu() * self.control_scale
         self.scales = [float(v) for v in sl]
+        # run the control adapter on a second stream, concurrently with the base UNet (its kernels are
+        # small: 64-256 channels, grids that leave most SMs idle); joined at every zero-conv injection
+        self.overlap_control = os.environ.get("RDEIC_NO_OVERLAP") is None
+        self._side: Optional[torch.cuda.Stream] = None
         self._ctx_cache: Dict[tuple, tuple] = {}
         self._hint_cache: Dict[tuple, torch.Tensor] = {}
 
@@ -434,21 +440,54 @@ class NoiseEstimatorEngine:
             for blk in self.base.output_blocks:
                 hb = self._run_block(blk, hb, hs_base.pop(), cb)
         else:
-            cc = _Ctx(self._time_rows(self.ctrl, t_emb), kv_ctrl)
+            keep: List[object] = []           # nothing allocated in this step is freed (hence reused) before
+            main = torch.cuda.current_stream()  # the step ends: cross-stream reads stay valid without record_stream
+            overlap = self.overlap_control
+            if overlap and self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side if overlap else main
+
+            @contextmanager
+            def on_side():
+                if not overlap:
+                    yield
+                    return
+                prev = ops.WS_SLOT
+                ops.WS_SLOT = 1
+                try:
+                    with torch.cuda.stream(side):
+                        yield
+                finally:
+                    ops.WS_SLOT = prev
+
+            if overlap:
+                side.wait_stream(main)            # fork: x8, t_emb, conditioning are ready on main
+            with on_side():
+                cc = _Ctx(self._time_rows(self.ctrl, t_emb), kv_ctrl)
             hc = x8
             hs_ctr: List[Act] = []
             si = 0
             for i, (bb, bc) in enumerate(zip(self.base.input_blocks, self.ctrl.input_blocks)):
+                with on_side():
+                    hc = self._run_block(bc, hc, None, cc, x_in2=hint if i == 0 else None)
+                    ev = side.record_event() if overlap else None
                 hb = self._run_block(bb, hb, None, cb)
-                hc = self._run_block(bc, hc, None, cc, x_in2=hint if i == 0 else None)
+                if overlap:
+                    main.wait_event(ev)           # join: the injection reads h_ctr
                 hb = self._inject(self.enc_zero[i], hb, hc, self.scales[si])
                 si += 1
                 hs_base.append(hb)
                 hs_ctr.append(hc)
+                keep.extend((hb, hc))
+            with on_side():
+                hc = self._run_block(self.ctrl.middle, hc, None, cc)
+                ev = side.record_event() if overlap else None
             hb = self._run_block(self.base.middle, hb, None, cb)
-            hc = self._run_block(self.ctrl.middle, hc, None, cc)
+            if overlap:
+                main.wait_event(ev)
             hb = self._inject(self.mid_zero, hb, hc, self.scales[si])
             si += 1
+            keep.extend((hb, hc, cc))
             for i, blk in enumerate(self.base.output_blocks):
                 hb = self._inject(self.dec_zero[i], hb, hs_ctr.pop(), self.scales[si])
                 si += 1

@@ -327,10 +327,12 @@ def image_to_u8(x: torch.Tensor) -> torch.Tensor:
 # normalisation
 # ---------------------------------------------------------------------------------------------
 _gn_ws = {}
+WS_SLOT = 0     # workspaces are per (device, slot): kernels running concurrently on two streams
+                # (base UNet / control adapter overlap) must not share scratch memory
 
 
 def _gn_workspace(B: int, device) -> torch.Tensor:
-    key = (B, str(device))
+    key = (B, str(device), WS_SLOT)
     ws = _gn_ws.get(key)
     if ws is None:
         nbytes = _lib.load().rdeic_groupnorm_workspace_bytes(B, 1, 8)
@@ -371,10 +373,11 @@ _splitk_ws = {}
 
 def _splitk_workspace(device) -> torch.Tensor:
     """Caller-owned split-K scratch (the library never allocates): 64 MB per device."""
-    ws = _splitk_ws.get(str(device))
+    key = (str(device), WS_SLOT)
+    ws = _splitk_ws.get(key)
     if ws is None:
         ws = torch.empty(64 << 20, dtype=torch.uint8, device=device)
-        _splitk_ws[str(device)] = ws
+        _splitk_ws[key] = ws
     return ws
 
 
