@@ -87,7 +87,9 @@ struct FastDiv {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x); __fdividef = rcp.approx + mul (an IEEE divide costs ~10x more instructions, which made
+// the GroupNorm+SiLU apply pass issue-bound instead of HBM-bound)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
     return __uint_as_float(((uint32_t)b) << 16);

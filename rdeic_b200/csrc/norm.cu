@@ -149,19 +149,30 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     const int VL = C >> 3, VL1 = C1 >> 3, VL2 = C2 >> 3;
     const int b = blockIdx.y;
     const int cg = C / G;
-    if (threadIdx.x < G) {
+    {   // finalise the statistics: 8 threads per group split the chunk partials (fixed order ->
+        // deterministic), fp64 combine; a single thread per group would serialise nchunk L2 round trips
+        const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
         double a = 0.0, c = 0.0;
-        for (int k = 0; k < nchunk; ++k) {
-            const float2 v = partial[((int64_t)b * nchunk + k) * G + threadIdx.x];
-            a += (double)v.x;
-            c += (double)v.y;
+        if (g < G) {
+            for (int k = part; k < nchunk; k += 8) {
+                const float2 v = partial[((int64_t)b * nchunk + k) * G + g];
+                a += (double)v.x;
+                c += (double)v.y;
+            }
         }
-        const double n = (double)HW * cg;
-        const double mean = a / n;
-        double var = c / n - mean * mean;   // biased variance, as nn.GroupNorm
-        if (var < 0.0) var = 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+        for (int o = 4; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (g < G && part == 0) {
+            const double n = (double)HW * cg;
+            const double mean = a / n;
+            double var = c / n - mean * mean;   // biased variance, as nn.GroupNorm
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = (float)mean;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kGnThreads) {
@@ -171,34 +182,53 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         s_shift[c] = beta[c] - s_mean[g] * sc;
     }
     __syncthreads();
-    const int64_t total = HW * VL;
+    // Each thread keeps ONE 8-channel lane for the whole pass, so its scale/shift live in registers
+    // (reading them from shared memory per element made the kernel smem-bandwidth bound: 4 LDS.128
+    // per 16 bytes of payload) and the loop has no index division.
     const int64_t o1 = (int64_t)b * HW * VL1, o2 = (int64_t)b * HW * VL2;
     uint4* bo = out + (int64_t)b * HW * VL;
-    for (int64_t i = blockIdx.x * (int64_t)kGnThreads + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * kGnThreads) {
-        uint32_t pq, lq;
-        div_vl.divmod((uint32_t)i, pq, lq);          // host guarantees HW * VL < 2^31
-        const int64_t p = pq;
-        const int l = (int)lq;
-        float f[8];
-        if (l < VL1) load8<kF32>(x1, o1 + p * VL1 + l, f);
-        else load8<kF32>(x2, o2 + p * VL2 + (l - VL1), f);
-        const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[l * 8]);
-        const float4 sc1 = *reinterpret_cast<const float4*>(&s_scale[l * 8 + 4]);
-        const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[l * 8]);
-        const float4 sh1 = *reinterpret_cast<const float4*>(&s_shift[l * 8 + 4]);
-        f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y);
-        f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
-        f[4] = fmaf(f[4], sc1.x, sh1.x); f[5] = fmaf(f[5], sc1.y, sh1.y);
-        f[6] = fmaf(f[6], sc1.z, sh1.z); f[7] = fmaf(f[7], sc1.w, sh1.w);
-        if (silu) {
+    const int nchunk_a = gridDim.x;
+    const int64_t per = (HW + nchunk_a - 1) / nchunk_a;
+    const int64_t p0 = blockIdx.x * per;
+    const int64_t p1 = (p0 + per < HW) ? p0 + per : HW;
+    const int lanes_per_pass = VL < kGnThreads ? VL : kGnThreads;
+    const int rows_per_iter = kGnThreads / lanes_per_pass;
+    const int row = threadIdx.x / lanes_per_pass, lane_in = threadIdx.x - row * lanes_per_pass;
+    for (int lane_base = 0; lane_base < VL; lane_base += lanes_per_pass) {
+        const int l = lane_base + lane_in;
+        if (row >= rows_per_iter || l >= VL) continue;
+        float sc[8], sh[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+        for (int k = 0; k < 8; ++k) { sc[k] = s_scale[l * 8 + k]; sh[k] = s_shift[l * 8 + k]; }
+        const bool first = l < VL1;
+        const void* src = first ? x1 : x2;
+        const int64_t stride = first ? VL1 : VL2;
+        const int64_t off = (first ? o1 + l : o2 + (l - VL1));
+        auto finish = [&](float* f, int64_t p) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+            if (silu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            st_stream_u4(bo + p * VL + l, o);
+        };
+        int64_t p = p0 + row;
+        for (; p + 3 * (int64_t)rows_per_iter < p1; p += 4 * (int64_t)rows_per_iter) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8<kF32>(src, off + (p + u * (int64_t)rows_per_iter) * stride, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) finish(f[u], p + u * (int64_t)rows_per_iter);
         }
-        uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-        st_stream_u4(bo + i, o);
+        for (; p < p1; p += rows_per_iter) {
+            float f[8];
+            load8<kF32>(src, off + p * stride, f);
+            finish(f, p);
+        }
     }
 }
 
@@ -306,13 +336,8 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     else
         launch_k(gn_stats_kernel<false>, dim3(nchunk, B), kGnThreads, 0, s, x1, C1, x2, C2, HW, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
-    const int64_t vecs = HW * (C / 8);
-    RDEIC_CHECK_ARG(vecs < (1ll << 31), "rdeic_groupnorm_nhwc: per-sample tensor too large (HW*C/8 must be < 2^31)");
     const FastDiv div_vl((uint32_t)(C / 8));
-    int64_t blocks = ceil_div64(vecs, (int64_t)kGnThreads * 4);
-    const int64_t cap = (8 * kNumSMs + B - 1) / B;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
+    int64_t blocks = nchunk;          // same pixel chunking as the statistics pass
     if (in_is_f32)
         launch_k(gn_apply_kernel<true>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
