@@ -22,8 +22,10 @@ constexpr int kAK = 128;                      // keys per tile
 constexpr int kAStages = 3;                   // K/V ring
 constexpr int kATile = kAK * kAD * 2;         // 16 KB: one Q, K or V tile
 constexpr int kAPBytes = kAQ * kAK * 2;       // 32 KB: one P buffer (two 64-key panels)
-constexpr int kAThreads = 192;                // warp0 TMA, warp1 MMA, warps 2-5 softmax
-constexpr int kASmem = kATile * (1 + 2 * kAStages) + 2 * kAPBytes + 1024 + 256;
+constexpr int kASoftWarps = 8;                 // two threads per query row (64 keys / 32 O columns each)
+constexpr int kAThreads = 64 + 32 * kASoftWarps;   // warp0 TMA, warp1 MMA, warps 2-9 softmax
+constexpr int kAXBytes = 2 * 2 * kAQ * 4 + 2 * kAQ * 4;   // row-max exchange [parity][half][row] + row-sum exchange
+constexpr int kASmem = kATile * (1 + 2 * kAStages) + 2 * kAPBytes + kAXBytes + 1024 + 256;
 constexpr uint32_t kColS = 0, kColO = 256;    // TMEM columns: S0,S1 at 0/128 ; O0,O1 at 256/320
 
 struct AttDev {
@@ -61,7 +63,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     uint8_t* s_k = s_q + kATile;
     uint8_t* s_v = s_k + kAStages * kATile;
     uint8_t* s_p = s_v + kAStages * kATile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAPBytes);
+    float* s_xmax = reinterpret_cast<float*>(s_p + 2 * kAPBytes);          // [2][2][128]
+    float* s_xsum = s_xmax + 2 * 2 * kAQ;                                  // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAPBytes + kAXBytes);
     uint64_t* q_full = bars;                  // [1]
     uint64_t* kv_full = bars + 1;             // [kAStages]
     uint64_t* kv_empty = kv_full + kAStages;  // [kAStages]
@@ -83,9 +87,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         for (int s = 0; s < kAStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 4);
+            mbar_init(&p_full[i], kASoftWarps);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_empty[i], 4);
+            mbar_init(&o_empty[i], kASoftWarps);
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -146,30 +150,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             issue_pv(T - 1);
         }
     } else {
-        // ===== softmax / correction / epilogue: one query row per thread =====
+        // ===== softmax / correction / epilogue: two threads per query row =====
+        // Warps w and w+4 (same TMEM lane quadrant) share 32 rows: the first takes keys 0-63 of each
+        // tile and O columns 0-31, the second keys 64-127 and O columns 32-63.  They exchange the row
+        // maximum through shared memory once per tile (64-thread named barrier) and the row sum once
+        // at the end; with 2 softmax warps per scheduler the exp / convert chains overlap.
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sc = p.scale_log2;
-        float o[kAD];
+        constexpr int kOC = kAD / 2;             // O columns per thread
+        float o[kOC];
 #pragma unroll
-        for (int i = 0; i < kAD; ++i) o[i] = 0.f;
+        for (int i = 0; i < kOC; ++i) o[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
 
         auto add_o = [&](int i) {
             const uint32_t bf = i & 1;
             mbar_wait(&o_full[bf], (i >> 1) & 1);
             tc_fence_after();
+            uint32_t r[32];
+            const uint32_t ta = tmem_base + lane_addr + kColO + bf * kAD + half * kOC;
+            tmem_ld16(ta, r);
+            tmem_ld16(ta + 16, r + 16);
+            tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < kAD / 32; ++h) {
-                uint32_t r[32];
-                const uint32_t ta = tmem_base + lane_addr + kColO + bf * kAD + h * 32;
-                tmem_ld16(ta, r);
-                tmem_ld16(ta + 16, r + 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) o[h * 32 + c] += __uint_as_float(r[c]);
-            }
+            for (int c = 0; c < 32; ++c) o[c] += __uint_as_float(r[c]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[bf]);
@@ -179,11 +187,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             const uint32_t bf = j & 1;
             mbar_wait(&s_full[bf], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t ts = tmem_base + lane_addr + kColS + bf * kAK;
-            // pass 1: row maximum
+            const uint32_t ts = tmem_base + lane_addr + kColS + bf * kAK + half * 64;
+            // pass 1: maximum over this thread's 64 keys, then across the pair
             float mx = -INFINITY;
 #pragma unroll
-            for (int c4 = 0; c4 < kAK / 32; ++c4) {
+            for (int c4 = 0; c4 < 2; ++c4) {
                 uint32_t r[32];
                 tmem_ld16(ts + c4 * 32, r);
                 tmem_ld16(ts + c4 * 32 + 16, r + 16);
@@ -191,13 +199,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
                 for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
             }
+            s_xmax[(bf * 2 + half) * kAQ + row] = mx;
+            pair_sync();
+            mx = fmaxf(mx, s_xmax[(bf * 2 + (half ^ 1)) * kAQ + row]);
             const float m_new = fmaxf(m_run, mx * sc);
             const float corr = ex2_approx(m_run - m_new);
-            // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled K-major smem (A operand of P V)
+            // pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled K-major smem (one 64-key panel row)
             float rowsum = 0.f;
-            uint8_t* prow = s_p + bf * kAPBytes + row * 128;
+            uint8_t* prow = s_p + bf * kAPBytes + half * (kAQ * 128) + row * 128;
 #pragma unroll
-            for (int c4 = 0; c4 < kAK / 32; ++c4) {
+            for (int c4 = 0; c4 < 2; ++c4) {
                 uint32_t r[32];
                 tmem_ld16(ts + c4 * 32, r);
                 tmem_ld16(ts + c4 * 32 + 16, r + 16);
@@ -212,9 +223,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int chunk = c4 * 4 + q;                 // 16-byte chunk = 8 keys
-                    uint8_t* dst = prow + (chunk >> 3) * (kAQ * 128) + (((chunk & 7) ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    const int chunk = c4 * 4 + q;                 // 16-byte chunk = 8 keys, within the panel
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
             l_run = fmaf(l_run, corr, rowsum);
@@ -226,13 +237,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             // fold in the previous tile's O while the tensor core works on this one
             if (j > 0) add_o(j - 1);
 #pragma unroll
-            for (int i = 0; i < kAD; ++i) o[i] *= corr;
+            for (int i = 0; i < kOC; ++i) o[i] *= corr;
         }
         add_o(T - 1);
-        const float inv = 1.0f / l_run;
-        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(qt * kAQ + row) * p.ldo + head * kAD;
+        s_xsum[half * kAQ + row] = l_run;
+        pair_sync();
+        const float inv = 1.0f / (l_run + s_xsum[(half ^ 1) * kAQ + row]);
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(qt * kAQ + row) * p.ldo + head * kAD + half * kOC;
 #pragma unroll
-        for (int v8 = 0; v8 < kAD / 8; ++v8) {
+        for (int v8 = 0; v8 < kOC / 8; ++v8) {
             uint4 w;
             w.x = pack_bf16x2(o[8 * v8] * inv, o[8 * v8 + 1] * inv);
             w.y = pack_bf16x2(o[8 * v8 + 2] * inv, o[8 * v8 + 3] * inv);
