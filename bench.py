@@ -274,9 +274,13 @@ def run_b200(args):
         peaks = json.loads(pk.read_text())
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    traffic = None
+    ks = ROOT / "profiles" / "r01_decode_kernel_summary.json"
+    if ks.exists():     # per-launch DRAM bytes of the same kernel from the committed ncu capture of this workload
+        traffic = json.loads(ks.read_text()).get("conv_gemm_dram_bytes_per_launch")
     roofline = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv3x3/conv1x1/linear)", "bound": "tensor",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "launches_per_step": len(prof),
+                "traffic": traffic, "launches_per_step": len(prof),
                 "flops_per_launch": g_fl / max(len(prof), 1), "ms_per_launch": g_ms / max(len(prof), 1),
                 "share_of_step": g_ms / (ms_dev / args.steps),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"

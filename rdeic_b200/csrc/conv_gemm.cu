@@ -644,8 +644,11 @@ static int launch_conv2(const CUtensorMap& ta, const CUtensorMap& ta2, const CUt
 template <int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
-    // bf16 residual streams (VAE) take the instantiation that prefetches the residual ahead
-    if (d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, 1>(ta, ta2, tb, d, m_tiles, splits, s);
+    // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
+    // kept for experiments only: with the affine fast path both measured slower than loading the
+    // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
+    static const bool pre16 = getenv("RDEIC_RESID_PREFETCH") != nullptr;
+    if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, 1>(ta, ta2, tb, d, m_tiles, splits, s);
     static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
     if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv2<BN, 2>(ta, ta2, tb, d, m_tiles, splits, s);
     return launch_conv2<BN, 0>(ta, ta2, tb, d, m_tiles, splits, s);

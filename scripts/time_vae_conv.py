@@ -1,0 +1,27 @@
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from rdeic_b200 import ops  # noqa: E402
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(1)
+rnd = lambda *s: torch.randn(*s, generator=g, device=dev)
+def t(fn, n=10):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for (B, H, W, C) in [(8, 512, 512, 128), (8, 256, 256, 256)]:
+    x = rnd(B, H, W, C).bfloat16()
+    w = ops.pack_conv_weight(rnd(C, C, 3, 3) / (3 * C ** 0.5))
+    b = rnd(C)
+    r16 = rnd(B, H, W, C).bfloat16()
+    r32 = r16.float()
+    fl = 2.0 * B * H * W * C * 9 * C
+    for name, kw in [("no resid", {}), ("bf16 resid", dict(resid=r16)), ("f32 resid", dict(resid=r32)),
+                     ("f32 resid dual", dict(resid=r32, dual=True))]:
+        us = t(lambda: ops.conv_gemm(x, w, C, 9, bias=b, **kw))
+        print(f"[{B},{H},{W},{C}] {name:16s} {us:8.1f} us  {fl/us/1e6:7.1f} TF/s", flush=True)
