@@ -262,6 +262,10 @@ def run_b200(args):
     decode_device()
     torch.cuda.synchronize()
     ops.GEMM_PROFILE = []
+    # Park the GPU behind a ~150 ms spin so the host gets ahead and every (event, kernel, event) triple
+    # is already queued when the GPU reaches it: otherwise each bracket also times the host's ~10 us
+    # enqueue gap, which for 1 577 short launches is a sizeable over-count.
+    torch.cuda._sleep(int(0.15 * 1.9e9))
     decode_device()
     torch.cuda.synchronize()
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None

@@ -1,0 +1,43 @@
+"""Representative launches of each kernel class for the committed ncu --set full capture:
+0 conv3x3 320->320 @64^2 (UNet level 0, fp32 residual + dual write)   1 conv3x3 512->512 @128^2 (VAE)
+2 linear K=320 N=320 + fp32 residual   3 GEGLU linear K=320 N=2560   4 tcgen05 attention N=4096 h=5 d=64
+5 GroupNorm+SiLU [8,512,512,128]   6 LayerNorm [32768,320]   7 relay_update   8 ckbd encode phase"""
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from rdeic_b200 import ops  # noqa: E402
+from rdeic_b200.ckbd import get_scale_table  # noqa: E402
+from rdeic_b200.engine import Conv  # noqa: E402
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(1)
+rnd = lambda *s: torch.randn(*s, generator=g, device=dev)
+x320 = rnd(8, 64, 64, 320).bfloat16(); w320 = ops.pack_conv_weight(rnd(320, 320, 3, 3) / 54); b320 = rnd(320); r32 = rnd(8, 64, 64, 320)
+x512 = rnd(8, 128, 128, 512).bfloat16(); w512 = ops.pack_conv_weight(rnd(512, 512, 3, 3) / 68); b512 = rnd(512)
+xl = rnd(32768, 320).bfloat16(); wl = ops.pack_conv_weight(rnd(320, 320) / 18); rl = rnd(32768, 320)
+gg = Conv.load({"p.weight": rnd(2560, 320).cpu() / 18, "p.bias": rnd(2560).cpu()}, "p", dev, geglu=True)
+qkv = rnd(8, 4096, 960).bfloat16()
+gn = rnd(8, 512, 512, 128).bfloat16(); gam, bet = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+g3, b3 = torch.ones(320, device=dev), torch.zeros(320, device=dev)
+u = [rnd(1 << 24) for _ in range(3)]
+y, mu = rnd(8, 64, 128, 128) * 6, rnd(8, 64, 128, 128) * 2
+sc = torch.exp(torch.rand(8, 64, 128, 128, generator=g, device=dev) * 8 - 3); tab = get_scale_table().to(dev)
+fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True),
+       lambda: ops.conv_gemm(x512, w512, 512, 9, bias=b512),
+       lambda: ops.linear(xl, wl, 320, bias=b320, resid=rl, out_f32=True),
+       lambda: ops.linear(xl, gg.w, gg.n_out, bias=gg.b, act=2),
+       lambda: ops.attention(qkv[..., :320], qkv[..., 320:640], qkv[..., 640:], 5, 64, 0.125),
+       lambda: ops.groupnorm(gn, gam, bet, 32, 1e-6, True),
+       lambda: ops.layernorm(xl, g3, b3),
+       lambda: ops.relay_update(u[0], u[1], u[2], 1.2, 0.8, 0.4, 0.6, 0.3),
+       lambda: ops.ckbd_encode_phase(y, sc, mu, tab, 0.11, 0)]
+for _ in range(2):
+    for f in fns:
+        f()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for f in fns:
+    f()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("done")
