@@ -25,8 +25,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;   // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..9 epilogue
+// warp0 TMA, warp1 MMA(+TMEM alloc), then kEW epilogue warps (8 or 12: two or three per TMEM lane
+// quadrant; 12 gives the latency-bound epilogue of small-K problems one more warp per scheduler at the
+// price of a 128-register cap and one pipeline stage)
+constexpr int kMaxEpiWarps = 12;
 
 struct ConvDev {
     int a_n, a_h, a_w;
@@ -115,11 +117,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x + 0.5f * fabsf(x) * erf_abs;                 // 0.5 x (1 + sign(x) erf|.|)
 }
 
-template <int BN>
+template <int BN, int kEW>
 struct TileCfg {
+    static constexpr int kThreads = 64 + 32 * kEW;
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kATileBytes + kBBytes;
-    static constexpr int kStagingBytes = kNumEpiWarps * 4096;          // 32 rows x 128 B per epilogue warp
+    static constexpr int kStagingBytes = kEW * 4096;                   // 32 rows x 128 B per epilogue warp
     static constexpr int kMaxSmem = 227 * 1024;
     static constexpr int kStagesRaw = (kMaxSmem - kStagingBytes - 1024 - 256) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -132,13 +135,14 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN, int kResidMode>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BN, int kResidMode, int kEW>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
     pdl_trigger();
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, kEW>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kCStride = kEW / 4;            // epilogue warps per TMEM lane quadrant = chunk stride
     // residual handling in the epilogue: 0 = loaded at the top of phase B, 1 = bf16 residual
     // prefetched two chunks deep, 2 = fp32 residual prefetched one phase ahead (single buffer)
     constexpr bool kPrefetchResid = (kResidMode == 1);
@@ -173,7 +177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], kNumEpiWarps);
+            mbar_init(&acc_empty[b], kEW);
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -262,7 +266,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // Two warps share each TMEM lane quadrant and take alternate 32-column chunks.
         const int ew = warp - 2;                      // 0..7
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int half = ew >> 2;                     // which alternate chunks
+        const int half = ew >> 2;                     // which chunks of the tile: half, half + kCStride, ...
         const int r = quad * 32 + lane;               // row inside the M tile
         const int rw = r & (tw - 1);
         const int rh = (r >> p.tw_log2) & (th - 1);
@@ -301,7 +305,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             constexpr int kChunks = BN / 32;
             // chunks this warp owns: half, half+2, ...
             int last_c = -1;
-            for (int ci = half; ci < kChunks; ci += 2)
+            for (int ci = half; ci < kChunks; ci += kCStride)
                 if (col0 + ci * 32 < p.n_out) last_c = ci;
             // phase-B row mapping: row = 4*i + lane/8; its global row index / validity come from the
             // lane that owns that accumulator row (a shuffle is cheaper than 16 live registers here:
@@ -357,11 +361,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
 #pragma unroll 1
-            for (int ci = half; ci < kChunks; ci += 2) {
+            for (int ci = half; ci < kChunks; ci += kCStride) {
                 const int c = ci * 32;
                 const int nbase = col0 + c;
                 if (nbase >= p.n_out) break;                                      // warp-uniform
-                if (kPrefetchResid) prefetch(ci + 2, rnext);
+                if (kPrefetchResid) prefetch(ci + kCStride, rnext);
                 uint32_t acc[32];
                 tmem_ld16(tmem_acc + (uint32_t)c, acc);
                 tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
@@ -529,7 +533,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 8; ++i) rcur[kPrefetchResid ? i : 0] = rnext[kPrefetchResid ? i : 0];
                 }
-                if (kAheadF32) prefetch_f32(ci + 2);     // in flight during the next chunk's TMEM load + phase A
+                if (kAheadF32) prefetch_f32(ci + kCStride);     // in flight during the next chunk's TMEM load + phase A
                 __syncwarp();
             }
         }
@@ -622,21 +626,20 @@ static void pick_m_tile(int N, int H, int W, bool force_tn1, int* tw_o, int* th_
 }
 static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
-template <int BN, int kPre>
-static int launch_conv2(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+template <int BN, int kPre, int kEW>
+static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, kEW>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    launch_k(conv_gemm_kernel<BN, kPre>, grid, kNumThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d);
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -648,10 +651,14 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     // kept for experiments only: with the affine fast path both measured slower than loading the
     // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
     static const bool pre16 = getenv("RDEIC_RESID_PREFETCH") != nullptr;
-    if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv2<BN, 1>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv3<BN, 1, 8>(ta, ta2, tb, d, m_tiles, splits, s);
     static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
-    if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv2<BN, 2>(ta, ta2, tb, d, m_tiles, splits, s);
-    return launch_conv2<BN, 0>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv3<BN, 2, 8>(ta, ta2, tb, d, m_tiles, splits, s);
+    // few k-blocks per tile -> the epilogue, not the tensor pipe, sets the pace: use 12 epilogue warps
+    static const int epi12_kb = getenv("RDEIC_EPI12_KB") ? atoi(getenv("RDEIC_EPI12_KB")) : 10;
+    const int total_kb = d.taps * (d.cblk1 + d.cblk2);
+    if (total_kb <= epi12_kb) return launch_conv3<BN, 0, 12>(ta, ta2, tb, d, m_tiles, splits, s);
+    return launch_conv3<BN, 0, 8>(ta, ta2, tb, d, m_tiles, splits, s);
 }
 
 static int pick_block_n(int n_out, int m_tiles, int hint) {
