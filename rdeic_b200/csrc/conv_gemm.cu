@@ -518,6 +518,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
                         }
                     }
+                } else if (affine && vec_io && eo.out_bf16 && !eo.out_f32 && (nbase >> 1) + 16 <= eo.n_cols) {
+                    // GEGLU fast path: full in-bounds tile, consecutive rows, bf16 output only
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = 8 * i + (lane & 7), q = lane >> 3;
+                        const float4 val = stg[row * 8 + (q ^ (row & 7))];
+                        *reinterpret_cast<uint2*>(eo.out_bf16 + ((int64_t)m_slab + row) * eo.ldo + (nbase >> 1) + 4 * q) =
+                            make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
