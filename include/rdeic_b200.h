@@ -131,6 +131,10 @@ int rdeic_geglu(const void* in_bf16, void* out_bf16, int64_t rows, int F,
 /* nearest x2 upsample NHWC bf16 (openaimodel.py:106-113, model.py:63-67). */
 int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
                           rdeic_stream_t stream);
+/* nn.PixelShuffle(2) of the sub-pixel convs (model/layers/conv.py:7-10) on NHWC bf16:
+ * in [B,H,W,4C] with channels ordered (i, j, c) -> out [B,2H,2W,C]. */
+int rdeic_pixel_shuffle2_nhwc(const void* in, void* out, int B, int H, int W, int C,
+                              rdeic_stream_t stream);
 /* im2col for the stride-2 pad-1 3x3 Downsample conv (openaimodel.py:150-152):
  * in NHWC [B,H,W,C] -> out [B*(H/2)*(W/2), 9*Cp] with Cp = C rounded up to 64. */
 int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C,
@@ -178,7 +182,8 @@ int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const floa
 typedef struct rdeic_conv_params {
     const void* a;        int a_n, a_h, a_w, a_c;
     const void* a2;       int a2_c;
-    int taps;             /* 1 (1x1 / linear) or 9 (3x3, pad 1) */
+    int taps;             /* 1 (1x1 / linear), 9 (3x3, pad 1) or 25 (5x5, pad 2: model/compression.py:23,
+                             compression_modules.py:80-84) */
     const void* w;        /* packed bf16 weights */
     int64_t w_batch_stride;
     int w_k, w_ld;        /* 0,0 = packed layout; else true K extent / row stride (elements) of an
@@ -189,13 +194,19 @@ typedef struct rdeic_conv_params {
     const void* resid;    int resid_is_f32; int ld_resid;
     float alpha;
     int act;              /* 0 none, 1 SiLU, 2 GEGLU: weight rows interleaved in blocks of
-                             16 values | 16 gates (rdeic_b200/engine.py), writes n_out/2 columns */
+                             16 values | 16 gates (rdeic_b200/engine.py), writes n_out/2 columns;
+                             3 LeakyReLU(act_param) (model/layers/res_blk.py:18-21,50-53,79),
+                             4 exact GELU (compression_modules.py:81-83,96-99) */
     void* out_bf16;
     float* out_f32;
     int ldo;
     int tile_n_hint;      /* 0 = library picks BLOCK_N */
     void* workspace;      /* optional split-K scratch (fp32 partials); NULL disables split-K */
     int64_t workspace_bytes;
+    /* ABI 2 */
+    float act_param;      /* LeakyReLU negative slope */
+    int a_ld, a2_ld;      /* pixel stride (elements) of a / a2 when they are channel slices of a wider
+                             NHWC buffer (torch.cat inputs of compression.py:170-190); 0 = a_c / a2_c */
 } rdeic_conv_params;
 
 int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream);

@@ -44,6 +44,8 @@ class ConvParams(C.Structure):
         ("tile_n_hint", i32),
         ("workspace", vp),
         ("workspace_bytes", i64),
+        ("act_param", f32),
+        ("a_ld", i32), ("a2_ld", i32),
     ]
 
 
@@ -74,6 +76,7 @@ SIGNATURES = {
     "rdeic_silu_bf16": [vp, i32, vp, i64, vp],
     "rdeic_geglu": [vp, vp, i64, i32, vp],
     "rdeic_upsample2x_nhwc": [vp, vp, i32, i32, i32, i32, vp],
+    "rdeic_pixel_shuffle2_nhwc": [vp, vp, i32, i32, i32, i32, vp],
     "rdeic_im2col_3x3_s2": [vp, vp, i32, i32, i32, i32, vp],
     "rdeic_softmax_rows": [vp, i32, vp, i64, i32, f32, vp],
     "rdeic_transpose_bf16": [vp, vp, i32, i32, i32, vp],

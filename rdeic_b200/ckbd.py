@@ -75,8 +75,27 @@ class GaussianConditional:
         self.scale_bound = float(scale_bound)
 
     def update_scale_table(self, scale_table, force=False):
+        """compressai GaussianConditional.update_scale_table: new table + the rANS coder's quantised CDF
+        tables.  Those tables are consumed only by compressai's own coder, so they are built by
+        compressai when it is installed (`cdf_tables()`); the index / symbol arithmetic needs only
+        the scale table."""
         self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32).to(self.scale_table.device).contiguous()
+        self._tables = None
         return True
+
+    def cdf_tables(self):
+        """(quantized_cdf, cdf_lengths, offsets) as the Python lists compression.py:163-165 hands to the
+        rANS coder, or (None, None, None) without compressai (loopback coders ignore them)."""
+        if getattr(self, "_tables", None) is None:
+            try:
+                from compressai.entropy_models import GaussianConditional as _GC
+            except ImportError:
+                return None, None, None
+            g = _GC(None)
+            g.update_scale_table(self.scale_table.cpu(), force=True)
+            self._tables = (g.quantized_cdf.tolist(), g.cdf_length.reshape(-1).int().tolist(),
+                            g.offset.reshape(-1).int().tolist())
+        return self._tables
 
     def build_indexes(self, scales: torch.Tensor) -> torch.Tensor:
         return ops.build_indexes(scales, self.scale_table, self.scale_bound)
@@ -93,6 +112,41 @@ class GaussianConditional:
     def dequantize(self, inputs: torch.Tensor, means: Optional[torch.Tensor] = None) -> torch.Tensor:
         means = torch.zeros(inputs.shape, dtype=torch.float32, device=inputs.device) if means is None else means
         return ops.dequantize(inputs.to(torch.int32), means.expand(inputs.shape).contiguous())
+
+
+class TorchacHyperLatentCoder:
+    """utils/ckbd.py:118-141: the VQ indices of the hyper latent are coded by torchac against a
+    uniform CDF over the codebook.  torchac is a host library (out of scope, like the rANS coder);
+    this wrapper only restates the reference's calls into it."""
+
+    def __init__(self, codebook_size: int):
+        self.codebook_size = codebook_size
+
+    def _cdf(self, shape):
+        b, h, w = shape
+        k = self.codebook_size
+        cdf = torch.cumsum(torch.full((k,), 1.0 / k), dim=0)
+        cdf = torch.cat([torch.zeros(1), cdf]).view(1, 1, 1, -1).expand(b, h, w, -1).clone()
+        cdf[..., -1] = 1.0
+        return cdf
+
+    @staticmethod
+    def _torchac():
+        try:
+            import torchac
+        except ImportError as e:
+            raise RuntimeError("the hyper-latent byte coder needs torchac (utils/ckbd.py:4); install it or pass "
+                               "hyper_latent_coder= to Compression") from e
+        return torchac
+
+    def compress(self, encoding_indices: torch.Tensor):
+        ac = self._torchac()
+        return ac.encode_float_cdf(self._cdf(encoding_indices.shape), encoding_indices.to(torch.int16).to("cpu"),
+                                   check_input_bounds=True)
+
+    def decompress(self, string, shape) -> torch.Tensor:
+        h, w = shape
+        return self._torchac().decode_float_cdf(self._cdf((1, int(h), int(w))), string)
 
 
 class _Pinned:

@@ -3,7 +3,7 @@
 The drop-in consumes the reference's `configs/model/rdeic.yaml` unchanged
 (`RDEIC.from_config(path)`).  Benchmarks and tests that run where the reference tree is absent
 (the GPU box) use `default_params()`, which restates only the decode-relevant fields of that YAML
-(reference configs/model/rdeic.yaml:3-15,26,33-67,69-91).
+(reference configs/model/rdeic.yaml:3-15,26,33-67,69-91,102-111).
 """
 from __future__ import annotations
 
@@ -22,7 +22,10 @@ def default_params() -> Dict[str, Any]:
                 control_stage_config=dict(target="model.rdeic.NoiseEstimator", params=ctrl),
                 unet_config=dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=unet),
                 first_stage_config=dict(target="ldm.models.autoencoder.AutoencoderKL",
-                                        params=dict(embed_dim=4, ddconfig=dd)))
+                                        params=dict(embed_dim=4, ddconfig=dd)),
+                preprocess_config=dict(target="model.compression.Compression",
+                                       params=dict(in_nc=512, out_nc=4, N=256, M=256, slice_num=10,
+                                                   slice_ch=[8, 8, 8, 8, 16, 16, 32, 32, 64, 64], codebook_size=16384)))
 
 
 def small_params() -> Dict[str, Any]:
@@ -32,4 +35,5 @@ def small_params() -> Dict[str, Any]:
     p["control_stage_config"]["params"].update(model_channels=64, num_head_channels=16, control_model_ratio=0.5,
                                                hint_channels=32, context_dim=64)
     p["first_stage_config"]["params"]["ddconfig"]["ch"] = 32
+    p["preprocess_config"]["params"].update(in_nc=32, N=48, M=32, slice_num=3, slice_ch=[8, 8, 16], codebook_size=512)
     return p

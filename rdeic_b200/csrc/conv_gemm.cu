@@ -42,6 +42,7 @@ struct ConvDev {
     const void* resid; int resid_is_f32; int ld_resid;
     float alpha;
     int act;
+    float act_param;               // LeakyReLU negative slope (act == 3)
     __nv_bfloat16* out_bf16;
     float* out_f32;
     int ldo;
@@ -216,6 +217,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const int tap = kb / cbt, cb = kb - tap * cbt;
                     int dy = 0, dx = 0;
                     if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                    else if (p.taps == 25) { dy = tap / 5 - 2; dx = tap % 5 - 2; }
                     if (cb < p.cblk1)
                         tma_load_4d(&tm_a, smem_a + s * kATileBytes, &full_bar[s], cb * kBlockK,
                                     w0 + dx, h0 + dy, n0);
@@ -415,6 +417,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (p.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                    } else if (p.act == 3) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_param;
+                    } else if (p.act == 4) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     } else if (geglu) {
                         // columns [0,16) of the chunk are values, [16,32) their gates (weights are
                         // interleaved that way at load): attention.py:54-56  x * gelu(gate)
@@ -560,7 +568,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_total, int n_out,
                      int rows_per_sample, const float* __restrict__ bias,
-                     const float* __restrict__ row_bias, int row_bias_ld, int act, EpiOut eo) {
+                     const float* __restrict__ row_bias, int row_bias_ld, int act, float act_param, EpiOut eo) {
     pdl_trigger();
     pdl_wait();
     const int n4 = (n_out + 3) >> 2;
@@ -584,6 +592,8 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_to
             if (bias) v[j] += bias[n + j];
             if (row_bias) v[j] += row_bias[gn * row_bias_ld + n + j];
             if (act == 1) v[j] = silu_f(v[j]);
+            else if (act == 3) v[j] = v[j] > 0.f ? v[j] : v[j] * act_param;
+            else if (act == 4) v[j] = gelu_erf(v[j]);
         }
         epi_store4(eo, m, n, make_float4(v[0], v[1], v[2], v[3]));
     }
@@ -699,8 +709,8 @@ int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, in
                            int kw, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(w_oihw && dst, "rdeic_pack_conv_weight: null pointer");
     RDEIC_CHECK_ARG(n_out > 0 && c1 > 0 && c2 >= 0, "rdeic_pack_conv_weight: bad channel counts");
-    RDEIC_CHECK_ARG((kh == 1 && kw == 1) || (kh == 3 && kw == 3),
-                    "rdeic_pack_conv_weight: only 1x1 and 3x3 kernels are supported (got %dx%d)", kh, kw);
+    RDEIC_CHECK_ARG((kh == 1 && kw == 1) || (kh == 3 && kw == 3) || (kh == 5 && kw == 5),
+                    "rdeic_pack_conv_weight: only 1x1, 3x3 and 5x5 kernels are supported (got %dx%d)", kh, kw);
     const int taps = kh * kw;
     const int cp1 = (c1 + 63) / 64 * 64, cp2 = (c2 + 63) / 64 * 64;
     const int64_t total = (int64_t)n_out * taps * (cp1 + cp2);
@@ -719,9 +729,13 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
                     "rdeic_conv_gemm: channel counts (%d, %d) must be multiples of 8 (TMA 16-byte strides)",
                     p->a_c, p->a2_c);
     RDEIC_CHECK_ARG(p->a2_c == 0 || p->a2, "rdeic_conv_gemm: a2_c > 0 needs a2");
-    RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9, "rdeic_conv_gemm: taps must be 1 or 9");
+    RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9 || p->taps == 25, "rdeic_conv_gemm: taps must be 1, 9 or 25");
+    const int a_ld = p->a_ld ? p->a_ld : p->a_c, a2_ld = p->a2_ld ? p->a2_ld : p->a2_c;
+    RDEIC_CHECK_ARG(a_ld >= p->a_c && a2_ld >= p->a2_c && a_ld % 8 == 0 && a2_ld % 8 == 0,
+                    "rdeic_conv_gemm: a_ld/a2_ld (%d, %d) must be multiples of 8 and >= the channel counts", a_ld, a2_ld);
     RDEIC_CHECK_ARG(p->n_out > 0 && p->ldo > 0, "rdeic_conv_gemm: bad n_out/ldo");
-    RDEIC_CHECK_ARG(p->act >= 0 && p->act <= 2, "rdeic_conv_gemm: act must be 0 (none), 1 (SiLU) or 2 (GEGLU)");
+    RDEIC_CHECK_ARG(p->act >= 0 && p->act <= 4,
+                    "rdeic_conv_gemm: act must be 0 (none), 1 (SiLU), 2 (GEGLU), 3 (LeakyReLU) or 4 (GELU)");
     RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w) % 16 == 0,
                     "rdeic_conv_gemm: operands must be 16-byte aligned");
     RDEIC_CHECK_ARG(((uintptr_t)p->out_bf16 | (uintptr_t)p->out_f32 | (uintptr_t)p->resid |
@@ -752,7 +766,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.w_batched = p->w_batch_stride != 0;
     d.bias = p->bias; d.row_bias = p->row_bias; d.row_bias_ld = p->row_bias_ld;
     d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
-    d.alpha = p->alpha; d.act = p->act;
+    d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param;
     d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
     d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0;
     d.m_total = (int64_t)p->a_n * p->a_h * p->a_w;
@@ -768,15 +782,13 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     CUtensorMap ta, ta2, tb;
     {
         uint64_t dims[4] = {(uint64_t)p->a_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
-        uint64_t str[3] = {(uint64_t)p->a_c * 2, (uint64_t)p->a_c * 2 * p->a_w,
-                           (uint64_t)p->a_c * 2 * p->a_w * p->a_h};
+        uint64_t str[3] = {(uint64_t)a_ld * 2, (uint64_t)a_ld * 2 * p->a_w, (uint64_t)a_ld * 2 * p->a_w * p->a_h};
         uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw_eff, (uint32_t)th_eff, (uint32_t)tn};
         if (int e = encode_map(&ta, p->a, 4, dims, str, box, "A")) return e;
         ta2 = ta;
         if (p->a2_c) {
             uint64_t dims2[4] = {(uint64_t)p->a2_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
-            uint64_t str2[3] = {(uint64_t)p->a2_c * 2, (uint64_t)p->a2_c * 2 * p->a_w,
-                                (uint64_t)p->a2_c * 2 * p->a_w * p->a_h};
+            uint64_t str2[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * p->a_w, (uint64_t)a2_ld * 2 * p->a_w * p->a_h};
             if (int e = encode_map(&ta2, p->a2, 4, dims2, str2, box, "A2")) return e;
         }
         const uint64_t kp = (uint64_t)p->taps * (d.cblk1 + d.cblk2) * kBlockK;
@@ -828,7 +840,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         const int64_t work = d.m_total * ((p->n_out + 3) / 4);
         launch_k(splitk_reduce_kernel, grid_for(work, 256), 256, 0, s, 
             d.partial, splits, d.m_total, p->n_out, p->a_h * p->a_w, p->bias, p->row_bias, p->row_bias_ld,
-            p->act, eo);
+            p->act, p->act_param, eo);
         RDEIC_LAUNCH_CHECK();
     }
     return 0;

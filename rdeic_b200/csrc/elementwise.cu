@@ -213,6 +213,26 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
     }
 }
 
+// PixelShuffle(2) on NHWC bf16 whose 4C input channels are ordered (i, j, c) (the sub-pixel conv's
+// weight rows are permuted that way at load): out[b, 2h+i, 2w+j, c] = in[b, h, w, (2i+j)C + c]
+__global__ void __launch_bounds__(kThreads)
+pixel_shuffle2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                      int cv) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t total = (int64_t)B * (2 * H) * (2 * W) * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv);
+        int64_t p = i / cv;
+        const int ow = (int)(p % (2 * W)); p /= (2 * W);
+        const int oh = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        const int sub = ((oh & 1) << 1) | (ow & 1);
+        out[i] = in[((((int64_t)b * H + (oh >> 1)) * W + (ow >> 1)) * 4 + sub) * cv + c];
+    }
+}
+
 // stride-2 pad-1 3x3 im2col: out row m = (b, oh, ow), col = tap*Cp + c
 __global__ void __launch_bounds__(kThreads)
 im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
@@ -429,6 +449,17 @@ int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
     RDEIC_CHECK_ARG(C > 0 && C % 8 == 0, "rdeic_upsample2x_nhwc: C=%d must be a multiple of 8", C);
     const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
     launch_k(upsample2x_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream), 
+        (const uint4*)in, (uint4*)out, B, H, W, C / 8);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_pixel_shuffle2_nhwc(const void* in, void* out, int B, int H, int W, int C,
+                              rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0, "rdeic_pixel_shuffle2_nhwc: bad args");
+    RDEIC_CHECK_ARG(C > 0 && C % 8 == 0, "rdeic_pixel_shuffle2_nhwc: C=%d must be a multiple of 8", C);
+    const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
+    launch_k(pixel_shuffle2_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream),
         (const uint4*)in, (uint4*)out, B, H, W, C / 8);
     RDEIC_LAUNCH_CHECK();
     return 0;

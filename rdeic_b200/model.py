@@ -50,10 +50,13 @@ class RDEIC:
     def __init__(self, control_stage_config: Mapping[str, Any], unet_config: Mapping[str, Any],
                  first_stage_config: Mapping[str, Any], used_timesteps: int = 300, timesteps: int = 1000,
                  linear_start: float = 1e-4, linear_end: float = 2e-2, scale_factor: float = 1.0,
-                 device: Union[str, torch.device] = "cuda", use_cuda_graph: bool = True, **ignored):
+                 device: Union[str, torch.device] = "cuda", use_cuda_graph: bool = True,
+                 preprocess_config: Optional[Mapping[str, Any]] = None, **ignored):
         self.control_stage_config = dict(control_stage_config)
         self.unet_config = dict(unet_config)
         self.first_stage_config = dict(first_stage_config)
+        self.preprocess_config = dict(preprocess_config) if preprocess_config else None
+        self.preprocess_model = None                     # rdeic.py:641 instantiate_from_config(preprocess_config)
         self.device = torch.device(device)
         self.scale_factor = float(scale_factor)
         self.use_cuda_graph = use_cuda_graph
@@ -116,7 +119,26 @@ class RDEIC:
                 raise KeyError(f"Missing key(s) in state_dict: {e}") from e
             raise
         self._graphs.clear()
+        # the learned compressor (decompress side of the relay decode: c_latent and guide_hint)
+        pp = self.preprocess_config and dict(self.preprocess_config.get("params", self.preprocess_config))
+        if pp and "in_nc" in pp and any(k.startswith("preprocess_model.") for k in sd):
+            from .compression import Compression
+
+            self.preprocess_model = Compression(device=self.device, **pp).load_state_dict(sd, strict=False)
         return self
+
+    @torch.no_grad()
+    def apply_condition_decompress(self, stream_path):
+        """rdeic.py:671-676: bitstream file -> (c_latent, guide_hint)."""
+        from pathlib import Path
+
+        from .utils import read_body
+
+        if self.preprocess_model is None:
+            raise RuntimeError("RDEIC: the checkpoint held no preprocess_model.* weights")
+        with Path(stream_path).open("rb") as f:
+            strings, shape = read_body(f)
+        return self.preprocess_model.decompress(strings, shape)
 
     def to(self, device):
         if torch.device(device).type != "cuda":

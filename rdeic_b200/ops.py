@@ -242,8 +242,12 @@ def nchw_to_nhwc_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, ldc
 
 
 def nhwc_to_nchw_f32(src: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
-    B, H, W, ldc = src.shape
-    Cc = Cc or ldc
+    """src may be a channel slice of a dense NHWC tensor (its pixel stride is the ldc passed down)."""
+    B, H, W, cs = src.shape
+    Cc = Cc or cs
+    ldc = src.stride(-2)
+    if not _is_nhwc_slice(src):
+        raise TypeError("nhwc_to_nchw_f32: expected a dense NHWC tensor or a channel slice of one")
     is_f32 = 1 if src.dtype == torch.float32 else 0
     if not is_f32 and src.dtype != BF16:
         raise TypeError("nhwc_to_nchw_f32: expected bf16 or fp32")
@@ -287,6 +291,16 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     B, H, W, Cc = x.shape
     out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=BF16, device=x.device)
     check(_lib.load().rdeic_upsample2x_nhwc(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "rdeic_upsample2x_nhwc")
+    return out
+
+
+def pixel_shuffle2(x: torch.Tensor) -> torch.Tensor:
+    """nn.PixelShuffle(2) on NHWC bf16 [B,H,W,4C] whose channels are ordered (i, j, c) -> [B,2H,2W,C]."""
+    B, H, W, C4 = x.shape
+    x = _need(x, BF16, "pixel_shuffle2")
+    out = torch.empty((B, 2 * H, 2 * W, C4 // 4), dtype=BF16, device=x.device)
+    check(_lib.load().rdeic_pixel_shuffle2_nhwc(_ptr(x), _ptr(out), B, H, W, C4 // 4, _stream()),
+          "rdeic_pixel_shuffle2_nhwc")
     return out
 
 
@@ -401,15 +415,17 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
               dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0,
-              split_k: bool = True):
+              split_k: bool = True, act_param: float = 0.0):
     """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out].
 
     Output selection: bf16 by default, fp32 with `out_f32`, both with `dual` (returns the pair
     (fp32, bf16): the fp32 master of a residual stream plus its bf16 tensor-core operand copy).
     `out` may pre-allocate the destination (a tensor, or an (fp32, bf16) pair for `dual`)."""
-    if a.dtype != BF16 or not a.is_contiguous():
-        raise TypeError("conv_gemm: A must be contiguous bf16 NHWC")
     N, H, W, Cc = a.shape
+    if a.dtype != BF16 or not _is_nhwc_slice(a):
+        raise TypeError("conv_gemm: A must be bf16 NHWC, dense or a channel slice of a dense NHWC tensor")
+    if a2 is not None and (a2.dtype != BF16 or not _is_nhwc_slice(a2) or a2.shape[:3] != a.shape[:3]):
+        raise TypeError("conv_gemm: a2 must be bf16 NHWC with the pixel grid of A")
     n_cols = n_out // 2 if act == 2 else n_out
     of = oh = None
     if dual:
@@ -424,6 +440,8 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     p = ConvParams()
     p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, H, W, Cc
     p.a2, p.a2_c = (_ptr(a2), a2.shape[-1]) if a2 is not None else (None, 0)
+    p.a_ld = a.stride(-2)
+    p.a2_ld = a2.stride(-2) if a2 is not None else 0
     p.taps = taps
     p.w = _ptr(w_packed)
     p.w_batch_stride = w_batch_stride
@@ -436,6 +454,7 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         p.resid, p.resid_is_f32, p.ld_resid = _ptr(resid), int(resid.dtype == torch.float32), resid.stride(-2)
     p.alpha = alpha
     p.act = act
+    p.act_param = act_param
     p.out_f32, p.out_bf16 = _ptr(of), _ptr(oh)
     ref = of if of is not None else oh
     if of is not None and oh is not None and of.stride(-2) != oh.stride(-2):
@@ -457,6 +476,13 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     if dual:
         return of, oh
     return ref
+
+
+def _is_nhwc_slice(t: torch.Tensor) -> bool:
+    """dense [N,H,W,C], or channels [c0, c0+C) of a dense [N,H,W,ld] tensor."""
+    N, H, W, _ = t.shape
+    ld = t.stride(-2)
+    return t.stride(-1) == 1 and ld >= t.shape[-1] and (H == 1 or t.stride(1) == W * ld) and (N == 1 or t.stride(0) == H * W * ld)
 
 
 def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw):

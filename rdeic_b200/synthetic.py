@@ -168,6 +168,101 @@ def state_dict_spec(params: Mapping) -> List[Spec]:
     return base + ctrl + z + _vae_decoder("first_stage_model", dd)
 
 
+# ---------------------------------------------------------------------------------------------
+# preprocess_model: the learned compressor (model/compression.py:10-50)
+# ---------------------------------------------------------------------------------------------
+def _cres(p: str, cin: int, cout: int) -> List[Spec]:
+    """model/layers/res_blk.py:65-96 ResidualBlock."""
+    s = _conv(p + ".conv1", cout, cin, 3) + _conv(p + ".conv2", cout, cout, 3)
+    if cin != cout:
+        s += _conv(p + ".adaptor", cout, cin, 1)
+    return s
+
+
+def _cres_up(p: str, cin: int, cout: int) -> List[Spec]:
+    """res_blk.py:39-63 ResidualBlockUpsample (sub-pixel 1x1 convs, model/layers/conv.py:7-10)."""
+    return _conv(p + ".subpel_conv.0", 4 * cout, cin, 1) + _conv(p + ".conv", cout, cout, 3) + \
+        _conv(p + ".upsample.0", 4 * cout, cin, 1)
+
+
+def _cres_down(p: str, cin: int, cout: int) -> List[Spec]:
+    """res_blk.py:6-37 ResidualBlockWithStride."""
+    return _conv(p + ".conv1", cout, cin, 3) + _conv(p + ".conv2", cout, cout, 3) + _conv(p + ".downsample", cout, cin, 1)
+
+
+def compression_state_dict_spec(pp: Mapping, prefix: str = "preprocess_model.") -> List[Spec]:
+    """Every tensor of `Compression(in_nc, out_nc, N, M, slice_num, slice_ch, codebook_size)` in the
+    order of the reference constructor (model/compression.py:11-50, compression_modules.py:7-104)."""
+    in_nc, out_nc, N, M = int(pp["in_nc"]), int(pp["out_nc"]), int(pp["N"]), int(pp["M"])
+    sc = [int(c) for c in pp["slice_ch"]]
+    P = prefix
+    s: List[Spec] = []
+    ga = P + "encoder.g_a."
+    s += _cres(ga + "0", in_nc, M)
+    for i in (1, 2, 3):
+        s += _cres(ga + str(i), M, M)
+    s += _cres_down(ga + "4", M, M)
+    for i in (5, 6, 7):
+        s += _cres(ga + str(i), M, M)
+    s += _conv(ga + "8", M, M, 3)
+    he = P + "hyper_enc.hyper_enc."
+    s += _cres(he + "0", M, N) + _cres(he + "1", N, N) + _cres_down(he + "2", N, N) + _cres_down(he + "3", N, N)
+    hd = P + "hyper_dec.hyper_dec."
+    s += _cres_up(hd + "0", N, M) + _cres_up(hd + "1", M, M) + _cres(hd + "2", M, M * 3 // 2) + _cres(hd + "3", M * 3 // 2, 2 * M)
+    gs = P + "decoder.g_s."
+    s += _conv(gs + "0", M, M, 3)
+    for i in (1, 2, 3):
+        s += _cres(gs + str(i), M, M)
+    s += _cres_up(gs + "4", M, M)
+    for i in (5, 6, 7, 8):
+        s += _cres(gs + str(i), M, M)
+    s += _conv(P + "out", out_nc, M, 3)
+    for i, c in enumerate(sc):
+        s += _conv(f"{P}local_context.{i}", 2 * c, c, 5)
+    for i, c in enumerate(sc):
+        if i:
+            q = f"{P}channel_context.{i}.fushion."
+            s += _conv(q + "0", 224, sum(sc[:i]), 5) + _conv(q + "2", 128, 224, 5) + _conv(q + "4", 2 * c, 128, 5)
+
+    def ep(q: str, cin: int, cout: int) -> List[Spec]:
+        return _conv(q + "0", cout * 5 // 3, cin, 1) + _conv(q + "2", cout * 4 // 3, cout * 5 // 3, 1) + \
+            _conv(q + "4", cout, cout * 4 // 3, 1)
+
+    for i, c in enumerate(sc):
+        s += ep(f"{P}entropy_parameters_anchor.{i}.fusion.", 2 * M + (2 * c if i else 0), 2 * c)
+    for i, c in enumerate(sc):
+        s += ep(f"{P}entropy_parameters_nonanchor.{i}.fusion.", 2 * M + (4 * c if i else 2 * c), 2 * c)
+    K = int(pp["codebook_size"])
+    s.append((P + "quantize.embedding.weight", (K, N), "code"))
+    s.append((P + "quantize.embed_prob", (K,), "prob"))
+    return s
+
+
+def make_compression_state_dict(pp: Mapping, seed: int = 232, device="cpu", prefix: str = "preprocess_model.") -> Dict[str, torch.Tensor]:
+    """Seeded compressor checkpoint.  Weights are variance-preserving (uniform +-sqrt(3/fan_in)) and
+    the VQ codebook is N(0,1) so that, unlike PyTorch's shrinking default init, the entropy
+    parameters spread over the scale table and the symbols are not all zero."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape, kind in compression_state_dict_spec(pp, prefix):
+        if kind == "w":
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) * math.sqrt(3.0 / fan_in)
+        elif kind == "b":
+            t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) * 0.1
+        elif kind == "code":
+            t = torch.randn(shape, generator=g, device=dev)
+        elif kind == "prob":
+            t = torch.zeros(shape, device=dev)
+        else:
+            raise ValueError(kind)
+        sd[key] = t.float()
+    return sd
+
+
 def make_state_dict(params: Mapping, seed: int = 231, device="cpu", control_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Seeded random checkpoint (fp32) with the reference layout."""
     dev = torch.device(device)

@@ -12,6 +12,8 @@ Files written
   full_vae_decode.npz      reference decode_first_stage, full width, 16x16 latent
   full_sampler.npz         reference SpacedSampler.sample (2 steps) and DDIMSampler.sample (2 steps)
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
+  {small,full}_compression.npz       reference model/compression.py Compression.compress -> .decompress
+  {small,full}_compression_keys.json its state_dict keys + shapes
   entropy_ref.npz          reference utils/ckbd.py checkerboard ops, utils/func.py scale table and
                            model/compression_modules.py VectorQuantiser.quant / get_codebook_entry
 """
@@ -167,11 +169,93 @@ def run_entropy():
     print("entropy goldens", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def compression_inputs(pp, B, h, w):
+    """Feature map fed to `Compression.compress` (the VAE encoder's 512-channel output at H/8)."""
+    g = torch.Generator().manual_seed(53)
+    return torch.randn(B, int(pp["in_nc"]), h, w, generator=g)
+
+
+def run_compression(tag, params, B, h, w):
+    """§8(f) rank 1/3: run the reference `Compression.compress` -> `.decompress` (model/compression.py:
+    151-273) with its own conv stacks and orchestration.  Absent third-party pieces are replaced as
+    SURVEY.md §8c prescribes: compressai's GaussianConditional arithmetic by the oracle restatement,
+    the rANS coder by the loopback hand-off, torchac by an identity hand-off of the VQ indices."""
+    import importlib
+
+    rh.import_reference()
+    comp = importlib.import_module("model.compression")
+    from oracle import compression as oc, entropy as oe
+
+    pp = params["preprocess_config"]["params"]
+    m = comp.Compression(**pp).eval()
+    sd = synthetic.make_compression_state_dict(pp, seed=232)
+    res = m.load_state_dict({k[len("preprocess_model."):]: v for k, v in sd.items()}, strict=True)
+    keys = {k: list(v.shape) for k, v in m.state_dict().items()}
+    (HERE / f"{tag}_compression_keys.json").write_text(json.dumps(keys, indent=0, sort_keys=True))
+
+    table = oe.get_scale_table()
+
+    class GC:            # compressai 1.2.4 entry points used by utils/ckbd.py:81-82,92-93,102,111
+        quantized_cdf = torch.zeros(1, 1)
+        cdf_length = torch.zeros(1)
+        offset = torch.zeros(1)
+
+        def build_indexes(self, scales):
+            return torch.from_numpy(oe.build_indexes(scales.numpy(), table))
+
+        def quantize(self, x, mode, means=None):
+            assert mode == "symbols"
+            return torch.from_numpy(oe.quantize_symbols(x.numpy(), None if means is None else means.numpy()))
+
+    del m.gaussian_conditional          # the shim registered it as a child module
+    m.__dict__["gaussian_conditional"] = GC()
+    coder = oc.LoopbackCoder()
+
+    class Enc:
+        def encode_with_indexes(self, symbols, indexes, *a):
+            coder.encode_with_indexes(symbols, indexes)
+
+        def flush(self):
+            return b"loopback"
+
+    class Dec:
+        def set_stream(self, s):
+            coder.pos = 0
+
+        def decode_stream(self, indexes, *a):
+            return coder.decode_stream(indexes)
+
+    comp.BufferedRansEncoder, comp.RansDecoder = Enc, Dec
+    held = {}
+    comp.compress_hyper_latent = lambda idx, K: held.setdefault("z_idx", idx.clone())
+    comp.decompress_hyper_latent = lambda s, shape, codebook_size: s
+
+    x = compression_inputs(pp, B, h, w)
+    with torch.no_grad():
+        y = m.encoder(x)
+        z = m.hyper_enc(y)
+        out = m.compress(x)
+        c_latent, guide_hint = m.decompress(out["strings"], out["shape"])
+        hyper = m.hyper_dec(m.quantize.get_codebook_entry(held["z_idx"].long()))
+    sym, idx = np.asarray(coder.symbols, dtype=np.int32), np.asarray(coder.indexes, dtype=np.int32)
+    print(tag, "compression: y", tuple(y.shape), "std %.2f" % float(y.std()), "symbols nonzero %.2f" % float((sym != 0).mean()),
+          "max|sym|", int(np.abs(sym).max()), "index range", int(idx.min()), int(idx.max()),
+          "distinct indexes", len(np.unique(idx)))
+    np.savez_compressed(HERE / f"{tag}_compression.npz", x=x.numpy(), y=y.numpy(), z=z.numpy(),
+                        z_idx=held["z_idx"].numpy().astype(np.int64), hyper_params=hyper.numpy(), symbols=sym,
+                        indexes=idx, c_latent=c_latent.numpy(), guide_hint=guide_hint.numpy())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["entropy", "small", "full"]
+    which = sys.argv[1:] or ["entropy", "compression", "small", "full"]
     if "entropy" in which:
         run_entropy()
+    if "compression" in which:
+        from rdeic_b200 import configs
+
+        run_compression("small", configs.small_params(), 2, 16, 24)
+        run_compression("full", configs.default_params(), 1, 16, 16)
     if "small" in which:
         run_config("small", rh.SMALL_OVERRIDES, (16, 16), (8, 8), (8, 16))
     if "full" in which:

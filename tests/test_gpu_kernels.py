@@ -503,3 +503,89 @@ def test_attention_fused_qkv_slices(cuda):
     t = qkv.to(cuda).bfloat16()
     out = ops.attention(t[..., :C], t[..., C:2 * C], t[..., 2 * C:], heads, d, d ** -0.5).float().cpu()
     assert (out - ref).abs().max() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# compressor layers: 5x5 taps, LeakyReLU / GELU epilogues, channel-slice operands,
+# sub-pixel shuffle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 8, 16), (2, 8, 12, 224, 128), (1, 16, 16, 128, 64),
+                                            (1, 5, 7, 16, 224), (1, 64, 96, 8, 224)])
+def test_conv5x5_tc(cuda, B, H, W, Cin, Cout):
+    """25-tap implicit GEMM == F.conv2d(kernel 5, padding 2) (model/compression.py:23, compression_modules.py:80-84)."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(61)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    w = _bf(torch.randn(Cout, Cin, 5, 5, generator=g) / math.sqrt(25 * Cin))
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=2).permute(0, 2, 3, 1)
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    out = ops.conv_gemm(a, ops.pack_conv_weight(w.to(cuda)), Cout, 25, bias=b.to(cuda), out_f32=True).cpu()
+    assert _rel(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("act,slope", [(3, 0.01), (3, 0.1), (4, 0.0)])
+def test_conv_leaky_relu_gelu_epilogues(cuda, act, slope):
+    """act(conv + bias) + residual, the order of res_blk.py:30-36,57-62,88-95; also through split-K."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(62)
+    for (B, H, W, Cin, Cout, k) in [(1, 16, 16, 256, 384, 3), (2, 8, 8, 528, 26, 1), (1, 4, 4, 512, 512, 3)]:
+        x = _bf(torch.randn(B, Cin, H, W, generator=g))
+        w = _bf(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin))
+        b = torch.randn(Cout, generator=g)
+        resid = _bf(torch.randn(B, H, W, Cout, generator=g))
+        pre = F.conv2d(x, w, b, padding=k // 2)
+        ref = (F.leaky_relu(pre, slope) if act == 3 else F.gelu(pre)).permute(0, 2, 3, 1) + resid
+        a = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+        n_pad = (Cout + 7) // 8 * 8
+        wpad = torch.cat([w, torch.zeros(n_pad - Cout, Cin, k, k)], 0)
+        bpad = torch.cat([b, torch.zeros(n_pad - Cout)], 0)
+        rpad = torch.cat([resid, torch.zeros(B, H, W, n_pad - Cout)], -1)
+        out = ops.conv_gemm(a, ops.pack_conv_weight(wpad.to(cuda)), n_pad, k * k, bias=bpad.to(cuda), act=act,
+                            act_param=slope, resid=rpad.to(cuda).bfloat16(), out_f32=True).cpu()
+        assert _rel(out[..., :Cout], ref) < 1e-3, (Cin, Cout, k)
+        assert torch.count_nonzero(out[..., Cout:]) == 0           # padded channels stay exactly 0
+
+
+def test_conv_channel_slice_operands(cuda):
+    """A, a2 and the output as channel windows of wider NHWC buffers (a_ld / a2_ld / ldo): the
+    torch.cat inputs of compression.py:170-190 without materialising them."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(63)
+    B, H, W = 2, 8, 12
+    wide = _bf(torch.randn(B, H, W, 96, generator=g))               # use channels [16, 48)
+    hyper = _bf(torch.randn(B, H, W, 64, generator=g))
+    c1, c2, n = 32, 64, 16
+    w = _bf(torch.randn(n, c1 + c2, 1, 1, generator=g) / math.sqrt(c1 + c2))
+    b = torch.randn(n, generator=g)
+    x = torch.cat([wide[..., 16:48], hyper], -1).permute(0, 3, 1, 2)
+    ref = F.conv2d(x, w, b).permute(0, 2, 3, 1)
+    wd, hd = wide.to(cuda).bfloat16(), hyper.to(cuda).bfloat16()
+    dst = torch.full((B, H, W, 40), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.conv_gemm(wd[..., 16:48], ops.pack_conv_weight(w.to(cuda), c1=c1), n, 1, a2=hd, bias=b.to(cuda), out=dst[..., 8:24])
+    got = dst.float().cpu()
+    assert _rel(got[..., 8:24], ref) < 6e-3                         # bf16 output rounding
+    assert torch.all(got[..., :8] == 7.0) and torch.all(got[..., 24:] == 7.0)
+    # 5x5 over a channel prefix (channel_context reads y_hat[..., :sum(slice_ch[:i])] in place)
+    w5 = _bf(torch.randn(24, 40, 5, 5, generator=g) / math.sqrt(25 * 40))
+    ref5 = F.conv2d(wide[..., :40].permute(0, 3, 1, 2), w5, None, padding=2).permute(0, 2, 3, 1)
+    out5 = ops.conv_gemm(wd[..., :40], ops.pack_conv_weight(w5.to(cuda)), 24, 25, out_f32=True).cpu()
+    assert _rel(out5, ref5) < 1e-3
+    with pytest.raises(TypeError):
+        ops.conv_gemm(wd[:, ::2], ops.pack_conv_weight(w5.to(cuda)), 24, 25)        # rows skipped: not one pixel stride
+
+
+def test_pixel_shuffle2_bit_exact(cuda):
+    """sub-pixel conv tail (model/layers/conv.py:7-10): (i, j, c)-ordered channels -> nn.PixelShuffle(2)."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(64)
+    B, H, W, C = 2, 3, 5, 24
+    x = _bf(torch.randn(B, 4 * C, H, W, generator=g))                # torch order: c*4 + 2i + j
+    ref = F.pixel_shuffle(x, 2).permute(0, 2, 3, 1)
+    xp = x.view(B, C, 4, H, W).transpose(1, 2).reshape(B, 4 * C, H, W)      # (2i + j)*C + c
+    out = ops.pixel_shuffle2(xp.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()).float().cpu()
+    assert torch.equal(out, ref)
