@@ -155,14 +155,17 @@ class _Pinned:
     def __init__(self):
         self.buf = {}
 
-    def to_host(self, t: torch.Tensor, slot: str) -> np.ndarray:
-        n = t.numel()
+    def get(self, n: int, slot: str) -> torch.Tensor:
         b = self.buf.get(slot)
         if b is None or b.numel() < n:
             b = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
             self.buf[slot] = b
-        b[:n].copy_(t.reshape(-1), non_blocking=True)
         return b[:n]
+
+    def to_host(self, t: torch.Tensor, slot: str) -> torch.Tensor:
+        b = self.get(t.numel(), slot)
+        b.copy_(t.reshape(-1), non_blocking=True)
+        return b
 
     def sync(self):
         torch.cuda.current_stream().synchronize()
@@ -171,7 +174,37 @@ class _Pinned:
 _pinned = _Pinned()
 
 
+class SymbolStream:
+    """GPU-resident stand-in for the `symbols_list` / `indexes_list` Python lists of
+    model/compression.py:167-168.  The encode-phase kernels write their int32
+    output straight into consecutive windows of one device buffer in stream order; nothing crosses
+    PCIe and nothing synchronises until `host()` — ONE pinned copy for the whole image batch instead
+    of 20 `.reshape(-1).tolist()` round trips (utils/ckbd.py:83-84,94-95)."""
+
+    def __init__(self, capacity: int, device):
+        self.buf = torch.empty(capacity, dtype=torch.int32, device=device)
+        self.n = 0
+
+    def window(self, n: int) -> torch.Tensor:
+        if self.n + n > self.buf.numel():
+            raise RuntimeError("SymbolStream: capacity exceeded")
+        w = self.buf[self.n:self.n + n]
+        self.n += n
+        return w
+
+    def host(self, slot: str) -> np.ndarray:
+        """int32 numpy view of a pinned buffer (valid until the next `host()` of the same slot)."""
+        h = _pinned.to_host(self.buf[:self.n], slot)
+        _pinned.sync()
+        return h.numpy()
+
+
 def _phase(gc: GaussianConditional, y, scales, means, symbols_list, indexes_list, which: int):
+    if isinstance(symbols_list, SymbolStream):
+        n = y.numel() // 2
+        _, _, y_hat = ops.ckbd_encode_phase(y, scales, means, gc.scale_table, gc.scale_bound, which,
+                                            sym_out=symbols_list.window(n), idx_out=indexes_list.window(n))
+        return y_hat
     sym, idx, y_hat = ops.ckbd_encode_phase(y, scales, means, gc.scale_table, gc.scale_bound, which)
     hs, hi = _pinned.to_host(sym, "sym"), _pinned.to_host(idx, "idx")
     _pinned.sync()
@@ -192,12 +225,18 @@ def compress_nonanchor(gaussian_conditional, nonanchor, scales_nonanchor, means_
 
 
 def _dephase(gc: GaussianConditional, scales, means, decoder, cdf, cdf_lengths, offsets, which: int):
+    """One host hand-off per phase is inherent (the coder needs this phase's indexes to produce the
+    symbols the next GPU phase depends on); it goes through pinned int32 buffers both ways.  A coder
+    that sets `accepts_arrays = True` receives / returns int32 numpy arrays (views of those pinned
+    buffers); compressai's pybind coder gets the Python list it expects."""
     means_sq, idx = ops.ckbd_squeeze_indexes(scales, means, gc.scale_table, gc.scale_bound, which)
     hi = _pinned.to_host(idx, "idx")
     _pinned.sync()
-    symbols = decoder.decode_stream(hi.tolist(), cdf, cdf_lengths, offsets)
-    sym = torch.as_tensor(np.asarray(symbols, dtype=np.int32)).reshape(means_sq.shape).to(means_sq.device,
-                                                                                        non_blocking=True)
+    arrays = getattr(decoder, "accepts_arrays", False)
+    symbols = decoder.decode_stream(hi.numpy() if arrays else hi.tolist(), cdf, cdf_lengths, offsets)
+    hs = _pinned.get(idx.numel(), "sym_in")
+    hs.numpy()[:] = np.asarray(symbols, dtype=np.int32)
+    sym = hs.to(means_sq.device, non_blocking=True).view(means_sq.shape)
     return ops.ckbd_decode_phase(sym, means_sq, which)
 
 

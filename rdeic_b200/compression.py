@@ -46,10 +46,11 @@ class SliceCoder:
         return scales.contiguous(), means.contiguous(), ctx
 
     @torch.no_grad()
-    def compress(self, y: torch.Tensor, hyper_params: torch.Tensor):
-        """compression.py:161-206 -> (symbols, indexes, y_hat)."""
-        symbols: List[int] = []
-        indexes: List[int] = []
+    def compress(self, y: torch.Tensor, hyper_params: torch.Tensor, symbols=None, indexes=None):
+        """compression.py:161-206 -> (symbols, indexes, y_hat).  `symbols` / `indexes` default to the
+        reference's Python lists; pass two `ckbd.SymbolStream`s to keep them on the GPU."""
+        symbols = [] if symbols is None else symbols
+        indexes = [] if indexes is None else indexes
         y_hat_slices: List[torch.Tensor] = []
         off = 0
         for idx, c in enumerate(self.slice_ch):
@@ -206,8 +207,13 @@ class Compression:
         z_q, encoding_indices = self.quantize.quant(z)
         z_strings = hyp.compress(encoding_indices)
         coder = _FusedSliceCoder(self, self._hyper_params(z_q))
-        symbols, indexes, _ = coder.compress(y, None)
+        n_sym = y.numel()                                    # one symbol per latent element
+        symbols, indexes = ckbd.SymbolStream(n_sym, self.device), ckbd.SymbolStream(n_sym, self.device)
+        coder.compress(y, None, symbols, indexes)            # no host synchronisation inside
+        symbols, indexes = symbols.host("sym_all"), indexes.host("idx_all")
         encoder = enc_cls()
+        if not getattr(encoder, "accepts_arrays", False):    # compressai's pybind coder takes lists
+            symbols, indexes = symbols.tolist(), indexes.tolist()
         encoder.encode_with_indexes(symbols, indexes, *self._cdfs())
         return {"strings": [[encoder.flush()], [z_strings]], "shape": z.shape[-2:]}
 

@@ -140,14 +140,19 @@ def ckbd_squeeze_indexes(scales, means, table, lower_bound: float, which: int):
     return means_sq, idx
 
 
-def ckbd_encode_phase(y, scales, means, table, lower_bound: float, which: int):
+def ckbd_encode_phase(y, scales, means, table, lower_bound: float, which: int, sym_out=None, idx_out=None):
+    """`sym_out` / `idx_out`: optional flat int32 windows of a stream-order staging buffer."""
     y = _need(y, torch.float32, "ckbd_encode_phase")
     scales = _need(scales, torch.float32, "ckbd_encode_phase")
     means = _need(means, torch.float32, "ckbd_encode_phase")
     table = _need(table, torch.float32, "ckbd_encode_phase")
     B, Cc, H, W = y.shape
-    sym = torch.empty((B, Cc, H, W // 2), dtype=torch.int32, device=y.device)
-    idx = torch.empty_like(sym)
+    n = B * Cc * H * (W // 2)
+    for t in (sym_out, idx_out):
+        if t is not None and (t.dtype != torch.int32 or t.numel() != n or not t.is_contiguous()):
+            raise ValueError("ckbd_encode_phase: staging windows must be contiguous int32 of B*C*H*W/2 elements")
+    sym = sym_out.view(B, Cc, H, W // 2) if sym_out is not None else torch.empty((B, Cc, H, W // 2), dtype=torch.int32, device=y.device)
+    idx = idx_out.view(B, Cc, H, W // 2) if idx_out is not None else torch.empty_like(sym)
     y_hat = torch.empty_like(y)
     check(_lib.load().rdeic_ckbd_encode_phase(_ptr(y), _ptr(scales), _ptr(means), _ptr(table), table.numel(),
                                               lower_bound, _ptr(sym), _ptr(idx), _ptr(y_hat), B, Cc, H, W, which,

@@ -14,6 +14,7 @@ Files written
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
   {small,full}_compression.npz       reference model/compression.py Compression.compress -> .decompress
   {small,full}_compression_keys.json its state_dict keys + shapes
+  bitstream_ref.bin        bytes written by the reference utils/utils.py write_body (shape (8,12), 2 strings)
   entropy_ref.npz          reference utils/ckbd.py checkerboard ops, utils/func.py scale table and
                            model/compression_modules.py VectorQuantiser.quant / get_codebook_entry
 """
@@ -246,11 +247,34 @@ def run_compression(tag, params, B, h, w):
                         indexes=idx, c_latent=c_latent.numpy(), guide_hint=guide_hint.numpy())
 
 
+def run_bitstream():
+    """§8(f) rank 2: bytes written by the reference's own utils/utils.py write_body."""
+    import importlib
+    import io
+
+    rh.import_reference()
+    u = importlib.import_module("utils.utils")
+    g = torch.Generator().manual_seed(5)
+    y_string = bytes(torch.randint(0, 256, (1500,), generator=g).tolist())
+    z_string = bytes(torch.randint(0, 256, (41,), generator=g).tolist())
+    f = io.BytesIO()
+    n = u.write_body(f, (8, 12), [[y_string], [z_string]])
+    data = f.getvalue()
+    assert n == len(data)
+    f.seek(0)
+    strings, shape = u.read_body(f)
+    assert strings == [[y_string], [z_string]] and tuple(shape) == (8, 12)
+    (HERE / "bitstream_ref.bin").write_bytes(data)
+    print("bitstream golden", len(data), "bytes")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["entropy", "compression", "small", "full"]
+    which = sys.argv[1:] or ["entropy", "bitstream", "compression", "small", "full"]
     if "entropy" in which:
         run_entropy()
+    if "bitstream" in which:
+        run_bitstream()
     if "compression" in which:
         from rdeic_b200 import configs
 

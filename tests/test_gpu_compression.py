@@ -98,8 +98,9 @@ def test_decompress_reference_stream(cuda, tag):
     assert tuple(c.shape) == g["c_latent"].shape and tuple(gh.shape) == g["guide_hint"].shape
 
 
-@pytest.mark.parametrize("tag,B,h,w", [("small", 2, 16, 24), ("small", 1, 8, 8), ("full", 1, 16, 16), ("full", 2, 32, 48)])
-def test_compress_decompress_roundtrip_is_bit_exact(cuda, tag, B, h, w):
+@pytest.mark.parametrize("tag,B,h,w,arrays", [("small", 2, 16, 24, False), ("small", 1, 8, 8, True), ("full", 1, 16, 16, True),
+                                              ("full", 2, 32, 48, False)])
+def test_compress_decompress_roundtrip_is_bit_exact(cuda, tag, B, h, w, arrays):
     """Determinism contract: the decoder rebuilds exactly the CDF indexes the encoder used (the
     loopback coder raises otherwise), y_hat is bit-identical on both sides, and a second run
     reproduces the first bit for bit."""
@@ -109,18 +110,25 @@ def test_compress_decompress_roundtrip_is_bit_exact(cuda, tag, B, h, w):
     loop = ocomp.LoopbackCoder()
 
     class Enc:
+        accepts_arrays = arrays          # True: int32 numpy views of the pinned staging buffers; False: Python lists
+
         def encode_with_indexes(self, symbols, indexes, *a):
+            assert isinstance(symbols, np.ndarray if arrays else list)
             loop.encode_with_indexes(symbols, indexes)
 
         def flush(self):
             return b"loopback"
 
     class Dec:
+        accepts_arrays = arrays
+
         def set_stream(self, s):
             loop.pos = 0
 
         def decode_stream(self, indexes, *a):
-            return loop.decode_stream(indexes)
+            assert isinstance(indexes, np.ndarray if arrays else list)
+            out = loop.decode_stream(indexes)
+            return np.asarray(out, dtype=np.int32) if arrays else out
 
     m = Compression(device=cuda, rans_encoder=Enc, rans_decoder=Dec, hyper_latent_coder=IdentityHyperCoder(),
                     **pp).load_state_dict(sd)

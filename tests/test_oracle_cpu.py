@@ -227,3 +227,67 @@ def test_entropy_oracle_matches_reference_golden():
     assert np.array_equal(idx, gold["vq_idx"]) and idx.reshape(-1)[0] == 7
     assert np.array_equal(b(zq), b(gold["vq_zq"]))
     assert np.array_equal(b(oe.vq_lookup(idx, cb.numpy())), b(gold["vq_entry"]))
+
+
+# ---- §8(f): learned compressor and bitstream container ----------------------------------------------
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_compression_spec_matches_reference_keys(tag):
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    pp = params["preprocess_config"]["params"]
+    ref = json.loads((GOLD / f"{tag}_compression_keys.json").read_text())
+    spec = {k[len("preprocess_model."):]: list(s) for k, s, _ in synthetic.compression_state_dict_spec(pp)}
+    assert spec == ref
+    if tag == "full":
+        assert len(spec) == 316
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_compression_oracle_matches_reference_golden(tag):
+    """oracle/compression_nets.py vs the reference's own Compression.compress -> .decompress
+    (tests/golden/*_compression.npz): integer outputs identical, float outputs to fp32 round-off."""
+    from oracle import compression_nets as ocn
+
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    pp = params["preprocess_config"]["params"]
+    sd = synthetic.make_compression_state_dict(pp, seed=232)
+    g = np.load(GOLD / f"{tag}_compression.npz")
+    r = ocn.compress(sd, torch.from_numpy(g["x"]), pp["slice_ch"])
+    close = lambda a, b: float(np.abs(np.asarray(a) - b).max()) <= 2e-4 * float(np.abs(b).max())
+    assert close(r["y"], g["y"]) and close(r["hyper_params"], g["hyper_params"])
+    assert np.array_equal(r["z_idx"].numpy(), g["z_idx"])
+    # a symbol / index may flip only where fp32 summation order moved a value across a rounding boundary
+    assert float((np.asarray(r["symbols"]) == g["symbols"]).mean()) > 0.999
+    assert float((np.asarray(r["indexes"]) == g["indexes"]).mean()) > 0.999
+    c, gh, y_hat, _ = ocn.decompress(sd, g["z_idx"], g["symbols"].tolist(), g["indexes"].tolist(), pp["slice_ch"])
+    assert close(c, g["c_latent"]) and close(gh, g["guide_hint"])
+    assert float((y_hat - torch.from_numpy(g["y"])).abs().max()) <= 0.5 + 1e-3
+    assert len(np.unique(g["indexes"])) > 20 and int(np.abs(g["symbols"]).max()) > 8     # non-degenerate data
+
+
+def test_bitstream_container_matches_reference_bytes(tmp_path):
+    """rdeic_b200.utils read_body / write_body vs bytes written by the reference's utils/utils.py."""
+    import io
+    import struct
+
+    from rdeic_b200 import utils
+
+    data = (GOLD / "bitstream_ref.bin").read_bytes()
+    strings, shape = utils.read_body(io.BytesIO(data))
+    assert tuple(shape) == (8, 12) and [len(s[0]) for s in strings] == [1500, 41]
+    f = io.BytesIO()
+    assert utils.write_body(f, shape, strings) == len(data)
+    assert f.getvalue() == data
+    # edge cases: empty string list, zero-length string, truncated stream
+    f = io.BytesIO()
+    utils.write_body(f, (1, 2), [])
+    assert f.getvalue() == struct.pack(">3I", 1, 2, 0) and utils.read_body(io.BytesIO(f.getvalue())) == ([], (1, 2))
+    f = io.BytesIO()
+    utils.write_body(f, (3, 3), [[b""], [b"x"]])
+    assert utils.read_body(io.BytesIO(f.getvalue())) == ([[b""], [b"x"]], (3, 3))
+    with pytest.raises(struct.error):
+        utils.read_body(io.BytesIO(data[:100]))
+    p = tmp_path / "a.bin"
+    p.write_bytes(data)
+    assert utils.filesize(str(p)) == len(data)
+    with pytest.raises(ValueError):
+        utils.filesize(str(tmp_path / "missing.bin"))
