@@ -44,3 +44,38 @@ def relay_decode(model, cond: Dict, steps: int, sampler: str = "ddpm", guidance_
     if as_uint8:
         return model.decode_first_stage_u8(samples)
     return model.decode_first_stage(samples)
+
+
+@torch.no_grad()
+def decode_streams(model, stream_paths: Sequence[str], c_crossattn: List[torch.Tensor], steps: int,
+                   sizes: Optional[Sequence] = None, batch_size: int = 8, sampler: str = "ddpm",
+                   guidance_scale: float = 1.0) -> List[torch.Tensor]:
+    """The receiver side of inference.py:57-87 / inference_partition.py:438-520 for a folder of
+    bitstreams: decompress every stream (learned compressor on the GPU, byte coders on the host),
+    bucket the conditionings by latent size, relay-decode each bucket in batches and crop the
+    padding (inference.py:156) when the original (h, w) `sizes` are given.
+    `c_crossattn[0]` is the [1,77,1024] embedding of the empty prompt (inference.py:134), repeated per
+    batch.  Returns uint8 HWC tensors on the GPU, in input order."""
+    from .utils import group_by_padded_size
+
+    conds = [model.apply_condition_decompress(p) for p in stream_paths]
+    latent_sizes = [(c.shape[-2] * 8, c.shape[-1] * 8) for c, _ in conds]
+    out: List[Optional[torch.Tensor]] = [None] * len(conds)
+    ctx = c_crossattn[0]
+    for _, members in group_by_padded_size(latent_sizes, batch_size, scale=8):
+        c_latent = torch.cat([conds[i][0] for i in members], 0)
+        hint = torch.cat([conds[i][1] for i in members], 0)
+        n = c_latent.shape[0]
+        cond = {"c_latent": [c_latent], "c_crossattn": [ctx.expand(n, -1, -1).contiguous() if ctx.shape[0] == 1 else ctx[:n]],
+                "guide_hint": hint}
+        imgs = relay_decode(model, cond, steps, sampler=sampler, guidance_scale=guidance_scale)
+        k = 0
+        for i in members:
+            b = conds[i][0].shape[0]
+            img = imgs[k:k + b]
+            k += b
+            if sizes is not None:
+                h, w = sizes[i]
+                img = img[:, :h, :w]
+            out[i] = img[0] if b == 1 else img
+    return out

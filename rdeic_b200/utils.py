@@ -59,3 +59,27 @@ def filesize(filepath: str) -> int:
     if not Path(filepath).is_file():
         raise ValueError(f'Invalid file "{filepath}".')
     return Path(filepath).stat().st_size
+
+
+def pad(img, scale: int):
+    """utils/image/common.py:251-258: zero-pad an HWC numpy image at the bottom / right to multiples of `scale`."""
+    import math
+
+    import numpy as np
+
+    h, w = img.shape[:2]
+    ph = 0 if h % scale == 0 else math.ceil(h / scale) * scale - h
+    pw = 0 if w % scale == 0 else math.ceil(w / scale) * scale - w
+    return np.pad(img, pad_width=((0, ph), (0, pw), (0, 0)), mode="constant", constant_values=0)
+
+
+def group_by_padded_size(sizes, batch_size: int, scale: int = 64):
+    """inference_partition.py:438-452: bucket images by their padded (H, W) and cut each bucket into
+    batches, in the reference's order (buckets sorted by key, members in input order).
+    sizes: [(h, w), ...] -> [((pad_h, pad_w), [indices...]), ...]."""
+    groups = {}
+    for i, (h, w) in enumerate(sizes):
+        key = ((h + scale - 1) // scale * scale, (w + scale - 1) // scale * scale)
+        groups.setdefault(key, []).append(i)
+    bs = max(1, int(batch_size))
+    return [(key, groups[key][i:i + bs]) for key in sorted(groups) for i in range(0, len(groups[key]), bs)]

@@ -180,3 +180,46 @@ def test_rdeic_facade_decompress_from_file(cuda, tmp_path):
         write_body(f, g["z"].shape[-2:], [[b"yy"], [b"zz"]])
     c_latent, guide_hint = model.apply_condition_decompress(str(path))
     assert rel_l2(c_latent.cpu(), g["c_latent"]) < 2e-2 and rel_l2(guide_hint.cpu(), g["guide_hint"]) < 2e-2
+
+
+def test_decode_streams_groups_and_crops(cuda, tmp_path):
+    """§8(f) rank 4: bitstream files -> decompress -> size buckets -> relay decode -> cropped uint8 images."""
+    from rdeic_b200 import RDEIC, configs, synthetic
+    from rdeic_b200.pipeline import decode_streams
+    from rdeic_b200.utils import write_body
+
+    params = configs.small_params()
+    pp = params["preprocess_config"]["params"]
+    sd = synthetic.make_state_dict(params, seed=231)
+    sd.update(synthetic.make_compression_state_dict(pp, seed=232))
+    model = RDEIC.from_config({"params": params}, device=cuda).load_state_dict(sd)
+    pm = model.preprocess_model
+    n_lat = lambda hz, wz: pp["M"] * (hz * 4) * (wz * 4)          # symbols of one image whose z is hz x wz
+    zshapes = [(2, 3), (1, 1), (2, 3)]
+    g = torch.Generator().manual_seed(9)
+
+    class Dec:
+        accepts_arrays = True
+
+        def set_stream(self, s):
+            self.n = int.from_bytes(s, "big")
+
+        def decode_stream(self, indexes, *a):
+            return torch.randint(-3, 4, (len(indexes),), generator=g, dtype=torch.int32).numpy()
+
+    class Hyp:
+        def decompress(self, s, shape):
+            return torch.randint(0, pp["codebook_size"], (1, int(shape[0]), int(shape[1])), generator=g)
+
+    pm._rans_encoder, pm._rans_decoder, pm._hyper_coder = (lambda: None), Dec, Hyp()
+    paths = []
+    for i, (hz, wz) in enumerate(zshapes):
+        p = tmp_path / f"s{i}"
+        with p.open("wb") as f:
+            write_body(f, (hz, wz), [[n_lat(hz, wz).to_bytes(4, "big")], [b"z"]])
+        paths.append(str(p))
+    ctx = torch.randn(1, 77, params["unet_config"]["params"]["context_dim"], generator=g).to(cuda)
+    sizes = [(120, 190), (64, 64), (128, 192)]
+    imgs = decode_streams(model, paths, [ctx], steps=2, sizes=sizes, batch_size=4)
+    assert [tuple(i.shape) for i in imgs] == [(120, 190, 3), (64, 64, 3), (128, 192, 3)]
+    assert all(i.dtype == torch.uint8 and i.is_cuda for i in imgs)

@@ -101,3 +101,20 @@ def test_world2_gloo_broadcast_shard_gather_tiles():
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
         assert ret[r] == (True, True, True, True, True), (r, ret[r])
+
+
+def test_pad_and_size_grouping():
+    """Caller glue of SURVEY §8(f) rank 4: utils/image/common.py:251 pad, inference_partition.py:438-452 grouping."""
+    import numpy as np
+
+    from rdeic_b200.utils import group_by_padded_size, pad
+
+    img = np.arange(5 * 70 * 3, dtype=np.uint8).reshape(5, 70, 3)
+    p = pad(img, 64)
+    assert p.shape == (64, 128, 3) and np.array_equal(p[:5, :70], img) and p[5:].sum() == 0 and p[:, 70:].sum() == 0
+    assert pad(np.zeros((64, 128, 3), np.uint8), 64).shape == (64, 128, 3)
+    sizes = [(500, 700), (512, 768), (100, 100), (510, 705), (128, 128), (65, 1)]
+    groups = group_by_padded_size(sizes, batch_size=2)
+    assert groups == [((128, 64), [5]), ((128, 128), [2, 4]), ((512, 704), [0]), ((512, 768), [1, 3])]
+    assert group_by_padded_size([(512, 768)] * 3, batch_size=2) == [((512, 768), [0, 1]), ((512, 768), [2])]
+    assert group_by_padded_size([], 4) == []
