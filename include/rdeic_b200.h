@@ -135,9 +135,11 @@ int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
  * in [B,H,W,4C] with channels ordered (i, j, c) -> out [B,2H,2W,C]. */
 int rdeic_pixel_shuffle2_nhwc(const void* in, void* out, int B, int H, int W, int C,
                               rdeic_stream_t stream);
-/* im2col for the stride-2 pad-1 3x3 Downsample conv (openaimodel.py:150-152):
- * in NHWC [B,H,W,C] -> out [B*(H/2)*(W/2), 9*Cp] with Cp = C rounded up to 64. */
-int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C,
+/* im2col for the stride-2 3x3 convs: in NHWC [B,H,W,C] -> out [B*(H/2)*(W/2), 9*Cp] with
+ * Cp = C rounded up to 64.  pad_lo = 1: symmetric padding 1 (openaimodel.py:150-152 Downsample,
+ * model/layers/res_blk.py:17 conv3x3 stride 2); pad_lo = 0: the VAE encoder's bottom/right-only
+ * padding (ldm/modules/diffusionmodules/model.py:82-84 `pad = (0,1,0,1)`). */
+int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C, int pad_lo,
                         rdeic_stream_t stream);
 /* row softmax of fp32/bf16 logits with scale, bf16 output: [rows, n]. */
 int rdeic_softmax_rows(const void* in, int in_is_f32, void* out_bf16, int64_t rows, int n,

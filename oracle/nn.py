@@ -239,6 +239,25 @@ def vae_decode(sd: SD, z, scale_factor: float = 0.18215, prefix: str = "first_st
     return _conv(sd, D + ".conv_out", h)
 
 
+def vae_encode_hc(sd: SD, x, prefix: str = "first_stage_model"):
+    """autoencoder.py:91-95 encode_hc -> model.py:551-577 Encoder.forward_hc: returns `c`, the feature
+    map after norm_out + swish (the posterior is unused by model/rdeic.py:660-663)."""
+    E = prefix + ".encoder"
+    h = _conv(sd, E + ".conv_in", x)
+    n_levels = _count(sd, E + ".down.")
+    for lvl in range(n_levels):
+        for i in range(_count(sd, f"{E}.down.{lvl}.block.")):
+            h = _vae_resnet(sd, f"{E}.down.{lvl}.block.{i}", h)
+        if (f"{E}.down.{lvl}.downsample.conv.weight") in sd:
+            # model.py:82-84: pad (0,1,0,1), stride-2 conv, no padding
+            w, b = sd[f"{E}.down.{lvl}.downsample.conv.weight"], sd[f"{E}.down.{lvl}.downsample.conv.bias"]
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), w, b, stride=2, padding=0)
+    h = _vae_resnet(sd, E + ".mid.block_1", h)
+    h = _vae_attn(sd, E + ".mid.attn_1", h)
+    h = _vae_resnet(sd, E + ".mid.block_2", h)
+    return F.silu(_gn(sd, E + ".norm_out", h, 1e-6))
+
+
 def to_uint8(x: torch.Tensor) -> torch.Tensor:
     """inference.py:85-87: ((x+1)/2).clamp(0,1) -> b h w c * 255 -> clip -> uint8."""
     x = ((x + 1) / 2).clamp(0, 1)

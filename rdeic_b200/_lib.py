@@ -77,7 +77,7 @@ SIGNATURES = {
     "rdeic_geglu": [vp, vp, i64, i32, vp],
     "rdeic_upsample2x_nhwc": [vp, vp, i32, i32, i32, i32, vp],
     "rdeic_pixel_shuffle2_nhwc": [vp, vp, i32, i32, i32, i32, vp],
-    "rdeic_im2col_3x3_s2": [vp, vp, i32, i32, i32, i32, vp],
+    "rdeic_im2col_3x3_s2": [vp, vp, i32, i32, i32, i32, i32, vp],
     "rdeic_softmax_rows": [vp, i32, vp, i64, i32, f32, vp],
     "rdeic_transpose_bf16": [vp, vp, i32, i32, i32, vp],
     "rdeic_image_to_u8": [vp, vp, i64, i32, vp],

@@ -236,7 +236,7 @@ pixel_shuffle2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int
 // stride-2 pad-1 3x3 im2col: out row m = (b, oh, ow), col = tap*Cp + c
 __global__ void __launch_bounds__(kThreads)
 im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
-                 int C, int Cp) {
+                 int C, int Cp, int pad_lo) {
     pdl_trigger();
     pdl_wait();
     const int Ho = H / 2, Wo = W / 2;
@@ -250,7 +250,7 @@ im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, i
         const int ow = (int)(q % Wo); q /= Wo;
         const int oh = (int)(q % Ho);
         const int b = (int)(q / Ho);
-        const int ih = 2 * oh + tap / 3 - 1, iw = 2 * ow + tap % 3 - 1;
+        const int ih = 2 * oh + tap / 3 - pad_lo, iw = 2 * ow + tap % 3 - pad_lo;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (c < cv && ih >= 0 && ih < H && iw >= 0 && iw < W)
             v = in[(((int64_t)b * H + ih) * W + iw) * cv + c];
@@ -465,15 +465,16 @@ int rdeic_pixel_shuffle2_nhwc(const void* in, void* out, int B, int H, int W, in
     return 0;
 }
 
-int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C,
+int rdeic_im2col_3x3_s2(const void* in, void* out, int B, int H, int W, int C, int pad_lo,
                         rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0, "rdeic_im2col_3x3_s2: bad args");
     RDEIC_CHECK_ARG(C > 0 && C % 8 == 0, "rdeic_im2col_3x3_s2: C=%d must be a multiple of 8", C);
     RDEIC_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "rdeic_im2col_3x3_s2: H, W must be even");
+    RDEIC_CHECK_ARG(pad_lo == 0 || pad_lo == 1, "rdeic_im2col_3x3_s2: pad_lo must be 0 or 1");
     const int Cp = (C + 63) / 64 * 64;
     const int64_t total = (int64_t)B * (H / 2) * (W / 2) * 9 * (Cp / 8);
     launch_k(im2col_s2_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream), 
-        (const uint4*)in, (uint4*)out, B, H, W, C, Cp);
+        (const uint4*)in, (uint4*)out, B, H, W, C, Cp, pad_lo);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -510,48 +510,24 @@ class VaeRes:
     cout: int
 
 
-class VAEDecoderEngine:
-    def __init__(self, sd: SD, scale_factor: float, device="cuda", prefix: str = "first_stage_model"):
-        dev = torch.device(device)
-        self.device = dev
-        D = prefix + ".decoder"
-        # ddpm.py:843 `1/scale_factor * z` folded into the 1x1 post_quant_conv weights (autoencoder.py:98)
-        self.post_quant = Conv.load(sd, prefix + ".post_quant_conv", dev, scale=1.0 / scale_factor)
-        self.conv_in = Conv.load(sd, D + ".conv_in", dev)
+def _load_vae_res(sd: SD, p: str, dev) -> VaeRes:
+    nin = Conv.load(sd, p + ".nin_shortcut", dev) if (p + ".nin_shortcut.weight") in sd else None
+    c1 = Conv.load(sd, p + ".conv1", dev)
+    return VaeRes(Norm.load(sd, p + ".norm1", dev), c1, Norm.load(sd, p + ".norm2", dev),
+                  Conv.load(sd, p + ".conv2", dev), nin, c1.n_out)
 
-        def rb(p):
-            nin = Conv.load(sd, p + ".nin_shortcut", dev) if (p + ".nin_shortcut.weight") in sd else None
-            c1 = Conv.load(sd, p + ".conv1", dev)
-            return VaeRes(Norm.load(sd, p + ".norm1", dev), c1, Norm.load(sd, p + ".norm2", dev),
-                          Conv.load(sd, p + ".conv2", dev), nin, c1.n_out)
 
-        self.mid1 = rb(D + ".mid.block_1")
-        self.mid2 = rb(D + ".mid.block_2")
-        a = D + ".mid.attn_1"
+class _VaeMid:
+    """mid.block_1 -> mid.attn_1 -> mid.block_2, shared by the VAE encoder and decoder
+    (ldm/modules/diffusionmodules/model.py:92-205,511-522,627-637)."""
+
+    def __init__(self, sd: SD, M: str, dev):
+        self.mid1 = _load_vae_res(sd, M + ".block_1", dev)
+        self.mid2 = _load_vae_res(sd, M + ".block_2", dev)
+        a = M + ".attn_1"
         self.attn_norm = Norm.load(sd, a + ".norm", dev)
         self.attn_q, self.attn_k, self.attn_v = (Conv.load(sd, a + n, dev) for n in (".q", ".k", ".v"))
         self.attn_out = Conv.load(sd, a + ".proj_out", dev)
-        self.levels = []
-        lvl = 0
-        while any(k.startswith(f"{D}.up.{lvl}.") for k in sd):
-            blocks = []
-            i = 0
-            while (f"{D}.up.{lvl}.block.{i}.conv1.weight") in sd:
-                blocks.append(rb(f"{D}.up.{lvl}.block.{i}"))
-                i += 1
-            up = Conv.load(sd, f"{D}.up.{lvl}.upsample.conv", dev) if (f"{D}.up.{lvl}.upsample.conv.weight") in sd else None
-            self.levels.append((blocks, up))
-            lvl += 1
-        self.norm_out = Norm.load(sd, D + ".norm_out", dev)
-        # conv_out has 3 output channels; pad to 4 (zero weights) so every output row is one aligned
-        # 16-byte vector and the epilogue takes its coalesced path (12-byte rows cannot).
-        wo, bo = sd[D + ".conv_out.weight"].float(), sd[D + ".conv_out.bias"].float()
-        self.out_ch = wo.shape[0]
-        pad = (-self.out_ch) % 4
-        if pad:
-            wo = torch.cat([wo, torch.zeros(pad, *wo.shape[1:], device=wo.device)], 0)
-            bo = torch.cat([bo, torch.zeros(pad, device=bo.device)], 0)
-        self.conv_out = Conv.load({"w.weight": wo, "w.bias": bo}, "w", dev)
 
     @staticmethod
     def _res(w: VaeRes, x):
@@ -577,6 +553,104 @@ class VAEDecoderEngine:
         out = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.view(B, N, C))
         return out.view(B, H, W, C)
 
+    def _mid(self, x):
+        return self._res(self.mid2, self._attn(self._res(self.mid1, x)))
+
+
+class VAEEncoderEngine(_VaeMid):
+    """The sender side's first stage: `AutoencoderKL.encode_hc` ->
+    `Encoder.forward_hc` (ldm/models/autoencoder.py:91-95, ldm/modules/diffusionmodules/model.py:551-577).
+    `apply_condition_compress` (model/rdeic.py:660-663) uses only `c`, the 512-channel feature map
+    after norm_out + swish, so conv_out / quant_conv / the posterior are not computed."""
+
+    def __init__(self, sd: SD, device="cuda", prefix: str = "first_stage_model"):
+        dev = torch.device(device)
+        self.device = dev
+        E = prefix + ".encoder"
+        super().__init__(sd, E + ".mid", dev)
+        self.conv_in = Conv.load(sd, E + ".conv_in", dev)
+        self.levels = []
+        lvl = 0
+        while any(k.startswith(f"{E}.down.{lvl}.") for k in sd):
+            blocks = []
+            i = 0
+            while (f"{E}.down.{lvl}.block.{i}.conv1.weight") in sd:
+                blocks.append(_load_vae_res(sd, f"{E}.down.{lvl}.block.{i}", dev))
+                i += 1
+            down = Conv.load(sd, f"{E}.down.{lvl}.downsample.conv", dev) if (f"{E}.down.{lvl}.downsample.conv.weight") in sd else None
+            self.levels.append((blocks, down))
+            lvl += 1
+        self.norm_out = Norm.load(sd, E + ".norm_out", dev)
+
+    @torch.no_grad()
+    def encode_hc_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B,3,H,W] fp32 NCHW in [-1,1] -> c NHWC bf16 [B,H/8,W/8,512]."""
+        if not x.is_cuda:
+            raise ops._lib.RdeicLibraryError("VAEEncoderEngine needs CUDA tensors; there is no CPU path")
+        h = ops.nchw_to_nhwc_bf16(x.float().contiguous(), ldc=8)
+        # 13 residual blocks deep: keep an fp32 master of the residual stream next to the bf16 copy the
+        # tensor cores read (same scheme as the UNet step), or bf16 re-rounding compounds to 1.5e-2
+        a = Act(*ops.conv_gemm(h, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b, dual=True))
+        for blocks, down in self.levels:
+            for b in blocks:
+                a = self._res32(b, a)
+            if down is not None:
+                # model.py:82-84: pad (0,1,0,1) then a stride-2 conv without padding
+                B, H, W, C = a.h.shape
+                col = ops.im2col_3x3_s2(a.h, pad_lo=0)
+                of, oh = ops.linear(col, down.w, down.n_out, bias=down.b, dual=True)
+                a = Act(of.view(B, H // 2, W // 2, down.n_out), oh.view(B, H // 2, W // 2, down.n_out))
+        a = self._res32(self.mid1, a)
+        a = self._res32(self.mid2, Act(None, self._attn(a.h)))
+        return ops.groupnorm(a.f, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
+
+    @staticmethod
+    def _res32(w: VaeRes, x: Act) -> Act:
+        src = x.f if x.f is not None else x.h
+        h = ops.groupnorm(src, w.n1.g, w.n1.b, 32, 1e-6, True)
+        h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b)
+        h = ops.groupnorm(h, w.n2.g, w.n2.b, 32, 1e-6, True)
+        xs = src if w.nin is None else ops.conv_gemm(x.h, w.nin.w, w.cout, 1, bias=w.nin.b, out_f32=True)
+        return Act(*ops.conv_gemm(h, w.c2.w, w.cout, 9, bias=w.c2.b, resid=xs, dual=True))
+
+    @torch.no_grad()
+    def encode_hc(self, x: torch.Tensor) -> torch.Tensor:
+        """The `c` of autoencoder.py:91-95 as NCHW fp32."""
+        return ops.nhwc_to_nchw_f32(self.encode_hc_nhwc(x))
+
+
+class VAEDecoderEngine(_VaeMid):
+    def __init__(self, sd: SD, scale_factor: float, device="cuda", prefix: str = "first_stage_model"):
+        dev = torch.device(device)
+        self.device = dev
+        D = prefix + ".decoder"
+        super().__init__(sd, D + ".mid", dev)
+        # ddpm.py:843 `1/scale_factor * z` folded into the 1x1 post_quant_conv weights (autoencoder.py:98)
+        self.post_quant = Conv.load(sd, prefix + ".post_quant_conv", dev, scale=1.0 / scale_factor)
+        self.conv_in = Conv.load(sd, D + ".conv_in", dev)
+        rb = lambda p: _load_vae_res(sd, p, dev)
+        self.levels = []
+        lvl = 0
+        while any(k.startswith(f"{D}.up.{lvl}.") for k in sd):
+            blocks = []
+            i = 0
+            while (f"{D}.up.{lvl}.block.{i}.conv1.weight") in sd:
+                blocks.append(rb(f"{D}.up.{lvl}.block.{i}"))
+                i += 1
+            up = Conv.load(sd, f"{D}.up.{lvl}.upsample.conv", dev) if (f"{D}.up.{lvl}.upsample.conv.weight") in sd else None
+            self.levels.append((blocks, up))
+            lvl += 1
+        self.norm_out = Norm.load(sd, D + ".norm_out", dev)
+        # conv_out has 3 output channels; pad to 4 (zero weights) so every output row is one aligned
+        # 16-byte vector and the epilogue takes its coalesced path (12-byte rows cannot).
+        wo, bo = sd[D + ".conv_out.weight"].float(), sd[D + ".conv_out.bias"].float()
+        self.out_ch = wo.shape[0]
+        pad = (-self.out_ch) % 4
+        if pad:
+            wo = torch.cat([wo, torch.zeros(pad, *wo.shape[1:], device=wo.device)], 0)
+            bo = torch.cat([bo, torch.zeros(pad, device=bo.device)], 0)
+        self.conv_out = Conv.load({"w.weight": wo, "w.bias": bo}, "w", dev)
+
     @torch.no_grad()
     def decode_nhwc(self, z: torch.Tensor) -> torch.Tensor:
         """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,4] in [-1,1] (channel 3 is padding)."""
@@ -587,9 +661,7 @@ class VAEDecoderEngine:
         zq = torch.zeros((B, h, w, 8), dtype=BF16, device=z.device)
         ops.conv_gemm(z8, self.post_quant.w, self.post_quant.n_out, 1, bias=self.post_quant.b, out=zq)
         x = ops.conv_gemm(zq, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b)
-        x = self._res(self.mid1, x)
-        x = self._attn(x)
-        x = self._res(self.mid2, x)
+        x = self._mid(x)
         for blocks, up in reversed(self.levels):
             for b in blocks:
                 x = self._res(b, x)

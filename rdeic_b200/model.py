@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from ._lib import RdeicLibraryError
-from .engine import NoiseEstimatorEngine, VAEDecoderEngine
+from .engine import NoiseEstimatorEngine, VAEDecoderEngine, VAEEncoderEngine
 
 
 def load_yaml_config(path_or_cfg: Union[str, Mapping[str, Any]]) -> Dict[str, Any]:
@@ -119,6 +119,9 @@ class RDEIC:
                 raise KeyError(f"Missing key(s) in state_dict: {e}") from e
             raise
         self._graphs.clear()
+        self.first_stage_encoder = None                  # sender side (optional in a decode-only checkpoint)
+        if "first_stage_model.encoder.conv_in.weight" in sd:
+            self.first_stage_encoder = VAEEncoderEngine(sd, device=self.device)
         # the learned compressor (decompress side of the relay decode: c_latent and guide_hint)
         pp = self.preprocess_config and dict(self.preprocess_config.get("params", self.preprocess_config))
         if pp and "in_nc" in pp and any(k.startswith("preprocess_model.") for k in sd):
@@ -126,6 +129,29 @@ class RDEIC:
 
             self.preprocess_model = Compression(device=self.device, **pp).load_state_dict(sd, strict=False)
         return self
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        """ddpm.py:858-860 -> AutoencoderKL.encode_hc: (posterior, c).  Only `c` is consumed on this
+        path (rdeic.py:661), so the posterior is not computed and None is returned in its place."""
+        if self.first_stage_encoder is None:
+            raise RuntimeError("RDEIC: the checkpoint held no first_stage_model.encoder.* weights")
+        return None, self.first_stage_encoder.encode_hc(x.to(self.device, torch.float32))
+
+    @torch.no_grad()
+    def apply_condition_compress(self, x, stream_path, H, W):
+        """rdeic.py:659-669: image batch in [0,1] -> bitstream file, returns bpp."""
+        from pathlib import Path
+
+        from .utils import filesize, write_body
+
+        if self.preprocess_model is None:
+            raise RuntimeError("RDEIC: the checkpoint held no preprocess_model.* weights")
+        _, h = self.encode_first_stage(x * 2 - 1)
+        out = self.preprocess_model.compress(h * self.scale_factor)
+        with Path(stream_path).open("wb") as f:
+            write_body(f, out["shape"], out["strings"])
+        return float(filesize(stream_path)) * 8 / (H * W)
 
     @torch.no_grad()
     def apply_condition_decompress(self, stream_path):

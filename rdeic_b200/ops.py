@@ -309,11 +309,12 @@ def pixel_shuffle2(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def im2col_3x3_s2(x: torch.Tensor) -> torch.Tensor:
+def im2col_3x3_s2(x: torch.Tensor, pad_lo: int = 1) -> torch.Tensor:
+    """pad_lo = 1: padding 1 on every side; 0: bottom/right only (VAE encoder Downsample)."""
     B, H, W, Cc = x.shape
     Cp = (Cc + 63) // 64 * 64
     out = torch.empty((B * (H // 2) * (W // 2), 9 * Cp), dtype=BF16, device=x.device)
-    check(_lib.load().rdeic_im2col_3x3_s2(_ptr(x), _ptr(out), B, H, W, Cc, _stream()), "rdeic_im2col_3x3_s2")
+    check(_lib.load().rdeic_im2col_3x3_s2(_ptr(x), _ptr(out), B, H, W, Cc, pad_lo, _stream()), "rdeic_im2col_3x3_s2")
     return out
 
 

@@ -144,9 +144,41 @@ def _vae_decoder(P: str, dd: Mapping) -> List[Spec]:
     return s
 
 
-def state_dict_spec(params: Mapping) -> List[Spec]:
+def _vae_encoder(P: str, dd: Mapping) -> List[Spec]:
+    """ldm/modules/diffusionmodules/model.py:455-522 Encoder + autoencoder.py:37 quant_conv (106 + 2 keys)."""
+    ch, ch_mult, nrb, zc = int(dd["ch"]), list(dd["ch_mult"]), int(dd["num_res_blocks"]), int(dd["z_channels"])
+    E = P + ".encoder"
+    s: List[Spec] = _conv(E + ".conv_in", ch, int(dd["in_channels"]), 3)
+
+    def rb(p, cin, cout):
+        r = _norm(p + ".norm1", cin) + _conv(p + ".conv1", cout, cin, 3) + _norm(p + ".norm2", cout) + _conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            r += _conv(p + ".nin_shortcut", cout, cin, 1)
+        return r
+
+    block_in = ch
+    for lvl, mult in enumerate(ch_mult):
+        block_out = ch * mult
+        for i in range(nrb):
+            s += rb(f"{E}.down.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != len(ch_mult) - 1:
+            s += _conv(f"{E}.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    s += rb(E + ".mid.block_1", block_in, block_in)
+    s += _norm(E + ".mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        s += _conv(f"{E}.mid.attn_1.{n}", block_in, block_in, 1)
+    s += rb(E + ".mid.block_2", block_in, block_in)
+    zz = 2 * zc if dd.get("double_z", True) else zc
+    s += _norm(E + ".norm_out", block_in) + _conv(E + ".conv_out", zz, block_in, 3)
+    s += _conv(P + ".quant_conv", 2 * zc, zz, 1)
+    return s
+
+
+def state_dict_spec(params: Mapping, encoder: bool = False) -> List[Spec]:
     """Every decode-path tensor of the RDEIC checkpoint for the given `params` block of
-    configs/model/rdeic.yaml: base UNet, control adapter + zero convs, VAE decoder."""
+    configs/model/rdeic.yaml: base UNet, control adapter + zero convs, VAE decoder; with `encoder`
+    also the sender side's VAE encoder (appended last, so the decode-path tensors keep their values)."""
     up = dict(params["unet_config"]["params"])
     cp = dict(params["control_stage_config"]["params"])
     dd = dict(params["first_stage_config"]["params"]["ddconfig"])
@@ -165,7 +197,8 @@ def state_dict_spec(params: Mapping) -> List[Spec]:
     for i in range(1, len(c_enc)):                                          # rdeic.py:150-153
         z += _conv(f"control_model.dec_zero_convs_out.{i}.0", b_dec[i - 1], c_enc[-(i + 1)], 1, zero=True)
     z.append(("control_model.scale_list", (2 * len(c_enc) + 1,), "buf"))
-    return base + ctrl + z + _vae_decoder("first_stage_model", dd)
+    out = base + ctrl + z + _vae_decoder("first_stage_model", dd)
+    return out + _vae_encoder("first_stage_model", dd) if encoder else out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -263,12 +296,13 @@ def make_compression_state_dict(pp: Mapping, seed: int = 232, device="cpu", pref
     return sd
 
 
-def make_state_dict(params: Mapping, seed: int = 231, device="cpu", control_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+def make_state_dict(params: Mapping, seed: int = 231, device="cpu", control_scale: float = 1.0,
+                    encoder: bool = False) -> Dict[str, torch.Tensor]:
     """Seeded random checkpoint (fp32) with the reference layout."""
     dev = torch.device(device)
     g = torch.Generator(device=dev).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, kind in state_dict_spec(params):
+    for key, shape, kind in state_dict_spec(params, encoder=encoder):
         if kind in ("w", "b"):
             fan_in = 1
             if kind == "w":

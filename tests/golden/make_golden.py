@@ -14,6 +14,7 @@ Files written
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
   {small,full}_compression.npz       reference model/compression.py Compression.compress -> .decompress
   {small,full}_compression_keys.json its state_dict keys + shapes
+  {small,full}_vae_encode.npz   reference AutoencoderKL.encode_hc feature map; vae_encoder_keys.json its keys
   bitstream_ref.bin        bytes written by the reference utils/utils.py write_body (shape (8,12), 2 strings)
   entropy_ref.npz          reference utils/ckbd.py checkerboard ops, utils/func.py scale table and
                            model/compression_modules.py VectorQuantiser.quant / get_codebook_entry
@@ -247,6 +248,25 @@ def run_compression(tag, params, B, h, w):
                         indexes=idx, c_latent=c_latent.numpy(), guide_hint=guide_hint.numpy())
 
 
+def run_vae_encode(tag, overrides, hw):
+    """§8(f) rank 3: the reference AutoencoderKL.encode_hc (autoencoder.py:91-95) feature map `c`."""
+    model, mods = rh.build_reference_model(overrides)
+    params = rh.load_config(overrides)["params"]
+    sd = synthetic.make_state_dict(params, seed=WEIGHT_SEED, encoder=True)
+    enc_keys = {k: list(v.shape) for k, v in model.state_dict().items()
+                if k.startswith(("first_stage_model.encoder.", "first_stage_model.quant_conv."))}
+    assert enc_keys == {k: list(v.shape) for k, v in sd.items() if k in enc_keys} and len(enc_keys) == 108, len(enc_keys)
+    if tag == "full":
+        (HERE / "vae_encoder_keys.json").write_text(json.dumps(enc_keys, indent=0, sort_keys=True))
+    model.load_state_dict(sd, strict=False)
+    H, W = hw
+    x = torch.rand(1, 3, H, W, generator=torch.Generator().manual_seed(71)) * 2 - 1
+    with torch.no_grad():
+        _, c = model.encode_first_stage(x)
+    print(tag, "vae encode_hc", tuple(c.shape), float(c.abs().max()))
+    np.savez_compressed(HERE / f"{tag}_vae_encode.npz", x=x.numpy(), c=c.numpy())
+
+
 def run_bitstream():
     """§8(f) rank 2: bytes written by the reference's own utils/utils.py write_body."""
     import importlib
@@ -270,11 +290,14 @@ def run_bitstream():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["entropy", "bitstream", "compression", "small", "full"]
+    which = sys.argv[1:] or ["entropy", "bitstream", "vae_encode", "compression", "small", "full"]
     if "entropy" in which:
         run_entropy()
     if "bitstream" in which:
         run_bitstream()
+    if "vae_encode" in which:
+        run_vae_encode("small", rh.SMALL_OVERRIDES, (64, 96))
+        run_vae_encode("full", None, (64, 64))
     if "compression" in which:
         from rdeic_b200 import configs
 

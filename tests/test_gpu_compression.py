@@ -223,3 +223,77 @@ def test_decode_streams_groups_and_crops(cuda, tmp_path):
     imgs = decode_streams(model, paths, [ctx], steps=2, sizes=sizes, batch_size=4)
     assert [tuple(i.shape) for i in imgs] == [(120, 190, 3), (64, 64, 3), (128, 192, 3)]
     assert all(i.dtype == torch.uint8 and i.is_cuda for i in imgs)
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_vae_encoder_matches_reference(cuda, tag):
+    """§8(f) rank 3: AutoencoderKL.encode_hc feature map vs the reference's own output."""
+    from rdeic_b200 import configs, synthetic
+    from rdeic_b200.engine import VAEEncoderEngine
+
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    sd = synthetic.make_state_dict(params, seed=231, encoder=True)
+    g = np.load(GOLD / f"{tag}_vae_encode.npz")
+    c = VAEEncoderEngine(sd, device=cuda).encode_hc(torch.from_numpy(g["x"]).to(cuda))
+    assert tuple(c.shape) == g["c"].shape
+    # 26 convs deep with bf16 operands and random (non-contracting) weights: operand rounding adds up
+    # to 1.3e-2 (full) / 1.5e-2 (small) even with the fp32 residual master (scripts/diag_vae_encoder.py)
+    assert rel_l2(c.cpu(), g["c"]) < 2e-2
+
+
+def test_sender_to_receiver_through_a_file(cuda, tmp_path):
+    """inference.py:56-57: apply_condition_compress -> bitstream file -> apply_condition_decompress, all
+    conv stacks on the GPU, coders in memory; the conditioning that comes back equals what the sender's
+    own synthesis of its y_hat gives (bit for bit)."""
+    from rdeic_b200 import RDEIC, configs, synthetic
+
+    params = configs.small_params()
+    pp = params["preprocess_config"]["params"]
+    sd = synthetic.make_state_dict(params, seed=231, encoder=True)
+    sd.update(synthetic.make_compression_state_dict(pp, seed=232))
+    model = RDEIC.from_config({"params": params}, device=cuda).load_state_dict(sd)
+    store = {}
+
+    class Enc:
+        accepts_arrays = True
+
+        def encode_with_indexes(self, symbols, indexes, *a):
+            store["sym"], store["idx"] = symbols.copy(), indexes.copy()
+
+        def flush(self):
+            return b"Y" * 37
+
+    class Dec:
+        accepts_arrays = True
+
+        def set_stream(self, s):
+            assert s == b"Y" * 37
+            self.pos = 0
+
+        def decode_stream(self, indexes, *a):
+            n = len(indexes)
+            assert np.array_equal(indexes, store["idx"][self.pos:self.pos + n])      # encoder / decoder in sync
+            out = store["sym"][self.pos:self.pos + n]
+            self.pos += n
+            return out
+
+    class Hyp:
+        def compress(self, idx):
+            store["z"] = idx.clone()
+            return b"Z" * 5
+
+        def decompress(self, s, shape):
+            assert s == b"Z" * 5 and tuple(shape) == tuple(store["z"].shape[-2:])
+            return store["z"]
+
+    pm = model.preprocess_model
+    pm._rans_encoder, pm._rans_decoder, pm._hyper_coder = Enc, Dec, Hyp()
+    H, W = 128, 192
+    x = torch.rand(1, 3, H, W, generator=torch.Generator().manual_seed(3)).to(cuda)
+    path = tmp_path / "img"
+    bpp = model.apply_condition_compress(x, str(path), H, W)
+    assert bpp == (12 + 4 + 37 + 4 + 5) * 8 / (H * W)                   # container header + 2 length-prefixed strings
+    c_latent, guide_hint = model.apply_condition_decompress(str(path))
+    assert tuple(c_latent.shape) == (1, 4, H // 8, W // 8) and tuple(guide_hint.shape) == (1, pp["M"], H // 8, W // 8)
+    assert len(store["sym"]) == pp["M"] * (H // 16) * (W // 16)
+    assert torch.isfinite(c_latent).all() and torch.isfinite(guide_hint).all()

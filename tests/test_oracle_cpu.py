@@ -291,3 +291,20 @@ def test_bitstream_container_matches_reference_bytes(tmp_path):
     assert utils.filesize(str(p)) == len(data)
     with pytest.raises(ValueError):
         utils.filesize(str(tmp_path / "missing.bin"))
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_oracle_vae_encoder_matches_reference_golden(tag):
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    sd = synthetic.make_state_dict(params, seed=231, encoder=True)
+    g = np.load(GOLD / f"{tag}_vae_encode.npz")
+    c = onn.vae_encode_hc(sd, torch.from_numpy(g["x"]))
+    assert float((c - torch.from_numpy(g["c"])).abs().max()) < 1e-4
+    if tag == "full":
+        ref = json.loads((GOLD / "vae_encoder_keys.json").read_text())
+        spec = {k: list(s) for k, s, _ in synthetic.state_dict_spec(params, encoder=True) if k in ref}
+        assert spec == ref and len(ref) == 108                      # encoder 106 + quant_conv 2
+        # appending the encoder leaves every decode-path tensor of the seeded checkpoint unchanged
+        base = synthetic.make_state_dict(configs.small_params(), seed=231)
+        ext = synthetic.make_state_dict(configs.small_params(), seed=231, encoder=True)
+        assert all(torch.equal(base[k], ext[k]) for k in base)
