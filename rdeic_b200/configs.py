@@ -35,5 +35,5 @@ def small_params() -> Dict[str, Any]:
     p["control_stage_config"]["params"].update(model_channels=64, num_head_channels=16, control_model_ratio=0.5,
                                                hint_channels=32, context_dim=64)
     p["first_stage_config"]["params"]["ddconfig"]["ch"] = 32
-    p["preprocess_config"]["params"].update(in_nc=32, N=48, M=32, slice_num=3, slice_ch=[8, 8, 16], codebook_size=512)
+    p["preprocess_config"]["params"].update(in_nc=128, N=48, M=32, slice_num=3, slice_ch=[8, 8, 16], codebook_size=512)
     return p

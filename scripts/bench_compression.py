@@ -69,6 +69,7 @@ def timed(fn, n):
     return (time.perf_counter() - t0) / n * 1e3, r
 
 
+m.use_cuda_graph = False
 ops.LAUNCHES = 0
 out = m.compress(x)
 torch.cuda.synchronize()
@@ -77,8 +78,13 @@ ops.LAUNCHES = 0
 m.decompress(out["strings"], out["shape"])
 torch.cuda.synchronize()
 launches_d = ops.LAUNCHES
-ms_c, out = timed(lambda: m.compress(x), 5)
-ms_d, _ = timed(lambda: m.decompress(out["strings"], out["shape"]), 5)
+m.use_cuda_graph = True
+ms_c, out = timed(lambda: m.compress(x), 10)
+ms_d, _ = timed(lambda: m.decompress(out["strings"], out["shape"]), 10)
+m.use_cuda_graph = False
+ms_c_eager, _ = timed(lambda: m.compress(x), 5)
+ms_d_eager, _ = timed(lambda: m.decompress(out["strings"], out["shape"]), 5)
+m.use_cuda_graph = True
 # GPU-only part of decompress: hyper decoder + synthesis (no host hand-off in between)
 z_q = m.quantize.get_codebook_entry(out["strings"][1][0].long())
 ms_h, hyper = timed(lambda: m._hyper_params(z_q), 20)
@@ -86,7 +92,8 @@ y_hat = torch.randn(B, pp["M"], 32, 32, device=dev)
 ms_s, _ = timed(lambda: m._synthesis(y_hat), 20)
 
 res = {"workload": f"512x512 image, batch {B}: feature map [B,512,64,64] -> y [B,256,32,32], z [B,256,8,8]",
-       "compress_ms": ms_c, "decompress_ms": ms_d, "hyper_decoder_ms": ms_h, "synthesis_ms": ms_s,
+       "compress_ms": ms_c, "decompress_ms": ms_d, "compress_ms_no_graph": ms_c_eager,
+       "decompress_ms_no_graph": ms_d_eager, "hyper_decoder_ms": ms_h, "synthesis_ms": ms_s,
        "kernel_launches": {"compress": launches_c, "decompress": launches_d},
        "symbols_per_image": len(loop.symbols) // B}
 if B == 1:
