@@ -140,12 +140,14 @@ def crop_cond(cond: Dict, y0: int, x0: int, th: int, tw: int) -> Dict:
 
 
 def decode_tiled(decode_fn, cond: Dict, tile: int = 96, overlap: int = 16, scale: int = 8,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, dst: int = 0):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, dst: int = 0, batched: bool = False):
     """Decode ONE large image (batch 1) as overlapping latent tiles dealt round-robin across ranks
     (BASELINE config 4: 2048x1365 -> latent 256x176).  `decode_fn(cond_tile, tile_index) ->
     float tensor [1,3,th*scale,tw*scale]` is the per-tile relay decode (each tile is an independent
     decode unit: GroupNorm / attention statistics are per tile, so the result is NOT the full-frame
-    decode — the reference never tiles).  Returns the blended image on `dst`."""
+    decode — the reference never tiles).  With `batched`, a rank's tiles (all the same
+    size) are stacked along the batch axis and decoded by ONE call `decode_fn(cond_tiles, indices) ->
+    [n,3,th*scale,tw*scale]`.  Returns the blended image on `dst`."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
     if world_size is None:
@@ -155,7 +157,15 @@ def decode_tiled(decode_fn, cond: Dict, tile: int = 96, overlap: int = 16, scale
     h, w = lat.shape[-2:]
     plan = plan_tiles(h, w, tile, overlap)
     mine = list(range(rank, len(plan), world_size))
-    outs = [decode_fn(crop_cond(cond, *plan[i]), i)[0].float() for i in mine]
+    if batched and mine:
+        crops = [crop_cond(cond, *plan[i]) for i in mine]
+        ctx = cond["c_crossattn"][0]
+        stacked = {"c_latent": [torch.cat([c["c_latent"][0] for c in crops], 0)],
+                   "c_crossattn": [ctx.expand(len(mine), -1, -1).contiguous()],
+                   "guide_hint": torch.cat([c["guide_hint"] for c in crops], 0)}
+        outs = list(decode_fn(stacked, mine).float().unbind(0))
+    else:
+        outs = [decode_fn(crop_cond(cond, *plan[i]), i)[0].float() for i in mine]
     th, tw = plan[0][2], plan[0][3]
     dev = lat.device
     if world_size == 1:

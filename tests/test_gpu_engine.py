@@ -200,3 +200,10 @@ def test_tiled_decode_matches_per_tile_oracle(small_model, cuda):
     pq = psnr(img.numpy(), ref.numpy(), 2.0)
     print(f"[small] tiled decode ({len(plan)} tiles) PSNR vs per-tile oracle {pq:.1f} dB")
     assert pq >= PSNR_MIN
+
+    def decode_batched(c, idx):         # all tiles of this rank in one batch (samples are independent)
+        ns = [torch.cat([crop(n, *plan[i]) for i in idx], 0) for n in dn]
+        return relay_decode(small_model, c, 2, start_noise=ns[0], step_noises=ns[1:], as_uint8=False)
+
+    img_b = parallel.decode_tiled(decode_batched, cond, tile=tile, overlap=ov, batched=True).cpu()
+    assert psnr(img_b.numpy(), ref.numpy(), 2.0) >= PSNR_MIN

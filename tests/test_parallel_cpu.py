@@ -89,6 +89,14 @@ def _worker(rank, world, port, ret):
         ref = torch.nn.functional.interpolate(lat[:, :3], scale_factor=s, mode="nearest")[0]
         ok_tiles = (img is None) if rank != 0 else torch.allclose(img, ref, atol=1e-5)
         ok_deal = all(i % world == rank for i in seen)
+        # same through the batched form: a rank's tiles stacked along the batch axis, one call
+
+        def fake_decode_batched(c, idx):
+            assert c["c_latent"][0].shape[0] == len(idx) == c["c_crossattn"][0].shape[0] == c["guide_hint"].shape[0]
+            return torch.nn.functional.interpolate(c["c_latent"][0][:, :3], scale_factor=s, mode="nearest")
+
+        img_b = parallel.decode_tiled(fake_decode_batched, big, tile=24, overlap=8, scale=s, batched=True)
+        ok_tiles = ok_tiles and ((img_b is None) if rank != 0 else torch.allclose(img_b, ref, atol=1e-5))
         ret[rank] = (ok_bcast, ok_shard, ok_gather, ok_tiles, ok_deal)
     finally:
         dist.destroy_process_group()
