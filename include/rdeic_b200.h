@@ -161,6 +161,13 @@ int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
  * materialising it; x2 may be NULL with C2 = 0.  out [B,HW,C1+C2] bf16.
  * workspace: rdeic_groupnorm_workspace_bytes(B, HW, C) bytes. */
 int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C);
+/* Same, with the statistics taken from the producers' epilogues (rdeic_conv_params.stats_out of the
+ * GEMMs that wrote x1 / x2: [B*HW/32][C1] and [B*HW/32][C2] (sum, sumsq) pairs) instead of a pass
+ * over the tensors; HW must be a multiple of 32. */
+int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, const void* x2, int C2,
+                               const float* stats2, int in_is_f32, const float* gamma,
+                               const float* beta, void* out, int B, int64_t HW, int groups,
+                               float eps, int silu, void* workspace, rdeic_stream_t stream);
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
                          const float* gamma, const float* beta, void* out, int B, int64_t HW,
                          int groups, float eps, int silu, void* workspace,
@@ -209,7 +216,16 @@ typedef struct rdeic_conv_params {
     float act_param;      /* LeakyReLU negative slope */
     int a_ld, a2_ld;      /* pixel stride (elements) of a / a2 when they are channel slices of a wider
                              NHWC buffer (torch.cat inputs of compression.py:170-190); 0 = a_c / a2_c */
+    /* ABI 3 */
+    float* stats_out;     /* optional: [ceil(M/32)][n_out] pairs (sum, sum of squares) of the values
+                             written, per 32-row slab and output column — the GroupNorm statistics of
+                             the consumer (util.py:224, model.py:48) fused into the producer's epilogue.
+                             Needs rdeic_conv_stats_supported(a_n, a_h, a_w); disables split-K. */
 } rdeic_conv_params;
+
+/* 1 if rdeic_conv_gemm can emit stats_out for an [a_n, a_h, a_w] pixel grid (every M tile full and
+ * row-contiguous), else 0. */
+int rdeic_conv_stats_supported(int a_n, int a_h, int a_w);
 
 int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream);
 /* openaimodel.py:203 etc.: OIHW fp32 [n_out, c1+c2, kh, kw] -> packed bf16 (see above).

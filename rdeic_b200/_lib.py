@@ -46,6 +46,7 @@ class ConvParams(C.Structure):
         ("workspace_bytes", i64),
         ("act_param", f32),
         ("a_ld", i32), ("a2_ld", i32),
+        ("stats_out", vp),
     ]
 
 
@@ -83,8 +84,10 @@ SIGNATURES = {
     "rdeic_image_to_u8": [vp, vp, i64, i32, vp],
     "rdeic_groupnorm_workspace_bytes": [i32, i64, i32],
     "rdeic_groupnorm_nhwc": [vp, i32, vp, i32, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
+    "rdeic_groupnorm_from_stats": [vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "rdeic_layernorm": [vp, i32, vp, vp, vp, i64, i32, f32, vp],
     "rdeic_conv_gemm": [C.POINTER(ConvParams), vp],
+    "rdeic_conv_stats_supported": [i32, i32, i32],
     "rdeic_pack_conv_weight": [vp, vp, i32, i32, i32, i32, i32, vp],
     "rdeic_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, vp],
 }

@@ -46,6 +46,7 @@ struct ConvDev {
     __nv_bfloat16* out_bf16;
     float* out_f32;
     int ldo;
+    float* stats_out;              // optional [M/32][n_out] (sum, sumsq) per 32-row slab and column
     float* partial;                // split-K: raw fp32 accumulators [split][M][n_out]
     int kb_per_split;              // k-blocks per k-split slice (= all of them without split-K)
     int splits, n_tiles;
@@ -136,7 +137,7 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN, int kResidMode, int kEW>
+template <int BN, int kResidMode, int kEW, bool kStats>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
@@ -441,6 +442,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const int q = lane & 7;
                         const int64_t m0 = (int64_t)m_slab + (lane >> 3);
                         float4 rv[8];
+                        // GroupNorm statistics of the tensor being written, fused here so the
+                        // consumer's stats pass (a full re-read of the tensor) disappears
+                        float4 st_s = make_float4(0.f, 0.f, 0.f, 0.f), st_q = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (eo.resid) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
@@ -470,6 +474,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             if (eo.out_bf16)
                                 *reinterpret_cast<uint2*>(eo.out_bf16 + off) =
                                     make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+                            if (kStats) {
+                                st_s.x += val.x; st_s.y += val.y; st_s.z += val.z; st_s.w += val.w;
+                                st_q.x = fmaf(val.x, val.x, st_q.x); st_q.y = fmaf(val.y, val.y, st_q.y);
+                                st_q.z = fmaf(val.z, val.z, st_q.z); st_q.w = fmaf(val.w, val.w, st_q.w);
+                            }
+                        }
+                        if (kStats) {
+                            // lanes l, l+8, l+16, l+24 hold the same 4 columns for different rows
+#pragma unroll
+                            for (int o = 8; o <= 16; o <<= 1) {
+                                st_s.x += __shfl_xor_sync(0xffffffffu, st_s.x, o); st_s.y += __shfl_xor_sync(0xffffffffu, st_s.y, o);
+                                st_s.z += __shfl_xor_sync(0xffffffffu, st_s.z, o); st_s.w += __shfl_xor_sync(0xffffffffu, st_s.w, o);
+                                st_q.x += __shfl_xor_sync(0xffffffffu, st_q.x, o); st_q.y += __shfl_xor_sync(0xffffffffu, st_q.y, o);
+                                st_q.z += __shfl_xor_sync(0xffffffffu, st_q.z, o); st_q.w += __shfl_xor_sync(0xffffffffu, st_q.w, o);
+                            }
+                            if (lane < 8) {
+                                float4* dst = reinterpret_cast<float4*>(
+                                    p.stats_out + (((int64_t)(m_slab >> 5)) * p.n_out + nbase + 4 * q) * 2);
+                                dst[0] = make_float4(st_s.x, st_q.x, st_s.y, st_q.y);
+                                dst[1] = make_float4(st_s.z, st_q.z, st_s.w, st_q.w);
+                            }
                         }
                     } else if (fast_chunk(ci)) {
                         int mr[8], okr[8];
@@ -645,20 +670,29 @@ static void pick_m_tile(int N, int H, int W, bool force_tn1, int* tw_o, int* th_
 }
 static int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
-template <int BN, int kPre, int kEW>
+// Fused GroupNorm statistics need every M tile to be full and "affine" (each epilogue warp's 32
+// accumulator rows are 32 consecutive output rows): the same predicate the kernel evaluates per tile.
+static bool stats_tiling_ok(int N, int H, int W, bool force_tn1) {
+    int tw, th, tn;
+    pick_m_tile(N, H, W, force_tn1, &tw, &th, &tn);
+    if (W % tw || H % th || N % tn) return false;
+    return tw >= 32 || (tw == W && (tw * th >= 32 || th == H));
+}
+
+template <int BN, int kPre, int kEW, bool kStats = false>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN, kEW>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -669,6 +703,7 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
     // kept for experiments only: with the affine fast path both measured slower than loading the
     // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
+    if (d.stats_out) return launch_conv3<BN, 0, 8, true>(ta, ta2, tb, d, m_tiles, splits, s);
     static const bool pre16 = getenv("RDEIC_RESID_PREFETCH") != nullptr;
     if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv3<BN, 1, 8>(ta, ta2, tb, d, m_tiles, splits, s);
     static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
@@ -704,6 +739,10 @@ static int pick_block_n(int n_out, int m_tiles, int hint) {
 using namespace rdeic;
 
 extern "C" {
+
+int rdeic_conv_stats_supported(int a_n, int a_h, int a_w) {
+    return (a_n > 0 && a_h > 0 && a_w > 0 && stats_tiling_ok(a_n, a_h, a_w, false)) ? 1 : 0;
+}
 
 int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, int c2, int kh,
                            int kw, rdeic_stream_t stream) {
@@ -769,6 +808,15 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param;
     d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
     d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0;
+    d.stats_out = p->stats_out;
+    if (p->stats_out) {
+        RDEIC_CHECK_ARG(p->act != 2 && p->w_batch_stride == 0 && p->n_out % 32 == 0 && p->ldo % 4 == 0 &&
+                            (!p->resid || p->ld_resid % 4 == 0) && (uintptr_t)p->stats_out % 16 == 0,
+                        "rdeic_conv_gemm: stats_out needs a plain conv/linear with n_out %% 32 == 0 and 16-byte rows");
+        RDEIC_CHECK_ARG(stats_tiling_ok(p->a_n, p->a_h, p->a_w, false),
+                        "rdeic_conv_gemm: stats_out is not supported for a %dx%dx%d pixel grid "
+                        "(ask rdeic_conv_stats_supported first)", p->a_n, p->a_h, p->a_w);
+    }
     d.m_total = (int64_t)p->a_n * p->a_h * p->a_w;
     if (p->act == 2) {
         RDEIC_CHECK_ARG(p->n_out % 32 == 0 && !p->resid && p->ldo >= p->n_out / 2,
@@ -810,7 +858,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.n_tiles = n_tiles;
     d.kb_per_split = total_kb;
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
-    if (p->act != 2 && p->workspace && tiles <= kNumSMs / 2 && total_kb >= 8) {
+    if (p->act != 2 && !p->stats_out && p->workspace && tiles <= kNumSMs / 2 && total_kb >= 8) {
         int want = (int)(kNumSMs / tiles);
         if (want > total_kb / 4) want = total_kb / 4;
         if (want > 16) want = 16;

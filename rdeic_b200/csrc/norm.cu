@@ -133,6 +133,49 @@ gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
 }
 
+// Statistics handed over by the producing GEMMs: st[slab*Csrc + c] = (sum, sumsq) of channel c over
+// 32 consecutive pixels.  Same grid and output layout as gn_stats_kernel (one CTA per pixel chunk
+// and sample -> partial[(b*nchunk + chunk)*G + g]), but it reads M/32 x C pairs instead of the
+// tensor: rows of the slab table are contiguous over channels, so the loads are fully coalesced.
+__global__ void __launch_bounds__(kGnThreads)
+gn_fold_stats_kernel(const float2* __restrict__ st1, int C1, const float2* __restrict__ st2, int C2,
+                     int64_t slabs_per_sample, int G, float2* __restrict__ partial) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float s_csum[kGnMaxC];
+    __shared__ float s_csq[kGnMaxC];
+    const int C = C1 + C2;
+    const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+    const int64_t per = (slabs_per_sample + nchunk - 1) / nchunk;
+    const int64_t s0 = chunk * per;
+    const int64_t s1 = (s0 + per < slabs_per_sample) ? s0 + per : slabs_per_sample;
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        const bool first = c < C1;
+        const float2* src = first ? st1 + c : st2 + (c - C1);
+        const int64_t stride = first ? C1 : C2;
+        const int64_t base = (int64_t)b * slabs_per_sample;
+        float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+        int64_t sl = s0;
+        for (; sl + 1 < s1; sl += 2) {               // two independent loads in flight
+            const float2 u = src[(base + sl) * stride], v = src[(base + sl + 1) * stride];
+            a0 += u.x; q0 += u.y; a1 += v.x; q1 += v.y;
+        }
+        if (sl < s1) { const float2 u = src[(base + sl) * stride]; a0 += u.x; q0 += u.y; }
+        s_csum[c] = a0 + a1;
+        s_csq[c] = q0 + q1;
+    }
+    __syncthreads();
+    const int cg = C / G;
+    if (threadIdx.x < G) {
+        float a = 0.f, c = 0.f;
+        for (int k = 0; k < cg; ++k) {
+            a += s_csum[threadIdx.x * cg + k];
+            c += s_csq[threadIdx.x * cg + k];
+        }
+        partial[((int64_t)b * nchunk + chunk) * G + threadIdx.x] = make_float2(a, c);
+    }
+}
+
 template <bool kF32>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
@@ -344,6 +387,40 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     else
         launch_k(gn_apply_kernel<false>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, const void* x2, int C2,
+                               const float* stats2, int in_is_f32, const float* gamma,
+                               const float* beta, void* out, int B, int64_t HW, int groups,
+                               float eps, int silu, void* workspace, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x1 && stats1 && gamma && beta && out && workspace, "rdeic_groupnorm_from_stats: null pointer");
+    RDEIC_CHECK_ARG(C2 == 0 || (x2 && stats2), "rdeic_groupnorm_from_stats: C2 > 0 needs x2 and stats2");
+    if (C2 == 0) { x2 = nullptr; stats2 = nullptr; }
+    const int C = C1 + C2;
+    RDEIC_CHECK_ARG(B > 0 && B <= 65535 && HW > 0 && HW % 32 == 0,
+                    "rdeic_groupnorm_from_stats: HW must be a positive multiple of 32");
+    RDEIC_CHECK_ARG(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && C <= kGnMaxC,
+                    "rdeic_groupnorm_from_stats: bad channel counts (%d, %d)", C1, C2);
+    RDEIC_CHECK_ARG(groups > 0 && groups <= kGnMaxGroups && C % groups == 0,
+                    "rdeic_groupnorm_from_stats: groups=%d invalid for C=%d", groups, C);
+    RDEIC_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0,
+                    "rdeic_groupnorm_from_stats: tensors must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    int nfold = gn_num_chunks(B, HW);
+    if (nfold > HW / 32) nfold = (int)(HW / 32);
+    launch_k(gn_fold_stats_kernel, dim3(nfold, B), kGnThreads, 0, s, (const float2*)stats1, C1,
+             (const float2*)stats2, C2, HW / 32, groups, (float2*)workspace);
+    RDEIC_LAUNCH_CHECK();
+    const FastDiv div_vl((uint32_t)(C / 8));
+    const int nchunk = gn_num_chunks(B, HW);
+    if (in_is_f32)
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
+    else
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
+            x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

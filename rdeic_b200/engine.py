@@ -529,20 +529,24 @@ class _VaeMid:
         self.attn_q, self.attn_k, self.attn_v = (Conv.load(sd, a + n, dev) for n in (".q", ".k", ".v"))
         self.attn_out = Conv.load(sd, a + ".proj_out", dev)
 
+    # Every GroupNorm input on this path is written by a conv_gemm epilogue, which also emits the
+    # per-slab (sum, sumsq) of what it wrote; `st` carries them to the consumer so that GroupNorm is
+    # one pass (apply) instead of two (statistics + apply).  st is None when the pixel grid does not
+    # tile cleanly: groupnorm then runs its own statistics pass.
     @staticmethod
-    def _res(w: VaeRes, x):
-        """model.py:128-151 with temb None; GroupNorm eps 1e-6 (model.py:48)."""
-        h = ops.groupnorm(x, w.n1.g, w.n1.b, 32, 1e-6, True)
-        h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b)
-        h = ops.groupnorm(h, w.n2.g, w.n2.b, 32, 1e-6, True)
+    def _res(w: VaeRes, x, st=None):
+        """model.py:128-151 with temb None; GroupNorm eps 1e-6 (model.py:48).  -> (out, stats of out)"""
+        h = ops.groupnorm(x, w.n1.g, w.n1.b, 32, 1e-6, True, stats1=st)
+        h, st_h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b, stats=True)
+        h = ops.groupnorm(h, w.n2.g, w.n2.b, 32, 1e-6, True, stats1=st_h)
         xs = x if w.nin is None else ops.conv_gemm(x, w.nin.w, w.cout, 1, bias=w.nin.b)
-        return ops.conv_gemm(h, w.c2.w, w.cout, 9, bias=w.c2.b, resid=xs)
+        return ops.conv_gemm(h, w.c2.w, w.cout, 9, bias=w.c2.b, resid=xs, stats=True)
 
-    def _attn(self, x):
+    def _attn(self, x, st=None):
         """model.py:181-205: single head, d = C = 512; logits fp32, softmax fp32, P bf16."""
         B, H, W, C = x.shape
         N = H * W
-        hn = ops.groupnorm(x, self.attn_norm.g, self.attn_norm.b, 32, 1e-6, False).view(B, N, C)
+        hn = ops.groupnorm(x, self.attn_norm.g, self.attn_norm.b, 32, 1e-6, False, stats1=st).view(B, N, C)
         q = ops.linear(hn, self.attn_q.w, C, bias=self.attn_q.b)
         k = ops.linear(hn, self.attn_k.w, C, bias=self.attn_k.b)
         v = ops.linear(hn, self.attn_v.w, C, bias=self.attn_v.b)
@@ -550,11 +554,12 @@ class _VaeMid:
         p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
         vt = ops.transpose_bf16(v)                                   # [B, C, N]: K-major B operand for P V
         o = ops.conv_gemm(p.view(B, 1, N, N), vt, C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
-        out = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.view(B, N, C))
-        return out.view(B, H, W, C)
+        out, st_o = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.view(B, N, C),
+                               stats=True)
+        return out.view(B, H, W, C), st_o
 
-    def _mid(self, x):
-        return self._res(self.mid2, self._attn(self._res(self.mid1, x)))
+    def _mid(self, x, st=None):
+        return self._res(self.mid2, *self._attn(*self._res(self.mid1, x, st)))
 
 
 class VAEEncoderEngine(_VaeMid):
@@ -601,7 +606,7 @@ class VAEEncoderEngine(_VaeMid):
                 of, oh = ops.linear(col, down.w, down.n_out, bias=down.b, dual=True)
                 a = Act(of.view(B, H // 2, W // 2, down.n_out), oh.view(B, H // 2, W // 2, down.n_out))
         a = self._res32(self.mid1, a)
-        a = self._res32(self.mid2, Act(None, self._attn(a.h)))
+        a = self._res32(self.mid2, Act(None, self._attn(a.h)[0]))
         return ops.groupnorm(a.f, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
 
     @staticmethod
@@ -660,14 +665,14 @@ class VAEDecoderEngine(_VaeMid):
         B, h, w, _ = z8.shape
         zq = torch.zeros((B, h, w, 8), dtype=BF16, device=z.device)
         ops.conv_gemm(z8, self.post_quant.w, self.post_quant.n_out, 1, bias=self.post_quant.b, out=zq)
-        x = ops.conv_gemm(zq, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b)
-        x = self._mid(x)
+        x, st = ops.conv_gemm(zq, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b, stats=True)
+        x, st = self._mid(x, st)
         for blocks, up in reversed(self.levels):
             for b in blocks:
-                x = self._res(b, x)
+                x, st = self._res(b, x, st)
             if up is not None:
-                x = ops.conv_gemm(ops.upsample2x(x), up.w, up.n_out, 9, bias=up.b)
-        x = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
+                x, st = ops.conv_gemm(ops.upsample2x(x), up.w, up.n_out, 9, bias=up.b, stats=True)
+        x = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, 32, 1e-6, True, stats1=st)
         return ops.conv_gemm(x, self.conv_out.w, self.conv_out.n_out, 9, bias=self.conv_out.b, out_f32=True)
 
     @torch.no_grad()

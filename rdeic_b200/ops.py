@@ -21,7 +21,7 @@ LAUNCHES = 0          # kernels launched by this module (graph replays add their
 GEMM_PROFILE = None   # when a list: conv_gemm appends (start_event, end_event, flops)
 
 
-_KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_vq_quant": 3}
+_KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_groupnorm_from_stats": 2, "rdeic_vq_quant": 3}
 
 
 def check(status: int, what: str) -> None:
@@ -362,14 +362,23 @@ def _gn_workspace(B: int, device) -> torch.Tensor:
 
 
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
-              x2: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x1 [B,H,W,C1] (+ x2 [B,H,W,C2]) bf16 NHWC -> [B,H,W,C1+C2] bf16."""
+              x2: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+              stats1: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x1 [B,H,W,C1] (+ x2 [B,H,W,C2]) bf16 NHWC -> [B,H,W,C1+C2] bf16.  With `stats1` (and `stats2`
+    when x2 is given) — the slab statistics the producing conv_gemm emitted — the statistics pass over
+    the tensors is skipped."""
     B, H, W, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[-1]
     if x2 is not None and x2.dtype != x1.dtype:
         raise TypeError("groupnorm: both sources must share a dtype")
     out = torch.empty((B, H, W, C1 + C2), dtype=BF16, device=x1.device)
     ws = workspace if workspace is not None else _gn_workspace(B, x1.device)
+    if stats1 is not None and (x2 is None or stats2 is not None):
+        check(_lib.load().rdeic_groupnorm_from_stats(_ptr(x1), C1, _ptr(stats1), _ptr(x2), C2, _ptr(stats2),
+                                                     int(x1.dtype == torch.float32), _ptr(gamma), _ptr(beta), _ptr(out),
+                                                     B, H * W, groups, eps, 1 if silu else 0, _ptr(ws), _stream()),
+              "rdeic_groupnorm_from_stats")
+        return out
     check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, int(x1.dtype == torch.float32), _ptr(gamma),
                                            _ptr(beta), _ptr(out), B, H * W, groups, eps, 1 if silu else 0, _ptr(ws),
                                            _stream()), "rdeic_groupnorm_nhwc")
@@ -421,12 +430,15 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
               dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0,
-              split_k: bool = True, act_param: float = 0.0):
+              split_k: bool = True, act_param: float = 0.0, stats: bool = False):
     """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out].
 
     Output selection: bf16 by default, fp32 with `out_f32`, both with `dual` (returns the pair
     (fp32, bf16): the fp32 master of a residual stream plus its bf16 tensor-core operand copy).
-    `out` may pre-allocate the destination (a tensor, or an (fp32, bf16) pair for `dual`)."""
+    `out` may pre-allocate the destination (a tensor, or an (fp32, bf16) pair for `dual`).
+    `stats`: also return the per-32-row-slab (sum, sumsq) of every output column ([M/32, n_out, 2]
+    fp32) for `groupnorm(..., stats1=...)`; returned as the last element of the result tuple, or
+    None when the pixel grid does not tile cleanly (`conv_stats_supported`)."""
     N, H, W, Cc = a.shape
     if a.dtype != BF16 or not _is_nhwc_slice(a):
         raise TypeError("conv_gemm: A must be bf16 NHWC, dense or a channel slice of a dense NHWC tensor")
@@ -467,6 +479,10 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         raise ValueError("conv_gemm: dual outputs must share the row stride")
     p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
+    st = None
+    if stats and conv_stats_supported(N, H, W) and n_out % 32 == 0 and act != 2:
+        st = torch.empty(((N * H * W + 31) // 32, n_out, 2), dtype=torch.float32, device=a.device)
+        p.stats_out = _ptr(st)
     if split_k:
         ws = _splitk_workspace(a.device)
         p.workspace, p.workspace_bytes = _ptr(ws), ws.numel()
@@ -479,9 +495,21 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         GEMM_PROFILE.append((e0, e1, 2.0 * N * H * W * n_out * k_true))
     else:
         check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
+    if stats:
+        return (of, oh, st) if dual else (ref, st)
     if dual:
         return of, oh
     return ref
+
+
+_stats_ok = {}
+
+
+def conv_stats_supported(N: int, H: int, W: int) -> bool:
+    key = (N, H, W)
+    if key not in _stats_ok:
+        _stats_ok[key] = bool(_lib.load().rdeic_conv_stats_supported(N, H, W)) and (H * W) % 32 == 0
+    return _stats_ok[key]
 
 
 def _is_nhwc_slice(t: torch.Tensor) -> bool:
@@ -501,10 +529,17 @@ def linear(x: torch.Tensor, w_packed: torch.Tensor, n_out: int, **kw):
     out = kw.pop("out", None)
     if out is not None:
         out = tuple(o.view(1, 1, M, o.shape[-1]) for o in out) if isinstance(out, tuple) else out.view(1, 1, M, out.shape[-1])
+    stats = kw.get("stats", False)
     y = conv_gemm(x.reshape(1, 1, M, K), w_packed, n_out, 1, resid=resid, out=out, **kw)
+    st = None
+    if stats:
+        *y, st = y
+        y = y[0] if len(y) == 1 else tuple(y)
     if isinstance(y, tuple):
-        return tuple(t.view(*x.shape[:-1], t.shape[-1]) for t in y)
-    return y.view(*x.shape[:-1], y.shape[-1])
+        y = tuple(t.view(*x.shape[:-1], t.shape[-1]) for t in y)
+        return y + (st,) if stats else y
+    y = y.view(*x.shape[:-1], y.shape[-1])
+    return (y, st) if stats else y
 
 
 def attention(q, k, v, heads: int, d: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:

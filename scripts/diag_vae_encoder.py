@@ -42,7 +42,7 @@ for tag in ("small", "full"):
     a = e._res32(e.mid1, a)
     hr = onn._vae_resnet(sd, E + ".mid.block_1", hr)
     cmp("mid1", a.f, hr)
-    t = e._attn(a.h)
+    t = e._attn(a.h)[0]
     hr = onn._vae_attn(sd, E + ".mid.attn_1", hr)
     cmp("attn", t, hr)
     a = e._res32(e.mid2, Act(None, t))

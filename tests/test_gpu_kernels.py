@@ -589,3 +589,49 @@ def test_pixel_shuffle2_bit_exact(cuda):
     xp = x.view(B, C, 4, H, W).transpose(1, 2).reshape(B, 4 * C, H, W)      # (2i + j)*C + c
     out = ops.pixel_shuffle2(xp.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()).float().cpu()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,f32", [(2, 32, 32, 128, 128, 3, False), (8, 8, 8, 64, 320, 3, True),
+                                                    (1, 64, 64, 320, 320, 1, True), (2, 16, 16, 256, 64, 3, False),
+                                                    (1, 128, 128, 128, 128, 3, False)])
+def test_groupnorm_from_fused_conv_stats(cuda, B, H, W, Cin, Cout, k, f32):
+    """GroupNorm statistics emitted by the producing GEMM's epilogue == a statistics pass over the
+    tensor it wrote (util.py:224 / model.py:48 semantics unchanged), single and two-source."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(71)
+    x = _bf(torch.randn(B, H, W, Cin, generator=g)).to(cuda).bfloat16()
+    w = ops.pack_conv_weight((_bf(torch.randn(Cout, Cin, k, k, generator=g)) / math.sqrt(k * k * Cin)).to(cuda))
+    b = torch.randn(Cout, generator=g).to(cuda)
+    resid = torch.randn(B, H, W, Cout, generator=g).to(cuda)
+    resid = resid if f32 else resid.bfloat16()
+    assert ops.conv_stats_supported(B, H, W)
+    if f32:
+        of, oh, st = ops.conv_gemm(x, w, Cout, k * k, bias=b, resid=resid, dual=True, stats=True)
+        y = of
+    else:
+        y, st = ops.conv_gemm(x, w, Cout, k * k, bias=b, resid=resid, stats=True)
+    assert st is not None and tuple(st.shape) == (B * H * W // 32, Cout, 2)
+    # slab sums against torch on the stored tensor (fp32 master exactly; bf16 output to rounding)
+    ref = y.float().view(B * H * W // 32, 32, Cout)
+    tol = 1e-4 if f32 else 2e-2
+    assert _rel(st[..., 0].cpu(), ref.sum(1).cpu()) < tol and _rel(st[..., 1].cpu(), (ref * ref).sum(1).cpu()) < tol
+    gamma, beta = (1 + 0.1 * torch.randn(Cout, generator=g)).to(cuda), (0.1 * torch.randn(Cout, generator=g)).to(cuda)
+    a = ops.groupnorm(y, gamma, beta, 32, 1e-5, True)
+    f = ops.groupnorm(y, gamma, beta, 32, 1e-5, True, stats1=st)
+    assert _rel(f.float().cpu(), a.float().cpu()) < (2e-3 if f32 else 6e-3)
+    # two sources (decoder concat, openaimodel.py:804): same tensor twice
+    g2, b2 = torch.cat([gamma, gamma]), torch.cat([beta, beta])
+    a2 = ops.groupnorm(y, g2, b2, 32, 1e-5, False, x2=y)
+    f2 = ops.groupnorm(y, g2, b2, 32, 1e-5, False, x2=y, stats1=st, stats2=st)
+    assert _rel(f2.float().cpu(), a2.float().cpu()) < (2e-3 if f32 else 6e-3)
+
+
+def test_conv_stats_unsupported_grid_falls_back(cuda):
+    from rdeic_b200 import ops
+
+    assert not ops.conv_stats_supported(1, 6, 10)            # ragged tiles
+    x = torch.randn(1, 6, 10, 64, device=cuda).bfloat16()
+    w = ops.pack_conv_weight(torch.randn(64, 64, 3, 3, device=cuda) / 24)
+    y, st = ops.conv_gemm(x, w, 64, 9, stats=True)
+    assert st is None and tuple(y.shape) == (1, 6, 10, 64)
