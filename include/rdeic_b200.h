@@ -223,9 +223,10 @@ typedef struct rdeic_conv_params {
                              Needs rdeic_conv_stats_supported(a_n, a_h, a_w); disables split-K. */
 } rdeic_conv_params;
 
-/* 1 if rdeic_conv_gemm can emit stats_out for an [a_n, a_h, a_w] pixel grid (every M tile full and
- * row-contiguous), else 0. */
-int rdeic_conv_stats_supported(int a_n, int a_h, int a_w);
+/* 1 if rdeic_conv_gemm should emit stats_out for an [a_n, a_h, a_w] pixel grid, n_out columns and
+ * k_blocks = taps * ceil(C/64) reduction blocks: every M tile full and row-contiguous, and the layer
+ * is not one the library runs split-K (those keep split-K and a separate statistics pass); else 0. */
+int rdeic_conv_stats_supported(int a_n, int a_h, int a_w, int n_out, int k_blocks);
 
 int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream);
 /* openaimodel.py:203 etc.: OIHW fp32 [n_out, c1+c2, kh, kw] -> packed bf16 (see above).

@@ -740,8 +740,18 @@ using namespace rdeic;
 
 extern "C" {
 
-int rdeic_conv_stats_supported(int a_n, int a_h, int a_w) {
-    return (a_n > 0 && a_h > 0 && a_w > 0 && stats_tiling_ok(a_n, a_h, a_w, false)) ? 1 : 0;
+int rdeic_conv_stats_supported(int a_n, int a_h, int a_w, int n_out, int k_blocks) {
+    if (a_n <= 0 || a_h <= 0 || a_w <= 0 || n_out <= 0 || n_out % 32) return 0;
+    if (!stats_tiling_ok(a_n, a_h, a_w, false)) return 0;
+    // layers that rdeic_conv_gemm would run split-K (few tiles, long reduction) keep split-K: their
+    // epilogue lives in the reduce kernel and the tensors are small enough for a statistics pass
+    int tw, th, tn;
+    pick_m_tile(a_n, a_h, a_w, false, &tw, &th, &tn);
+    const int64_t m_tiles = (int64_t)((a_w + tw - 1) / tw) * ((a_h + th - 1) / th) * ((a_n + tn - 1) / tn);
+    const int bn = pick_block_n(n_out, (int)m_tiles, 0);
+    const int64_t tiles = m_tiles * ((n_out + bn - 1) / bn);
+    if (tiles <= kNumSMs / 2 && k_blocks >= 8) return 0;
+    return 1;
 }
 
 int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, int c2, int kh,

@@ -253,12 +253,14 @@ def _load_unet(sd: SD, prefix: str, dev, *, model_channels: int, width: int, in_
 # UNet + control step
 # ---------------------------------------------------------------------------------------------
 class Act:
-    """An activation in HBM: fp32 master `f` (may be None) and bf16 tensor-core copy `h`."""
+    """An activation in HBM: fp32 master `f` (may be None) and bf16 tensor-core copy `h`, plus — when
+    the GEMM that wrote it could emit them — the per-slab channel statistics `st` that let a following
+    GroupNorm skip its statistics pass (None: GroupNorm computes its own)."""
 
-    __slots__ = ("f", "h")
+    __slots__ = ("f", "h", "st")
 
-    def __init__(self, f: Optional[torch.Tensor], h: Optional[torch.Tensor]):
-        self.f, self.h = f, h
+    def __init__(self, f: Optional[torch.Tensor], h: Optional[torch.Tensor], st: Optional[torch.Tensor] = None):
+        self.f, self.h, self.st = f, h, st
 
 
 class _Ctx:
@@ -354,20 +356,21 @@ class NoiseEstimatorEngine:
     # vs the fp32 reference 1.2e-2 -> see profiles/), at ~1.5x the bytes of block-boundary tensors.
     @staticmethod
     def _res(w: ResBlockW, x: "Act", x2: Optional["Act"], c: _Ctx) -> "Act":
-        h = ops.groupnorm(x.f, w.n_in.g, w.n_in.b, w.groups_in, 1e-5, True, x2=None if x2 is None else x2.f)
+        h = ops.groupnorm(x.f, w.n_in.g, w.n_in.b, w.groups_in, 1e-5, True, x2=None if x2 is None else x2.f,
+                          stats1=x.st, stats2=None if x2 is None else x2.st)
         rb = c.emb_rows[:, w.emb_off:w.emb_off + w.cout]
-        h = ops.conv_gemm(h, w.conv1.w, w.cout, 9, bias=w.conv1.b, row_bias=rb)
-        h = ops.groupnorm(h, w.n_out_norm.g, w.n_out_norm.b, w.groups_out, 1e-5, True)
+        h, st = ops.conv_gemm(h, w.conv1.w, w.cout, 9, bias=w.conv1.b, row_bias=rb, stats=True)
+        h = ops.groupnorm(h, w.n_out_norm.g, w.n_out_norm.b, w.groups_out, 1e-5, True, stats1=st)
         xs = x.f
         if w.skip is not None:
             xs = ops.conv_gemm(x.h, w.skip.w, w.cout, 1, a2=None if x2 is None else x2.h, bias=w.skip.b, out_f32=True)
-        return Act(*ops.conv_gemm(h, w.conv2.w, w.cout, 9, bias=w.conv2.b, resid=xs, dual=True))
+        return Act(*ops.conv_gemm(h, w.conv2.w, w.cout, 9, bias=w.conv2.b, resid=xs, dual=True, stats=True))
 
     @staticmethod
     def _attn(w: TransformerW, x: "Act", c: _Ctx) -> "Act":
         B, H, W, C = x.f.shape
         scale = w.d_head ** -0.5
-        hn = ops.groupnorm(x.f, w.norm.g, w.norm.b, w.groups, 1e-6, False)
+        hn = ops.groupnorm(x.f, w.norm.g, w.norm.b, w.groups, 1e-6, False, stats1=x.st)
         h = ops.linear(hn.view(B, H * W, C), w.proj_in.w, C, bias=w.proj_in.b, out_f32=True)   # token stream, fp32
         n1 = ops.layernorm(h, w.ln1.g, w.ln1.b)
         qkv = ops.linear(n1, w.qkv.w, 3 * C)
@@ -381,8 +384,9 @@ class NoiseEstimatorEngine:
         n3 = ops.layernorm(h, w.ln3.g, w.ln3.b)
         f = ops.linear(n3, w.ff1.w, w.ff1.n_out, bias=w.ff1.b, act=2)       # GEGLU fused in the epilogue
         hb = ops.linear(f, w.ff2.w, C, bias=w.ff2.b, resid=h)                 # only consumer is proj_out's A operand
-        of, oh = ops.linear(hb, w.proj_out.w, C, bias=w.proj_out.b, resid=x.f.view(B, H * W, C), dual=True)
-        return Act(of.view(B, H, W, C), oh.view(B, H, W, C))
+        of, oh, st = ops.conv_gemm(hb.view(B, H, W, -1), w.proj_out.w, C, 1, bias=w.proj_out.b, resid=x.f, dual=True,
+                                   stats=True)
+        return Act(of, oh, st)
 
     def _run_block(self, layers: List[Layer], x: "Act", x2: Optional["Act"], c: _Ctx, x_in2=None) -> "Act":
         for L in layers:
@@ -394,12 +398,13 @@ class NoiseEstimatorEngine:
             elif L.kind == "down":
                 B, H, W, C = x.h.shape
                 col = ops.im2col_3x3_s2(x.h)
-                of, oh = ops.linear(col, L.w.w, L.w.n_out, bias=L.w.b, dual=True)
-                x = Act(of.view(B, H // 2, W // 2, L.w.n_out), oh.view(B, H // 2, W // 2, L.w.n_out))
+                of, oh, st = ops.conv_gemm(col.view(B, H // 2, W // 2, -1), L.w.w, L.w.n_out, 1, bias=L.w.b, dual=True,
+                                           stats=True)
+                x = Act(of, oh, st)
             elif L.kind == "up":
-                x = Act(*ops.conv_gemm(ops.upsample2x(x.h), L.w.w, L.w.n_out, 9, bias=L.w.b, dual=True))
+                x = Act(*ops.conv_gemm(ops.upsample2x(x.h), L.w.w, L.w.n_out, 9, bias=L.w.b, dual=True, stats=True))
             elif L.kind == "conv_in":
-                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, a2=x_in2, bias=L.w.b, dual=True))
+                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, a2=x_in2, bias=L.w.b, dual=True, stats=True))
             else:
                 raise RuntimeError(L.kind)
         return x
@@ -407,7 +412,9 @@ class NoiseEstimatorEngine:
     def _inject(self, z: Conv, hb: "Act", hc: "Act", scale: float) -> "Act":
         """h_base = h_base + zero_conv(h_ctr) * scale (rdeic.py:194,203,207) as the residual epilogue of
         the 1x1 GEMM, updating both copies of h_base in place."""
-        ops.conv_gemm(hc.h, z.w, z.n_out, 1, bias=z.b, resid=hb.f, alpha=scale, dual=True, out=(hb.f, hb.h))
+        # the statistics of the updated h_base replace the now stale ones of its producer
+        _, _, hb.st = ops.conv_gemm(hc.h, z.w, z.n_out, 1, bias=z.b, resid=hb.f, alpha=scale, dual=True,
+                                    out=(hb.f, hb.h), stats=True)
         return hb
 
     # ----- one relay step -------------------------------------------------------------------------
@@ -492,7 +499,8 @@ class NoiseEstimatorEngine:
                 hb = self._inject(self.dec_zero[i], hb, hs_ctr.pop(), self.scales[si])
                 si += 1
                 hb = self._run_block(blk, hb, hs_base.pop(), cb)
-        hn = ops.groupnorm(hb.f, self.base.out_norm.g, self.base.out_norm.b, find_denominator(hb.f.shape[-1], 32), 1e-5, True)
+        hn = ops.groupnorm(hb.f, self.base.out_norm.g, self.base.out_norm.b, find_denominator(hb.f.shape[-1], 32), 1e-5, True,
+                           stats1=hb.st)
         o = ops.conv_gemm(hn, self.base.out_conv.w, self.out_channels, 9, bias=self.base.out_conv.b, out_f32=True)
         return ops.nhwc_to_nchw_f32(o)
 

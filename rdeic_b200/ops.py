@@ -480,7 +480,8 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
     st = None
-    if stats and conv_stats_supported(N, H, W) and n_out % 32 == 0 and act != 2:
+    kb = taps * ((Cc + 63) // 64 + ((a2.shape[-1] + 63) // 64 if a2 is not None else 0))
+    if stats and act != 2 and w_batch_stride == 0 and conv_stats_supported(N, H, W, n_out, kb):
         st = torch.empty(((N * H * W + 31) // 32, n_out, 2), dtype=torch.float32, device=a.device)
         p.stats_out = _ptr(st)
     if split_k:
@@ -505,10 +506,11 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
 _stats_ok = {}
 
 
-def conv_stats_supported(N: int, H: int, W: int) -> bool:
-    key = (N, H, W)
+def conv_stats_supported(N: int, H: int, W: int, n_out: int = 32, k_blocks: int = 1) -> bool:
+    """Whether conv_gemm(stats=True) will emit GroupNorm statistics for this problem shape."""
+    key = (N, H, W, n_out, k_blocks)
     if key not in _stats_ok:
-        _stats_ok[key] = bool(_lib.load().rdeic_conv_stats_supported(N, H, W)) and (H * W) % 32 == 0
+        _stats_ok[key] = bool(_lib.load().rdeic_conv_stats_supported(N, H, W, n_out, k_blocks)) and (H * W) % 32 == 0
     return _stats_ok[key]
 
 

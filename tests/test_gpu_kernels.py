@@ -591,9 +591,9 @@ def test_pixel_shuffle2_bit_exact(cuda):
     assert torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,k,f32", [(2, 32, 32, 128, 128, 3, False), (8, 8, 8, 64, 320, 3, True),
-                                                    (1, 64, 64, 320, 320, 1, True), (2, 16, 16, 256, 64, 3, False),
-                                                    (1, 128, 128, 128, 128, 3, False)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,f32", [(16, 32, 32, 128, 128, 3, False), (8, 8, 8, 64, 320, 1, True),
+                                                    (1, 64, 64, 320, 320, 1, True), (16, 32, 32, 256, 64, 3, False),
+                                                    (1, 128, 128, 128, 128, 3, False), (2, 64, 64, 320, 320, 3, True)])
 def test_groupnorm_from_fused_conv_stats(cuda, B, H, W, Cin, Cout, k, f32):
     """GroupNorm statistics emitted by the producing GEMM's epilogue == a statistics pass over the
     tensor it wrote (util.py:224 / model.py:48 semantics unchanged), single and two-source."""
@@ -605,7 +605,7 @@ def test_groupnorm_from_fused_conv_stats(cuda, B, H, W, Cin, Cout, k, f32):
     b = torch.randn(Cout, generator=g).to(cuda)
     resid = torch.randn(B, H, W, Cout, generator=g).to(cuda)
     resid = resid if f32 else resid.bfloat16()
-    assert ops.conv_stats_supported(B, H, W)
+    assert ops.conv_stats_supported(B, H, W, Cout, k * k * ((Cin + 63) // 64))
     if f32:
         of, oh, st = ops.conv_gemm(x, w, Cout, k * k, bias=b, resid=resid, dual=True, stats=True)
         y = of
@@ -631,6 +631,8 @@ def test_conv_stats_unsupported_grid_falls_back(cuda):
     from rdeic_b200 import ops
 
     assert not ops.conv_stats_supported(1, 6, 10)            # ragged tiles
+    assert not ops.conv_stats_supported(8, 8, 8, 1280, 9 * 20)     # a split-K layer keeps split-K
+    assert ops.conv_stats_supported(8, 8, 8, 1280, 4)
     x = torch.randn(1, 6, 10, 64, device=cuda).bfloat16()
     w = ops.pack_conv_weight(torch.randn(64, 64, 3, 3, device=cuda) / 24)
     y, st = ops.conv_gemm(x, w, 64, 9, stats=True)
