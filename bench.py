@@ -261,14 +261,25 @@ def run_b200(args):
     model.use_cuda_graph = False
     decode_device()
     torch.cuda.synchronize()
-    ops.GEMM_PROFILE = []
-    # Park the GPU behind a ~150 ms spin so the host gets ahead and every (event, kernel, event) triple
-    # is already queued when the GPU reaches it: otherwise each bracket also times the host's ~10 us
-    # enqueue gap, which for 1 577 short launches is a sizeable over-count.
-    torch.cuda._sleep(int(0.15 * 1.9e9))
+    # Park the GPU behind a ~40 ms spin every 150 profiled launches so the host stays ahead and every
+    # (event, kernel, event) triple is already queued when the GPU reaches it: otherwise each bracket
+    # also times the host's ~15 us Python enqueue gap, which for 1 577 short launches is a sizeable
+    # over-count.  (One long spin at the start is not enough: the launch queue holds ~1 000 entries,
+    # so the host can only get that far ahead.)  The spins are outside every bracket.
+    class _Parked(list):
+        def append(self, item):
+            if len(self) % 150 == 0:
+                torch.cuda._sleep(int(0.04 * 1.9e9))
+            super().append(item)
+
+    # one stream for this pass: a bracket around a kernel that shares the GPU with the control
+    # adapter's stream would time the sharing, not the kernel
+    overlap, model.control_model.overlap_control = model.control_model.overlap_control, False
+    ops.GEMM_PROFILE = _Parked()
     decode_device()
     torch.cuda.synchronize()
-    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    prof, ops.GEMM_PROFILE = list(ops.GEMM_PROFILE), None
+    model.control_model.overlap_control = overlap
     model.use_cuda_graph = True
     g_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
     g_fl = sum(f for _, _, f in prof)
