@@ -297,6 +297,59 @@ softmax_rows_kernel(const void* __restrict__ in, __nv_bfloat16* __restrict__ out
     }
 }
 
+// fp32 rows of n <= 8192 (n % 4 == 0): the row lives in registers (up to 8 float4 per thread), one
+// 16-byte read and one 8-byte write per 4 elements — the VAE mid-attention logits [B*N, N] are read
+// once instead of three times.
+template <int kVec>
+__global__ void __launch_bounds__(256)
+softmax_rows_f32_reg_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int n4, float scale) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t row = blockIdx.x;
+    const float4* src = in + row * n4;
+    __shared__ float red[8];
+    float4 v[kVec];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        const int i = threadIdx.x + 256 * j;
+        v[j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (i < n4) {
+            const uint4 u = ld_stream_u4(src + i);
+            const float4 t = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            v[j] = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
+        }
+        m = fmaxf(m, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        v[j].x = __expf(v[j].x - m); v[j].y = __expf(v[j].y - m);
+        v[j].z = __expf(v[j].z - m); v[j].w = __expf(v[j].w - m);
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        const int i = threadIdx.x + 256 * j;
+        if (i < n4)
+            out[row * n4 + i] = make_uint2(pack_bf16x2(v[j].x * inv, v[j].y * inv), pack_bf16x2(v[j].z * inv, v[j].w * inv));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                       int R, int C) {
@@ -484,7 +537,12 @@ int rdeic_softmax_rows(const void* in, int in_is_f32, void* out_bf16, int64_t ro
     RDEIC_CHECK_ARG(in && out_bf16 && rows >= 0 && n > 0, "rdeic_softmax_rows: bad args");
     RDEIC_CHECK_ARG(rows < (1ll << 31), "rdeic_softmax_rows: too many rows");
     if (rows == 0) return 0;
-    if (in_is_f32) launch_k(softmax_rows_kernel<true>, (unsigned)rows, 256, 0, as_stream(stream), in, (__nv_bfloat16*)out_bf16, n, scale);
+    const bool vec = in_is_f32 && n % 4 == 0 && n <= 8192 && ((uintptr_t)in | (uintptr_t)out_bf16) % 16 == 0;
+    if (vec && n <= 1024) launch_k(softmax_rows_f32_reg_kernel<1>, (unsigned)rows, 256, 0, as_stream(stream), (const float4*)in, (uint2*)out_bf16, n / 4, scale);
+    else if (vec && n <= 2048) launch_k(softmax_rows_f32_reg_kernel<2>, (unsigned)rows, 256, 0, as_stream(stream), (const float4*)in, (uint2*)out_bf16, n / 4, scale);
+    else if (vec && n <= 4096) launch_k(softmax_rows_f32_reg_kernel<4>, (unsigned)rows, 256, 0, as_stream(stream), (const float4*)in, (uint2*)out_bf16, n / 4, scale);
+    else if (vec) launch_k(softmax_rows_f32_reg_kernel<8>, (unsigned)rows, 256, 0, as_stream(stream), (const float4*)in, (uint2*)out_bf16, n / 4, scale);
+    else if (in_is_f32) launch_k(softmax_rows_kernel<true>, (unsigned)rows, 256, 0, as_stream(stream), in, (__nv_bfloat16*)out_bf16, n, scale);
     else launch_k(softmax_rows_kernel<false>, (unsigned)rows, 256, 0, as_stream(stream), in, (__nv_bfloat16*)out_bf16, n, scale);
     RDEIC_LAUNCH_CHECK();
     return 0;

@@ -268,9 +268,11 @@ def test_geglu_upsample_im2col_transpose_softmax(cuda):
     t = _bf(torch.randn(3, 33, 50, generator=g))
     assert torch.equal(ops.transpose_bf16(t.to(cuda).bfloat16()).float().cpu(), t.transpose(1, 2))
 
-    s = torch.randn(5, 777, generator=g) * 3
-    sm = ops.softmax_rows(s.to(cuda), 0.7).float().cpu()
-    assert torch.allclose(sm, F.softmax(s * 0.7, dim=-1), atol=2e-3)
+    for n in (777, 64, 1024, 1100, 4096, 8192, 8196):      # scalar fallback and every register-resident width
+        s = torch.randn(5, n, generator=g) * 3
+        sm = ops.softmax_rows(s.to(cuda), 0.7).float().cpu()
+        assert torch.allclose(sm, F.softmax(s * 0.7, dim=-1), atol=2e-3), n
+        assert torch.allclose(sm.sum(-1), torch.ones(5), atol=2e-2), n
 
 
 def test_image_to_u8(cuda):
