@@ -703,7 +703,11 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
     // kept for experiments only: with the affine fast path both measured slower than loading the
     // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
-    if (d.stats_out) return launch_conv3<BN, 0, 8, true>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (d.stats_out) {
+        static const int epi12_kb_s = getenv("RDEIC_EPI12_KB") ? atoi(getenv("RDEIC_EPI12_KB")) : 10;
+        if (d.taps * (d.cblk1 + d.cblk2) <= epi12_kb_s) return launch_conv3<BN, 0, 12, true>(ta, ta2, tb, d, m_tiles, splits, s);
+        return launch_conv3<BN, 0, 8, true>(ta, ta2, tb, d, m_tiles, splits, s);
+    }
     static const bool pre16 = getenv("RDEIC_RESID_PREFETCH") != nullptr;
     if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv3<BN, 1, 8>(ta, ta2, tb, d, m_tiles, splits, s);
     static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
