@@ -12,6 +12,7 @@
 // the control adapter's d = 16 heads stay on the mma.sync kernel in attention.cu.
 #include "common.cuh"
 #include "sm100.cuh"
+#include <stdlib.h>
 #include "../../include/rdeic_b200.h"
 
 namespace rdeic {
@@ -262,6 +263,221 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two query tiles per CTA ("ping-pong"): 256 query rows, two softmax warp groups (A: rows 0-127,
+// B: rows 128-255) of four warps, ONE thread per query row — no pair exchange, no named barrier.
+// The exp pass is MUFU bound; everything around it (max pass, O fold-in, rescale, barrier waits) is
+// not.  With one group per CTA those phases leave the MUFU pipe idle; with two groups that drift half
+// a period apart one group's MUFU phase covers the other's bookkeeping, and the single MMA thread
+// always has the other group's S / PV to issue.  S, P and O are single-buffered per group: program
+// order inside a group already guarantees the hand-offs (P(j+1) and PV(j+1) come after add_o(j)).
+// ---------------------------------------------------------------------------------------------
+constexpr int kA2Q = 256;
+constexpr int kA2Threads = 64 + 32 * 8;
+constexpr int kA2Smem = 2 * kATile /*Q*/ + 2 * kAStages * kATile /*K,V*/ + 2 * kAPBytes /*P_A,P_B*/ + 1024 + 256;
+constexpr uint32_t kA2ColS = 0, kA2ColO = 256;    // S_A 0, S_B 128 ; O_A 256, O_B 320
+
+__global__ void __launch_bounds__(kA2Threads, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_q = smem;                                   // 2 tiles: rows 0-127 | 128-255
+    uint8_t* s_k = s_q + 2 * kATile;
+    uint8_t* s_v = s_k + kAStages * kATile;
+    uint8_t* s_p = s_v + kAStages * kATile;                // P_A | P_B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAPBytes);
+    uint64_t* q_full = bars;                  // [1]
+    uint64_t* kv_full = bars + 1;             // [kAStages]
+    uint64_t* kv_empty = kv_full + kAStages;  // [kAStages]
+    uint64_t* s_full = kv_empty + kAStages;   // [2] per group: S tile ready
+    uint64_t* s_free = s_full + 2;            // [2] per group: S tile consumed
+    uint64_t* p_full = s_free + 2;            // [2] per group: P tile written
+    uint64_t* o_full = p_full + 2;            // [2] per group: PV tile ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int T = p.tiles_k;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1);
+            mbar_init(&s_free[g], 4);
+            mbar_init(&p_full[g], 4);
+            mbar_init(&o_full[g], 1);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * kATile);
+            tma_load_3d(&tm_q, s_q, q_full, head * kAD, qt * kA2Q, b);
+            tma_load_3d(&tm_q, s_q + kATile, q_full, head * kAD, qt * kA2Q + kAQ, b);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % kAStages;
+                mbar_wait(&kv_empty[s], ((j / kAStages) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], 2 * kATile);
+                tma_load_3d(&tm_k, s_k + s * kATile, &kv_full[s], head * kAD, j * kAK, b);
+                tma_load_3d(&tm_v, s_v + s * kATile, &kv_full[s], head * kAD, j * kAK, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_mn(kAQ, kAK, false);
+            constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);
+            auto issue_s = [&](int g, int j) {
+                if (j > 0) mbar_wait(&s_free[g], (j - 1) & 1);      // softmax_g(j-1) has read S_g
+                tc_fence_after();
+                const uint64_t dq = make_smem_desc(smem_u32(s_q + g * kATile));
+                const uint64_t dk = make_smem_desc(smem_u32(s_k + (j % kAStages) * kATile));
+#pragma unroll
+                for (int k = 0; k < kAD / 16; ++k)
+                    umma_bf16(tmem_base + kA2ColS + g * kAK, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[g]);
+            };
+            auto issue_pv = [&](int g, int i) {
+                mbar_wait(&p_full[g], i & 1);
+                tc_fence_after();
+                const uint32_t pb = smem_u32(s_p + g * kAPBytes);
+                const uint64_t dv = make_smem_desc_mn(smem_u32(s_v + (i % kAStages) * kATile));
+#pragma unroll
+                for (int ks = 0; ks < kAK / 16; ++ks) {
+                    const uint64_t dp = make_smem_desc(pb + (ks >> 2) * (kAQ * 128) + (ks & 3) * 32);
+                    umma_bf16(tmem_base + kA2ColO + g * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o, ks != 0);
+                }
+                umma_commit(&o_full[g]);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < T; ++j) {
+                mbar_wait(&kv_full[j % kAStages], (j / kAStages) & 1);
+                // steady-state arrival order of the waits: A frees S, A finishes P, then B half a period later
+                issue_s(0, j);
+                if (j > 0) issue_pv(0, j - 1);
+                issue_s(1, j);
+                if (j > 0) { issue_pv(1, j - 1); umma_commit(&kv_empty[(j - 1) % kAStages]); }
+            }
+            issue_pv(0, T - 1);
+            issue_pv(1, T - 1);
+            umma_commit(&kv_empty[(T - 1) % kAStages]);
+        }
+    } else {
+        const int g = (warp - 2) >> 2;              // softmax group: 0 = A, 1 = B
+        const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;           // row inside the group's 128-row tile
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float sc = p.scale_log2;
+        float o[kAD];
+#pragma unroll
+        for (int i = 0; i < kAD; ++i) o[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t ts = tmem_base + lane_addr + kA2ColS + g * kAK;
+        const uint32_t to = tmem_base + lane_addr + kA2ColO + g * kAD;
+        uint8_t* prow0 = s_p + g * kAPBytes + row * 128;
+
+        auto add_o = [&](int i) {
+            mbar_wait(&o_full[g], i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t r[32];
+                tmem_ld16(to + c2 * 32, r);
+                tmem_ld16(to + c2 * 32 + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c2 * 32 + c] += __uint_as_float(r[c]);
+            }
+            tc_fence_before();
+        };
+
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t r[32];
+                tmem_ld16(ts + c4 * 32, r);
+                tmem_ld16(ts + c4 * 32 + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+            }
+            const float m_new = fmaxf(m_run, mx * sc);
+            const float corr = ex2_approx(m_run - m_new);
+            // fold in the previous tile's PV (also proves P_g and O_g are free again), rescale
+            if (j > 0) add_o(j - 1);
+#pragma unroll
+            for (int i = 0; i < kAD; ++i) o[i] *= corr;
+            float rowsum = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t r[32];
+                tmem_ld16(ts + c4 * 32, r);
+                tmem_ld16(ts + c4 * 32 + 16, r + 16);
+                tmem_ld_wait();
+                if (c4 == 3) {                     // last read of S_g: the MMA thread may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_free[g]);
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * c]), sc, -m_new));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * c + 1]), sc, -m_new));
+                    rowsum += p0 + p1;
+                    pk[c] = pack_bf16x2(p0, p1);
+                }
+                uint8_t* prow = prow0 + (c4 >> 1) * (kAQ * 128);      // 64-key panel
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int chunk = (c4 & 1) * 4 + q;
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
+                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l_run = fmaf(l_run, corr, rowsum);
+            m_run = m_new;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+        }
+        add_o(T - 1);
+        const float inv = 1.0f / l_run;
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(qt * kA2Q + g * kAQ + row) * p.ldo + head * kAD;
+#pragma unroll
+        for (int v8 = 0; v8 < kAD / 8; ++v8) {
+            uint4 w;
+            w.x = pack_bf16x2(o[8 * v8] * inv, o[8 * v8 + 1] * inv);
+            w.y = pack_bf16x2(o[8 * v8 + 2] * inv, o[8 * v8 + 3] * inv);
+            w.z = pack_bf16x2(o[8 * v8 + 4] * inv, o[8 * v8 + 5] * inv);
+            w.w = pack_bf16x2(o[8 * v8 + 6] * inv, o[8 * v8 + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + 8 * v8) = w;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // host: true when the tcgen05 kernel can take the problem
 bool attention_tc_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                             int64_t q_bs, int64_t k_bs, int64_t v_bs, const void* q, const void* k, const void* v,
@@ -297,6 +513,19 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
     d.out = (__nv_bfloat16*)out;
     d.ldo = ldo;
     d.o_bs = o_bs;
+    // two query tiles per CTA when that still leaves several waves of CTAs
+    static const int pp_min = getenv("RDEIC_ATTN_PINGPONG_MIN") ? atoi(getenv("RDEIC_ATTN_PINGPONG_MIN")) : 2 * kNumSMs;
+    if (Nq % kA2Q == 0 && (int64_t)(Nq / kA2Q) * heads * B >= pp_min) {
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+            attr2_set = true;
+        }
+        dim3 grid2(Nq / kA2Q, heads, B);
+        launch_k(attention_tc2_kernel, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
+        RDEIC_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(Nq / kAQ, heads, B);
     launch_k(attention_tc_kernel, grid, kAThreads, kASmem, stream, tq, tk, tv, d);
     RDEIC_LAUNCH_CHECK();

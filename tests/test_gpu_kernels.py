@@ -470,11 +470,12 @@ def test_split_k_matches_single_pass(cuda, M, K, N):
 
 
 # ------------------------------------------------------------------------------------------
-# attention: bf16 P, fp32 softmax: abs tol 2e-2 on O(1) outputs
+# attention: bf16 P, fp32 softmax: abs tol 2e-2 on O(1) outputs.  The last two shapes have enough
+# CTAs (>= 2 per SM at 256 query rows each) to take the two-query-tile "ping-pong" tcgen05 kernel.
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", [(2, 5, 256, 256, 64), (1, 10, 100, 77, 64), (1, 4, 1024, 1024, 16),
                                              (2, 16, 64, 77, 16), (1, 20, 64, 64, 64), (1, 2, 4096, 4096, 64),
-                                             (1, 3, 70, 130, 16)])
+                                             (1, 3, 70, 130, 16), (8, 10, 1024, 1024, 64), (5, 15, 1024, 384, 64)])
 def test_attention(cuda, B, heads, Nq, Nk, d):
     from rdeic_b200 import ops
 
