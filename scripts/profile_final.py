@@ -1,7 +1,9 @@
 """Representative launches of each kernel class for the committed ncu --set full capture:
 0 conv3x3 320->320 @64^2 (UNet level 0, fp32 residual + dual write)   1 conv3x3 512->512 @128^2 (VAE)
 2 linear K=320 N=320 + fp32 residual   3 GEGLU linear K=320 N=2560   4 tcgen05 attention N=4096 h=5 d=64
-5 GroupNorm+SiLU [8,512,512,128]   6 LayerNorm [32768,320]   7 relay_update   8 ckbd encode phase"""
+5 GroupNorm+SiLU [8,512,512,128] (stats + apply)   6 LayerNorm [32768,320]   7 relay_update   8 ckbd encode phase
+9 conv3x3 128->128 @512^2 (VAE) emitting GroupNorm statistics   10 GroupNorm from those statistics (fold + apply)
+11 conv5x5 8->224 @32^2 batch 8 (compressor channel context)"""
 import sys
 from pathlib import Path
 import torch
@@ -22,6 +24,9 @@ g3, b3 = torch.ones(320, device=dev), torch.zeros(320, device=dev)
 u = [rnd(1 << 24) for _ in range(3)]
 y, mu = rnd(8, 64, 128, 128) * 6, rnd(8, 64, 128, 128) * 2
 sc = torch.exp(torch.rand(8, 64, 128, 128, generator=g, device=dev) * 8 - 3); tab = get_scale_table().to(dev)
+w128 = ops.pack_conv_weight(rnd(128, 128, 3, 3) / 34)
+_, st128 = ops.conv_gemm(gn, w128, 128, 9, bias=gam, resid=gn, stats=True)
+x8 = rnd(8, 32, 32, 8).bfloat16(); w5 = ops.pack_conv_weight(rnd(224, 8, 5, 5) / 14); b224 = rnd(224)
 fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True),
        lambda: ops.conv_gemm(x512, w512, 512, 9, bias=b512),
        lambda: ops.linear(xl, wl, 320, bias=b320, resid=rl, out_f32=True),
@@ -30,7 +35,10 @@ fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True
        lambda: ops.groupnorm(gn, gam, bet, 32, 1e-6, True),
        lambda: ops.layernorm(xl, g3, b3),
        lambda: ops.relay_update(u[0], u[1], u[2], 1.2, 0.8, 0.4, 0.6, 0.3),
-       lambda: ops.ckbd_encode_phase(y, sc, mu, tab, 0.11, 0)]
+       lambda: ops.ckbd_encode_phase(y, sc, mu, tab, 0.11, 0),
+       lambda: ops.conv_gemm(gn, w128, 128, 9, bias=gam, resid=gn, stats=True),
+       lambda: ops.groupnorm(gn, gam, bet, 32, 1e-6, True, stats1=st128),
+       lambda: ops.conv_gemm(x8, w5, 224, 25, bias=b224, act=4)]
 for _ in range(2):
     for f in fns:
         f()
