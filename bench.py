@@ -321,6 +321,97 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# the learned compressor either side of the decode (not the headline line)
+# ---------------------------------------------------------------------------------------------
+def run_compressor(args):
+    """`--compressor B`: compress / decompress of B 512x512 images through `rdeic_b200.compression.
+    Compression` (feature map [B,512,64,64] -> y [B,256,32,32], z [B,256,8,8]); byte coders replaced by
+    an in-memory replay (rANS / torchac are host libraries outside this path); at B = 1 the CPU oracle
+    (reference algorithm, torch fp32, all host cores) is timed beside it on the same image."""
+    from rdeic_b200 import build, configs, ops, synthetic
+    from rdeic_b200.compression import Compression
+
+    build.build()
+    B = args.compressor
+    dev = torch.device("cuda:0")
+    pp = configs.default_params()["preprocess_config"]["params"]
+    sd = synthetic.make_compression_state_dict(pp, seed=232)
+
+    class Loop:
+        accepts_arrays = True       # int32 numpy views of the pinned hand-off buffers, no Python lists
+
+        def __init__(self):
+            self.symbols, self.pos = [], 0
+
+        def encode_with_indexes(self, symbols, indexes, *a):
+            self.symbols = symbols.copy()
+
+        def flush(self):
+            return b""
+
+        def set_stream(self, s):
+            self.pos = 0
+
+        def decode_stream(self, indexes, *a):
+            n = len(indexes)
+            out = self.symbols[self.pos:self.pos + n]
+            self.pos += n
+            return out
+
+    class Hyp:
+        def compress(self, idx):
+            return idx
+
+        def decompress(self, s, shape):
+            return s
+
+    loop = Loop()
+    m = Compression(device=dev, rans_encoder=lambda: loop, rans_decoder=lambda: loop, hyper_latent_coder=Hyp(), **pp)
+    m.load_state_dict(sd)
+    x = torch.randn(B, pp["in_nc"], 64, 64, generator=torch.Generator().manual_seed(3))
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3, r
+
+    m.use_cuda_graph = False
+    ops.LAUNCHES = 0
+    out = m.compress(x)
+    torch.cuda.synchronize()
+    launches_c = ops.LAUNCHES
+    ops.LAUNCHES = 0
+    m.decompress(out["strings"], out["shape"])
+    torch.cuda.synchronize()
+    launches_d = ops.LAUNCHES
+    ms_c_eager, _ = timed(lambda: m.compress(x), 5)
+    ms_d_eager, _ = timed(lambda: m.decompress(out["strings"], out["shape"]), 5)
+    m.use_cuda_graph = True
+    ms_c, out = timed(lambda: m.compress(x), 10)
+    ms_d, _ = timed(lambda: m.decompress(out["strings"], out["shape"]), 10)
+    res = {"workload": f"512x512 image, batch {B}: feature map [B,512,64,64] -> y [B,256,32,32], z [B,256,8,8]",
+           "compress_ms": ms_c, "decompress_ms": ms_d, "compress_ms_no_graph": ms_c_eager,
+           "decompress_ms_no_graph": ms_d_eager, "kernel_launches": {"compress": launches_c, "decompress": launches_d},
+           "symbols_per_image": len(loop.symbols) // B}
+    if B == 1:
+        from oracle import compression_nets as ocn
+
+        torch.set_num_threads(os.cpu_count())
+        t0 = time.perf_counter()
+        r = ocn.compress(sd, x, pp["slice_ch"])
+        t1 = time.perf_counter()
+        ocn.decompress(sd, r["z_idx"].numpy(), r["symbols"], r["indexes"], pp["slice_ch"])
+        t2 = time.perf_counter()
+        res["cpu_baseline"] = {"compress_ms": (t1 - t0) * 1e3, "decompress_ms": (t2 - t1) * 1e3, "cores": os.cpu_count(),
+                               "kind": "port", "sample": "one 512x512 image"}
+    print(json.dumps(res), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,8 +419,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compressor", type=int, default=0, metavar="B",
+                    help="measure the learned compressor (SURVEY 8f rows) on B 512x512 images instead of the decode")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.compressor:
+        run_compressor(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -237,7 +237,7 @@ def test_vae_encoder_matches_reference(cuda, tag):
     c = VAEEncoderEngine(sd, device=cuda).encode_hc(torch.from_numpy(g["x"]).to(cuda))
     assert tuple(c.shape) == g["c"].shape
     # 26 convs deep with bf16 operands and random (non-contracting) weights: operand rounding adds up
-    # to 1.3e-2 (full) / 1.5e-2 (small) even with the fp32 residual master (scripts/diag_vae_encoder.py)
+    # to 1.3e-2 (full) / 1.5e-2 (small) even with the fp32 residual master (tests/tools/diag_vae_encoder.py)
     assert rel_l2(c.cpu(), g["c"]) < 2e-2
 
 
