@@ -28,7 +28,6 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 // warp0 TMA, warp1 MMA(+TMEM alloc), then kEW epilogue warps (8 or 12: two or three per TMEM lane
 // quadrant; 12 gives the latency-bound epilogue of small-K problems one more warp per scheduler at the
 // price of a 128-register cap and one pipeline stage)
-constexpr int kMaxEpiWarps = 12;
 
 struct ConvDev {
     int a_n, a_h, a_w;
