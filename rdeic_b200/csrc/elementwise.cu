@@ -195,21 +195,26 @@ geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows
     }
 }
 
-// nearest x2 upsample, NHWC bf16, 8 channels per thread
+// nearest x2 upsample, NHWC bf16: one thread per INPUT 16-byte vector, four streaming stores (the 2x2
+// output pixels) — a quarter of the loads and index divisions of an output-indexed copy
 __global__ void __launch_bounds__(kThreads)
 upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                   int cv) {
     pdl_trigger();
     pdl_wait();
-    const int64_t total = (int64_t)B * (2 * H) * (2 * W) * cv;
+    const int64_t total = (int64_t)B * H * W * cv;
+    const int64_t orow = (int64_t)2 * W * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cv);
         int64_t p = i / cv;
-        const int ow = (int)(p % (2 * W)); p /= (2 * W);
-        const int oh = (int)(p % (2 * H));
-        const int b = (int)(p / (2 * H));
-        out[i] = in[(((int64_t)b * H + (oh >> 1)) * W + (ow >> 1)) * cv + c];
+        const int iw = (int)(p % W); p /= W;            // p = b*H + ih
+        const uint4 v = ld_stream_u4(in + i);
+        uint4* o = out + (2 * p) * orow + (int64_t)(2 * iw) * cv + c;
+        st_stream_u4(o, v);
+        st_stream_u4(o + cv, v);
+        st_stream_u4(o + orow, v);
+        st_stream_u4(o + orow + cv, v);
     }
 }
 
@@ -500,8 +505,8 @@ int rdeic_upsample2x_nhwc(const void* in, void* out, int B, int H, int W, int C,
                           rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0, "rdeic_upsample2x_nhwc: bad args");
     RDEIC_CHECK_ARG(C > 0 && C % 8 == 0, "rdeic_upsample2x_nhwc: C=%d must be a multiple of 8", C);
-    const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
-    launch_k(upsample2x_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream), 
+    const int64_t total = (int64_t)B * H * W * (C / 8);
+    launch_k(upsample2x_kernel, grid_for(total, kThreads), kThreads, 0, as_stream(stream),
         (const uint4*)in, (uint4*)out, B, H, W, C / 8);
     RDEIC_LAUNCH_CHECK();
     return 0;

@@ -79,11 +79,21 @@ small = torch.randn(8, 64, 64, 320, generator=g, device=dev).bfloat16()
 g320, b320 = torch.ones(320, device=dev), torch.zeros(320, device=dev)
 rec("groupnorm_silu[8,512,512,128]bf16", 4 * gn_in.numel(), lambda: ops.groupnorm(gn_in, gam, bet, 32, 1e-6, True),
     lambda: ops.groupnorm(small, g320, b320, 32, 1e-5, True))
+# the decode path: statistics come from the producing GEMM's epilogue (slab table), GroupNorm = fold + apply
+w128 = ops.pack_conv_weight(torch.randn(128, 128, 3, 3, generator=g, device=dev) / 34)
+_, st128 = ops.conv_gemm(gn_in, w128, 128, 9, stats=True)
+rec("groupnorm_silu[8,512,512,128]bf16, statistics from the producer's epilogue", 4 * gn_in.numel(),
+    lambda: ops.groupnorm(gn_in, gam, bet, 32, 1e-6, True, stats1=st128))
+del st128
 f32s = small.float()
 rec("groupnorm_silu[8,64,64,320]f32->bf16(in-situ size)", 6 * small.numel(), lambda: ops.groupnorm(f32s, g320, b320, 32, 1e-5, True))
 ln_in = torch.randn(1 << 18, 320, generator=g, device=dev).bfloat16()
 rec("layernorm[2^18,320]bf16", 4 * ln_in.numel(), lambda: ops.layernorm(ln_in, g320, b320),
     lambda: ops.layernorm(small.view(-1, 320), g320, b320))
+ln32 = ln_in.float()
+rec("layernorm[2^18,320]f32->bf16 (the UNet token stream)", 6 * ln_in.numel(), lambda: ops.layernorm(ln32, g320, b320),
+    lambda: ops.layernorm(f32s.view(-1, 320), g320, b320))
+del ln32
 up_in = torch.randn(8, 256, 256, 256, generator=g, device=dev).bfloat16()
 rec("upsample2x[8,256,256,256]", 2 * up_in.numel() * 5, lambda: ops.upsample2x(up_in))
 print(json.dumps({"peak_gbs_measured": PEAK, "kernels": res}))
