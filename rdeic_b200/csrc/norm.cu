@@ -290,8 +290,10 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
     pdl_wait();
     const int VL = C >> 3;
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    // grid-stride over rows: at most 8 resident CTAs per SM walk the tensor (32 768 short-lived CTAs
+    // spent more time being scheduled than loading)
+    for (int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5); row < rows;
+         row += (int64_t)gridDim.x * kLnWarps) {
     float f[kLnMaxVec][8];
     float sum = 0.f;
 #pragma unroll
@@ -341,6 +343,7 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
             o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
             st_stream_u4(out + row * VL + l, o);
         }
+    }
     }
 }
 
@@ -434,8 +437,8 @@ int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const floa
     RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0,
                     "rdeic_layernorm: pointers must be 16-byte aligned");
     if (rows == 0) return 0;
-    const int64_t blocks = ceil_div64(rows, kLnWarps);
-    RDEIC_CHECK_ARG(blocks < (1ll << 31), "rdeic_layernorm: too many rows");
+    int64_t blocks = ceil_div64(rows, kLnWarps);
+    if (blocks > 8ll * kNumSMs) blocks = 8ll * kNumSMs;
     const int nv = (C / 8 + 31) / 32;   // 16-byte vectors per lane
     cudaStream_t s = as_stream(stream);
 #define RDEIC_LN(F32, NV) launch_k(layernorm_kernel<F32, NV>, (unsigned)blocks, kLnWarps * 32, 0, s, x, gamma, beta, (uint4*)out, rows, C, eps)
