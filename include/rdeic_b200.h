@@ -244,6 +244,44 @@ int rdeic_attention(const void* q, const void* k, const void* v, void* out, int 
                     int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale,
                     rdeic_stream_t stream);
 
+/* ---- fp32 kernel mode (north_star: per-step rel-L2 <= 1e-5) ----------------------------------
+ * The same UNet + control step on plain fp32 NHWC tensors and CUDA-core fp32 FMA with fp64 folding
+ * of the k reduction (rdeic_b200/csrc/fp32_mode.cu).  Verification mode, not the throughput mode. */
+
+/* conv2d / F.linear (openaimodel.py:203,229,240,106,150,566,750; attention.py:52,72,162-169,314,328):
+ * a [a_n,a_h,a_w,c1] (+ a2 [..,c2], the torch.cat of openaimodel.py:804 / rdeic.py:190), ksize 1|3
+ * (pad ksize/2), stride 1|2, optional nearest x2 upsample of the input first (openaimodel.py:106-113);
+ * w fp32 [n_out][ksize*ksize][c1+c2]; out = resid + alpha * act(conv + bias + row_bias[sample]). */
+typedef struct rdeic_conv_f32_params {
+    const float* a;       int a_n, a_h, a_w, c1;
+    const float* a2;      int c2;
+    int ksize, stride, up;
+    const float* w;
+    int n_out;
+    const float* bias;
+    const float* row_bias; int row_bias_ld;
+    const float* resid;   int ld_resid;
+    float alpha;
+    int act;              /* 0 none, 1 SiLU */
+    float* out;           int ldo;
+} rdeic_conv_f32_params;
+int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream);
+/* attention.py:171-203 in fp32: q [B,Nq,*], k/v [B,Nk,*] fp32, heads as consecutive d-wide column groups, d <= 64. */
+int rdeic_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int heads, int Nq,
+                        int Nk, int d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs,
+                        int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale, rdeic_stream_t stream);
+/* attention.py:54-56 GEGLU, exact erf: in [rows, 2F] (value | gate) fp32 -> out [rows, F] fp32. */
+int rdeic_geglu_f32(const float* in, float* out, int64_t rows, int F, rdeic_stream_t stream);
+/* util.py:161-181 with an fp32 result. */
+int rdeic_timestep_embedding_f32(const int64_t* t, float* out, int B, int dim, float max_period,
+                                 rdeic_stream_t stream);
+/* GroupNorm(+SiLU) / LayerNorm with fp32 input and fp32 output (same statistics kernels as the bf16 path). */
+int rdeic_groupnorm_nhwc_f32(const float* x1, int C1, const float* x2, int C2, const float* gamma,
+                             const float* beta, float* out, int B, int64_t HW, int groups, float eps,
+                             int silu, void* workspace, rdeic_stream_t stream);
+int rdeic_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int C,
+                        float eps, rdeic_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,24 @@ class ConvParams(C.Structure):
     ]
 
 
+class ConvF32Params(C.Structure):
+    """Mirror of `rdeic_conv_f32_params` (fp32 kernel mode)."""
+
+    _fields_ = [
+        ("a", vp), ("a_n", i32), ("a_h", i32), ("a_w", i32), ("c1", i32),
+        ("a2", vp), ("c2", i32),
+        ("ksize", i32), ("stride", i32), ("up", i32),
+        ("w", vp),
+        ("n_out", i32),
+        ("bias", vp),
+        ("row_bias", vp), ("row_bias_ld", i32),
+        ("resid", vp), ("ld_resid", i32),
+        ("alpha", f32),
+        ("act", i32),
+        ("out", vp), ("ldo", i32),
+    ]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "rdeic_last_error": [],
@@ -89,6 +107,12 @@ SIGNATURES = {
     "rdeic_conv_gemm": [C.POINTER(ConvParams), vp],
     "rdeic_conv_stats_supported": [i32, i32, i32, i32, i32],
     "rdeic_pack_conv_weight": [vp, vp, i32, i32, i32, i32, i32, vp],
+    "rdeic_conv_f32": [C.POINTER(ConvF32Params), vp],
+    "rdeic_attention_f32": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, vp],
+    "rdeic_geglu_f32": [vp, vp, i64, i32, vp],
+    "rdeic_timestep_embedding_f32": [vp, vp, i32, i32, f32, vp],
+    "rdeic_groupnorm_nhwc_f32": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
+    "rdeic_layernorm_f32": [vp, vp, vp, vp, i64, i32, f32, vp],
     "rdeic_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i64, i64, f32, vp],
 }
 _RESTYPES = {"rdeic_last_error": C.c_char_p, "rdeic_groupnorm_workspace_bytes": i64}

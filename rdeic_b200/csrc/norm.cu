@@ -176,7 +176,7 @@ gn_fold_stats_kernel(const float2* __restrict__ st1, int C1, const float2* __res
     }
 }
 
-template <bool kF32>
+template <bool kF32, bool kOutF32 = false>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -229,7 +229,7 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     // (reading them from shared memory per element made the kernel smem-bandwidth bound: 4 LDS.128
     // per 16 bytes of payload) and the loop has no index division.
     const int64_t o1 = (int64_t)b * HW * VL1, o2 = (int64_t)b * HW * VL2;
-    uint4* bo = out + (int64_t)b * HW * VL;
+    uint4* bo = out + (int64_t)b * HW * VL * (kOutF32 ? 2 : 1);
     const int nchunk_a = gridDim.x;
     const int64_t per = (HW + nchunk_a - 1) / nchunk_a;
     const int64_t p0 = blockIdx.x * per;
@@ -250,6 +250,18 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         auto finish = [&](float* f, int64_t p) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+            if (kOutF32) {               // fp32 kernel mode: exact exp / division, fp32 result
+                if (silu) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.0f + expf(-f[k]));
+                }
+                uint4 o0, o1;
+                o0.x = __float_as_uint(f[0]); o0.y = __float_as_uint(f[1]); o0.z = __float_as_uint(f[2]); o0.w = __float_as_uint(f[3]);
+                o1.x = __float_as_uint(f[4]); o1.y = __float_as_uint(f[5]); o1.z = __float_as_uint(f[6]); o1.w = __float_as_uint(f[7]);
+                st_stream_u4(bo + (p * VL + l) * 2, o0);
+                st_stream_u4(bo + (p * VL + l) * 2 + 1, o1);
+                return;
+            }
             if (silu) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
@@ -281,7 +293,7 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
 constexpr int kLnMaxVecLimit = 5;
 constexpr int kLnWarps = 8;
 
-template <bool kF32, int kLnMaxVec>
+template <bool kF32, int kLnMaxVec, bool kOutF32 = false>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
@@ -338,6 +350,14 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
             y[5] = (f[j][5] - mean) * rstd * g1.y + b1.y;
             y[6] = (f[j][6] - mean) * rstd * g1.z + b1.z;
             y[7] = (f[j][7] - mean) * rstd * g1.w + b1.w;
+            if (kOutF32) {
+                uint4 o0, o1;
+                o0.x = __float_as_uint(y[0]); o0.y = __float_as_uint(y[1]); o0.z = __float_as_uint(y[2]); o0.w = __float_as_uint(y[3]);
+                o1.x = __float_as_uint(y[4]); o1.y = __float_as_uint(y[5]); o1.z = __float_as_uint(y[6]); o1.w = __float_as_uint(y[7]);
+                st_stream_u4(out + (row * VL + l) * 2, o0);
+                st_stream_u4(out + (row * VL + l) * 2 + 1, o1);
+                continue;
+            }
             uint4 o;
             o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
             o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
@@ -424,6 +444,48 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
     else
         launch_k(gn_apply_kernel<false>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_groupnorm_nhwc_f32(const float* x1, int C1, const float* x2, int C2, const float* gamma,
+                             const float* beta, float* out, int B, int64_t HW, int groups, float eps,
+                             int silu, void* workspace, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x1 && gamma && beta && out && workspace, "rdeic_groupnorm_nhwc_f32: null pointer");
+    RDEIC_CHECK_ARG(C2 == 0 || x2, "rdeic_groupnorm_nhwc_f32: C2 > 0 needs x2");
+    if (C2 == 0) x2 = nullptr;
+    const int C = C1 + C2;
+    RDEIC_CHECK_ARG(B > 0 && B <= 65535 && HW > 0, "rdeic_groupnorm_nhwc_f32: bad tensor dims");
+    RDEIC_CHECK_ARG(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && C <= kGnMaxC,
+                    "rdeic_groupnorm_nhwc_f32: bad channel counts (%d, %d)", C1, C2);
+    RDEIC_CHECK_ARG(groups > 0 && groups <= kGnMaxGroups && C % groups == 0,
+                    "rdeic_groupnorm_nhwc_f32: groups=%d invalid for C=%d", groups, C);
+    RDEIC_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0,
+                    "rdeic_groupnorm_nhwc_f32: tensors must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    const int nchunk = gn_num_chunks(B, HW);
+    launch_k(gn_stats_kernel<true>, dim3(nchunk, B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2, C2, HW, groups,
+             (float2*)workspace);
+    RDEIC_LAUNCH_CHECK();
+    const FastDiv div_vl((uint32_t)(C / 8));
+    launch_k(gn_apply_kernel<true, true>, dim3((unsigned)nchunk, B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2,
+             C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, int64_t rows, int C,
+                        float eps, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x && gamma && beta && out && rows >= 0, "rdeic_layernorm_f32: bad args");
+    RDEIC_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVecLimit,
+                    "rdeic_layernorm_f32: C=%d must be a multiple of 8 and <= %d", C, 8 * 32 * kLnMaxVecLimit);
+    RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0,
+                    "rdeic_layernorm_f32: pointers must be 16-byte aligned");
+    if (rows == 0) return 0;
+    int64_t blocks = ceil_div64(rows, kLnWarps);
+    if (blocks > 8ll * kNumSMs) blocks = 8ll * kNumSMs;
+    launch_k(layernorm_kernel<true, 5, true>, (unsigned)blocks, kLnWarps * 32, 0, as_stream(stream), (const void*)x, gamma,
+             beta, (uint4*)out, rows, C, eps);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

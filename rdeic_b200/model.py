@@ -51,7 +51,7 @@ class RDEIC:
                  first_stage_config: Mapping[str, Any], used_timesteps: int = 300, timesteps: int = 1000,
                  linear_start: float = 1e-4, linear_end: float = 2e-2, scale_factor: float = 1.0,
                  device: Union[str, torch.device] = "cuda", use_cuda_graph: bool = True,
-                 preprocess_config: Optional[Mapping[str, Any]] = None, **ignored):
+                 preprocess_config: Optional[Mapping[str, Any]] = None, precision: str = "bf16", **ignored):
         self.control_stage_config = dict(control_stage_config)
         self.unet_config = dict(unet_config)
         self.first_stage_config = dict(first_stage_config)
@@ -59,7 +59,12 @@ class RDEIC:
         self.preprocess_model = None                     # rdeic.py:641 instantiate_from_config(preprocess_config)
         self.device = torch.device(device)
         self.scale_factor = float(scale_factor)
-        self.use_cuda_graph = use_cuda_graph
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f'precision must be "bf16" or "fp32", got {precision!r}')
+        # "fp32": the UNet + control step runs in the fp32 kernel mode (engine_f32.NoiseEstimatorF32:
+        # CUDA-core fp32, <= 1e-5 per step against the reference); the VAE and everything else are unchanged
+        self.precision = precision
+        self.use_cuda_graph = use_cuda_graph and precision == "bf16"
         self.register_schedule(timesteps, linear_start, linear_end)
         # rdeic.py:638-639
         assert used_timesteps <= self.num_timesteps, \
@@ -112,7 +117,12 @@ class RDEIC:
         up = dict(self.unet_config.get("params", self.unet_config))
         cp = dict(self.control_stage_config.get("params", self.control_stage_config))
         try:
-            self.control_model = NoiseEstimatorEngine(sd, up, cp, device=self.device)
+            if self.precision == "fp32":
+                from .engine_f32 import NoiseEstimatorF32
+
+                self.control_model = NoiseEstimatorF32(sd, up, cp, device=self.device)
+            else:
+                self.control_model = NoiseEstimatorEngine(sd, up, cp, device=self.device)
             self.first_stage_model = VAEDecoderEngine(sd, self.scale_factor, device=self.device)
         except KeyError as e:
             if strict:

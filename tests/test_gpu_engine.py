@@ -250,3 +250,49 @@ def test_baseline_size_batch8_512(full_model, cuda):
     q = psnr(img.numpy(), img_ref.numpy(), 2.0)
     print(f"[full 512^2] unet step rel-L2 {e:.3e}; vae decode PSNR {q:.1f} dB")
     assert e <= UNET_TOL and q >= PSNR_MIN
+
+
+FP32_TOL = 1e-5
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_fp32_kernel_mode_unet_step(cuda, tag):
+    """north_star: per-step UNet output rel-L2 <= 1e-5 for the fp32 kernel mode, against the reference's
+    own fp32 output (golden), conditional and unconditional branches."""
+    from rdeic_b200 import RDEIC
+
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    sd = synthetic.make_state_dict(params, seed=231)
+    model = RDEIC.from_config({"params": params}, device=cuda, precision="fp32").load_state_dict(sd)
+    gold = np.load(GOLD / f"{tag}_unet_step.npz")
+    h, w = gold["hw"]
+    hint_c = params["control_stage_config"]["params"]["hint_channels"]
+    ctx_dim = params["unet_config"]["params"]["context_dim"]
+    c_latent, hint, ctx, _ = inputs(1, h, w, hint_c, ctx_dim, 1)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    x, t = torch.from_numpy(gold["x"]).to(cuda), torch.from_numpy(gold["t"]).to(cuda)
+    e1 = rel_l2(model.apply_model(x, t, cond).cpu().numpy(), gold["eps"])
+    e2 = rel_l2(model.apply_model_unconditional(x, t, cond).cpu().numpy(), gold["eps_uncond"])
+    print(f"[{tag}] fp32 kernel mode: unet step rel-L2 cond {e1:.3e} uncond {e2:.3e}")
+    assert e1 <= FP32_TOL and e2 <= FP32_TOL
+
+
+def test_fp32_kernel_mode_sampler(cuda):
+    """The relay sampler on top of the fp32 step (small config, 2 and 3 steps) stays within 1e-5."""
+    from rdeic_b200 import RDEIC, SpacedSampler
+
+    params = configs.small_params()
+    model = RDEIC.from_config({"params": params}, device=cuda, precision="fp32").load_state_dict(
+        synthetic.make_state_dict(params, seed=231))
+    gold = np.load(GOLD / "small_sampler.npz")
+    B, h, w = 2, 8, 16
+    c_latent, hint, ctx, noises = inputs(B, h, w, 32, 64, 8)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    t = torch.full((B,), model.used_timesteps - 1, dtype=torch.long, device=cuda)
+    x_T = model.q_sample(c_latent.to(cuda), t, noises[0].to(cuda))
+    for steps in (2, 3):
+        s = SpacedSampler(model, var_type="fixed_small")
+        s.noise_fn = lambda i, like: noises[1 + i]
+        e = rel_l2(s.sample(steps, (B, 4, h, w), cond, x_T=x_T).cpu().numpy(), gold[f"spaced_{steps}"])
+        print(f"[small] fp32 kernel mode: spaced {steps} steps rel-L2 {e:.3e}")
+        assert e <= FP32_TOL
