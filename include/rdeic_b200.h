@@ -266,7 +266,8 @@ typedef struct rdeic_conv_f32_params {
     float* out;           int ldo;
 } rdeic_conv_f32_params;
 int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream);
-/* attention.py:171-203 in fp32: q [B,Nq,*], k/v [B,Nk,*] fp32, heads as consecutive d-wide column groups, d <= 64. */
+/* attention.py:171-203 in fp32: q [B,Nq,*], k/v [B,Nk,*] fp32, heads as consecutive d-wide column groups, d <= 512
+ * (the VAE mid attention, model.py:181-205, is one 512-wide head). */
 int rdeic_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int heads, int Nq,
                         int Nk, int d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs,
                         int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale, rdeic_stream_t stream);

@@ -124,8 +124,10 @@ conv_f32_kernel(const ConvF32Dev p) {
     }
 }
 
-// One warp per (query row, head, batch): online softmax in fp32, every lane owns up to 2 of the d <= 64
-// head dims; logits are reduced across the warp with shuffles.
+// One warp per (query row, head, batch): online softmax in fp32, lane l owns head dims l, l+32, ...
+// (kDL per lane: 2 for the UNet's d <= 64 heads, 16 for the VAE's single 512-wide head); logits are
+// reduced across the warp with shuffles.
+template <int kDL>
 __global__ void __launch_bounds__(128)
 attention_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                      float* __restrict__ out, int heads, int Nq, int Nk, int d, int64_t ldq, int64_t ldk,
@@ -137,25 +139,41 @@ attention_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, c
     const float* qp = q + b * q_bs + qi * ldq + head * d;
     const float* kp = k + b * k_bs + head * d;
     const float* vp = v + b * v_bs + head * d;
-    const int d0 = lane, d1 = lane + 32;
-    const float q0 = d0 < d ? qp[d0] * scale : 0.f, q1 = d1 < d ? qp[d1] * scale : 0.f;
-    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    float qv[kDL], o[kDL];
+#pragma unroll
+    for (int i = 0; i < kDL; ++i) {
+        const int dd = lane + 32 * i;
+        qv[i] = dd < d ? qp[dd] * scale : 0.f;
+        o[i] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
     for (int j = 0; j < Nk; ++j) {
         const float* kr = kp + (int64_t)j * ldk;
-        float s = (d0 < d ? q0 * kr[d0] : 0.f) + (d1 < d ? q1 * kr[d1] : 0.f);
+        float s = 0.f;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        for (int i = 0; i < kDL; ++i) {
+            const int dd = lane + 32 * i;
+            if (dd < d) s = fmaf(qv[i], kr[dd], s);
+        }
+#pragma unroll
+        for (int o_ = 16; o_; o_ >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o_);
         const float m_new = fmaxf(m, s);
         const float corr = expf(m - m_new), pj = expf(s - m_new);
         const float* vr = vp + (int64_t)j * ldv;
         l = l * corr + pj;
-        o0 = o0 * corr + (d0 < d ? pj * vr[d0] : 0.f);
-        o1 = o1 * corr + (d1 < d ? pj * vr[d1] : 0.f);
+#pragma unroll
+        for (int i = 0; i < kDL; ++i) {
+            const int dd = lane + 32 * i;
+            o[i] = o[i] * corr + (dd < d ? pj * vr[dd] : 0.f);
+        }
         m = m_new;
     }
     float* op = out + b * o_bs + qi * ldo + head * d;
-    if (d0 < d) op[d0] = o0 / l;
-    if (d1 < d) op[d1] = o1 / l;
+#pragma unroll
+    for (int i = 0; i < kDL; ++i) {
+        const int dd = lane + 32 * i;
+        if (dd < d) op[dd] = o[i] / l;
+    }
 }
 
 // attention.py:54-56: out = value * gelu(gate), in [rows, 2F] (value | gate), exact erf
@@ -223,10 +241,14 @@ int rdeic_attention_f32(const float* q, const float* k, const float* v, float* o
                         int Nk, int d, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs,
                         int64_t k_bs, int64_t v_bs, int64_t o_bs, float scale, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(q && k && v && out, "rdeic_attention_f32: null pointer");
-    RDEIC_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0 && d > 0 && d <= 64, "rdeic_attention_f32: bad dims (d <= 64)");
+    RDEIC_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0 && d > 0 && d <= 512, "rdeic_attention_f32: bad dims (d <= 512)");
     dim3 grid((unsigned)((Nq + 3) / 4), (unsigned)heads, (unsigned)B);
-    attention_f32_kernel<<<grid, 128, 0, as_stream(stream)>>>(q, k, v, out, heads, Nq, Nk, d, ldq, ldk, ldv, ldo, q_bs,
-                                                               k_bs, v_bs, o_bs, scale);
+    if (d <= 64)
+        attention_f32_kernel<2><<<grid, 128, 0, as_stream(stream)>>>(q, k, v, out, heads, Nq, Nk, d, ldq, ldk, ldv, ldo,
+                                                                      q_bs, k_bs, v_bs, o_bs, scale);
+    else
+        attention_f32_kernel<16><<<grid, 128, 0, as_stream(stream)>>>(q, k, v, out, heads, Nq, Nk, d, ldq, ldk, ldv, ldo,
+                                                                       q_bs, k_bs, v_bs, o_bs, scale);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

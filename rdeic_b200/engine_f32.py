@@ -238,3 +238,54 @@ class NoiseEstimatorF32:
                 hb = self.block(f"{B_}.output_blocks.{i}", hb, hs_base.pop(), eb, ctx, self.base_d_head, False)
         h = self.gn(hb, B_ + ".out.0", 1e-5, True)
         return self.conv(h, B_ + ".out.2").permute(0, 3, 1, 2).contiguous()
+
+
+class VAEDecoderF32(NoiseEstimatorF32):
+    """fp32 kernel mode of `decode_first_stage` (ddpm.py:835-844 -> autoencoder.py:97-100 -> model.py:653-686)
+    on the same fp32 kernels."""
+
+    def __init__(self, sd: SD, scale_factor: float, device="cuda", prefix: str = "first_stage_model"):
+        self.dev = torch.device(device)
+        self.sd, self.P, self.scale_factor = sd, prefix, float(scale_factor)
+        self._w, self._v, self._ws = {}, {}, None
+
+    def _resnet(self, p: str, x):
+        """model.py:128-151 (temb None), GroupNorm eps 1e-6."""
+        h = self.conv(self.gn(x, p + ".norm1", 1e-6, True), p + ".conv1")
+        xs = self.conv(x, p + ".nin_shortcut") if (p + ".nin_shortcut.weight") in self.sd else x
+        return self.conv(self.gn(h, p + ".norm2", 1e-6, True), p + ".conv2", resid=xs)
+
+    def _attn(self, p: str, x):
+        """model.py:181-205: one head of width C."""
+        B, H, W, Cc = x.shape
+        hn = self.gn(x, p + ".norm", 1e-6, False).view(B, H * W, Cc)
+        a = self.attention(self.linear(hn, p + ".q"), self.linear(hn, p + ".k"), self.linear(hn, p + ".v"), 1)
+        return self.linear(a, p + ".proj_out", resid=x.view(B, H * W, Cc)).view(B, H, W, Cc)
+
+    @torch.no_grad()
+    def decode(self, z):
+        """[B,4,h,w] fp32 NCHW latent -> [B,3,8h,8w] fp32 in [-1,1]."""
+        if not z.is_cuda:
+            raise _lib.RdeicLibraryError("VAEDecoderF32 needs CUDA tensors; there is no CPU path")
+        P, D = self.P, self.P + ".decoder"
+        pq = P + ".post_quant_conv.weight"
+        if pq not in self._w:      # ddpm.py:843 `1/scale_factor * z` folded into the 1x1 post_quant_conv weights
+            self._w[pq] = (self.sd[pq].to(self.dev, F32) / self.scale_factor).permute(0, 2, 3, 1).contiguous()
+        x = z.to(self.dev, F32).permute(0, 2, 3, 1).contiguous()
+        x = self.conv(self.conv(x, P + ".post_quant_conv"), D + ".conv_in")
+        x = self._resnet(D + ".mid.block_1", x)
+        x = self._attn(D + ".mid.attn_1", x)
+        x = self._resnet(D + ".mid.block_2", x)
+        for lvl in reversed(range(self._count(D + ".up."))):
+            for i in range(self._count(f"{D}.up.{lvl}.block.")):
+                x = self._resnet(f"{D}.up.{lvl}.block.{i}", x)
+            if (f"{D}.up.{lvl}.upsample.conv.weight") in self.sd:
+                x = self.conv(x, f"{D}.up.{lvl}.upsample.conv", up=1)
+        x = self.conv(self.gn(x, D + ".norm_out", 1e-6, True), D + ".conv_out")
+        return x.permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def decode_u8(self, z):
+        """inference.py:85-87 on the fp32 image: uint8 [B,H,W,3]."""
+        img = self.decode(z).permute(0, 2, 3, 1).contiguous()       # NHWC fp32, 3 channels
+        return ops.image_to_u8(img)

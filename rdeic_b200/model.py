@@ -123,7 +123,12 @@ class RDEIC:
                 self.control_model = NoiseEstimatorF32(sd, up, cp, device=self.device)
             else:
                 self.control_model = NoiseEstimatorEngine(sd, up, cp, device=self.device)
-            self.first_stage_model = VAEDecoderEngine(sd, self.scale_factor, device=self.device)
+            if self.precision == "fp32":
+                from .engine_f32 import VAEDecoderF32
+
+                self.first_stage_model = VAEDecoderF32(sd, self.scale_factor, device=self.device)
+            else:
+                self.first_stage_model = VAEDecoderEngine(sd, self.scale_factor, device=self.device)
         except KeyError as e:
             if strict:
                 raise KeyError(f"Missing key(s) in state_dict: {e}") from e

@@ -296,3 +296,44 @@ def test_fp32_kernel_mode_sampler(cuda):
         e = rel_l2(s.sample(steps, (B, 4, h, w), cond, x_T=x_T).cpu().numpy(), gold[f"spaced_{steps}"])
         print(f"[small] fp32 kernel mode: spaced {steps} steps rel-L2 {e:.3e}")
         assert e <= FP32_TOL
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_fp32_kernel_mode_vae_and_decode(cuda, tag):
+    """fp32 kernel mode of decode_first_stage against the reference golden, and the uint8 post-process."""
+    from rdeic_b200 import RDEIC
+
+    params = configs.small_params() if tag == "small" else configs.default_params()
+    model = RDEIC.from_config({"params": params}, device=cuda, precision="fp32").load_state_dict(
+        synthetic.make_state_dict(params, seed=231))
+    gold = np.load(GOLD / f"{tag}_vae_decode.npz")
+    z = torch.from_numpy(gold["z"]).to(cuda)
+    img = model.decode_first_stage(z).cpu().numpy()
+    e = rel_l2(img, gold["img"])
+    print(f"[{tag}] fp32 kernel mode: vae decode rel-L2 {e:.3e} PSNR {psnr(img, gold['img'], 2.0):.1f} dB")
+    assert e <= FP32_TOL
+    u8 = model.decode_first_stage_u8(z).cpu().numpy()
+    ref_u8 = (((gold["img"] + 1) / 2).clip(0, 1).transpose(0, 2, 3, 1) * 255).clip(0, 255).astype(np.uint8)
+    assert float((u8 != ref_u8).mean()) < 1e-3          # a value within 1e-6 of an integer boundary may flip
+
+
+def test_full_size_decode_bf16_vs_fp32_mode(full_model, cuda):
+    """BASELINE config[1] end to end at full size: the 5-step 512x512 decode of the bf16 throughput mode
+    against the same decode in the fp32 kernel mode (itself within 1e-6 of the reference per step):
+    final image PSNR >= 40 dB (north_star), i.e. the bf16 error does not blow up over the relay steps."""
+    from rdeic_b200 import RDEIC
+    from rdeic_b200.pipeline import relay_decode
+
+    params = configs.default_params()
+    ref_model = RDEIC.from_config({"params": params}, device=cuda, precision="fp32").load_state_dict(
+        synthetic.make_state_dict(params, seed=231))
+    B, h, w, steps = 2, 64, 64, 5
+    c_latent, hint, ctx, noises = inputs(B, h, w, 256, 1024, steps + 1)
+    d = lambda t: t.to(cuda)
+    cond = {"c_latent": [d(c_latent)], "c_crossattn": [d(ctx)], "guide_hint": d(hint)}
+    nz = [d(n) for n in noises]
+    img16 = relay_decode(full_model, cond, steps, start_noise=nz[0], step_noises=nz[1:], as_uint8=False).cpu().numpy()
+    img32 = relay_decode(ref_model, cond, steps, start_noise=nz[0], step_noises=nz[1:], as_uint8=False).cpu().numpy()
+    p = psnr(img16, img32, 2.0)
+    print(f"[full 512^2, 5 steps] bf16 mode vs fp32 kernel mode: image PSNR {p:.1f} dB rel-L2 {rel_l2(img16, img32):.3e}")
+    assert p >= PSNR_MIN
