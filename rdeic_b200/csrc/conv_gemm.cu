@@ -118,16 +118,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x + 0.5f * fabsf(x) * erf_abs;                 // 0.5 x (1 + sign(x) erf|.|)
 }
 
-template <int BN, int kEW>
+// kMT = M tiles per work item: with kMT == 2 one CTA walks two adjacent 128-row M tiles against the
+// SAME B (weight) stage, so the weight tile crosses L2 -> shared memory once per 256 output rows.
+// For N <= 128 the weight tile is as large as the activation tile and both are re-fetched per tile
+// (conv 128->128 at 512^2: 9.7 GB of L2->SM traffic, ~13 TB/s, which is what bounds it).
+template <int BN, int kEW, int kMT = 1>
 struct TileCfg {
+    static_assert(kMT * BN <= 256, "two accumulator buffers must fit the 512 TMEM columns");
     static constexpr int kThreads = 64 + 32 * kEW;
     static constexpr int kBBytes = BN * kBlockK * 2;
-    static constexpr int kStageBytes = kATileBytes + kBBytes;
+    static constexpr int kABytes = kMT * kATileBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStagingBytes = kEW * 4096;                   // 32 rows x 128 B per epilogue warp
     static constexpr int kMaxSmem = 227 * 1024;
     static constexpr int kStagesRaw = (kMaxSmem - kStagingBytes - 1024 - 256) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns per buffer
+    static constexpr int kAccCols = kMT * BN;
+    static constexpr int kAccStride = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : 256;   // TMEM columns per buffer
     static constexpr int kTmemCols = 2 * kAccStride;                   // double-buffered accumulator
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -136,12 +143,12 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN, int kResidMode, int kEW, bool kStats>
+template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
     pdl_trigger();
-    using Cfg = TileCfg<BN, kEW>;
+    using Cfg = TileCfg<BN, kEW, kMT>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kCStride = kEW / 4;            // epilogue warps per TMEM lane quadrant = chunk stride
     // residual handling in the epilogue: 0 = loaded at the top of phase B, 1 = bf16 residual
@@ -152,7 +159,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kStages * kATileBytes;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
     uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + Cfg::kStagingBytes);
     uint64_t* empty_bar = full_bar + kStages;
@@ -164,7 +171,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
     const int cbt = p.cblk1 + p.cblk2;
     const int total_kb = p.taps * cbt;
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int m_tiles = (p.tiles_w * p.tiles_h * p.tiles_n + kMT - 1) / kMT;   // work items along M
     const int mn_tiles = m_tiles * p.n_tiles;
     const int num_items = mn_tiles * p.splits;
 
@@ -200,13 +207,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int z = item / mn_tiles;
                 int rem = item - z * mn_tiles;
                 const int nt = rem / m_tiles;
-                int mt = rem - nt * m_tiles;
-                const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
-                const int tih = mt % p.tiles_h; mt /= p.tiles_h;
-                const int w0 = tiw * tw, h0 = tih * th;
-                const int n0 = mt * (kBlockM >> (p.tw_log2 + p.th_log2));
+                const int mi = rem - nt * m_tiles;
+                int w0[kMT], h0[kMT], n0[kMT];
+#pragma unroll
+                for (int u = 0; u < kMT; ++u) {
+                    int mt = mi * kMT + u;             // a tile index past the end lands at n0 >= a_n: TMA zero-fills
+                    const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
+                    const int tih = mt % p.tiles_h; mt /= p.tiles_h;
+                    w0[u] = tiw * tw; h0[u] = tih * th;
+                    n0[u] = mt * (kBlockM >> (p.tw_log2 + p.th_log2));
+                }
                 const int col0 = nt * BN;
-                const int wz = p.w_batched ? n0 : 0;
+                const int wz = p.w_batched ? n0[0] : 0;
                 const int kb_begin = z * p.kb_per_split;
                 const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
@@ -218,12 +230,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     int dy = 0, dx = 0;
                     if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
                     else if (p.taps == 25) { dy = tap / 5 - 2; dx = tap % 5 - 2; }
-                    if (cb < p.cblk1)
-                        tma_load_4d(&tm_a, smem_a + s * kATileBytes, &full_bar[s], cb * kBlockK,
-                                    w0 + dx, h0 + dy, n0);
-                    else
-                        tma_load_4d(&tm_a2, smem_a + s * kATileBytes, &full_bar[s],
-                                    (cb - p.cblk1) * kBlockK, w0 + dx, h0 + dy, n0);
+#pragma unroll
+                    for (int u = 0; u < kMT; ++u) {
+                        uint8_t* dst = smem_a + (s * kMT + u) * kATileBytes;
+                        if (cb < p.cblk1)
+                            tma_load_4d(&tm_a, dst, &full_bar[s], cb * kBlockK, w0[u] + dx, h0[u] + dy, n0[u]);
+                        else
+                            tma_load_4d(&tm_a2, dst, &full_bar[s], (cb - p.cblk1) * kBlockK, w0[u] + dx, h0[u] + dy, n0[u]);
+                    }
                     tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
                 }
             }
@@ -246,12 +260,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint64_t da = make_smem_desc(smem_u32(smem_a + s * kATileBytes));
                     const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int u = 0; u < kMT; ++u) {
+                        const uint64_t da = make_smem_desc(smem_u32(smem_a + (s * kMT + u) * kATileBytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
+                            umma_bf16(tmem_d + u * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
                 }
@@ -281,7 +298,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int z = item / mn_tiles;
             int rem = item - z * mn_tiles;
             const int nt = rem / m_tiles;
-            int mt = rem - nt * m_tiles;
+            const int mi = rem - nt * m_tiles;
+#pragma unroll 1
+            for (int u = 0; u < kMT; ++u) {           // the item's M tiles share one accumulator buffer
+            int mt = mi * kMT + u;
             const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
             const int tih = mt % p.tiles_h; mt /= p.tiles_h;
             const int gw = tiw * tw + rw, gh = tih * th + rh;
@@ -355,10 +375,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             };
             if (kAheadF32) prefetch_f32(half);
-            mbar_wait(&acc_full[buf], aph);
-            tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
-            if (last_c < 0) {                       // nothing to read: release the buffer right away
+            if (u == 0) {
+                mbar_wait(&acc_full[buf], aph);
+                tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + u * BN + ((uint32_t)(quad * 32) << 16);
+            if (last_c < 0 && u == kMT - 1) {       // nothing to read: release the buffer right away
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
@@ -373,7 +395,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
                 const bool full32 = nbase + 32 <= p.n_out;
                 tmem_ld_wait();
-                if (ci == last_c) {                  // all TMEM reads of this tile by this warp are done
+                if (ci == last_c && u == kMT - 1) {  // all TMEM reads of this item by this warp are done
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
@@ -577,6 +599,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (kAheadF32) prefetch_f32(ci + kCStride);     // in flight during the next chunk's TMEM load + phase A
                 __syncwarp();
             }
+            }   // u
         }
     }
     tc_fence_before();
@@ -678,20 +701,20 @@ static bool stats_tiling_ok(int N, int H, int W, bool force_tn1) {
     return tw >= 32 || (tw == W && (tw * th >= 32 || th == H));
 }
 
-template <int BN, int kPre, int kEW, bool kStats = false>
+template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
-    using Cfg = TileCfg<BN, kEW>;
+    using Cfg = TileCfg<BN, kEW, kMT>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
-    const int64_t items = (int64_t)m_tiles * d.n_tiles * splits;
+    const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -702,6 +725,15 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
     // kept for experiments only: with the affine fast path both measured slower than loading the
     // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
+    // N <= 128 with a long reduction and many tiles: two M tiles per item share each weight stage
+    if constexpr (BN == 128) {
+        static const bool dual_m = !(getenv("RDEIC_DUAL_M") && atoi(getenv("RDEIC_DUAL_M")) == 0);
+        if (dual_m && splits == 1 && !d.w_batched && d.taps * (d.cblk1 + d.cblk2) >= 9 &&
+            (int64_t)m_tiles * d.n_tiles >= 8 * kNumSMs) {
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, d, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, d, m_tiles, splits, s);
+        }
+    }
     if (d.stats_out) {
         static const int epi12_kb_s = getenv("RDEIC_EPI12_KB") ? atoi(getenv("RDEIC_EPI12_KB")) : 10;
         if (d.taps * (d.cblk1 + d.cblk2) <= epi12_kb_s) return launch_conv3<BN, 0, 12, true>(ta, ta2, tb, d, m_tiles, splits, s);

@@ -25,3 +25,15 @@ for (B, H, W, C) in [(8, 512, 512, 128), (8, 256, 256, 256)]:
                      ("f32 resid dual", dict(resid=r32, dual=True))]:
         us = t(lambda: ops.conv_gemm(x, w, C, 9, bias=b, **kw))
         print(f"[{B},{H},{W},{C}] {name:16s} {us:8.1f} us  {fl/us/1e6:7.1f} TF/s", flush=True)
+# N = 128 layers of the 512^2 level (two M tiles per item share the weight stage; RDEIC_DUAL_M=0 disables)
+x256 = rnd(8, 512, 512, 256).bfloat16()
+x128 = rnd(8, 512, 512, 128).bfloat16()
+w21 = ops.pack_conv_weight(rnd(128, 256, 3, 3) / 48)
+w11 = ops.pack_conv_weight(rnd(128, 128, 3, 3) / 34)
+wo = ops.pack_conv_weight(rnd(4, 128, 3, 3) / 34)
+b128, b4 = rnd(128), rnd(4)
+for name, fn, fl in [("256->128 stats", lambda: ops.conv_gemm(x256, w21, 128, 9, bias=b128, stats=True), 2.0 * 8 * 512 * 512 * 128 * 9 * 256),
+                     ("128->128 stats+resid", lambda: ops.conv_gemm(x128, w11, 128, 9, bias=b128, resid=x128, stats=True), 2.0 * 8 * 512 * 512 * 128 * 9 * 128),
+                     ("128->4 conv_out f32", lambda: ops.conv_gemm(x128, wo, 4, 9, bias=b4, out_f32=True), 2.0 * 8 * 512 * 512 * 4 * 9 * 128)]:
+    us = t(fn)
+    print(f"{name:24s} {us:8.1f} us  {fl/us/1e6:7.1f} TF/s", flush=True)

@@ -640,3 +640,36 @@ def test_conv_stats_unsupported_grid_falls_back(cuda):
     w = ops.pack_conv_weight(torch.randn(64, 64, 3, 3, device=cuda) / 24)
     y, st = ops.conv_gemm(x, w, 64, 9, stats=True)
     assert st is None and tuple(y.shape) == (1, 6, 10, 64)
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,stats", [(2, 288, 288, 128, 0, 128, True), (1, 1297, 128, 128, 0, 128, False),
+                                                     (1, 1297, 128, 64, 64, 128, True), (2, 288, 288, 256, 0, 96, False)])
+def test_conv3x3_two_m_tiles_per_item(cuda, B, H, W, C1, C2, Cout, stats):
+    """N <= 128 convs with many tiles run two M tiles per work item against one weight stage (even and
+    odd tile counts, two K segments, fused statistics); the result must not depend on the pairing."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(91)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = _bf(torch.randn(B, C1 + C2, H, W, generator=g)).to(cuda)
+        w = _bf(torch.randn(Cout, C1 + C2, 3, 3, generator=g) / math.sqrt(9 * (C1 + C2))).to(cuda)
+        b = torch.randn(Cout, generator=g).to(cuda)
+        resid = _bf(torch.randn(B, H, W, Cout, generator=g)).to(cuda)
+        ref = resid + F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    a = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    a1 = a[..., :C1].contiguous()
+    a2 = a[..., C1:].contiguous() if C2 else None
+    wp = ops.pack_conv_weight(w, c1=C1) if C2 else ops.pack_conv_weight(w)
+    res = ops.conv_gemm(a1, wp, Cout, 9, a2=a2, bias=b, resid=resid.bfloat16(), out_f32=not stats, stats=stats)
+    if stats:
+        y, st = res
+        assert st is not None
+        ref_b = y.float().view(B * H * W // 32, 32, Cout)
+        assert _rel(st[..., 0].cpu(), ref_b.sum(1).cpu()) < 2e-2 and _rel(st[..., 1].cpu(), (ref_b * ref_b).sum(1).cpu()) < 2e-2
+        assert _rel(y.float().cpu(), ref.cpu()) < 4e-3            # bf16 output rounding
+    else:
+        assert _rel(res.cpu(), ref.cpu()) < 1e-3
