@@ -59,7 +59,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* s_q = smem;
     uint8_t* s_k = s_q + kATile;
     uint8_t* s_v = s_k + kAStages * kATile;
@@ -282,7 +282,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* s_q = smem;                                   // 2 tiles: rows 0-127 | 128-255
     uint8_t* s_k = s_q + 2 * kATile;
     uint8_t* s_v = s_k + kAStages * kATile;

@@ -122,6 +122,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // SAME B (weight) stage, so the weight tile crosses L2 -> shared memory once per 256 output rows.
 // For N <= 128 the weight tile is as large as the activation tile and both are re-fetched per tile
 // (conv 128->128 at 512^2: 9.7 GB of L2->SM traffic, ~13 TB/s, which is what bounds it).
+// Two GELUs per call on the packed fp32x2 pipe (FFMA2 / FMUL2 / FADD2, sm_100): half the FMA-class
+// issue slots of the scalar form; same formula, same rounding per lane.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+#ifdef RDEIC_GELU_ERFF
+    return make_float2(gelu_erf(x.x), gelu_erf(x.y));
+#endif
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    const float2 ahx = make_float2(fabsf(hx.x), fabsf(hx.y));
+    const float2 z = __fmul2_rn(ahx, make_float2(1.41421356237309505f, 1.41421356237309505f));      // |x| / sqrt(2)
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+    float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+    p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+    p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+    const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+    const float2 pt = __fmul2_rn(p, t);
+    const float2 erf_abs = __ffma2_rn(make_float2(-pt.x, -pt.y), e, make_float2(1.0f, 1.0f));
+    return __ffma2_rn(ahx, erf_abs, hx);                         // 0.5 x + 0.5 |x| erf(|x|/sqrt2)
+}
+
 template <int BN, int kEW, int kMT = 1>
 struct TileCfg {
     static_assert(kMT * BN <= 256, "two accumulator buffers must fit the 512 TMEM columns");
@@ -156,8 +181,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     constexpr bool kPrefetchResid = (kResidMode == 1);
     constexpr bool kAheadF32 = (kResidMode == 2);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (not an integer round trip), so
+    // the compiler keeps the address space and the staging traffic is LDS/STS, not generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
     uint8_t* smem_stg = smem + kStages * Cfg::kStageBytes;
@@ -408,7 +434,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + j);
-                                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                                const float2 lo = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b4.x, b4.y));
+                                const float2 hi = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b4.z, b4.w));
+                                v[4 * j] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi.x; v[4 * j + 3] = hi.y;
                             }
                         }
                         if (p.row_bias && row_ok) {
@@ -421,7 +449,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
                                     const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb) + j);
-                                    v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                                    const float2 lo = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(r4.x, r4.y));
+                                    const float2 hi = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(r4.z, r4.w));
+                                    v[4 * j] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi.x; v[4 * j + 3] = hi.y;
                                 }
                             } else {
 #pragma unroll
@@ -444,12 +474,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_param;
                     } else if (p.act == 4) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 g2 = gelu_erf2(make_float2(v[j], v[j + 1]));
+                            v[j] = g2.x; v[j + 1] = g2.y;
+                        }
                     } else if (geglu) {
                         // columns [0,16) of the chunk are values, [16,32) their gates (weights are
                         // interleaved that way at load): attention.py:54-56  x * gelu(gate)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf(v[16 + j]);
+                        for (int j = 0; j < 16; j += 2) {
+                            const float2 o2 = __fmul2_rn(make_float2(v[j], v[j + 1]), gelu_erf2(make_float2(v[16 + j], v[17 + j])));
+                            v[j] = o2.x; v[j + 1] = o2.y;
+                        }
                     }
                 }
                 const int nchunks = geglu ? 4 : 8;
@@ -762,8 +798,10 @@ static int pick_block_n(int n_out, int m_tiles, int hint) {
         const int nt = (n_out + bn - 1) / bn;
         const int64_t tiles = (int64_t)m_tiles * nt;
         const int64_t per_sm = (tiles + kNumSMs - 1) / kNumSMs;      // persistent: tiles each CTA walks
-        // cost ~ tiles per SM * per-tile time; per-tile time ~ bn (MMA N) + fixed overhead
-        const double cost = (double)per_sm * (bn + 16);
+        // cost ~ tiles per SM * per-tile time; per-tile time ~ bn (MMA N) + fixed overhead (pipeline fill,
+        // epilogue tail: measured ~ 96 columns' worth on the K <= 1280 linears of UNet levels 1-2)
+        static const int overhead = getenv("RDEIC_TILE_OVERHEAD") ? atoi(getenv("RDEIC_TILE_OVERHEAD")) : 96;
+        const double cost = (double)per_sm * (bn + overhead);
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
     return best;
