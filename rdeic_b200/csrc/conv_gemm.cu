@@ -118,6 +118,77 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x + 0.5f * fabsf(x) * erf_abs;                 // 0.5 x (1 + sign(x) erf|.|)
 }
 
+// Phase B of the epilogue for the common case (32 consecutive, in-bounds output rows; 32 full columns):
+// the warp re-reads its 32x32 staged sub-tile so that 8 lanes cover 128 contiguous bytes of a row, adds
+// the residual and writes fp32 and/or bf16.  Compile-time variants (residual type, outputs, statistics)
+// selected by one warp-uniform switch per chunk: the generic form predicates every alternative, which
+// doubled the issued instructions of the epilogue-bound small-K linears.
+//   kRes: 0 none, 1 fp32, 2 bf16.   Pointers arrive offset to (first row of the lane, first column).
+template <int kRes, bool kF32, bool kB16, bool kStats>
+__device__ __forceinline__ void store_slab(const float4* __restrict__ stg, int lane, float alpha,
+                                           const void* __restrict__ resid, int64_t ld_resid,
+                                           float* __restrict__ of, __nv_bfloat16* __restrict__ ob, int64_t ldo,
+                                           float* __restrict__ stats_dst) {
+    const int q = lane & 7, r0 = lane >> 3;
+    float4 rv[8];
+    if (kRes == 1) {
+        const float* rp = reinterpret_cast<const float*>(resid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (int64_t)(4 * i) * ld_resid);
+    } else if (kRes == 2) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(resid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint2 u = *reinterpret_cast<const uint2*>(rp + (int64_t)(4 * i) * ld_resid);
+            unpack_bf16x2(u.x, rv[i].x, rv[i].y);
+            unpack_bf16x2(u.y, rv[i].z, rv[i].w);
+        }
+    }
+    float4 st_s = make_float4(0.f, 0.f, 0.f, 0.f), st_q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + r0;
+        float4 val = stg[row * 8 + (q ^ (row & 7))];
+        if (kRes != 0) {
+            val.x = fmaf(alpha, val.x, rv[i].x); val.y = fmaf(alpha, val.y, rv[i].y);
+            val.z = fmaf(alpha, val.z, rv[i].z); val.w = fmaf(alpha, val.w, rv[i].w);
+        }
+        if (kF32) *reinterpret_cast<float4*>(of + (int64_t)(4 * i) * ldo) = val;
+        if (kB16)
+            *reinterpret_cast<uint2*>(ob + (int64_t)(4 * i) * ldo) =
+                make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
+        if (kStats) {
+            st_s.x += val.x; st_s.y += val.y; st_s.z += val.z; st_s.w += val.w;
+            st_q.x = fmaf(val.x, val.x, st_q.x); st_q.y = fmaf(val.y, val.y, st_q.y);
+            st_q.z = fmaf(val.z, val.z, st_q.z); st_q.w = fmaf(val.w, val.w, st_q.w);
+        }
+    }
+    if (kStats) {
+        // lanes l, l+8, l+16, l+24 hold the same 4 columns for different rows
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            st_s.x += __shfl_xor_sync(0xffffffffu, st_s.x, o); st_s.y += __shfl_xor_sync(0xffffffffu, st_s.y, o);
+            st_s.z += __shfl_xor_sync(0xffffffffu, st_s.z, o); st_s.w += __shfl_xor_sync(0xffffffffu, st_s.w, o);
+            st_q.x += __shfl_xor_sync(0xffffffffu, st_q.x, o); st_q.y += __shfl_xor_sync(0xffffffffu, st_q.y, o);
+            st_q.z += __shfl_xor_sync(0xffffffffu, st_q.z, o); st_q.w += __shfl_xor_sync(0xffffffffu, st_q.w, o);
+        }
+        if (lane < 8) {
+            float4* dst = reinterpret_cast<float4*>(stats_dst);
+            dst[0] = make_float4(st_s.x, st_q.x, st_s.y, st_q.y);
+            dst[1] = make_float4(st_s.z, st_q.z, st_s.w, st_q.w);
+        }
+    }
+}
+
+template <int kRes, bool kStats>
+__device__ __forceinline__ void store_slab_out(const float4* stg, int lane, float alpha, const void* resid,
+                                               int64_t ld_resid, float* of, __nv_bfloat16* ob, int64_t ldo,
+                                               float* stats_dst) {
+    if (of && ob) store_slab<kRes, true, true, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
+    else if (of) store_slab<kRes, true, false, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
+    else store_slab<kRes, false, true, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
+}
+
 // kMT = M tiles per work item: with kMT == 2 one CTA walks two adjacent 128-row M tiles against the
 // SAME B (weight) stage, so the weight tile crosses L2 -> shared memory once per 256 output rows.
 // For N <= 128 the weight tile is as large as the activation tile and both are re-fetched per tile
@@ -495,64 +566,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (!geglu) {
-                    if (affine && fast_chunk(ci) && !(kPrefetchResid && pre_bf16) && !(kAheadF32 && ahead_f32)) {
+                    if (affine && fast_chunk(ci) && !(kPrefetchResid && pre_bf16) && !(kAheadF32 && ahead_f32) &&
+                        (eo.resid || eo.alpha == 1.0f)) {
+                        // GroupNorm statistics of the tensor being written are fused here (kStats) so the
+                        // consumer's statistics pass (a full re-read of the tensor) disappears
                         const int q = lane & 7;
                         const int64_t m0 = (int64_t)m_slab + (lane >> 3);
-                        float4 rv[8];
-                        // GroupNorm statistics of the tensor being written, fused here so the
-                        // consumer's stats pass (a full re-read of the tensor) disappears
-                        float4 st_s = make_float4(0.f, 0.f, 0.f, 0.f), st_q = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (eo.resid) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int64_t off = (m0 + 4 * i) * eo.ld_resid + nbase + 4 * q;
-                                if (eo.resid_is_f32) {
-                                    rv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(eo.resid) + off);
-                                } else {
-                                    const uint2 u = *reinterpret_cast<const uint2*>(
-                                        reinterpret_cast<const __nv_bfloat16*>(eo.resid) + off);
-                                    unpack_bf16x2(u.x, rv[i].x, rv[i].y);
-                                    unpack_bf16x2(u.y, rv[i].z, rv[i].w);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = 4 * i + (lane >> 3);
-                            float4 val = stg[row * 8 + (q ^ (row & 7))];
-                            if (eo.resid) {
-                                val.x = fmaf(eo.alpha, val.x, rv[i].x); val.y = fmaf(eo.alpha, val.y, rv[i].y);
-                                val.z = fmaf(eo.alpha, val.z, rv[i].z); val.w = fmaf(eo.alpha, val.w, rv[i].w);
-                            } else if (eo.alpha != 1.0f) {
-                                val.x *= eo.alpha; val.y *= eo.alpha; val.z *= eo.alpha; val.w *= eo.alpha;
-                            }
-                            const int64_t off = (m0 + 4 * i) * eo.ldo + nbase + 4 * q;
-                            if (eo.out_f32) *reinterpret_cast<float4*>(eo.out_f32 + off) = val;
-                            if (eo.out_bf16)
-                                *reinterpret_cast<uint2*>(eo.out_bf16 + off) =
-                                    make_uint2(pack_bf16x2(val.x, val.y), pack_bf16x2(val.z, val.w));
-                            if (kStats) {
-                                st_s.x += val.x; st_s.y += val.y; st_s.z += val.z; st_s.w += val.w;
-                                st_q.x = fmaf(val.x, val.x, st_q.x); st_q.y = fmaf(val.y, val.y, st_q.y);
-                                st_q.z = fmaf(val.z, val.z, st_q.z); st_q.w = fmaf(val.w, val.w, st_q.w);
-                            }
-                        }
-                        if (kStats) {
-                            // lanes l, l+8, l+16, l+24 hold the same 4 columns for different rows
-#pragma unroll
-                            for (int o = 8; o <= 16; o <<= 1) {
-                                st_s.x += __shfl_xor_sync(0xffffffffu, st_s.x, o); st_s.y += __shfl_xor_sync(0xffffffffu, st_s.y, o);
-                                st_s.z += __shfl_xor_sync(0xffffffffu, st_s.z, o); st_s.w += __shfl_xor_sync(0xffffffffu, st_s.w, o);
-                                st_q.x += __shfl_xor_sync(0xffffffffu, st_q.x, o); st_q.y += __shfl_xor_sync(0xffffffffu, st_q.y, o);
-                                st_q.z += __shfl_xor_sync(0xffffffffu, st_q.z, o); st_q.w += __shfl_xor_sync(0xffffffffu, st_q.w, o);
-                            }
-                            if (lane < 8) {
-                                float4* dst = reinterpret_cast<float4*>(
-                                    p.stats_out + (((int64_t)(m_slab >> 5)) * p.n_out + nbase + 4 * q) * 2);
-                                dst[0] = make_float4(st_s.x, st_q.x, st_s.y, st_q.y);
-                                dst[1] = make_float4(st_s.z, st_q.z, st_s.w, st_q.w);
-                            }
-                        }
+                        const int64_t o_off = m0 * eo.ldo + nbase + 4 * q;
+                        float* of = eo.out_f32 ? eo.out_f32 + o_off : nullptr;
+                        __nv_bfloat16* ob = eo.out_bf16 ? eo.out_bf16 + o_off : nullptr;
+                        float* sd = kStats ? p.stats_out + (((int64_t)(m_slab >> 5)) * p.n_out + nbase + 4 * q) * 2 : nullptr;
+                        const int64_t r_off = m0 * eo.ld_resid + nbase + 4 * q;
+                        if (!eo.resid)
+                            store_slab_out<0, kStats>(stg, lane, eo.alpha, nullptr, 0, of, ob, eo.ldo, sd);
+                        else if (eo.resid_is_f32)
+                            store_slab_out<1, kStats>(stg, lane, eo.alpha, reinterpret_cast<const float*>(eo.resid) + r_off,
+                                                      eo.ld_resid, of, ob, eo.ldo, sd);
+                        else
+                            store_slab_out<2, kStats>(stg, lane, eo.alpha,
+                                                      reinterpret_cast<const __nv_bfloat16*>(eo.resid) + r_off,
+                                                      eo.ld_resid, of, ob, eo.ldo, sd);
                     } else if (fast_chunk(ci)) {
                         int mr[8], okr[8];
                         float4 rv[8];
