@@ -168,6 +168,17 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
                                const float* stats2, int in_is_f32, const float* gamma,
                                const float* beta, void* out, int B, int64_t HW, int groups,
                                float eps, int silu, void* workspace, rdeic_stream_t stream);
+/* VAE decoder tail in one kernel: norm_out -> swish -> conv_out (3x3, pad 1, C = 128 -> n_out <= 4)
+ * -> optionally the caller's uint8 post-process (ldm/modules/diffusionmodules/model.py:683-686,
+ * inference.py:85-87).  x [B,H,W,C] bf16 NHWC (pre-norm), stats = the slab statistics its producer
+ * emitted (rdeic_conv_params.stats_out), w_packed bf16 [9 taps][8 (n_out zero-padded)][C],
+ * bias fp32 [n_out].  Outputs (either or both): out_f32 [B,H,W,ldo] fp32 (columns >= n_out zeroed),
+ * out_u8 [B,H,W,3] ((x+1)/2 clamp *255 truncated; needs n_out == 3).
+ * workspace: rdeic_groupnorm_workspace_bytes(B, H*W, C) bytes. */
+int rdeic_gn_silu_conv3x3_tail(const void* x, const float* stats, const float* gamma, const float* beta,
+                               const void* w_packed, const float* bias, int n_out, float* out_f32, int ldo,
+                               uint8_t* out_u8, int B, int H, int W, int C, int groups, float eps,
+                               void* workspace, rdeic_stream_t stream);
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
                          const float* gamma, const float* beta, void* out, int B, int64_t HW,
                          int groups, float eps, int silu, void* workspace,

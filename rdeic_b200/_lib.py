@@ -103,6 +103,7 @@ SIGNATURES = {
     "rdeic_groupnorm_workspace_bytes": [i32, i64, i32],
     "rdeic_groupnorm_nhwc": [vp, i32, vp, i32, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "rdeic_groupnorm_from_stats": [vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
+    "rdeic_gn_silu_conv3x3_tail": [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp],
     "rdeic_layernorm": [vp, i32, vp, vp, vp, i64, i32, f32, vp],
     "rdeic_conv_gemm": [C.POINTER(ConvParams), vp],
     "rdeic_conv_stats_supported": [i32, i32, i32, i32, i32],

@@ -287,6 +287,237 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VAE tail: norm_out -> swish -> conv_out (3x3, C -> 3) -> optional uint8 post-process, ONE kernel
+// (model.py:683-686 `h = self.norm_out(h); h = nonlinearity(h); h = self.conv_out(h)`, inference.py:85-87).
+// The tcgen05 implicit GEMM is the wrong tool for 3 output channels: one M=128 tcgen05.mma costs
+// >= 128 clocks whatever N is (the A operand has to be read from shared memory), so an N=32 tile runs
+// the tensor pipe at 1/8 rate and re-reads the activation 9 times from L2 (0.5-0.8 ms at 512^2, batch
+// 8).  Here a CTA stages an (8+2) x (32+2) pixel halo tile ONCE, applying GroupNorm scale/shift and
+// SiLU on the way into shared memory (zero outside the image = the conv's padding), and 8 warps run
+// mma.sync m16n8k16 (16 pixels x 8 padded output channels) over the 9 taps from shared memory.
+// The normalised activation never goes back to HBM (saves the gn_apply pass: 2 x 537 MB at 512^2).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailTH = 8, kTailTW = 32;
+constexpr int kTailC = 128;
+constexpr int kTailThreads = 512;
+constexpr int kTailPix = (kTailTH + 2) * (kTailTW + 2);              // 340 halo pixels
+constexpr int kTailPitch = kTailC * 2 + 16;                           // bytes per pixel (padded: conflict-free ldmatrix)
+constexpr int kTailTileBytes = kTailPix * kTailPitch;                 // 92 480
+constexpr int kTailWLane = 80;                                        // bytes per (tap, cout, k-quad) lane row: 64 + 16 pad
+constexpr int kTailWBytes = 9 * 8 * 4 * kTailWLane;                   // B fragments in per-lane order: 4 LDS.128 per tap
+constexpr int kTailSmem = 2 * kTailTileBytes + kTailWBytes;           // 208 000 B: one persistent CTA per SM
+constexpr int kTailIters = (kTailPix + kTailThreads / 16 - 1) / (kTailThreads / 16);   // halo pixels per thread (11)
+
+__device__ __forceinline__ float tail_u8(float x) {                  // inference.py:85-87, as image_to_u8_kernel
+    float v = __fdiv_rn(__fadd_rn(x, 1.0f), 2.0f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    v = __fmul_rn(v, 255.0f);
+    return fminf(fmaxf(v, 0.f), 255.f);
+}
+
+// Persistent CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... over (sample, tile row, tile column).
+// Two raw halo buffers: cp.async fills tile i+1 (zero-fill outside the image) while tile i is normalised in
+// place (GroupNorm scale/shift + SiLU, bf16) and contracted, so the HBM latency is off the critical path.
+__global__ void __launch_bounds__(kTailThreads, 1)
+gn_silu_conv3x3_tail_kernel(const uint4* __restrict__ x, int B, int H, int W, const float2* __restrict__ partial,
+                            int nfold, int G, float eps, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, const uint4* __restrict__ wpk,
+                            const float* __restrict__ bias, int n_out, float* __restrict__ out_f32, int ldo,
+                            uint8_t* __restrict__ out_u8, int tiles_w, int tiles_h) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) uint8_t tail_smem[];
+    uint8_t* s_w = tail_smem + 2 * kTailTileBytes;
+    __shared__ float s_scale[kTailC], s_shift[kTailC];
+    __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cg = kTailC / G;
+    const int tiles_per_sample = tiles_w * tiles_h;
+    const int total = B * tiles_per_sample;
+    const int l = tid & 15;                      // this thread's 8-channel lane in the staging passes
+
+    // this thread's halo pixels are the same in every tile: p = tid/16 + 32k -> (hy, hx) packed once
+    int hyx[kTailIters];
+#pragma unroll
+    for (int k = 0; k < kTailIters; ++k) {
+        const int p = (tid >> 4) + k * (kTailThreads / 16);
+        const int hy = p / (kTailTW + 2), hx = p - hy * (kTailTW + 2);
+        hyx[k] = p < kTailPix ? ((hy << 8) | hx) : -1;
+    }
+    auto issue_load = [&](int t, int buf) {
+        const int b = t / tiles_per_sample, r = t - b * tiles_per_sample;
+        const int th0 = (r / tiles_w) * kTailTH - 1, tw0 = (r % tiles_w) * kTailTW - 1;
+        const uint4* xb = x + (int64_t)b * H * W * (kTailC / 8) + l;
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(tail_smem + buf * kTailTileBytes) + l * 16 +
+                              (tid >> 4) * kTailPitch;
+#pragma unroll
+        for (int k = 0; k < kTailIters; ++k) {
+            if (hyx[k] < 0) break;
+            const int gh = th0 + (hyx[k] >> 8), gw = tw0 + (hyx[k] & 255);
+            const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+            const uint4* src = ok ? xb + ((int64_t)gh * W + gw) * (kTailC / 8) : x;
+            const int nbytes = ok ? 16 : 0;      // 0 source bytes -> 16 bytes of zeros = the conv's padding
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + k * (kTailThreads / 16) * kTailPitch),
+                         "l"(src), "r"(nbytes)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (blockIdx.x < total) issue_load(blockIdx.x, 0);
+    // weights [tap][cout 8][C] -> per-lane B fragment order: lane (cout g, k-quad q) owns, for channel block kb,
+    // words (kb*8 + q) and (kb*8 + q + 4) of its row; stored contiguously so a tap is 4 LDS.128 per lane
+    {
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(wpk);
+        for (int i = tid; i < 9 * 8 * (kTailC / 2); i += kTailThreads) {
+            const int row = i / (kTailC / 2), w = i % (kTailC / 2);
+            const int kb = w >> 3, qq = w & 3, j = (w >> 2) & 1;
+            *reinterpret_cast<uint32_t*>(s_w + (row * 4 + qq) * kTailWLane + (kb * 2 + j) * 4) = wsrc[i];
+        }
+    }
+    const int a_row = (lane & 7) + 8 * ((lane >> 3) & 1), a_kc = 8 * (lane >> 4);
+    const int orow = warp >> 1, mt = warp & 1;   // 16 warps: output row of the tile, 16-pixel half
+    const int q = lane & 3, g4 = lane >> 2;
+    const float bias0 = (2 * q < n_out) ? bias[2 * q] : 0.f, bias1 = (2 * q + 1 < n_out) ? bias[2 * q + 1] : 0.f;
+    float sc[8], sh[8];
+    int cur_b = -1, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int b = t / tiles_per_sample, r = t - b * tiles_per_sample;
+        const int th0 = (r / tiles_w) * kTailTH, tw0 = (r % tiles_w) * kTailTW;
+        if (t + (int)gridDim.x < total) issue_load(t + gridDim.x, buf ^ 1);
+        if (b != cur_b) {                        // new sample: statistics -> per-channel scale / shift
+            cur_b = b;
+            __syncthreads();
+            const int g = tid >> 3, part = tid & 7;              // 8 threads per group (G <= 32 -> first 256 threads)
+            double a = 0.0, c = 0.0;
+            if (g < G)
+                for (int k = part; k < nfold; k += 8) {
+                    const float2 v = partial[((int64_t)b * nfold + k) * G + g];
+                    a += (double)v.x; c += (double)v.y;
+                }
+#pragma unroll
+            for (int o = 4; o; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+            }
+            if (g < G && part == 0) {
+                const double n = (double)H * W * cg;
+                const double mean = a / n;
+                double var = c / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mean[g] = (float)mean;
+                s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+            }
+            __syncthreads();
+            if (tid < kTailC) {
+                const float k = gamma[tid] * s_rstd[tid / cg];
+                s_scale[tid] = k;
+                s_shift[tid] = beta[tid] - s_mean[tid / cg] * k;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sc[k] = s_scale[l * 8 + k]; sh[k] = s_shift[l * 8 + k]; }
+        }
+        if (t + (int)gridDim.x < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        uint8_t* s_x = tail_smem + buf * kTailTileBytes;
+        // normalise + SiLU in place (pixels outside the image stay zero)
+        {
+            uint8_t* base = s_x + l * 16 + (tid >> 4) * kTailPitch;
+            const int th1 = th0 - 1, tw1 = tw0 - 1;
+#pragma unroll
+            for (int k = 0; k < kTailIters; ++k) {
+                if (hyx[k] < 0) break;
+                const int gh = th1 + (hyx[k] >> 8), gw = tw1 + (hyx[k] & 255);
+                if ((unsigned)gh >= (unsigned)H || (unsigned)gw >= (unsigned)W) continue;
+                uint4* ptr = reinterpret_cast<uint4*>(base + k * (kTailThreads / 16) * kTailPitch);
+                const uint4 v = *ptr;
+                float f[8];
+                unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+                unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    // y = x*scale + shift ; silu(y) = y / (1 + 2^(-y log2 e)), packed fp32x2 where it exists
+                    const float2 y = __ffma2_rn(make_float2(f[j], f[j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+                    const float2 a = __fmul2_rn(y, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+                    float2 e, rr;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+                    const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr.x) : "f"(d.x));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr.y) : "f"(d.y));
+                    const float2 o = __fmul2_rn(y, rr);
+                    f[j] = o.x; f[j + 1] = o.y;
+                }
+                *ptr = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            }
+        }
+        __syncthreads();
+        // warp -> (output row, 16-pixel half); accumulators: pixel rows g4 / g4+8, channels 2q, 2q+1.
+        // Per tap all 8 channel blocks' fragments are loaded first (loads in flight together), then 8 MMAs
+        // alternate between two accumulators so consecutive MMAs do not wait on each other.
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t sx = (uint32_t)__cvta_generic_to_shared(s_x);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;               // halo coordinates: (row + dy, col + dx)
+            const uint32_t a_base = sx + (uint32_t)(((orow + dy) * (kTailTW + 2) + mt * 16 + dx + a_row) * kTailPitch + a_kc * 2);
+            const uint4* b_ptr = reinterpret_cast<const uint4*>(s_w + ((tap * 8 + g4) * 4 + q) * kTailWLane);
+            uint32_t bf[kTailC / 16][2], af[kTailC / 16][4];
+#pragma unroll
+            for (int kq = 0; kq < kTailC / 64; ++kq) {
+                const uint4 w4 = b_ptr[2 * kq], w5 = b_ptr[2 * kq + 1];
+                bf[4 * kq][0] = w4.x; bf[4 * kq][1] = w4.y; bf[4 * kq + 1][0] = w4.z; bf[4 * kq + 1][1] = w4.w;
+                bf[4 * kq + 2][0] = w5.x; bf[4 * kq + 2][1] = w5.y; bf[4 * kq + 3][0] = w5.z; bf[4 * kq + 3][1] = w5.w;
+            }
+#pragma unroll
+            for (int kb = 0; kb < kTailC / 16; ++kb) {
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(af[kb][0]), "=r"(af[kb][1]), "=r"(af[kb][2]), "=r"(af[kb][3])
+                             : "r"(a_base + (uint32_t)(kb * 32)));
+            }
+#pragma unroll
+            for (int kb = 0; kb < kTailC / 16; kb += 2) {
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, "
+                             "{%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                             : "r"(af[kb][0]), "r"(af[kb][1]), "r"(af[kb][2]), "r"(af[kb][3]), "r"(bf[kb][0]), "r"(bf[kb][1]));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, "
+                             "{%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                             : "+f"(acc2[0]), "+f"(acc2[1]), "+f"(acc2[2]), "+f"(acc2[3])
+                             : "r"(af[kb + 1][0]), "r"(af[kb + 1][1]), "r"(af[kb + 1][2]), "r"(af[kb + 1][3]),
+                               "r"(bf[kb + 1][0]), "r"(bf[kb + 1][1]));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += acc2[k];
+        // epilogue: q == 0 holds channels 0,1 ; q == 1 holds channels 2,3 of pixel rows g4 and g4+8
+        const int gh = th0 + orow;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int gw = tw0 + mt * 16 + g4 + 8 * hf;
+            const float v0 = acc[2 * hf] + bias0, v1 = acc[2 * hf + 1] + bias1;
+            const float v2 = __shfl_down_sync(0xffffffffu, v0, 1);        // channel 2 for the q == 0 lane
+            if (gh >= H || gw >= W) continue;
+            const int64_t pix = ((int64_t)b * H + gh) * W + gw;
+            if (out_f32 && q < 2) {
+                if (2 * q < ldo) out_f32[pix * ldo + 2 * q] = (2 * q < n_out) ? v0 : 0.f;
+                if (2 * q + 1 < ldo) out_f32[pix * ldo + 2 * q + 1] = (2 * q + 1 < n_out) ? v1 : 0.f;
+            }
+            if (out_u8 && q == 0) {
+                uint8_t* d = out_u8 + pix * 3;
+                d[0] = (uint8_t)__float2int_rz(tail_u8(v0));
+                d[1] = (uint8_t)__float2int_rz(tail_u8(v1));
+                d[2] = (uint8_t)__float2int_rz(tail_u8(v2));
+            }
+        }
+        __syncthreads();                         // everyone is done with this buffer before it is refilled
+    }
+}
+
 // LayerNorm: one warp per row, row held in registers (C <= 8*32*kLnMaxVec); kLnMaxVec is a template
 // parameter so narrow rows keep few registers live and the SM holds enough warps (= bytes in
 // flight) to cover HBM latency.
@@ -444,6 +675,41 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
     else
         launch_k(gn_apply_kernel<false>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_gn_silu_conv3x3_tail(const void* x, const float* stats, const float* gamma, const float* beta,
+                               const void* w_packed, const float* bias, int n_out, float* out_f32, int ldo,
+                               uint8_t* out_u8, int B, int H, int W, int C, int groups, float eps,
+                               void* workspace, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(x && stats && gamma && beta && w_packed && bias && workspace, "rdeic_gn_silu_conv3x3_tail: null pointer");
+    RDEIC_CHECK_ARG(out_f32 || out_u8, "rdeic_gn_silu_conv3x3_tail: no output pointer");
+    RDEIC_CHECK_ARG(C == kTailC, "rdeic_gn_silu_conv3x3_tail: C must be %d (got %d)", kTailC, C);
+    RDEIC_CHECK_ARG(n_out >= 1 && n_out <= 4 && (!out_u8 || n_out == 3) && (!out_f32 || ldo >= n_out),
+                    "rdeic_gn_silu_conv3x3_tail: n_out must be 1..4 (3 for uint8 output), ldo >= n_out");
+    RDEIC_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && ((int64_t)H * W) % 32 == 0,
+                    "rdeic_gn_silu_conv3x3_tail: H*W must be a positive multiple of 32");
+    RDEIC_CHECK_ARG(groups > 0 && groups <= kGnMaxGroups && C % groups == 0, "rdeic_gn_silu_conv3x3_tail: bad groups");
+    RDEIC_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)stats) % 16 == 0,
+                    "rdeic_gn_silu_conv3x3_tail: tensors must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    const int64_t HW = (int64_t)H * W;
+    int nfold = gn_num_chunks(B, HW);
+    if (nfold > HW / 32) nfold = (int)(HW / 32);
+    launch_k(gn_fold_stats_kernel, dim3(nfold, B), kGnThreads, 0, s, (const float2*)stats, C, (const float2*)nullptr, 0,
+             HW / 32, groups, (float2*)workspace);
+    RDEIC_LAUNCH_CHECK();
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDEIC_CUDA(cudaFuncSetAttribute(gn_silu_conv3x3_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
+        attr_set = true;
+    }
+    const int tiles_w = (W + kTailTW - 1) / kTailTW, tiles_h = (H + kTailTH - 1) / kTailTH;
+    const int64_t total = (int64_t)B * tiles_w * tiles_h;
+    launch_k(gn_silu_conv3x3_tail_kernel, dim3((unsigned)(total < kNumSMs ? total : kNumSMs)), kTailThreads, kTailSmem, s,
+             (const uint4*)x, B, H, W, (const float2*)workspace, nfold, groups, eps, gamma, beta, (const uint4*)w_packed,
+             bias, n_out, out_f32, ldo, out_u8, tiles_w, tiles_h);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

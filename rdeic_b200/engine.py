@@ -663,10 +663,23 @@ class VAEDecoderEngine(_VaeMid):
             wo = torch.cat([wo, torch.zeros(pad, *wo.shape[1:], device=wo.device)], 0)
             bo = torch.cat([bo, torch.zeros(pad, device=bo.device)], 0)
         self.conv_out = Conv.load({"w.weight": wo, "w.bias": bo}, "w", dev)
+        # the same layer for the fused tail kernel (norm_out + swish + conv_out [+ uint8] in one pass)
+        self.tail_w = ops.pack_tail_weight(sd[D + ".conv_out.weight"].float().to(dev))
+        self.tail_b = sd[D + ".conv_out.bias"].float().to(dev).contiguous()
+
+    def _tail(self, x: torch.Tensor, st, as_uint8: bool) -> torch.Tensor:
+        """model.py:683-686 (+ inference.py:85-87 with `as_uint8`)."""
+        if st is not None and x.shape[-1] == 128 and self.out_ch == 3:
+            return ops.gn_silu_conv3x3_tail(x, st, self.norm_out.g, self.norm_out.b, 32, 1e-6, self.tail_w, self.tail_b,
+                                            self.out_ch, as_uint8)
+        x = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, 32, 1e-6, True, stats1=st)
+        y = ops.conv_gemm(x, self.conv_out.w, self.conv_out.n_out, 9, bias=self.conv_out.b, out_f32=True)
+        return ops.image_to_u8(y) if as_uint8 else y
 
     @torch.no_grad()
-    def decode_nhwc(self, z: torch.Tensor) -> torch.Tensor:
-        """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,4] in [-1,1] (channel 3 is padding)."""
+    def decode_nhwc(self, z: torch.Tensor, as_uint8: bool = False) -> torch.Tensor:
+        """z [B,4,h,w] fp32 NCHW -> rgb NHWC fp32 [B,8h,8w,4] in [-1,1] (channel 3 is padding), or the uint8
+        HWC image [B,8h,8w,3] with `as_uint8`."""
         if not z.is_cuda:
             raise ops._lib.RdeicLibraryError("VAEDecoderEngine needs CUDA tensors; there is no CPU path")
         z8 = ops.nchw_to_nhwc_bf16(z.float().contiguous(), ldc=8)
@@ -680,8 +693,7 @@ class VAEDecoderEngine(_VaeMid):
                 x, st = self._res(b, x, st)
             if up is not None:
                 x, st = ops.conv_gemm(ops.upsample2x(x), up.w, up.n_out, 9, bias=up.b, stats=True)
-        x = ops.groupnorm(x, self.norm_out.g, self.norm_out.b, 32, 1e-6, True, stats1=st)
-        return ops.conv_gemm(x, self.conv_out.w, self.conv_out.n_out, 9, bias=self.conv_out.b, out_f32=True)
+        return self._tail(x, st, as_uint8)
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
@@ -691,4 +703,4 @@ class VAEDecoderEngine(_VaeMid):
     @torch.no_grad()
     def decode_u8(self, z: torch.Tensor) -> torch.Tensor:
         """Fused caller post-process (inference.py:85-87): uint8 HWC images."""
-        return ops.image_to_u8(self.decode_nhwc(z))
+        return self.decode_nhwc(z, as_uint8=True)

@@ -21,7 +21,8 @@ LAUNCHES = 0          # kernels launched by this module (graph replays add their
 GEMM_PROFILE = None   # when a list: conv_gemm appends (start_event, end_event, flops)
 
 
-_KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_groupnorm_from_stats": 2, "rdeic_vq_quant": 3}
+_KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_groupnorm_from_stats": 2, "rdeic_vq_quant": 3,
+                     "rdeic_gn_silu_conv3x3_tail": 2}
 
 
 def check(status: int, what: str) -> None:
@@ -382,6 +383,37 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, int(x1.dtype == torch.float32), _ptr(gamma),
                                            _ptr(beta), _ptr(out), B, H * W, groups, eps, 1 if silu else 0, _ptr(ws),
                                            _stream()), "rdeic_groupnorm_nhwc")
+    return out
+
+
+def pack_tail_weight(w: torch.Tensor) -> torch.Tensor:
+    """conv_out weight OIHW fp32 [n_out <= 4, C, 3, 3] -> bf16 [9 taps, 8 (zero-padded n_out), C] for `gn_silu_conv3x3_tail`."""
+    n_out, cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3) or n_out > 8:
+        raise ValueError("pack_tail_weight: expected a 3x3 kernel with at most 8 output channels")
+    out = torch.zeros((9, 8, cin), dtype=BF16, device=w.device)
+    out[:, :n_out] = w.float().permute(2, 3, 0, 1).reshape(9, n_out, cin).to(BF16)
+    return out.contiguous()
+
+
+def gn_silu_conv3x3_tail(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+                         eps: float, w_tail: torch.Tensor, bias: torch.Tensor, n_out: int, as_uint8: bool,
+                         ldo: int = 4) -> torch.Tensor:
+    """VAE decoder tail (model.py:683-686 + inference.py:85-87) in one kernel: GroupNorm (statistics from the
+    producing conv's epilogue) + SiLU + conv3x3 to n_out <= 4 channels, written as fp32 NHWC [B,H,W,ldo] or,
+    with `as_uint8`, as the caller's uint8 HWC image."""
+    B, H, W, Cc = x.shape
+    _need(x, BF16, "gn_silu_conv3x3_tail")
+    ws = _gn_workspace(B, x.device)
+    if as_uint8:
+        out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device)
+        of, ou = None, out
+    else:
+        out = torch.empty((B, H, W, ldo), dtype=torch.float32, device=x.device)
+        of, ou = out, None
+    check(_lib.load().rdeic_gn_silu_conv3x3_tail(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(w_tail), _ptr(bias),
+                                                 n_out, _ptr(of), ldo, _ptr(ou), B, H, W, Cc, groups, eps, _ptr(ws),
+                                                 _stream()), "rdeic_gn_silu_conv3x3_tail")
     return out
 
 

@@ -37,3 +37,12 @@ for name, fn, fl in [("256->128 stats", lambda: ops.conv_gemm(x256, w21, 128, 9,
                      ("128->4 conv_out f32", lambda: ops.conv_gemm(x128, wo, 4, 9, bias=b4, out_f32=True), 2.0 * 8 * 512 * 512 * 4 * 9 * 128)]:
     us = t(fn)
     print(f"{name:24s} {us:8.1f} us  {fl/us/1e6:7.1f} TF/s", flush=True)
+# fused tail: norm_out + swish + conv_out + uint8 vs the three-kernel path
+_, st = ops.conv_gemm(x128, w11, 128, 9, bias=b128, stats=True)
+gam, bet = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+wt = ops.pack_tail_weight(rnd(3, 128, 3, 3) / 34); b3 = rnd(3)
+def unfused():
+    xn = ops.groupnorm(x128, gam, bet, 32, 1e-6, True, stats1=st)
+    return ops.image_to_u8(ops.conv_gemm(xn, wo, 4, 9, bias=b4, out_f32=True))
+print(f"tail unfused (gn fold+apply, conv_out, u8) {t(unfused):8.1f} us", flush=True)
+print(f"tail fused                                 {t(lambda: ops.gn_silu_conv3x3_tail(x128, st, gam, bet, 32, 1e-6, wt, b3, 3, True)):8.1f} us", flush=True)

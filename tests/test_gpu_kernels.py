@@ -673,3 +673,38 @@ def test_conv3x3_two_m_tiles_per_item(cuda, B, H, W, C1, C2, Cout, stats):
         assert _rel(y.float().cpu(), ref.cpu()) < 4e-3            # bf16 output rounding
     else:
         assert _rel(res.cpu(), ref.cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 40, 48), (1, 8, 100)])
+def test_vae_tail_fused_matches_unfused(cuda, B, H, W):
+    """norm_out + swish + conv_out (+ uint8) in one kernel == GroupNorm kernel -> tcgen05 conv -> image_to_u8
+    (model.py:683-686, inference.py:85-87): same bf16 operand rounding, fp32 sums in another order."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(93)
+    C = 128
+    xin = _bf(torch.randn(B, H, W, 64, generator=g)).to(cuda).bfloat16()
+    wprod = ops.pack_conv_weight((_bf(torch.randn(C, 64, 3, 3, generator=g)) / 24).to(cuda))
+    x, st = ops.conv_gemm(xin, wprod, C, 9, stats=True)
+    if st is None:       # ragged pixel grid: statistics by a pass over the tensor, emitted in the slab layout
+        xs = x.float().view(B * H * W // 32, 32, C)
+        st = torch.stack([xs.sum(1), (xs * xs).sum(1)], -1).contiguous()
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda), (0.1 * torch.randn(C, generator=g)).to(cuda)
+    w = (torch.randn(3, C, 3, 3, generator=g) / 34).to(cuda)
+    b = (0.1 * torch.randn(3, generator=g)).to(cuda)
+    w4 = torch.cat([w, torch.zeros(1, C, 3, 3, device=cuda)], 0)
+    b4 = torch.cat([b, torch.zeros(1, device=cuda)], 0)
+    xn = ops.groupnorm(x, gamma, beta, 32, 1e-6, True, stats1=st)
+    ref = ops.conv_gemm(xn, ops.pack_conv_weight(w4), 4, 9, bias=b4, out_f32=True)
+    # and against torch on the same normalised bf16 activations
+    tref = F.conv2d(xn.float().permute(0, 3, 1, 2), _bf(w.cpu()).to(cuda), b, padding=1).permute(0, 2, 3, 1)
+    wt = ops.pack_tail_weight(w)
+    out = ops.gn_silu_conv3x3_tail(x, st, gamma, beta, 32, 1e-6, wt, b, 3, False)
+    assert tuple(out.shape) == (B, H, W, 4) and float(out[..., 3].abs().max()) == 0.0
+    assert _rel(out[..., :3].cpu(), ref[..., :3].cpu()) < 1e-3         # approx-intrinsic SiLU forms differ in the last bf16 bit of a few operands
+    assert _rel(out[..., :3].cpu(), tref.cpu()) < 1e-3
+    u8 = ops.gn_silu_conv3x3_tail(x, st, gamma, beta, 32, 1e-6, wt, b, 3, True)
+    ref8 = ops.image_to_u8(ref)
+    assert u8.dtype == torch.uint8 and tuple(u8.shape) == (B, H, W, 3)
+    d = (u8.int() - ref8.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-2     # a sum landing on a truncation boundary
