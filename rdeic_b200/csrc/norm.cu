@@ -7,6 +7,7 @@
 // ldm/modules/attention.py:96 Normalize (eps 1e-6), model/rdeic.py:483 GroupNorm_leq32,
 // ldm/modules/attention.py:273-275 nn.LayerNorm (eps 1e-5).
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/rdeic_b200.h"
 
 namespace rdeic {
@@ -21,6 +22,18 @@ static inline int gn_num_chunks(int B, int64_t HW) {
     int64_t max_by_rows = HW / 32 > 0 ? HW / 32 : 1;
     if (want > max_by_rows) want = max_by_rows;
     if (want > kGnMaxChunks) want = kGnMaxChunks;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+// Fold width for statistics that arrive as a slab table: kFoldSlabs slabs per fold CTA (the apply kernel's
+// prologue sums the nfold partials of its sample, 8 threads per group, four loads in flight).
+static inline int gn_num_fold(int B, int64_t HW) {
+    static const int per = getenv("RDEIC_GN_FOLD_SLABS") ? atoi(getenv("RDEIC_GN_FOLD_SLABS")) : 1;
+    const int64_t slabs = HW / 32;
+    int64_t want = (slabs + per - 1) / per;
+    const int cap = gn_num_chunks(B, HW);
+    if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;
 }
@@ -197,8 +210,18 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
         double a = 0.0, c = 0.0;
         if (g < G) {
-            for (int k = part; k < nchunk; k += 8) {
-                const float2 v = partial[((int64_t)b * nchunk + k) * G + g];
+            const float2* pp = partial + (int64_t)b * nchunk * G + g;
+            int k = part;
+            for (; k + 24 < nchunk; k += 32) {           // four independent L2 loads in flight, fixed order
+                const float2 v0 = pp[(int64_t)k * G], v1 = pp[(int64_t)(k + 8) * G];
+                const float2 v2 = pp[(int64_t)(k + 16) * G], v3 = pp[(int64_t)(k + 24) * G];
+                a += (double)v0.x; c += (double)v0.y;
+                a += (double)v1.x; c += (double)v1.y;
+                a += (double)v2.x; c += (double)v2.y;
+                a += (double)v3.x; c += (double)v3.y;
+            }
+            for (; k < nchunk; k += 8) {
+                const float2 v = pp[(int64_t)k * G];
                 a += (double)v.x;
                 c += (double)v.y;
             }
@@ -662,8 +685,7 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
     RDEIC_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0,
                     "rdeic_groupnorm_from_stats: tensors must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
-    int nfold = gn_num_chunks(B, HW);
-    if (nfold > HW / 32) nfold = (int)(HW / 32);
+    const int nfold = gn_num_fold(B, HW);
     launch_k(gn_fold_stats_kernel, dim3(nfold, B), kGnThreads, 0, s, (const float2*)stats1, C1,
              (const float2*)stats2, C2, HW / 32, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
@@ -695,8 +717,7 @@ int rdeic_gn_silu_conv3x3_tail(const void* x, const float* stats, const float* g
                     "rdeic_gn_silu_conv3x3_tail: tensors must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
     const int64_t HW = (int64_t)H * W;
-    int nfold = gn_num_chunks(B, HW);
-    if (nfold > HW / 32) nfold = (int)(HW / 32);
+    const int nfold = gn_num_fold(B, HW);
     launch_k(gn_fold_stats_kernel, dim3(nfold, B), kGnThreads, 0, s, (const float2*)stats, C, (const float2*)nullptr, 0,
              HW / 32, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
