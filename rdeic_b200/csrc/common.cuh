@@ -117,4 +117,17 @@ __device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
                  : "memory");
 }
 
+// streaming 256-bit accesses (sm_100: LDG/STG.256): one full 32-byte sector per lane and instruction, so a
+// warp moves 1 KB contiguously instead of two half-sector passes
+__device__ __forceinline__ void st_stream_u8(void* p, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y),
+                 "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_stream_u8(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
 }  // namespace rdeic

@@ -124,15 +124,34 @@ ckbd_merge_kernel(const float* __restrict__ a, const float* __restrict__ n,
 //   anchor: even row -> 1, odd row -> 0 ; non-anchor: even row -> 0, odd row -> 1
 __device__ __forceinline__ int pair_offset(int h, int which) { return (h & 1) ^ (which == 0); }
 
-// Log-domain guess for a sorted table (the reference's is exp(linspace(ln .11, ln 256, 64)),
-// utils/func.py:10-13): tab[L + 1] / tab[L + 2] hold ln(tab[0]) and L / (ln tab[L] - ln tab[0]).
-// The guess only seeds the search; the two fix-up loops compare against the table itself, so the
-// result is exactly  first k with s <= tab[k]  (L if none) for ANY sorted table and any s, NaN included.
+// Index search in a sorted table, seeded so that the common case is one or two table reads:
+//  mode 2 (positive lower bound, table spans <= 256 buckets): a bucket table keyed by the top bits of the
+//         float (exponent + 4 mantissa bits = 16 buckets per binade) holds, per bucket, the answer for the
+//         bucket's lowest value; any s in the bucket has answer >= that, so a short climb finishes it.
+//         No MUFU, no float->int conversion: the kernel stays HBM-bound instead of issue-bound.
+//  mode 1 (sorted, other cases): log-domain guess (the reference's table is exp(linspace(ln .11, ln 256, 64)),
+//         utils/func.py:10-13), tab[L + 1] / tab[L + 2] hold ln(tab[0]) and L / (ln tab[L] - ln tab[0]).
+//  mode 0: unsorted table, full count.
+// Every mode compares against the table itself, so the result is exactly  first k with s <= tab[k]
+// (L if none) for ANY table and any s, NaN included.
+constexpr int kMaxLevels = 256;
+constexpr int kLutOff = kMaxLevels + 4;          // s_tab: [0, L] table, [L+1, L+2] log seeds, then (base, nb), lut[256]
+constexpr int kLutSize = 256;
+constexpr int kTabFloats = kLutOff + kLutSize;
+
 __device__ __forceinline__ int scale_index(float scale, const float* __restrict__ tab, int L,
-                                           float lower_bound, bool sorted) {
+                                           float lower_bound, int mode) {
     // compressai LowerBound = torch.max(x, bound): NaN propagates.
     const float s = (scale != scale) ? scale : fmaxf(scale, lower_bound);
-    if (sorted) {
+    if (mode == 2) {
+        const int* meta = reinterpret_cast<const int*>(tab + kMaxLevels + 2);
+        int b = (int)(__float_as_uint(s) >> 19) - meta[0];       // s >= lower_bound > 0 (or NaN: huge key)
+        b = min(max(b, 0), meta[1]);
+        int k = reinterpret_cast<const int*>(tab + kLutOff)[b];
+        while (k < L && !(s <= tab[k])) ++k;
+        return k;
+    }
+    if (mode == 1) {
         // idx = L - #{k<L : s <= tab[k]} = first k with s <= tab[k] (L if none)
         float g = ceilf((__logf(s) - tab[L + 1]) * tab[L + 2]);
         int k = (g >= 0.f) ? ((g <= (float)L) ? (int)g : L) : 0;       // NaN -> 0
@@ -145,25 +164,40 @@ __device__ __forceinline__ int scale_index(float scale, const float* __restrict_
     return idx;
 }
 
-__device__ __forceinline__ bool load_table(const float* __restrict__ table, int levels,
-                                           float* s_tab, int* s_flag) {
+__device__ __forceinline__ int load_table(const float* __restrict__ table, int levels, float lower_bound,
+                                          float* s_tab, int* s_flag) {
     if (threadIdx.x == 0) *s_flag = 1;
     __syncthreads();
     for (int k = threadIdx.x; k < levels; k += blockDim.x) s_tab[k] = table[k];
     __syncthreads();
     for (int k = threadIdx.x; k + 1 < levels - 1; k += blockDim.x)
         if (!(s_tab[k] <= s_tab[k + 1])) *s_flag = 0;  // benign race: all writers store 0
+    const int L = levels - 1;
     if (threadIdx.x == 0) {                            // seeds of the log-domain guess (see scale_index)
-        const int L = levels - 1;
         const float l0 = logf(s_tab[0]), l1 = logf(s_tab[L]);
         s_tab[L + 1] = l0;
         s_tab[L + 2] = (l1 > l0) ? (float)L / (l1 - l0) : 0.f;
     }
     __syncthreads();
-    return *s_flag != 0 && s_tab[0] > 0.f;
+    if (!(*s_flag != 0 && s_tab[0] > 0.f)) return 0;
+    // bucket table: keys of lower_bound .. tab[L-1]; one more bucket catches everything above (and NaN)
+    const int base = (int)(__float_as_uint(lower_bound) >> 19);
+    const int top = (int)(__float_as_uint(L > 0 ? s_tab[L - 1] : s_tab[0]) >> 19);
+    const int nb = top - base + 1;                     // last valid bucket index
+    if (!(lower_bound > 0.f) || nb < 0 || nb >= kLutSize) return 1;
+    int* meta = reinterpret_cast<int*>(s_tab + kMaxLevels + 2);
+    int* lut = reinterpret_cast<int*>(s_tab + kLutOff);
+    if (threadIdx.x == 0) { meta[0] = base; meta[1] = nb; }
+    for (int b = threadIdx.x; b <= nb; b += blockDim.x) {
+        const float lo = __uint_as_float((uint32_t)(base + b) << 19);     // smallest value of the bucket
+        int k = 0;
+        while (k < L && !(lo <= s_tab[k])) ++k;
+        lut[b] = k;
+    }
+    __syncthreads();
+    return 2;
 }
 
-constexpr int kMaxLevels = 256;   // s_tab holds levels + 2 floats
 
 // mode 0: squeeze only (out_f)                      [ckbd.py:47-59]
 // mode 1: squeeze scales+means -> means_sq, indexes [ckbd.py:99-103,108-112]
@@ -174,10 +208,10 @@ ckbd_squeeze_kernel(const uint32_t* __restrict__ y, const float* __restrict__ sc
                     int H, int W, int which, int mode) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float s_tab[kMaxLevels + 2];
+    __shared__ float s_tab[kTabFloats];
     __shared__ int s_flag;
-    bool sorted = false;
-    if (mode == 1) sorted = load_table(table, levels, s_tab, &s_flag);
+    int sorted = 0;
+    if (mode == 1) sorted = load_table(table, levels, lower_bound, s_tab, &s_flag);
     const int Wh = W >> 1;
     const int64_t total = rows * Wh;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -200,10 +234,10 @@ ckbd_squeeze_vec_kernel(const uint32_t* __restrict__ y, const float* __restrict_
                         int64_t rows, int H, int W, int which, int mode, RowMap rm) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float s_tab[kMaxLevels + 2];
+    __shared__ float s_tab[kTabFloats];
     __shared__ int s_flag;
-    bool sorted = false;
-    if (mode == 1) sorted = load_table(table, levels, s_tab, &s_flag);
+    int sorted = 0;
+    if (mode == 1) sorted = load_table(table, levels, lower_bound, s_tab, &s_flag);
     const int Wq = W >> 3;  // groups of 8 inputs
     const int64_t total = rows * Wq;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -211,13 +245,13 @@ ckbd_squeeze_vec_kernel(const uint32_t* __restrict__ y, const float* __restrict_
         int64_t r; int col, h;
         rm.map(i, r, col, h);
         const int off = pair_offset(h, which);
-        const uint4 lo = ld_stream_u4(reinterpret_cast<const uint4*>(y) + 2 * i);
-        const uint4 hi = ld_stream_u4(reinterpret_cast<const uint4*>(y) + 2 * i + 1);
+        uint4 lo, hi;
+        ld_stream_u8(reinterpret_cast<const uint4*>(y) + 2 * i, lo, hi);
         uint4 o = off ? make_uint4(lo.y, lo.w, hi.y, hi.w) : make_uint4(lo.x, lo.z, hi.x, hi.z);
         st_stream_u4(reinterpret_cast<uint4*>(out_f) + i, o);
         if (mode == 1) {
-            const uint4 slo = ld_stream_u4(reinterpret_cast<const uint4*>(scales) + 2 * i);
-            const uint4 shi = ld_stream_u4(reinterpret_cast<const uint4*>(scales) + 2 * i + 1);
+            uint4 slo, shi;
+            ld_stream_u8(reinterpret_cast<const uint4*>(scales) + 2 * i, slo, shi);
             uint4 s = off ? make_uint4(slo.y, slo.w, shi.y, shi.w)
                           : make_uint4(slo.x, slo.z, shi.x, shi.z);
             int4 id;
@@ -269,8 +303,7 @@ ckbd_unsqueeze_vec_kernel(const uint4* __restrict__ sq, uint4* __restrict__ out,
         const uint4 v = ld_stream_u4(sq + i);
         const uint4 lo = off ? make_uint4(0u, v.x, 0u, v.y) : make_uint4(v.x, 0u, v.y, 0u);
         const uint4 hi = off ? make_uint4(0u, v.z, 0u, v.w) : make_uint4(v.z, 0u, v.w, 0u);
-        st_stream_u4(out + 2 * i, lo);
-        st_stream_u4(out + 2 * i + 1, hi);
+        st_stream_u8(out + 2 * i, lo, hi);
     }
 }
 
@@ -283,9 +316,9 @@ ckbd_encode_phase_kernel(const float* __restrict__ y, const float* __restrict__ 
                          int64_t rows, int H, int W, int which, RowMap rm) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float s_tab[kMaxLevels + 2];
+    __shared__ float s_tab[kTabFloats];
     __shared__ int s_flag;
-    const bool sorted = load_table(table, levels, s_tab, &s_flag);
+    const int sorted = load_table(table, levels, lower_bound, s_tab, &s_flag);
     const int Wh = W >> 1;
     const int64_t total = rows * Wh;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -367,9 +400,9 @@ build_indexes_kernel(const float* __restrict__ scales, const float* __restrict__
                      int levels, float lower_bound, int32_t* __restrict__ idx, int64_t numel) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float s_tab[kMaxLevels + 2];
+    __shared__ float s_tab[kTabFloats];
     __shared__ int s_flag;
-    const bool sorted = load_table(table, levels, s_tab, &s_flag);
+    const int sorted = load_table(table, levels, lower_bound, s_tab, &s_flag);
     const int L = levels - 1;
     const int64_t nv = numel >> 2;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -584,8 +617,8 @@ static int launch_squeeze(const float* y, const float* scales, const float* tabl
     if (mode == 1) RDEIC_CHECK_ARG(levels >= 2 && levels <= kMaxLevels, "%s: levels=%d out of range", who, levels);
     const int64_t rows = (int64_t)B * C * H;
     if (rows == 0 || W == 0) return 0;
-    bool vec = (W % 8 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out_f % 16 == 0);
-    if (mode == 1) vec = vec && ((uintptr_t)scales % 16 == 0) && ((uintptr_t)out_idx % 16 == 0);
+    bool vec = (W % 8 == 0) && ((uintptr_t)y % 32 == 0) && ((uintptr_t)out_f % 16 == 0);     // 256-bit loads
+    if (mode == 1) vec = vec && ((uintptr_t)scales % 32 == 0) && ((uintptr_t)out_idx % 16 == 0);
     if (vec)
         launch_k(ckbd_squeeze_vec_kernel, grid_for(rows * (W / 8), kThreads), kThreads, 0, as_stream(stream), 
             (const uint32_t*)y, scales, table, levels, lower_bound, (uint32_t*)out_f, out_idx,
@@ -623,7 +656,7 @@ int rdeic_ckbd_unsqueeze(const float* sq, float* out, int B, int C, int H, int W
     const int64_t rows = (int64_t)B * C * H;
     if (rows == 0 || Wh == 0) return 0;
     RDEIC_CHECK_ARG((uintptr_t)out % 8 == 0, "rdeic_ckbd_unsqueeze: out must be 8-byte aligned");
-    if (Wh % 4 == 0 && (uintptr_t)sq % 16 == 0 && (uintptr_t)out % 16 == 0)
+    if (Wh % 4 == 0 && (uintptr_t)sq % 16 == 0 && (uintptr_t)out % 32 == 0)     // 256-bit stores
         launch_k(ckbd_unsqueeze_vec_kernel, grid_for(rows * (Wh / 4), kThreads), kThreads, 0, as_stream(stream), 
             (const uint4*)sq, (uint4*)out, rows, H, Wh, which, RowMap(rows * (Wh / 4), Wh / 4, H));
     else
