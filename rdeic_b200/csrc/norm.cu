@@ -547,7 +547,10 @@ gn_silu_conv3x3_tail_kernel(const uint4* __restrict__ x, int B, int H, int W, co
 constexpr int kLnMaxVecLimit = 5;
 constexpr int kLnWarps = 8;
 
-template <bool kF32, int kLnMaxVec, bool kOutF32 = false>
+// kLanes = lanes per row: 32 (a warp per row) or 16 (two rows per warp): C = 320 is 40 vectors, which
+// a full warp covers as 32 + 8 (37 % of the issued lanes idle, and the kernel is issue-bound) but a
+// half warp covers as 16 + 16 + 8.
+template <bool kF32, int kLnMaxVec, bool kOutF32 = false, int kLanes = 32>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
@@ -555,29 +558,34 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
     pdl_trigger();
     pdl_wait();
     const int VL = C >> 3;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & (kLanes - 1);
+    constexpr int kRowsPerWarp = 32 / kLanes;
     // grid-stride over rows: at most 8 resident CTAs per SM walk the tensor (32 768 short-lived CTAs
     // spent more time being scheduled than loading)
-    for (int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5); row < rows;
-         row += (int64_t)gridDim.x * kLnWarps) {
+    // (a half warp whose row is past the end still runs the loop body with loads masked off, so the
+    // full-mask shuffles below stay convergent)
+    for (int64_t row0 = ((int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * kRowsPerWarp; row0 < rows;
+         row0 += (int64_t)gridDim.x * kLnWarps * kRowsPerWarp) {
+    const int64_t row = row0 + ((threadIdx.x & 31) / kLanes);
+    const bool live = row < rows;
     float f[kLnMaxVec][8];
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kLnMaxVec; ++j) {
-        const int l = lane + 32 * j;
-        if (l < VL) {
+        const int l = lane + kLanes * j;
+        if (l < VL && live) {
             load8<kF32>(x, row * VL + l, f[j]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) sum += f[j][k];
         }
     }
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = kLanes / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)C;
     float sq = 0.f;
 #pragma unroll
     for (int j = 0; j < kLnMaxVec; ++j) {
-        const int l = lane + 32 * j;
-        if (l < VL) {
+        const int l = lane + kLanes * j;
+        if (l < VL && live) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float d = f[j][k] - mean;
@@ -585,12 +593,12 @@ layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
             }
         }
     }
-    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = kLanes / 2; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / (float)C + eps);
 #pragma unroll
     for (int j = 0; j < kLnMaxVec; ++j) {
-        const int l = lane + 32 * j;
-        if (l < VL) {
+        const int l = lane + kLanes * j;
+        if (l < VL && live) {
             // (keeping gamma / beta in registers across rows was tried: 40 -> 77+ registers, a third of the
             // resident warps, 0.64 -> 0.60 of HBM; they are L1 hits here)
             const float4 g0 = *reinterpret_cast<const float4*>(gamma + l * 8);
@@ -792,6 +800,16 @@ int rdeic_layernorm(const void* x, int in_is_f32, const float* gamma, const floa
     if (blocks > 8ll * kNumSMs) blocks = 8ll * kNumSMs;
     const int nv = (C / 8 + 31) / 32;   // 16-byte vectors per lane
     cudaStream_t s = as_stream(stream);
+    if (C / 8 > 32 && C / 8 <= 48) {    // 33..48 vectors: half a warp per row, three vectors per lane
+        blocks = ceil_div64(rows, 2 * kLnWarps);
+        if (blocks > 8ll * kNumSMs) blocks = 8ll * kNumSMs;
+        if (in_is_f32)
+            launch_k(layernorm_kernel<true, 3, false, 16>, (unsigned)blocks, kLnWarps * 32, 0, s, x, gamma, beta, (uint4*)out, rows, C, eps);
+        else
+            launch_k(layernorm_kernel<false, 3, false, 16>, (unsigned)blocks, kLnWarps * 32, 0, s, x, gamma, beta, (uint4*)out, rows, C, eps);
+        RDEIC_LAUNCH_CHECK();
+        return 0;
+    }
 #define RDEIC_LN(F32, NV) launch_k(layernorm_kernel<F32, NV>, (unsigned)blocks, kLnWarps * 32, 0, s, x, gamma, beta, (uint4*)out, rows, C, eps)
     if (in_is_f32) {
         if (nv <= 1) RDEIC_LN(true, 1); else if (nv == 2) RDEIC_LN(true, 2); else if (nv == 3) RDEIC_LN(true, 3); else RDEIC_LN(true, 5);
