@@ -239,7 +239,13 @@ struct TileCfg {
 // items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1>
+// kSwap (with kMT == 2, BN == 128): operand roles exchanged.  One M=128 tcgen05.mma costs >= 128 clocks
+// whatever N is (its A operand is read from shared memory at a fixed rate), so an N = 128 tile runs the
+// tensor pipe at half rate.  With the WEIGHT tile as the M operand (128 output channels) and the item's
+// two pixel tiles as one N = 256 operand, the same FLOPs take half the MMA slots.  The accumulator is
+// then transposed (TMEM lane = output channel, column = pixel); phase A parks it in the staging buffer
+// already transposed back, so phase B (residual, stores, statistics) is unchanged.
+template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
@@ -358,6 +364,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
+                    if constexpr (kSwap) {
+                        // weights (BN = 128 rows) as the M operand, both pixel tiles (256 rows, contiguous) as N
+                        const uint64_t dpix = make_smem_desc(smem_u32(smem_a + s * Cfg::kABytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            umma_bf16(tmem_d, db + 2 * k, dpix + 2 * k, make_idesc(kMT * kBlockM), (kb | k) != 0);
+                    } else
 #pragma unroll
                     for (int u = 0; u < kMT; ++u) {
                         const uint64_t da = make_smem_desc(smem_u32(smem_a + (s * kMT + u) * kATileBytes));
@@ -370,6 +383,94 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
                 }
                 umma_commit(&acc_full[buf]);      // accumulator complete
+            }
+        }
+    } else if constexpr (kSwap) {
+        // ===== epilogue, exchanged operands: TMEM lane = output channel, column = pixel =====
+        // Host guarantees: every real tile is full and affine, n_out % 32 == 0, no per-sample bias, no GEGLU,
+        // one k-split, vector-aligned rows, alpha == 1 unless there is a residual.
+        const int ew = warp - 2;
+        const int quad = warp & 3;                    // channels col0 + 32 * quad + lane
+        const int half = ew >> 2;
+        float4* stg = reinterpret_cast<float4*>(smem_stg) + ew * 256;
+        float* stg_f = reinterpret_cast<float*>(stg);
+        const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+        const int tn_ = kBlockM >> (p.tw_log2 + p.th_log2);
+        constexpr int kChunks = kMT * kBlockM / 32;   // 32-pixel chunks of the item
+        uint32_t t = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
+            const int nt = item / m_tiles;
+            const int mi = item - nt * m_tiles;
+            const int col0 = nt * BN;
+            const int cbase = col0 + 32 * quad;
+            const bool ch_ok = cbase < p.n_out;
+            const float bias_c = (ch_ok && p.bias) ? p.bias[cbase + lane] : 0.f;
+            const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
+            int last_c = -1;
+            if (ch_ok)
+                for (int ci = half; ci < kChunks; ci += kCStride) last_c = ci;
+            if (last_c < 0) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+#pragma unroll 1
+            for (int ci = half; ci < kChunks && ch_ok; ci += kCStride) {
+                uint32_t acc[32];
+                tmem_ld16(tmem_acc + (uint32_t)(ci * 32), acc);
+                tmem_ld16(tmem_acc + (uint32_t)(ci * 32) + 16, acc + 16);
+                // coordinates of the chunk's first pixel (lane 0's row) while the load is in flight
+                int mt = mi * kMT + (ci >> 2);
+                const bool tile_ok = mt < total_tiles;
+                const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int tih = mt % p.tiles_h; mt /= p.tiles_h;
+                const int r0 = (ci & 3) * 32;
+                const int gw = tiw * tw + (r0 & (tw - 1)), gh = tih * th + ((r0 >> p.tw_log2) & (th - 1));
+                const int gn = mt * tn_ + (r0 >> (p.tw_log2 + p.th_log2));
+                const int64_t m_slab = ((int64_t)gn * p.a_h + gh) * p.a_w + gw;
+                tmem_ld_wait();
+                if (ci == last_c) {
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (!tile_ok) continue;                              // the partner of an odd last tile
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias_c;
+                if (p.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                } else if (p.act == 3) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_param;
+                } else if (p.act == 4) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                // transposed park: element (pixel j, channel lane) -> 16-byte chunk (lane/4) ^ (j & 7) of row j
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg_f[(j * 8 + ((lane >> 2) ^ (j & 7))) * 4 + (lane & 3)] = v[j];
+                __syncwarp();
+                {
+                    const int q = lane & 7;
+                    const int64_t m0 = m_slab + (lane >> 3);
+                    const int64_t o_off = m0 * p.ldo + cbase + 4 * q;
+                    float* of = p.out_f32 ? p.out_f32 + o_off : nullptr;
+                    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + o_off : nullptr;
+                    float* sd = kStats ? p.stats_out + ((m_slab >> 5) * p.n_out + cbase + 4 * q) * 2 : nullptr;
+                    const int64_t r_off = m0 * p.ld_resid + cbase + 4 * q;
+                    if (!p.resid)
+                        store_slab_out<0, kStats>(stg, lane, p.alpha, nullptr, 0, of, ob, p.ldo, sd);
+                    else if (p.resid_is_f32)
+                        store_slab_out<1, kStats>(stg, lane, p.alpha, reinterpret_cast<const float*>(p.resid) + r_off,
+                                                  p.ld_resid, of, ob, p.ldo, sd);
+                    else
+                        store_slab_out<2, kStats>(stg, lane, p.alpha, reinterpret_cast<const __nv_bfloat16*>(p.resid) + r_off,
+                                                  p.ld_resid, of, ob, p.ldo, sd);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -770,20 +871,20 @@ static bool stats_tiling_ok(int N, int H, int W, bool force_tn1) {
     return tw >= 32 || (tw == W && (tw * th >= 32 || th == H));
 }
 
-template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1>
+template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN, kEW, kMT>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -799,6 +900,14 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
         static const bool dual_m = !(getenv("RDEIC_DUAL_M") && atoi(getenv("RDEIC_DUAL_M")) == 0);
         if (dual_m && splits == 1 && !d.w_batched && d.taps * (d.cblk1 + d.cblk2) >= 9 &&
             (int64_t)m_tiles * d.n_tiles >= 8 * kNumSMs) {
+            // exchanged operand roles when the epilogue's fast path covers the whole problem
+            static const bool swap_ok = !(getenv("RDEIC_SWAP") && atoi(getenv("RDEIC_SWAP")) == 0);
+            const bool vec_io = (d.ldo & 3) == 0 && (!d.resid || (d.ld_resid & 3) == 0);
+            if (swap_ok && d.n_tiles == 1 && !d.row_bias && d.act != 2 && d.n_out % 32 == 0 && vec_io &&
+                (d.resid || d.alpha == 1.0f) && stats_tiling_ok(d.a_n, d.a_h, d.a_w, false)) {
+                if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, true>(ta, ta2, tb, d, m_tiles, splits, s);
+                return launch_conv3<BN, 0, 8, false, 2, true>(ta, ta2, tb, d, m_tiles, splits, s);
+            }
             if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, d, m_tiles, splits, s);
             return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, d, m_tiles, splits, s);
         }
