@@ -928,10 +928,16 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     return launch_conv3<BN, 0, 8>(ta, ta2, tb, d, m_tiles, splits, s);
 }
 
-static int pick_block_n(int n_out, int m_tiles, int hint) {
+// Tile width: cost ~ tiles per SM * per-tile time, per-tile time ~ bn (MMA N) + a fixed overhead (pipeline
+// fill, epilogue tail: ~96 columns' worth, fitted on the K <= 1280 linears of UNet levels 1-2).  A model that
+// charged the main loop the same for every width (on the theory that an M=128 MMA costs 128 clocks whatever
+// N is) was A/B-tested on one box and lost: UNet step 12.94 -> 13.60 ms, VAE 22.0 -> 23.8 ms.
+static int pick_block_n(int n_out, int m_tiles, int hint, int total_kb) {
+    (void)total_kb;
     if (hint == 32 || hint == 64 || hint == 128 || hint == 160 || hint == 256) return hint;
     if (n_out <= 32) return 32;
     if (n_out <= 64) return 64;
+    static const int overhead = getenv("RDEIC_TILE_OVERHEAD") ? atoi(getenv("RDEIC_TILE_OVERHEAD")) : 96;
     const int cands[3] = {256, 160, 128};
     int best = 128;
     double best_cost = 1e30;
@@ -940,9 +946,6 @@ static int pick_block_n(int n_out, int m_tiles, int hint) {
         const int nt = (n_out + bn - 1) / bn;
         const int64_t tiles = (int64_t)m_tiles * nt;
         const int64_t per_sm = (tiles + kNumSMs - 1) / kNumSMs;      // persistent: tiles each CTA walks
-        // cost ~ tiles per SM * per-tile time; per-tile time ~ bn (MMA N) + fixed overhead (pipeline fill,
-        // epilogue tail: measured ~ 96 columns' worth on the K <= 1280 linears of UNet levels 1-2)
-        static const int overhead = getenv("RDEIC_TILE_OVERHEAD") ? atoi(getenv("RDEIC_TILE_OVERHEAD")) : 96;
         const double cost = (double)per_sm * (bn + overhead);
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
@@ -963,7 +966,7 @@ int rdeic_conv_stats_supported(int a_n, int a_h, int a_w, int n_out, int k_block
     int tw, th, tn;
     pick_m_tile(a_n, a_h, a_w, false, &tw, &th, &tn);
     const int64_t m_tiles = (int64_t)((a_w + tw - 1) / tw) * ((a_h + th - 1) / th) * ((a_n + tn - 1) / tn);
-    const int bn = pick_block_n(n_out, (int)m_tiles, 0);
+    const int bn = pick_block_n(n_out, (int)m_tiles, 0, k_blocks);
     const int64_t tiles = m_tiles * ((n_out + bn - 1) / bn);
     if (tiles <= kNumSMs / 2 && k_blocks >= 8) return 0;
     return 1;
@@ -1050,7 +1053,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         RDEIC_CHECK_ARG(p->ldo >= p->n_out, "rdeic_conv_gemm: bad n_out/ldo");
     }
 
-    const int bn = pick_block_n(p->n_out, m_tiles, p->tile_n_hint);
+    const int bn = pick_block_n(p->n_out, m_tiles, p->tile_n_hint, p->taps * (d.cblk1 + d.cblk2));
 
     CUtensorMap ta, ta2, tb;
     {
