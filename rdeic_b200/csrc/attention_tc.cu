@@ -277,6 +277,12 @@ constexpr int kA2Threads = 64 + 32 * 8;
 constexpr int kA2Smem = 2 * kATile /*Q*/ + 2 * kAStages * kATile /*K,V*/ + 2 * kAPBytes /*P_A,P_B*/ + 1024 + 256;
 constexpr uint32_t kA2ColS = 0, kA2ColO = 256;    // S_A 0, S_B 128 ; O_A 256, O_B 320
 
+// kLazy: O stays in TMEM for the whole key loop (the PV MMAs accumulate in place) and is rescaled only
+// when a row's running maximum has grown by more than 2^8 since the reference maximum its exponents use
+// (exact: l and O carry the same factor, which cancels in O / l; P <= 256 is harmless in bf16).  The
+// per-step fold-in of PV (TMEM load + 64 adds + 64 multiplies per thread) disappears, and with the 64
+// accumulator registers gone the S tile is read from TMEM once (128 registers) instead of twice.
+template <bool kLazy>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
@@ -358,7 +364,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                 for (int ks = 0; ks < kAK / 16; ++ks) {
                     const uint64_t dp = make_smem_desc(pb + (ks >> 2) * (kAQ * 128) + (ks & 3) * 32);
-                    umma_bf16(tmem_base + kA2ColO + g * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o, ks != 0);
+                    umma_bf16(tmem_base + kA2ColO + g * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o,
+                              kLazy ? (i | ks) != 0 : ks != 0);
                 }
                 umma_commit(&o_full[g]);
             };
@@ -381,6 +388,90 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int row = quad * 32 + lane;           // row inside the group's 128-row tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float sc = p.scale_log2;
+        if constexpr (kLazy) {
+            float m_ref = -INFINITY, l_run = 0.f;
+            const uint32_t ts = tmem_base + lane_addr + kA2ColS + g * kAK;
+            const uint32_t to = tmem_base + lane_addr + kA2ColO + g * kAD;
+            uint8_t* prow0 = s_p + g * kAPBytes + row * 128;
+            for (int j = 0; j < T; ++j) {
+                mbar_wait(&s_full[g], j & 1);
+                tc_fence_after();
+                uint32_t sv[kAK];
+#pragma unroll
+                for (int c = 0; c < kAK; c += 16) tmem_ld16(ts + c, sv + c);
+                tmem_ld_wait();
+                tc_fence_before();                  // the only read of S_g: the MMA thread may overwrite it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[g]);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < kAK; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                const float m_new = mx * sc;
+                // PV(j-1) must have retired before P_g is overwritten (and before O_g is rescaled)
+                if (j > 0) {
+                    mbar_wait(&o_full[g], (j - 1) & 1);
+                    tc_fence_after();
+                }
+                const bool grow = m_new > m_ref + 8.0f;              // first tile: m_ref = -inf -> true
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_to = grow ? m_new : m_ref;
+                    const float corr = ex2_approx(m_ref - m_to);     // 1 for rows that keep their reference
+                    if (j > 0) {
+#pragma unroll
+                        for (int c2 = 0; c2 < kAD; c2 += 16) {       // 16 columns at a time: S occupies 128 registers
+                            uint32_t r[16];
+                            tmem_ld16(to + c2, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * corr);
+                            tmem_st16(to + c2, r);
+                        }
+                        tmem_st_wait();
+                        l_run *= corr;
+                    }
+                    m_ref = m_to;
+                }
+                float rowsum = 0.f, rowsum2 = 0.f;
+#pragma unroll
+                for (int c8 = 0; c8 < 16; ++c8) {                    // 8 keys -> one 16-byte chunk of P (S dies as we go)
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * c]), sc, -m_ref));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * c + 1]), sc, -m_ref));
+                        rowsum += p0; rowsum2 += p1;
+                        pk[c] = pack_bf16x2(p0, p1);
+                    }
+                    uint8_t* prow = prow0 + (c8 >> 3) * (kAQ * 128);      // 64-key panel
+                    *reinterpret_cast<uint4*>(prow + (((c8 & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                l_run += rowsum + rowsum2;
+                tc_fence_before();                  // the rescale's TMEM stores precede the PV the arrive releases
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g]);
+            }
+            mbar_wait(&o_full[g], (T - 1) & 1);
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(qt * kA2Q + g * kAQ + row) * p.ldo + head * kAD;
+#pragma unroll
+            for (int c2 = 0; c2 < kAD; c2 += 32) {
+                uint32_t r[32];
+                tmem_ld16(to + c2, r);
+                tmem_ld16(to + c2 + 16, r + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(r[8 * v8]) * inv, __uint_as_float(r[8 * v8 + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(r[8 * v8 + 2]) * inv, __uint_as_float(r[8 * v8 + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(r[8 * v8 + 4]) * inv, __uint_as_float(r[8 * v8 + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(r[8 * v8 + 6]) * inv, __uint_as_float(r[8 * v8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c2 + 8 * v8) = w;
+                }
+            }
+        } else {
         float o[kAD];
 #pragma unroll
         for (int i = 0; i < kAD; ++i) o[i] = 0.f;
@@ -469,6 +560,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             w.w = pack_bf16x2(o[8 * v8 + 6] * inv, o[8 * v8 + 7] * inv);
             *reinterpret_cast<uint4*>(dst + 8 * v8) = w;
         }
+        }   // !kLazy
     }
     tc_fence_before();
     __syncthreads();
@@ -518,11 +610,14 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
     if (Nq % kA2Q == 0 && (int64_t)(Nq / kA2Q) * heads * B >= pp_min) {
         static bool attr2_set = false;
         if (!attr2_set) {
-            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
             attr2_set = true;
         }
         dim3 grid2(Nq / kA2Q, heads, B);
-        launch_k(attention_tc2_kernel, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
+        static const bool lazy = !(getenv("RDEIC_ATTN_LAZY") && atoi(getenv("RDEIC_ATTN_LAZY")) == 0);
+        if (lazy) launch_k(attention_tc2_kernel<true>, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
+        else launch_k(attention_tc2_kernel<false>, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
         RDEIC_LAUNCH_CHECK();
         return 0;
     }

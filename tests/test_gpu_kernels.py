@@ -492,6 +492,28 @@ def test_attention(cuda, B, heads, Nq, Nk, d):
     assert _rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,heads,N", [(8, 10, 1024), (2, 5, 4096)])
+def test_attention_growing_logits(cuda, B, heads, N):
+    """Logits that keep growing along the key axis (and differently per row): the two-query-tile kernel keeps O
+    in TMEM and rescales it only when a row's maximum has grown by 2^8 — every row must rescale several
+    times here, some lanes of a warp without the others."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(33)
+    d = 64
+    q = _bf(torch.randn(B, N, heads * d, generator=g) * (0.5 + 3.0 * torch.rand(B, N, 1, generator=g)))
+    k = _bf(torch.randn(B, N, heads * d, generator=g) * torch.linspace(0.3, 4.0, N)[None, :, None])
+    v = _bf(torch.randn(B, N, heads * d, generator=g))
+    sp = lambda t: t.reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    sim = torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * d ** -0.5
+    assert float(sim.max()) > 30.0
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), sp(v)).permute(0, 2, 1, 3).reshape(B, N, heads * d)
+    out = ops.attention(q.to(cuda).bfloat16(), k.to(cuda).bfloat16(), v.to(cuda).bfloat16(), heads, d,
+                        d ** -0.5).float().cpu()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 6e-2 and _rel(out, ref) < 1e-2
+
+
 def test_attention_fused_qkv_slices(cuda):
     from rdeic_b200 import ops
 
