@@ -162,14 +162,18 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    real_stdout = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: NCCL prints its version banner from C on fd 1, so fd 1 is
+        # pointed at stderr for the whole run and the line is written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     from rdeic_b200 import RDEIC, build, configs, ops, parallel, synthetic
@@ -317,7 +321,11 @@ def run_b200(args):
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline}
         if sd_cpu is not None:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(sd_cpu, 1, 0).items() if k != "s_per_image"}
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
