@@ -285,6 +285,15 @@ def run_b200(args):
     decode_device()
     torch.cuda.synchronize()
     prof, ops.GEMM_PROFILE = list(ops.GEMM_PROFILE), None
+    # the same serialised (one stream, no graph) decode without brackets: the denominator of the kernel's
+    # share, like for like with the serialised ncu launch list under profiles/
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    decode_device()
+    s1.record()
+    torch.cuda.synchronize()
+    ms_serial = s0.elapsed_time(s1)
     model.control_model.overlap_control = overlap
     model.use_cuda_graph = True
     g_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
@@ -303,7 +312,8 @@ def run_b200(args):
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "traffic": traffic, "launches_per_step": len(prof),
                 "flops_per_launch": g_fl / max(len(prof), 1), "ms_per_launch": g_ms / max(len(prof), 1),
-                "share_of_step": g_ms / (ms_dev / args.steps),
+                "share_of_step": g_ms / ms_serial, "share_basis": "one-stream eager decode of the same batch "
+                f"({ms_serial:.1f} ms; the graphed, two-stream step is ms_per_step)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
 

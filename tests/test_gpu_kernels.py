@@ -730,3 +730,41 @@ def test_vae_tail_fused_matches_unfused(cuda, B, H, W):
     assert u8.dtype == torch.uint8 and tuple(u8.shape) == (B, H, W, 3)
     d = (u8.int() - ref8.int()).abs()
     assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-2     # a sum landing on a truncation boundary
+
+
+@pytest.mark.parametrize("variant", ["silu", "f32_resid_dual", "leaky_f32", "gelu_alpha"])
+def test_conv3x3_exchanged_roles_epilogues(cuda, variant):
+    """The exchanged-operand form (weights as the M operand, 256 pixels as N; N <= 128 convs with many tiles)
+    through its activation / residual / output variants, against torch on the same bf16 operands."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(95)
+    B, H, W, Cin, Cout = 2, 288, 288, 64, 128
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = _bf(torch.randn(B, Cin, H, W, generator=g)).to(cuda)
+        w = _bf(torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).to(cuda)
+        b = torch.randn(Cout, generator=g).to(cuda)
+        conv = F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    a = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    wp = ops.pack_conv_weight(w)
+    if variant == "silu":
+        out = ops.conv_gemm(a, wp, Cout, 9, bias=b, act=1).float()
+        assert _rel(out.cpu(), F.silu(conv).cpu()) < 4e-3
+    elif variant == "f32_resid_dual":
+        r = torch.randn(B, H, W, Cout, generator=g).to(cuda)
+        of, oh, st = ops.conv_gemm(a, wp, Cout, 9, bias=b, resid=r, alpha=0.5, dual=True, stats=True)
+        ref = r + 0.5 * conv
+        assert _rel(of.cpu(), ref.cpu()) < 1e-3 and torch.equal(oh.float(), of.bfloat16().float())
+        blk = of.view(B * H * W // 32, 32, Cout)
+        assert _rel(st[..., 0].cpu(), blk.sum(1).cpu()) < 1e-4
+    elif variant == "leaky_f32":
+        out = ops.conv_gemm(a, wp, Cout, 9, bias=b, act=3, act_param=0.1, out_f32=True)
+        assert _rel(out.cpu(), F.leaky_relu(conv, 0.1).cpu()) < 1e-3
+    else:
+        # alpha != 1 without a residual is outside the exchanged form's fast path: the library must fall back
+        out = ops.conv_gemm(a, wp, Cout, 9, bias=b, act=4, alpha=0.25, out_f32=True)
+        assert _rel(out.cpu(), (0.25 * F.gelu(conv)).cpu()) < 1e-3
