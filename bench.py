@@ -250,7 +250,11 @@ def run_b200(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    if args.profile_range:       # `ncu --profile-from-start off`: the launch list of exactly this region
+        torch.cuda.cudart().cudaProfilerStart()
     ms_dev, launches = timed(decode_device, args.steps)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
     clk = clocks.stop() if rank == 0 else None
     for _ in range(2):
         decode_e2e()
@@ -439,6 +443,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed device region (for ncu --profile-from-start off)")
     ap.add_argument("--compressor", type=int, default=0, metavar="B",
                     help="measure the learned compressor (SURVEY 8f rows) on B 512x512 images instead of the decode")
     args = ap.parse_args()

@@ -279,16 +279,56 @@ class RDEIC:
             ops.q_sample(x_start[i], noise[i], float(self._h_sqrt_ac[ti]), float(self._h_sqrt_1mac[ti]), out=out[i])
         return out
 
+    # Latents up to this many positions (B*h*w; 8 x 64 x 64 = one 512^2 batch of 8) replay the VAE decode
+    # from a CUDA graph: its first ~100 kernels (conv_in, mid block, mid attention on the latent grid) are
+    # shorter than a Python enqueue, so the eager decode starts launch-bound.  Larger batches are not
+    # graphed: their kernels hide the enqueue and a graph would pin several GB of activations per shape.
+    VAE_GRAPH_MAX_POSITIONS = 8 * 64 * 64
+
+    def _graphed_decode(self, z, as_uint8: bool):
+        """Replay the VAE decode (ddpm.py:835-844, autoencoder.py:97-100) from a CUDA graph keyed by the
+        latent shape; `z` is copied into the graph's static input, the result is cloned out of it."""
+        dec = self.first_stage_model
+        fn = dec.decode_u8 if as_uint8 else dec.decode
+        key = ("vae", tuple(z.shape), as_uint8)
+        g = self._graphs.get(key)
+        if g is None:
+            st = {"z": z.clone()}
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):                       # warm-up: lazy inits, workspaces
+                fn(st["z"])
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(graph):
+                st["out"] = fn(st["z"])
+            st["nodes"] = ops.LAUNCHES - n0                  # kernels captured (recorded, not executed)
+            ops.LAUNCHES = n0
+            st["graph"] = graph
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g = st
+        g["z"].copy_(z)
+        g["graph"].replay()
+        ops.LAUNCHES += g["nodes"]
+        return g["out"].clone()
+
+    def _decode(self, z, as_uint8: bool):
+        self._need_weights()
+        z = z.to(self.device, torch.float32).contiguous()
+        if self.use_cuda_graph and z.dim() == 4 and z.shape[0] * z.shape[2] * z.shape[3] <= self.VAE_GRAPH_MAX_POSITIONS:
+            return self._graphed_decode(z, as_uint8)
+        return self.first_stage_model.decode_u8(z) if as_uint8 else self.first_stage_model.decode(z)
+
     @torch.no_grad()
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         """ddpm.py:835-844 -> [B,3,H,W] fp32 in [-1,1]."""
         if predict_cids:
             raise NotImplementedError("predict_cids is not part of the RDEIC decode path")
-        self._need_weights()
-        return self.first_stage_model.decode(z.to(self.device))
+        return self._decode(z, False)
 
     @torch.no_grad()
     def decode_first_stage_u8(self, z):
         """decode_first_stage + the caller's post-process (inference.py:85-87) -> uint8 [B,H,W,3]."""
-        self._need_weights()
-        return self.first_stage_model.decode_u8(z.to(self.device))
+        return self._decode(z, True)

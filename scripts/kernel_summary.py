@@ -1,6 +1,6 @@
 """Per-kernel summary (launches, ms, share, DRAM bytes per launch) of an ncu launch list captured with
 --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv.
-Usage: python scripts/kernel_summary.py launches.csv out.json"""
+Usage: python scripts/kernel_summary.py launches.csv out.json ["source description"]"""
 import csv
 import json
 import sys
@@ -30,7 +30,7 @@ res = {"total_ms": tot / 1e6, "launches": sum(k["launches"] for k in per.values(
        "kernels": {n: {"launches": k["launches"], "ms": k["ns"] / 1e6, "share": k["ns"] / tot,
                        "dram_bytes_per_launch": k["dram"] / k["launches"]}
                    for n, k in sorted(per.items(), key=lambda kv: -kv[1]["ns"])},
-       "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum --clock-control none --cache-control none, "
+       "source": sys.argv[3] if len(sys.argv) > 3 else "ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum --clock-control none --cache-control none, "
                  "one 512^2 batch-8 5-step decode (scripts/profile_decode.py 5 8 all)"}
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps({k: res[k] for k in ("total_ms", "launches", "conv_gemm_dram_bytes_per_launch", "conv_gemm_share")}))

@@ -136,6 +136,32 @@ def test_graph_and_eager_agree(small_model, cuda):
     assert torch.equal(a, b)
 
 
+def test_vae_decode_graph_and_eager_agree(small_model, cuda):
+    """The graphed VAE decode (RDEIC._graphed_decode) replays the same kernels as the eager one: bit-identical
+    images, new latents picked up on every replay, and latents above VAE_GRAPH_MAX_POSITIONS stay eager."""
+    g = torch.Generator().manual_seed(11)
+    zs = [torch.randn(2, 4, 8, 16, generator=g).to(cuda) for _ in range(2)]
+    got = [(small_model.decode_first_stage_u8(z), small_model.decode_first_stage(z)) for z in zs]
+    for kind in (True, False):                                      # one graph per (shape, output kind)
+        assert ("vae", (2, 4, 8, 16), kind) in small_model._graphs
+    small_model.use_cuda_graph = False
+    try:
+        want = [(small_model.decode_first_stage_u8(z), small_model.decode_first_stage(z)) for z in zs]
+    finally:
+        small_model.use_cuda_graph = True
+    for (a8, af), (b8, bf) in zip(got, want):
+        assert a8.dtype == torch.uint8 and tuple(a8.shape) == (2, 64, 128, 3) and torch.equal(a8, b8)
+        assert tuple(af.shape) == (2, 3, 64, 128) and torch.equal(af, bf)
+    assert not torch.equal(got[0][0], got[1][0])
+    limit, type(small_model).VAE_GRAPH_MAX_POSITIONS = type(small_model).VAE_GRAPH_MAX_POSITIONS, 2 * 8 * 16 - 1
+    try:
+        small_model._graphs.pop(("vae", (2, 4, 8, 16), True))
+        assert torch.equal(small_model.decode_first_stage_u8(zs[0]), want[0][0])
+        assert ("vae", (2, 4, 8, 16), True) not in small_model._graphs   # ran eager: no graph was captured
+    finally:
+        type(small_model).VAE_GRAPH_MAX_POSITIONS = limit
+
+
 def test_model_raises_without_weights_and_on_cpu(cuda):
     from rdeic_b200 import RDEIC, _lib
 
