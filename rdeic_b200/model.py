@@ -279,11 +279,11 @@ class RDEIC:
             ops.q_sample(x_start[i], noise[i], float(self._h_sqrt_ac[ti]), float(self._h_sqrt_1mac[ti]), out=out[i])
         return out
 
-    # Latents up to this many positions (B*h*w; 8 x 64 x 64 = one 512^2 batch of 8) replay the VAE decode
-    # from a CUDA graph: its first ~100 kernels (conv_in, mid block, mid attention on the latent grid) are
-    # shorter than a Python enqueue, so the eager decode starts launch-bound.  Larger batches are not
-    # graphed: their kernels hide the enqueue and a graph would pin several GB of activations per shape.
-    VAE_GRAPH_MAX_POSITIONS = 8 * 64 * 64
+    # Latents up to this many positions (B*h*w; 64 x 64 = one 512^2 image) replay the VAE decode from a CUDA
+    # graph: at that size its ~110 kernels are shorter than their Python enqueues (measured on one box,
+    # scripts/ab_vae_graph.py: 3.59 -> 3.42 ms at batch 1, nothing measurable at batch 8: 22-23 ms either way).
+    # Larger batches stay eager: their kernels hide the enqueue and a graph would pin GBs of activations per shape.
+    VAE_GRAPH_MAX_POSITIONS = 64 * 64
 
     def _graphed_decode(self, z, as_uint8: bool):
         """Replay the VAE decode (ddpm.py:835-844, autoencoder.py:97-100) from a CUDA graph keyed by the
