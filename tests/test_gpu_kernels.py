@@ -27,7 +27,8 @@ def _rand_y(shape, seed, scale=6.0):
 # ------------------------------------------------------------------------------------------
 # entropy front end — bit exact
 # ------------------------------------------------------------------------------------------
-CK_SHAPES = [(1, 8, 32, 32), (2, 16, 7, 10), (1, 3, 5, 6), (3, 64, 32, 48), (1, 1, 1, 2), (1, 2, 9, 4)]
+# squeezed widths 16 / 24 (256-bit loads), 12 (128-bit loads), 5 / 3 / 1 / 2 (scalar)
+CK_SHAPES = [(1, 8, 32, 32), (2, 16, 7, 10), (1, 3, 5, 6), (3, 64, 32, 48), (1, 1, 1, 2), (1, 2, 9, 4), (2, 4, 6, 24)]
 
 
 @pytest.mark.parametrize("shape", CK_SHAPES)
@@ -99,7 +100,7 @@ def _entropy_inputs(shape, seed):
     return y.float(), mu.float(), sc.float(), table
 
 
-@pytest.mark.parametrize("numel", [1, 5, 64, 1000, 262144 + 3])
+@pytest.mark.parametrize("numel", [1, 5, 64, 1000, 1005, 262144 + 3])
 def test_quantize_dequantize_indexes_bit_exact(cuda, numel):
     from rdeic_b200 import ops
 
@@ -113,6 +114,11 @@ def test_quantize_dequantize_indexes_bit_exact(cuda, numel):
     assert np.array_equal(_bits(deq.cpu().numpy()), _bits(oe.dequantize(ref, mu.numpy())))
     idx = ops.build_indexes(sc.to(cuda), table.to(cuda), 0.11)
     assert np.array_equal(idx.cpu().numpy(), oe.build_indexes(sc.numpy(), table.numpy()))
+    if numel > 4:       # scales 16- but not 32-byte aligned: the 128-bit path
+        shifted = torch.cat([sc[:4], sc]).to(cuda)[4:]
+        assert shifted.data_ptr() % 32 == 16 and shifted.is_contiguous()
+        idx = ops.build_indexes(shifted, table.to(cuda), 0.11)
+        assert np.array_equal(idx.cpu().numpy(), oe.build_indexes(sc.numpy(), table.numpy()))
 
 
 def test_build_indexes_unsorted_table_falls_back(cuda):
