@@ -200,33 +200,39 @@ def run_b200(args):
     pin = lambda t: t.contiguous().pin_memory()
     host = {"c_latent": pin(c_latent), "hint": pin(hint), "ctx": pin(ctx), "noises": [pin(n) for n in noises]}
     d = {"c_latent": c_latent.to(dev), "hint": hint.to(dev), "ctx": ctx.to(dev), "noises": [n.to(dev) for n in noises]}
-    out_host = torch.empty((BATCH, H, W, 3), dtype=torch.uint8).pin_memory()
+    # a second HBM-resident batch: the device-timed steps alternate between the two, so every step decodes a batch
+    # whose conditioning differs from the previous step's and the step-invariant work done once per batch (cross-
+    # attention K/V of the text context, NHWC bf16 hint: NoiseEstimatorEngine.prepare_cond) is inside every step
+    c2, h2, x2, n2 = make_inputs(BATCH, h, w, seed_off=1000 * rank + 500)
+    d_alt = {"c_latent": c2.to(dev), "hint": h2.to(dev), "ctx": x2.to(dev), "noises": [n.to(dev) for n in n2]}
+    turn = [0]
     h2d = sum(t.numel() * t.element_size() for t in [host["c_latent"], host["hint"], host["ctx"], *host["noises"]])
-    d2h = out_host.numel()
+    d2h = BATCH * H * W * 3                                   # uint8 images read back per step
 
     def decode_device():
-        cond = {"c_latent": [d["c_latent"]], "c_crossattn": [d["ctx"]], "guide_hint": d["hint"]}
-        return relay_decode(model, cond, RELAY_STEPS, sampler="ddpm", start_noise=d["noises"][0],
-                            step_noises=d["noises"][1:])
+        b = (d, d_alt)[turn[0] & 1]
+        turn[0] += 1
+        eng = model.control_model          # a new batch: nothing of the previous one's conditioning is reused
+        eng._ctx_cache.clear()
+        eng._hint_cache.clear()
+        cond = {"c_latent": [b["c_latent"]], "c_crossattn": [b["ctx"]], "guide_hint": b["hint"]}
+        return relay_decode(model, cond, RELAY_STEPS, sampler="ddpm", start_noise=b["noises"][0],
+                            step_noises=b["noises"][1:])
 
-    # e2e: host -> device copies of this step's inputs, decode, device -> host of the uint8 images
-    e = {"c_latent": torch.empty_like(d["c_latent"]), "hint": torch.empty_like(d["hint"]),
-         "ctx": torch.empty_like(d["ctx"]), "noises": [torch.empty_like(n) for n in d["noises"]]}
+    # e2e: the public serving call for host-resident conditioning (pipeline.decode_host_batches): every step's
+    # inputs are copied host -> device from pinned memory and its uint8 images device -> host inside the timed
+    # region; the copies of step i+1 / i-1 are double buffered against the decode of step i
+    from rdeic_b200.pipeline import decode_host_batches
 
-    def decode_e2e():
-        e["c_latent"].copy_(host["c_latent"], non_blocking=True)
-        e["hint"].copy_(host["hint"], non_blocking=True)
-        e["ctx"].copy_(host["ctx"], non_blocking=True)
-        for dst, src in zip(e["noises"], host["noises"]):
-            dst.copy_(src, non_blocking=True)
-        cond = {"c_latent": [e["c_latent"]], "c_crossattn": [e["ctx"]], "guide_hint": e["hint"]}
-        img = relay_decode(model, cond, RELAY_STEPS, sampler="ddpm", start_noise=e["noises"][0],
-                           step_noises=e["noises"][1:])
-        out_host.copy_(img, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out_host
+    host_batch = {"c_latent": host["c_latent"], "guide_hint": host["hint"], "c_crossattn": host["ctx"],
+                  "start_noise": host["noises"][0], "step_noises": host["noises"][1:]}
+    e2e_last = {}
 
-    def timed(fn, k):
+    def decode_e2e(k):
+        for out in decode_host_batches(model, (host_batch for _ in range(k)), RELAY_STEPS, sampler="ddpm"):
+            e2e_last["img"] = out               # pinned host uint8 [B,H,W,3], complete when yielded
+
+    def timed(fn, k, batched=False):
         """K steps between barrier+sync on both sides, CUDA events on the launching stream, MAX over ranks."""
         if world > 1:
             dist.barrier()
@@ -234,8 +240,11 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = ops.LAUNCHES
         e0.record()
-        for _ in range(k):
-            fn()
+        if batched:
+            fn(k)                       # one call that runs all k steps (and ends with the last result on the host)
+        else:
+            for _ in range(k):
+                fn()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -256,9 +265,9 @@ def run_b200(args):
     if args.profile_range:
         torch.cuda.cudart().cudaProfilerStop()
     clk = clocks.stop() if rank == 0 else None
-    for _ in range(2):
-        decode_e2e()
-    ms_e2e, _ = timed(decode_e2e, args.steps)
+    decode_e2e(2)
+    ms_e2e, _ = timed(decode_e2e, args.steps, batched=True)
+    assert tuple(e2e_last["img"].shape) == (BATCH, H, W, 3) and d2h == e2e_last["img"].numel()
 
     # UNet-step ms (second half of the BASELINE metric): graph replay of one UNet+control step, B=8
     cond = {"c_latent": [d["c_latent"]], "c_crossattn": [d["ctx"]], "guide_hint": d["hint"]}
@@ -328,7 +337,10 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                            "l2": "no flush needed: per-step working set (1.9 GB bf16 weights + >1 GB activations) "
-                                 "exceeds the 126 MB L2", "sampler": "SpacedSampler fixed_small, CUDA-graphed UNet step"},
+                                 "exceeds the 126 MB L2", "sampler": "SpacedSampler fixed_small, CUDA-graphed UNet step",
+                           "inputs": "two HBM-resident batches alternate step to step: the once-per-batch conditioning work "
+                                     "(text K/V projections, NHWC bf16 hint) is inside every timed step; e2e: "
+                                     "pipeline.decode_host_batches, H2D/D2H double buffered against the decode"},
                 "unet_step_ms": ms_unet / 10, "vae_decode_ms": ms_vae / 3,
                 "e2e": {"value": n_img / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

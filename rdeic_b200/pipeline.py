@@ -6,7 +6,7 @@ inference_partition.py:280-310): from decompressed conditioning to uint8 images.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence
 
 import torch
 
@@ -79,3 +79,82 @@ def decode_streams(model, stream_paths: Sequence[str], c_crossattn: List[torch.T
                 img = img[:, :h, :w]
             out[i] = img[0] if b == 1 else img
     return out
+
+
+@torch.no_grad()
+def decode_host_batches(model, batches: Iterable[Dict], steps: int, sampler: str = "ddpm",
+                        guidance_scale: float = 1.0, ring: int = 3) -> Iterator[torch.Tensor]:
+    """The serving loop around `relay_decode` for conditioning that lives on the HOST (what
+    `apply_condition_decompress` leaves behind a byte coder, or a loader thread): a generator over
+    `batches` of host tensors that yields, per batch, the uint8 [B,H,W,3] images in pinned HOST memory.
+
+    Each batch is a dict with "c_latent" [B,4,h,w], "guide_hint" [B,Ch,h,w], "c_crossattn" [B,77,D] and,
+    optionally, "start_noise" and "step_noises" (list of [B,4,h,w]); pinned tensors copy asynchronously.
+
+    Double buffered on two copy streams: the host->device copy of batch i+1 and the device->host read of
+    batch i-1 run while batch i decodes, so per batch the GPU sees only the decode.  Every batch's inputs
+    are still copied host->device and its images device->host; a yielded tensor is complete (its copy
+    event has been synchronised) and stays valid until `ring - 1` further batches have been yielded."""
+    dev = model.device
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    slots: List[Optional[Dict]] = [None, None]                  # device-side input buffers
+    slot_free = [torch.cuda.Event(), torch.cuda.Event()]        # recorded when the decode reading a slot is queued
+    outs: List[Optional[torch.Tensor]] = [None] * max(ring, 2)  # pinned host images
+
+    def flat(hb: Dict) -> Dict[str, torch.Tensor]:
+        t = {"c_latent": hb["c_latent"], "guide_hint": hb["guide_hint"], "c_crossattn": hb["c_crossattn"]}
+        if hb.get("start_noise") is not None:
+            t["start_noise"] = hb["start_noise"]
+        for j, n in enumerate(hb.get("step_noises") or ()):
+            t[f"step_noise{j}"] = n
+        return t
+
+    def stage(i: int, hb: Dict) -> torch.cuda.Event:
+        src, s = flat(hb), i & 1
+        buf = slots[s]
+        if buf is None or buf.keys() != src.keys() or any(buf[k].shape != v.shape for k, v in src.items()):
+            buf = slots[s] = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in src.items()}
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(slot_free[s])                       # the decode two batches back has consumed the slot
+            for k, v in src.items():
+                buf[k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return ev
+
+    it = iter(batches)
+    nxt = next(it, None)
+    ev_nxt = stage(0, nxt) if nxt is not None else None
+    pending: Optional[tuple] = None
+    i = 0
+    while nxt is not None:
+        ev_i, buf = ev_nxt, slots[i & 1]
+        nxt = next(it, None)
+        if nxt is not None:
+            ev_nxt = stage(i + 1, nxt)                          # prefetch: queued before this batch's kernels
+        cur.wait_event(ev_i)
+        cond = {"c_latent": [buf["c_latent"]], "c_crossattn": [buf["c_crossattn"]], "guide_hint": buf["guide_hint"]}
+        noises = [buf[k] for k in sorted((k for k in buf if k.startswith("step_noise")), key=lambda k: int(k[10:]))]
+        img = relay_decode(model, cond, steps, sampler=sampler, guidance_scale=guidance_scale,
+                           start_noise=buf.get("start_noise"), step_noises=noises or None)
+        slot_free[i & 1].record(cur)
+        done = torch.cuda.Event()
+        done.record(cur)
+        o = i % len(outs)
+        if outs[o] is None or outs[o].shape != img.shape:
+            outs[o] = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            outs[o].copy_(img, non_blocking=True)
+            ev_out = torch.cuda.Event()
+            ev_out.record(s_out)
+        img.record_stream(s_out)
+        if pending is not None:                                 # the host runs at most one batch ahead of the GPU
+            pending[1].synchronize()
+            yield pending[0]
+        pending = (outs[o], ev_out)
+        i += 1
+    if pending is not None:
+        pending[1].synchronize()
+        yield pending[0]

@@ -235,6 +235,38 @@ def test_tiled_decode_matches_per_tile_oracle(small_model, cuda):
     assert psnr(img_b.numpy(), ref.numpy(), 2.0) >= PSNR_MIN
 
 
+def test_decode_host_batches_matches_relay_decode(small_model, cuda):
+    """pipeline.decode_host_batches (double-buffered host -> device -> host serving loop): every yielded
+    pinned-host image equals relay_decode of the same batch, in order, across slot and ring reuse, with a
+    shape change in the middle of the stream and with an un-pinned batch."""
+    from rdeic_b200.pipeline import decode_host_batches, relay_decode
+
+    def batch(seed, B, h, w, pinned=True):
+        g = torch.Generator().manual_seed(seed)
+        t = {"c_latent": torch.randn(B, 4, h, w, generator=g), "guide_hint": torch.randn(B, 32, h, w, generator=g),
+             "c_crossattn": torch.randn(B, 77, 64, generator=g), "start_noise": torch.randn(B, 4, h, w, generator=g),
+             "step_noises": [torch.randn(B, 4, h, w, generator=g) for _ in range(2)]}
+        if pinned:
+            t = {k: [n.pin_memory() for n in v] if isinstance(v, list) else v.pin_memory() for k, v in t.items()}
+        return t
+
+    hbs = [batch(1, 2, 8, 8), batch(2, 2, 8, 8), batch(3, 2, 8, 8), batch(4, 1, 8, 16), batch(5, 1, 8, 16, pinned=False),
+           batch(6, 2, 8, 8)]
+    got = []
+    for out in decode_host_batches(small_model, iter(hbs), 2):
+        assert out.device.type == "cpu" and out.is_pinned() and out.dtype == torch.uint8
+        got.append(out.clone())
+    assert len(got) == len(hbs)
+    for hb, img in zip(hbs, got):
+        cond = {"c_latent": [hb["c_latent"].to(cuda)], "c_crossattn": [hb["c_crossattn"].to(cuda)],
+                "guide_hint": hb["guide_hint"].to(cuda)}
+        want = relay_decode(small_model, cond, 2, start_noise=hb["start_noise"].to(cuda),
+                            step_noises=[n.to(cuda) for n in hb["step_noises"]]).cpu()
+        assert tuple(img.shape) == tuple(want.shape) and torch.equal(img, want)
+    assert not torch.equal(got[0], got[1])
+    assert list(decode_host_batches(small_model, iter([]), 2)) == []
+
+
 def test_baseline_size_batch8_512(full_model, cuda):
     """BASELINE config[1] at full size (512x512, batch 8, 5 relay steps) through size-independent
     properties plus one full-size oracle comparison:
