@@ -48,7 +48,8 @@ int rdeic_ckbd_merge(const float* anchor, const float* nonanchor, float* out, in
 /* utils/ckbd.py:47-59  ckbd_{anchor,nonanchor}_sequeeze: [B,C,H,W] -> [B,C,H,W/2]. */
 int rdeic_ckbd_squeeze(const float* y, float* out, int B, int C, int H, int W, int which,
                        rdeic_stream_t stream);
-/* utils/ckbd.py:61-73  ckbd_{anchor,nonanchor}_unsequeeze: [B,C,H,Wh] -> [B,C,H,2*Wh]. */
+/* utils/ckbd.py:61-73  ckbd_{anchor,nonanchor}_unsequeeze: [B,C,H,Wh] -> [B,C,H,2*Wh].
+ * `out` must be 8-byte aligned; Wh % 4 == 0 (or % 8) with 16- (32-) byte aligned pointers selects the vector paths. */
 int rdeic_ckbd_unsqueeze(const float* sq, float* out, int B, int C, int H, int Wh, int which,
                          rdeic_stream_t stream);
 /* compressai 1.2.4 EntropyModel.quantize(x, "symbols", means) as called at
@@ -60,7 +61,8 @@ int rdeic_dequantize(const int32_t* symbols, const float* means, float* out, int
                      rdeic_stream_t stream);
 /* compressai 1.2.4 GaussianConditional.build_indexes as called at utils/ckbd.py:81,92,102,111:
  * s = max(scale, lower_bound); idx = (levels-1) - #{k < levels-1 : s <= table[k]}.
- * `table` is the fp32 scale table produced by utils/func.py:10-13 (device pointer). */
+ * `table` is the fp32 scale table produced by utils/func.py:10-13 (device pointer).
+ * `scales` and `indexes` must be 16-byte aligned; 32-byte alignment selects the 256-bit path. */
 int rdeic_build_indexes(const float* scales, const float* table, int levels, float lower_bound,
                         int32_t* indexes, int64_t numel, rdeic_stream_t stream);
 /* Fused decode-side hand-off (utils/ckbd.py:99-115 minus the rANS call): squeeze scales and
