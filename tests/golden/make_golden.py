@@ -12,6 +12,8 @@ Files written
   full_vae_decode.npz      reference decode_first_stage, full width, 16x16 latent
   full_sampler.npz         reference SpacedSampler.sample (2 steps) and DDIMSampler.sample (2 steps)
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
+  full_c1_decode.npz       BASELINE config[0] end to end: the reference's q_sample -> SpacedSampler.sample (2 relay
+                           steps) -> decode_first_stage on one 256x256 image, full width (latent fp32, image fp16)
   {small,full}_compression.npz       reference model/compression.py Compression.compress -> .decompress
   {small,full}_compression_keys.json its state_dict keys + shapes
   {small,full}_vae_encode.npz   reference AutoencoderKL.encode_hc feature map; vae_encoder_keys.json its keys
@@ -126,6 +128,35 @@ def run_config(tag, overrides, unet_hw, vae_hw, samp_hw):
         out["ddim_2"] = samples.numpy()
         np.savez_compressed(HERE / f"{tag}_sampler.npz", **out)
         print(tag, "samplers", {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
+def run_c1():
+    """BASELINE config[0]: one synthetic 256x256 image, 2 relay steps, full-width model, fp32 on the CPU,
+    through the reference's own driver sequence (inference.py:63-87): q_sample at t = used_timesteps - 1,
+    SpacedSampler.sample, decode_first_stage.  Noise is injected where the reference draws it."""
+    model, mods = rh.build_reference_model(None)
+    params = rh.load_config(None)["params"]
+    load_synthetic_into_reference(model, params)
+    hint_c = params["control_stage_config"]["params"]["hint_channels"]
+    ctx_dim = params["unet_config"]["params"]["context_dim"]
+    B, h, w, steps = 1, 32, 32, 2
+    c_latent, hint, ctx, noises = inputs(B, h, w, hint_c, ctx_dim, 1 + steps)
+    cond = {"c_latent": [c_latent], "c_crossattn": [ctx], "guide_hint": hint}
+    pool = [n.clone() for n in noises[1:]]
+    orig_randn_like = torch.randn_like
+    torch.randn_like = lambda t_, **k: pool.pop(0)
+    try:
+        with torch.no_grad():
+            x_T = model.q_sample(c_latent, torch.full((B,), model.used_timesteps - 1, dtype=torch.long), noises[0])
+            s = mods["spaced"].SpacedSampler(model, var_type="fixed_small")
+            z = s.sample(steps, (B, 4, h, w), cond, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
+                         cond_fn=None, x_T=x_T)
+            img = model.decode_first_stage(z)
+    finally:
+        torch.randn_like = orig_randn_like
+    np.savez_compressed(HERE / "full_c1_decode.npz", z=z.numpy(), img=img.numpy().astype(np.float16),
+                        hw=np.array([h, w]), steps=np.array(steps))
+    print("c1 decode", tuple(img.shape), float(img.abs().max()), float(z.abs().max()))
 
 
 def entropy_inputs():
@@ -290,7 +321,7 @@ def run_bitstream():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["entropy", "bitstream", "vae_encode", "compression", "small", "full"]
+    which = sys.argv[1:] or ["entropy", "bitstream", "vae_encode", "compression", "small", "full", "c1"]
     if "entropy" in which:
         run_entropy()
     if "bitstream" in which:
@@ -307,3 +338,5 @@ if __name__ == "__main__":
         run_config("small", rh.SMALL_OVERRIDES, (16, 16), (8, 8), (8, 16))
     if "full" in which:
         run_config("full", None, (32, 32), (16, 16), (16, 16))
+    if "c1" in which:
+        run_c1()

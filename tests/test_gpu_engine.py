@@ -186,6 +186,36 @@ def test_full_samplers_vs_reference_golden(full_model, cuda):
     _check_samplers(full_model, "full", 1, 16, 16, 256, 1024, cuda)
 
 
+def test_c1_decode_vs_reference_golden(full_model, cuda):
+    """BASELINE config[0] (one 256x256 image, 2 relay steps) end to end through relay_decode, against the
+    image the reference's own q_sample -> SpacedSampler.sample -> decode_first_stage produced on the CPU in
+    fp32 (tests/golden/full_c1_decode.npz): final latent rel-L2 <= 1e-2, image PSNR >= 40 dB."""
+    from rdeic_b200.pipeline import relay_decode
+
+    gold = np.load(GOLD / "full_c1_decode.npz")
+    h, w = (int(v) for v in gold["hw"])
+    steps = int(gold["steps"])
+    c_latent, hint, ctx, noises = inputs(1, h, w, 256, 1024, 1 + steps)
+    cond = {"c_latent": [c_latent.to(cuda)], "c_crossattn": [ctx.to(cuda)], "guide_hint": hint.to(cuda)}
+    nz = [n.to(cuda) for n in noises]
+    img = relay_decode(full_model, cond, steps, start_noise=nz[0], step_noises=nz[1:], as_uint8=False).cpu().numpy()
+    ref = gold["img"].astype(np.float32)
+    p = psnr(img, ref, 2.0)
+    # the latent the samplers hand to the VAE, through the sampler API the reference driver uses
+    from rdeic_b200 import SpacedSampler
+
+    x_T = full_model.q_sample(c_latent.to(cuda), [full_model.used_timesteps - 1], nz[0])
+    s = SpacedSampler(full_model, var_type="fixed_small")
+    s.noise_fn = lambda i, like: nz[1 + i]
+    z = s.sample(steps, (1, 4, h, w), cond, x_T=x_T).cpu().numpy()
+    e = rel_l2(z, gold["z"])
+    print(f"[c1 256^2, {steps} steps] vs reference: latent rel-L2 {e:.3e}, image PSNR {p:.1f} dB")
+    assert e <= UNET_TOL and p >= PSNR_MIN
+    u8 = relay_decode(full_model, cond, steps, start_noise=nz[0], step_noises=nz[1:]).cpu().numpy()
+    ref_u8 = (((ref + 1) / 2).clip(0, 1).transpose(0, 2, 3, 1) * 255).clip(0, 255).astype(np.uint8)
+    assert psnr(u8, ref_u8, 255.0) >= PSNR_MIN - 1.0
+
+
 def test_tiled_decode_matches_per_tile_oracle(small_model, cuda):
     """BASELINE config 4 in miniature: one large latent decoded as overlapping tiles.  The oracle is
     the reference arithmetic applied per tile + the identical blend (the reference never tiles and

@@ -135,6 +135,26 @@ def test_oracle_samplers_match_reference_golden(small_sd):
 
 
 # ---- checkpoint layout contract ----------------------------------------------------------------
+def test_oracle_c1_decode_matches_reference_golden():
+    """BASELINE config[0] end to end at full width (one 256x256 image, 2 relay steps, fp32 CPU): the oracle's
+    q_sample -> spaced_sample -> vae_decode against what the reference's own q_sample / SpacedSampler.sample /
+    decode_first_stage produced (tests/golden/make_golden.py run_c1)."""
+    p = configs.default_params()
+    sd = synthetic.make_state_dict(p, seed=231)
+    gold = np.load(GOLD / "full_c1_decode.npz")
+    h, w = (int(v) for v in gold["hw"])
+    steps = int(gold["steps"])
+    c_latent, hint, ctx, noises = _inputs(1, h, w, 256, 1024, 1 + steps)
+    kw = _unet_kw(p)
+    with torch.no_grad():
+        x_T = osamp.q_sample(c_latent, 299, noises[0])
+        z = osamp.spaced_sample(lambda x, t: onn.noise_estimator_forward(sd, x, hint, t, ctx, **kw), x_T, steps, noises[1:])
+        img = onn.vae_decode(sd, z)
+    assert np.abs(z.numpy() - gold["z"]).max() < 1e-4
+    err = np.abs(img.numpy() - gold["img"].astype(np.float32)).max()
+    assert err < 2e-3, err                              # the fixture stores the image in fp16 (|x| < 2: ulp 1e-3)
+
+
 def test_state_dict_spec_matches_reference_keys():
     ref = json.loads((GOLD / "state_dict_keys.json").read_text())
     spec = {k: list(s) for k, s, _ in synthetic.state_dict_spec(configs.default_params())}
