@@ -39,6 +39,12 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
                  : "r"(s));
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
@@ -123,17 +129,18 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
                 mma_bf16_16816(s[j], qa[kk], b0, b1);
             }
         }
-        // scale into the exp2 domain, mask the ragged key tail
+        // mask the ragged key tail; row maxima on the raw logits (scale_log2 > 0, so the maximum commutes
+        // with the scaling and the scaling itself folds into the FFMA that feeds the exponential)
         const int key_base = tile * kKTile + 2 * t;
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < kKTile / 8; ++j) {
             const int key = key_base + 8 * j;
             const bool ok0 = key < Nk, ok1 = key + 1 < Nk;
-            s[j][0] = ok0 ? s[j][0] * scale_log2 : -INFINITY;
-            s[j][1] = ok1 ? s[j][1] * scale_log2 : -INFINITY;
-            s[j][2] = ok0 ? s[j][2] * scale_log2 : -INFINITY;
-            s[j][3] = ok1 ? s[j][3] * scale_log2 : -INFINITY;
+            s[j][0] = ok0 ? s[j][0] : -INFINITY;
+            s[j][1] = ok1 ? s[j][1] : -INFINITY;
+            s[j][2] = ok0 ? s[j][2] : -INFINITY;
+            s[j][3] = ok1 ? s[j][3] : -INFINITY;
             mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
             mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
         }
@@ -145,8 +152,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
         float corr[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const float m_new = fmaxf(m_run[r], mx[r]);   // finite: every tile has >= 1 valid key
-            corr[r] = exp2f(m_run[r] - m_new);
+            const float m_new = fmaxf(m_run[r], mx[r] * scale_log2);   // finite: every tile has >= 1 valid key
+            corr[r] = ex2_ftz(m_run[r] - m_new);
             m_run[r] = m_new;
             l_run[r] *= corr[r];
         }
@@ -155,14 +162,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
             o[j][0] *= corr[0]; o[j][1] *= corr[0];
             o[j][2] *= corr[1]; o[j][3] *= corr[1];
         }
-        // P = exp2(S - m), packed straight into A fragments for P V
+        // P = exp2(S * scale - m), packed straight into A fragments for P V.  One MUFU per element
+        // (exp2f adds a range test and two multiplies for denormal results, which a probability does
+        // not need): the loop is bound by the MUFU pipe instead of by instruction issue.
         uint32_t pa[kKTile / 16][4];
 #pragma unroll
         for (int j = 0; j < kKTile / 8; ++j) {
-            const float p0 = exp2f(s[j][0] - m_run[0]);
-            const float p1 = exp2f(s[j][1] - m_run[0]);
-            const float p2 = exp2f(s[j][2] - m_run[1]);
-            const float p3 = exp2f(s[j][3] - m_run[1]);
+            const float p0 = ex2_ftz(fmaf(s[j][0], scale_log2, -m_run[0]));
+            const float p1 = ex2_ftz(fmaf(s[j][1], scale_log2, -m_run[0]));
+            const float p2 = ex2_ftz(fmaf(s[j][2], scale_log2, -m_run[1]));
+            const float p3 = ex2_ftz(fmaf(s[j][3], scale_log2, -m_run[1]));
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
             pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -218,6 +227,7 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
     RDEIC_CHECK_ARG(q && k && v && out, "rdeic_attention: null pointer");
     RDEIC_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "rdeic_attention: empty problem");
     RDEIC_CHECK_ARG(d == 16 || d == 64, "rdeic_attention: head dim %d not instantiated (16, 64)", d);
+    RDEIC_CHECK_ARG(scale > 0.f, "rdeic_attention: scale must be positive (got %g)", (double)scale);
     RDEIC_CHECK_ARG(B <= 65535 && heads <= 65535, "rdeic_attention: grid too large");
     RDEIC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 &&
                         q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 2 == 0,
