@@ -264,8 +264,9 @@ int rdeic_attention(const void* q, const void* k, const void* v, void* out, int 
  * of the k reduction (rdeic_b200/csrc/fp32_mode.cu).  Verification mode, not the throughput mode. */
 
 /* conv2d / F.linear (openaimodel.py:203,229,240,106,150,566,750; attention.py:52,72,162-169,314,328):
- * a [a_n,a_h,a_w,c1] (+ a2 [..,c2], the torch.cat of openaimodel.py:804 / rdeic.py:190), ksize 1|3
- * (pad ksize/2), stride 1|2, optional nearest x2 upsample of the input first (openaimodel.py:106-113);
+ * a [a_n,a_h,a_w,c1] (+ a2 [..,c2], the torch.cat of openaimodel.py:804 / rdeic.py:190), ksize 1|3|5
+ * (pad ksize/2; 5x5: model/compression.py:23, compression_modules.py:80-84), stride 1|2, optional nearest
+ * x2 upsample of the input first (openaimodel.py:106-113);
  * w fp32 [n_out][ksize*ksize][c1+c2]; out = resid + alpha * act(conv + bias + row_bias[sample]). */
 typedef struct rdeic_conv_f32_params {
     const float* a;       int a_n, a_h, a_w, c1;
@@ -277,8 +278,13 @@ typedef struct rdeic_conv_f32_params {
     const float* row_bias; int row_bias_ld;
     const float* resid;   int ld_resid;
     float alpha;
-    int act;              /* 0 none, 1 SiLU */
+    int act;              /* 0 none, 1 SiLU, 3 LeakyReLU(act_param), 4 exact GELU (numbering of rdeic_conv_params) */
     float* out;           int ldo;
+    /* ABI 5: the learned compressor's entropy-parameter nets in fp32 (model/compression.py:215-273:
+     * CDF indexes must equal the reference's fp32 nets' or the arithmetic decoder desynchronises) */
+    float act_param;      /* LeakyReLU negative slope */
+    int a_ld, a2_ld;      /* pixel stride (elements) of a / a2 when they are channel windows of a wider NHWC
+                             buffer; 0 = c1 / c2 */
 } rdeic_conv_f32_params;
 int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream);
 /* attention.py:171-203 in fp32: q [B,Nq,*], k/v [B,Nk,*] fp32, heads as consecutive d-wide column groups, d <= 512

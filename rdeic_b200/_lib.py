@@ -65,6 +65,8 @@ class ConvF32Params(C.Structure):
         ("alpha", f32),
         ("act", i32),
         ("out", vp), ("ldo", i32),
+        ("act_param", f32),
+        ("a_ld", i32), ("a2_ld", i32),
     ]
 
 

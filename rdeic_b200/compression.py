@@ -21,6 +21,7 @@ import torch
 from . import ckbd, ops
 from .compression_modules import (ChannelContextEX, Decoder, Encoder, EntropyParametersEX, HyperDecoder, HyperEncoder,
                                   VectorQuantiser)
+from .compression_f32 import CompressionNetsF32
 from .layers import conv, load_conv
 
 BF16 = torch.bfloat16
@@ -134,6 +135,47 @@ class _FusedSliceCoder(SliceCoder):
             self.synced += 1
 
 
+class _F32SliceCoder(_FusedSliceCoder):
+    """The same fused data flow with every tensor that reaches `build_indexes` / the means in fp32 on the
+    fp32 kernels (`compression_f32.CompressionNetsF32`): `y_hat`, the context windows and `hyper_params`
+    are NHWC fp32 buffers, the torch.cat inputs of compression.py:170,184,190 are channel windows / the
+    kernel's second source.  This is the coder used by the default (`precision="mixed"`) and the all-fp32
+    modes: its CDF indexes agree with the reference's fp32 nets to fp32 round-off."""
+
+    def __init__(self, owner: "Compression", hyper_nhwc: torch.Tensor):
+        SliceCoder.__init__(self, owner.slice_ch, owner.gaussian_conditional, None, None, None, None)
+        B, h, w, _ = hyper_nhwc.shape
+        dev = hyper_nhwc.device
+        self.nets = owner.nets32
+        self.hyper = hyper_nhwc
+        self.y_hat = torch.zeros((B, h, w, sum(self.slice_ch)), dtype=torch.float32, device=dev)
+        self.ctx = [torch.empty((B, h, w, 4 * c if i else 2 * c), dtype=torch.float32, device=dev)
+                    for i, c in enumerate(self.slice_ch)]
+        self.synced = 0
+
+    def _params(self, idx, hyper_params, y_hat_slices, slice_anchor=None):
+        c = self.slice_ch[idx]
+        self._params_sync(y_hat_slices)
+        ctx = self.ctx[idx]
+        if slice_anchor is None:
+            if idx == 0:
+                p = self.nets.entropy_parameters("anchor", 0, self.hyper)
+            else:
+                self.nets.channel_context(idx, self.y_hat[..., :sum(self.slice_ch[:idx])], out=ctx[..., 2 * c:])
+                p = self.nets.entropy_parameters("anchor", idx, ctx[..., 2 * c:], x2=self.hyper)
+        else:
+            self.nets.local_context(idx, slice_anchor.permute(0, 2, 3, 1).contiguous(), out=ctx[..., :2 * c])
+            p = self.nets.entropy_parameters("nonanchor", idx, ctx, x2=self.hyper)
+        # NHWC -> the reference's NCHW for the integer kernels: layout change only
+        return p[..., :c].permute(0, 3, 1, 2).contiguous(), p[..., c:2 * c].permute(0, 3, 1, 2).contiguous(), None
+
+    def _params_sync(self, y_hat_slices):
+        while self.synced < len(y_hat_slices):
+            off = sum(self.slice_ch[:self.synced])
+            self.y_hat[..., off:off + self.slice_ch[self.synced]].copy_(y_hat_slices[self.synced].permute(0, 2, 3, 1))
+            self.synced += 1
+
+
 class _Plan:
     """CUDA-graph plan of one (batch, z-shape): the launch sequences between host hand-offs are
     captured once and replayed (≈250 launches per image collapse into 21 graph launches for
@@ -155,6 +197,16 @@ class _Plan:
     def _end(self, *exc):
         ctx, self._ctx = self._ctx, None
         ctx.__exit__(*(exc or (None, None, None)))
+
+    def release(self):
+        """Drop the graphs (and with them the private pool's activations) and the pinned hand-off buffers."""
+        for g in self.graphs:
+            g.reset()
+        self.graphs.clear()
+        for name in ("idx_host", "sym_host", "z_host", "z_q", "x", "c_latent", "guide_hint"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        self.pool = None
 
 
 class _DecompressPlan(_Plan):
@@ -232,8 +284,21 @@ class Compression:
 
     def __init__(self, in_nc, out_nc, N, M, slice_num, slice_ch, codebook_size, device="cuda",
                  rans_encoder: Optional[Callable] = None, rans_decoder: Optional[Callable] = None,
-                 hyper_latent_coder=None, use_cuda_graph: bool = True):
+                 hyper_latent_coder=None, use_cuda_graph: bool = True, precision: str = "mixed", max_plans: int = 4):
+        """`precision`:
+          "mixed" (default) — everything that feeds the coder's CDF indexes and means (`hyper_dec`,
+                    `channel_context`, `local_context`, `entropy_parameters_*`) runs on the fp32 kernels, so
+                    streams are exchangeable with the reference's fp32 nets; the analysis / synthesis
+                    transforms run on the tcgen05 bf16 kernels;
+          "bf16"  — every conv stack on the tensor cores: fastest, streams decodable only by this mode;
+          "fp32"  — every conv stack on the fp32 kernels (verification mode).
+        `max_plans`: CUDA-graph plans kept (LRU) — one per distinct (direction, batch, shape)."""
         assert slice_num == len(slice_ch) and sum(slice_ch) == M, "slice_ch must partition the M latent channels"
+        if precision not in ("mixed", "bf16", "fp32"):
+            raise ValueError(f"Compression: precision must be 'mixed', 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        self.max_plans = int(max_plans)
+        self.nets32 = None
         self.in_nc, self.out_nc, self.N, self.M = in_nc, out_nc, N, M
         self.slice_num, self.slice_ch = slice_num, list(slice_ch)
         self.codebook_size = codebook_size
@@ -243,7 +308,9 @@ class Compression:
         self._rans_encoder, self._rans_decoder, self._hyper_coder = rans_encoder, rans_decoder, hyper_latent_coder
         self.encoder = self.hyper_enc = self.hyper_dec = self.decoder = self.out = None
         self.use_cuda_graph = use_cuda_graph
-        self._plans: Dict = {}
+        self._plans: Dict = {}           # insertion-ordered: least recently used first
+        self._seen: Dict = {}
+        self.has_encoder = False
 
     # ---- weights ---------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "preprocess_model.", strict: bool = True):
@@ -255,32 +322,67 @@ class Compression:
         if not any(k.startswith(prefix) for k in sd) and any(k.startswith("module." + prefix) for k in sd):
             prefix = "module." + prefix
         dev, P, sc, M = self.device, prefix, self.slice_ch, self.M
-        self.hyper_dec = HyperDecoder(sd, P + "hyper_dec.", dev)
-        self.decoder = Decoder(sd, P + "decoder.", dev)
-        self.out = load_conv(sd, P + "out", dev)
-        self.local_context = [load_conv(sd, f"{P}local_context.{i}", dev) for i in range(self.slice_num)]
-        self.channel_context = [ChannelContextEX(sd, f"{P}channel_context.{i}.", dev) if i else None
-                                for i in range(self.slice_num)]
-        self.entropy_parameters_anchor = [EntropyParametersEX(sd, f"{P}entropy_parameters_anchor.{i}.", dev,
-                                                              c1=2 * sc[i] if i else None) for i in range(self.slice_num)]
-        self.entropy_parameters_nonanchor = [EntropyParametersEX(sd, f"{P}entropy_parameters_nonanchor.{i}.", dev,
-                                                                 c1=4 * sc[i] if i else 2 * sc[i])
-                                             for i in range(self.slice_num)]
+        bf16_transforms = self.precision in ("mixed", "bf16")
+        has_encoder = (P + "encoder.g_a.0.conv1.weight") in sd
+        if self.precision in ("mixed", "fp32"):
+            self.nets32 = CompressionNetsF32(sd, P, dev)
+        if bf16_transforms:
+            self.decoder = Decoder(sd, P + "decoder.", dev)
+            self.out = load_conv(sd, P + "out", dev)
+            if has_encoder:
+                self.encoder = Encoder(sd, P + "encoder.", dev)
+                self.hyper_enc = HyperEncoder(sd, P + "hyper_enc.", dev)
+        if self.precision == "bf16":
+            self.hyper_dec = HyperDecoder(sd, P + "hyper_dec.", dev)
+            self.local_context = [load_conv(sd, f"{P}local_context.{i}", dev) for i in range(self.slice_num)]
+            self.channel_context = [ChannelContextEX(sd, f"{P}channel_context.{i}.", dev) if i else None
+                                    for i in range(self.slice_num)]
+            self.entropy_parameters_anchor = [EntropyParametersEX(sd, f"{P}entropy_parameters_anchor.{i}.", dev,
+                                                                  c1=2 * sc[i] if i else None) for i in range(self.slice_num)]
+            self.entropy_parameters_nonanchor = [EntropyParametersEX(sd, f"{P}entropy_parameters_nonanchor.{i}.", dev,
+                                                                     c1=4 * sc[i] if i else 2 * sc[i])
+                                                 for i in range(self.slice_num)]
         self.quantize.load_state_dict(sd, P + "quantize.")
-        if (P + "encoder.g_a.0.conv1.weight") in sd:
-            self.encoder = Encoder(sd, P + "encoder.", dev)
-            self.hyper_enc = HyperEncoder(sd, P + "hyper_enc.", dev)
-        elif strict:
+        self.has_encoder = has_encoder
+        if not has_encoder and strict:
             raise KeyError(f"{P}encoder.* is missing from the checkpoint (pass strict=False for decode-only use)")
-        self._plans.clear()
+        self._drop_plans()
         return self
 
     def update(self, scale_table=None, force=False):
         """compression.py:275-280."""
-        self._plans.clear()                                  # the table is baked into captured launches
+        self._drop_plans()                                   # the table is baked into captured launches
         if scale_table is None:
             scale_table = ckbd.get_scale_table()
         return self.gaussian_conditional.update_scale_table(scale_table, force=force)
+
+    # ---- CUDA-graph plan cache -------------------------------------------------------------------------
+    def _drop_plans(self):
+        for plan in self._plans.values():
+            plan.release()
+        self._plans.clear()
+        self._seen.clear()
+
+    def _plan(self, key, factory):
+        """LRU of at most `max_plans` plans.  A shape runs eagerly the first time it is seen and gets a plan
+        (eager warm-up + capture + 21 graphs + a private activation pool + pinned hand-off buffers) only when
+        it comes back, so a mixed-resolution dataset (inference_partition.py:400-453 buckets) neither pays a
+        capture per one-off shape nor accumulates GPU / pinned memory without bound."""
+        if not self.use_cuda_graph or self.max_plans <= 0:
+            return None
+        plan = self._plans.pop(key, None)
+        if plan is None:
+            n = self._seen.get(key, 0) + 1
+            if len(self._seen) > 64:
+                self._seen.clear()
+            self._seen[key] = n
+            if n < 2:
+                return None
+            while len(self._plans) >= self.max_plans:
+                self._plans.pop(next(iter(self._plans))).release()
+            plan = factory()
+        self._plans[key] = plan                                # most recently used last
+        return plan
 
     # ---- host coders (out of scope: compressai rANS, torchac) ---------------------------------
     def _coders(self):
@@ -300,13 +402,29 @@ class Compression:
         return self.gaussian_conditional.cdf_tables()
 
     # ---- nets ------------------------------------------------------------------------------------
+    def _slice_coder(self, z_q: torch.Tensor) -> _FusedSliceCoder:
+        """hyper_dec (compression.py:158,222) + the slice coder of the configured precision."""
+        if self.precision == "bf16":
+            return _FusedSliceCoder(self, self.hyper_dec(ops.nchw_to_nhwc_bf16(z_q)))
+        return _F32SliceCoder(self, self.nets32.hyper_decoder(z_q.permute(0, 2, 3, 1).contiguous()))
+
     def _hyper_params(self, z_q: torch.Tensor) -> torch.Tensor:
-        return self.hyper_dec(ops.nchw_to_nhwc_bf16(z_q))
+        """hyper_params as NHWC (bf16 in the "bf16" mode, else fp32)."""
+        return self._slice_coder(z_q).hyper
 
     def _synthesis(self, y_hat: torch.Tensor):
+        if self.precision == "fp32":
+            return self._synthesis_nhwc(y_hat.permute(0, 2, 3, 1).contiguous())
         return self._synthesis_nhwc(ops.nchw_to_nhwc_bf16(y_hat))
 
     def _synthesis_nhwc(self, y_hat_nhwc: torch.Tensor):
+        """compression.py:268-270 -> (c_latent, guide_hint) NCHW fp32."""
+        if self.precision == "fp32":
+            gh = self.nets32.decoder(y_hat_nhwc)
+            c_latent = self.nets32.out(gh)
+            return (c_latent[..., :self.out_nc].permute(0, 3, 1, 2).contiguous(), gh.permute(0, 3, 1, 2).contiguous())
+        if y_hat_nhwc.dtype == torch.float32:                # mixed: y_hat holds integers + fp32 means
+            y_hat_nhwc = ops.f32_to_bf16(y_hat_nhwc)
         gh = self.decoder(y_hat_nhwc, out_f32=True)                                          # compression.py:268
         gh16 = ops.f32_to_bf16(gh)
         c_latent = conv(gh16, self.out, out_f32=True)                                        # :270
@@ -315,9 +433,14 @@ class Compression:
     @torch.no_grad()
     def analysis(self, x: torch.Tensor):
         """compression.py:152-154 -> (y, z) NCHW fp32."""
-        if self.encoder is None:
+        if not self.has_encoder:
             raise RuntimeError("this Compression was loaded without the analysis side (encoder.*, hyper_enc.*)")
-        y = self.encoder(ops.nchw_to_nhwc_bf16(x.to(self.device, torch.float32)), out_f32=True)
+        x = x.to(self.device, torch.float32)
+        if self.precision == "fp32":
+            y = self.nets32.encoder(x.permute(0, 2, 3, 1).contiguous())
+            z = self.nets32.hyper_encoder(y)
+            return y.permute(0, 3, 1, 2).contiguous(), z.permute(0, 3, 1, 2).contiguous()
+        y = self.encoder(ops.nchw_to_nhwc_bf16(x), out_f32=True)
         z = self.hyper_enc(ops.f32_to_bf16(y), out_f32=True)
         return ops.nhwc_to_nchw_f32(y), ops.nhwc_to_nchw_f32(z)
 
@@ -326,15 +449,14 @@ class Compression:
         """Everything of compression.py:152-203 that runs on the GPU: no host synchronisation inside."""
         y, z = self.analysis(x)
         z_q, encoding_indices = self.quantize.quant(z)
-        coder = _FusedSliceCoder(self, self._hyper_params(z_q))
+        coder = self._slice_coder(z_q)
         n_sym = y.numel()                                    # one symbol per latent element
         symbols, indexes = ckbd.SymbolStream(n_sym, self.device), ckbd.SymbolStream(n_sym, self.device)
         coder.compress(y, None, symbols, indexes)
         return symbols, indexes, encoding_indices
 
     def _decompress_body(self, z_q: torch.Tensor, handoff: Callable):
-        coder = _FusedSliceCoder(self, self._hyper_params(z_q))
-        return self._synthesis_nhwc(coder.decompress_with(handoff))
+        return self._synthesis_nhwc(self._slice_coder(z_q).decompress_with(handoff))
 
     @torch.no_grad()
     def compress(self, x: torch.Tensor):
@@ -343,11 +465,9 @@ class Compression:
         x = x.to(self.device, torch.float32)
         if x.dim() != 4 or x.shape[1] != self.in_nc or x.shape[2] % 8 or x.shape[3] % 8:
             raise ValueError(f"Compression.compress: expected [B,{self.in_nc},h,w] with h, w multiples of 8, got {tuple(x.shape)}")
-        if self.use_cuda_graph:
-            key = ("c",) + tuple(x.shape)
-            if key not in self._plans:
-                self._plans[key] = _CompressPlan(self, x.shape[0], x.shape[2], x.shape[3])
-            symbols, indexes, encoding_indices = self._plans[key].run(x)
+        plan = self._plan(("c",) + tuple(x.shape), lambda: _CompressPlan(self, x.shape[0], x.shape[2], x.shape[3]))
+        if plan is not None:
+            symbols, indexes, encoding_indices = plan.run(x)
         else:
             sym, idx, encoding_indices = self._compress_body(x)
             symbols, indexes = sym.host("sym_all"), idx.host("idx_all")
@@ -374,11 +494,9 @@ class Compression:
             """pinned int32 indexes -> the coder's symbols (int32 array-like)"""
             return decoder.decode_stream(idx_host.numpy() if arrays else idx_host.tolist(), *cdfs)
 
-        if self.use_cuda_graph:
-            key = ("d",) + tuple(z_q.shape)
-            if key not in self._plans:
-                self._plans[key] = _DecompressPlan(self, z_q.shape[0], z_q.shape[2], z_q.shape[3])
-            return self._plans[key].run(z_q, decode)
+        plan = self._plan(("d",) + tuple(z_q.shape), lambda: _DecompressPlan(self, z_q.shape[0], z_q.shape[2], z_q.shape[3]))
+        if plan is not None:
+            return plan.run(z_q, decode)
 
         def handoff(k, ind):
             hi = ckbd._pinned.to_host(ind, "idx")

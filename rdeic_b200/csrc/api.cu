@@ -27,5 +27,5 @@ int set_error(const char* fmt, ...) {
 
 extern "C" {
 const char* rdeic_last_error(void) { return rdeic::err_buf(); }
-int rdeic_abi_version(void) { return 4; }
+int rdeic_abi_version(void) { return 5; }
 }

@@ -20,12 +20,13 @@ constexpr int kFM = 64, kFN = 64, kFK = 16;      // CTA tile; 256 threads, 4x4 o
 struct ConvF32Dev {
     const float* a; const float* a2;
     int n, h, w, c1, c2;            // input grid and channel counts of the two concat sources
-    int ksize, stride, up;          // 1|3 ; 1|2 ; nearest x2 upsample before the conv (0|1)
+    int a_ld, a2_ld;                // pixel strides (a / a2 may be channel windows of wider NHWC buffers)
+    int ksize, stride, up;          // 1|3|5 ; 1|2 ; nearest x2 upsample before the conv (0|1)
     int oh, ow;
     const float* wt;                // [n_out][taps][c1 + c2]
     int n_out;
     const float* bias; const float* row_bias; int row_bias_ld;
-    const float* resid; int ld_resid; float alpha; int act;
+    const float* resid; int ld_resid; float alpha; int act; float act_param;
     float* out; int ldo;
 };
 
@@ -64,26 +65,34 @@ conv_f32_kernel(const ConvF32Dev p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { dacc[i][j] = 0.0; acc[i][j] = 0.f; }
 
-    int since_flush = 0;
-    for (int k0 = 0; k0 < K; k0 += kFK) {
-        // ---- A tile: implicit im2col gather (zero padding, stride, nearest upsample) ----
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    // A tile: implicit im2col gather (zero padding, stride, nearest upsample); B tile: packed weights.
+    // The next k chunk is fetched into registers while the current one is multiplied (the layers of the
+    // learned compressor have M = a few thousand pixels: a handful of CTAs whose k loop is latency bound).
+    auto fetch = [&](int k0, float4& av, float4& bv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv = make_float4(0.f, 0.f, 0.f, 0.f);
         const int k = k0 + lk;
-        if (lrow_ok && k < K) {
+        if (k >= K) return;
+        if (lrow_ok) {
             const int tap = k / C, c = k - tap * C;
             const int iy = loy * p.stride + tap / p.ksize - pad, ix = lox * p.stride + tap % p.ksize - pad;
             if (iy >= 0 && iy < hu && ix >= 0 && ix < wu) {
                 const int64_t pix = ((int64_t)lb * p.h + (iy >> p.up)) * p.w + (ix >> p.up);
-                av = (c < p.c1) ? *reinterpret_cast<const float4*>(p.a + pix * p.c1 + c)
-                                : *reinterpret_cast<const float4*>(p.a2 + pix * p.c2 + (c - p.c1));
+                av = (c < p.c1) ? *reinterpret_cast<const float4*>(p.a + pix * p.a_ld + c)
+                                : *reinterpret_cast<const float4*>(p.a2 + pix * p.a2_ld + (c - p.c1));
             }
         }
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ln < p.n_out && k < K) bv = *reinterpret_cast<const float4*>(p.wt + (int64_t)ln * K + k);
+        if (ln < p.n_out) bv = *reinterpret_cast<const float4*>(p.wt + (int64_t)ln * K + k);
+    };
+    int since_flush = 0;
+    float4 av, bv;
+    fetch(0, av, bv);
+    for (int k0 = 0; k0 < K; k0 += kFK) {
         __syncthreads();
         As[lk][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
         Bs[lk][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
         __syncthreads();
+        if (k0 + kFK < K) fetch(k0 + kFK, av, bv);
 #pragma unroll
         for (int kk = 0; kk < kFK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -117,6 +126,8 @@ conv_f32_kernel(const ConvF32Dev p) {
             if (p.row_bias) v += (double)p.row_bias[b * p.row_bias_ld + n];
             float f = (float)v;
             if (p.act == 1) f = f / (1.0f + expf(-f));
+            else if (p.act == 3) f = f > 0.f ? f : f * p.act_param;                        // LeakyReLU
+            else if (p.act == 4) f = 0.5f * f * (1.0f + erff(f * 0.70710678118654752f));  // exact GELU (F.gelu default)
             if (p.resid) f = fmaf(p.alpha, f, p.resid[m * p.ld_resid + n]);
             else f *= p.alpha;
             p.out[m * p.ldo + n] = f;
@@ -217,18 +228,24 @@ int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(p->c1 % 4 == 0 && p->c2 % 4 == 0, "rdeic_conv_f32: channel counts (%d, %d) must be multiples of 4",
                     p->c1, p->c2);
     RDEIC_CHECK_ARG(p->c2 == 0 || p->a2, "rdeic_conv_f32: c2 > 0 needs a2");
-    RDEIC_CHECK_ARG((p->ksize == 1 || p->ksize == 3) && (p->stride == 1 || p->stride == 2) && (p->up == 0 || p->up == 1),
-                    "rdeic_conv_f32: ksize in {1,3}, stride in {1,2}, up in {0,1}");
-    RDEIC_CHECK_ARG(p->act == 0 || p->act == 1, "rdeic_conv_f32: act must be 0 (none) or 1 (SiLU)");
+    RDEIC_CHECK_ARG((p->ksize == 1 || p->ksize == 3 || p->ksize == 5) && (p->stride == 1 || p->stride == 2) &&
+                        (p->up == 0 || p->up == 1),
+                    "rdeic_conv_f32: ksize in {1,3,5}, stride in {1,2}, up in {0,1}");
+    RDEIC_CHECK_ARG(p->act == 0 || p->act == 1 || p->act == 3 || p->act == 4,
+                    "rdeic_conv_f32: act must be 0 (none), 1 (SiLU), 3 (LeakyReLU) or 4 (exact GELU)");
+    const int a_ld = p->a_ld ? p->a_ld : p->c1, a2_ld = p->a2_ld ? p->a2_ld : p->c2;
+    RDEIC_CHECK_ARG(a_ld >= p->c1 && a2_ld >= p->c2 && a_ld % 4 == 0 && a2_ld % 4 == 0,
+                    "rdeic_conv_f32: a_ld/a2_ld (%d, %d) must be multiples of 4 and >= the channel counts", a_ld, a2_ld);
     RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w) % 16 == 0, "rdeic_conv_f32: operands must be 16-byte aligned");
     ConvF32Dev d;
     d.a = p->a; d.a2 = p->a2; d.n = p->a_n; d.h = p->a_h; d.w = p->a_w; d.c1 = p->c1; d.c2 = p->c2;
+    d.a_ld = a_ld; d.a2_ld = a2_ld;
     d.ksize = p->ksize; d.stride = p->stride; d.up = p->up;
     const int hu = p->a_h << p->up, wu = p->a_w << p->up;
     RDEIC_CHECK_ARG(hu % p->stride == 0 && wu % p->stride == 0, "rdeic_conv_f32: grid not divisible by the stride");
     d.oh = hu / p->stride; d.ow = wu / p->stride;
     d.wt = p->w; d.n_out = p->n_out; d.bias = p->bias; d.row_bias = p->row_bias; d.row_bias_ld = p->row_bias_ld;
-    d.resid = p->resid; d.ld_resid = p->ld_resid; d.alpha = p->alpha; d.act = p->act; d.out = p->out; d.ldo = p->ldo;
+    d.resid = p->resid; d.ld_resid = p->ld_resid; d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param; d.out = p->out; d.ldo = p->ldo;
     RDEIC_CHECK_ARG(p->ldo >= p->n_out && (!p->resid || p->ld_resid >= p->n_out), "rdeic_conv_f32: bad ldo / ld_resid");
     const int64_t M = (int64_t)d.n * d.oh * d.ow;
     dim3 grid((unsigned)ceil_div64(M, kFM), (unsigned)((p->n_out + kFN - 1) / kFN));

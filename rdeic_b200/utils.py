@@ -1,6 +1,9 @@
 """Bitstream container of the reference (utils/utils.py:24-74): big-endian `uint32 h, w, n_strings`
-followed by length-prefixed byte strings.  Byte-for-byte the reference's file format, so streams
-written by either side are read by the other."""
+followed by length-prefixed byte strings.  The container framing is byte-for-byte the reference's.  The
+entropy-coded payload inside decodes wherever the entropy-parameter nets reproduce the encoder's CDF indexes:
+`Compression(precision="mixed")` (the default) and `"fp32"` run those nets in fp32 like the reference, so
+streams are exchangeable with it; a stream written with `precision="bf16"` is only decodable by that mode
+(determinism contract)."""
 from __future__ import annotations
 
 import struct

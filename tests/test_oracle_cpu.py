@@ -210,7 +210,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rdeic_abi_version() == 4
+    assert lib.rdeic_abi_version() == 5
 
 
 def test_no_cpu_fallback():
