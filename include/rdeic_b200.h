@@ -234,6 +234,21 @@ typedef struct rdeic_conv_params {
                              written, per 32-row slab and output column — the GroupNorm statistics of
                              the consumer (util.py:224, model.py:48) fused into the producer's epilogue.
                              Needs rdeic_conv_stats_supported(a_n, a_h, a_w); disables split-K. */
+    /* ABI 5 */
+    int up2;              /* 1: nearest x2 upsample + conv3x3 (openaimodel.py:106-113, model.py:63-67) with the
+                             upsample folded away: output pixel (2y+py, 2x+px) only sees a 2x2 window of the INPUT,
+                             so each parity class (py, px) is a 2x2 conv with pre-summed weights.  taps = 4; w holds
+                             the four packed [n_out][4][cpad] matrices (parity 2 py + px) w_batch_stride elements
+                             apart; a is the [a_n, a_h, a_w] input, outputs (and resid) are [a_n, 2 a_h, 2 a_w]
+                             with row stride ldo; stats_out slabs are ordered [sample][parity][h][w]. */
+    int a2_center;        /* 1: the second source a2 (on the OUTPUT pixel grid) contributes the centre tap only, with its
+                             own packed weights w2 [n_out][cpad2]; w covers a alone ([n_out][taps][cpad1]).  Fuses
+                             `h = h + zero_conv(h_ctr) * scale` (rdeic.py:194,203,207: scale folded into w2 and the
+                             bias by the caller) or a 1x1 skip_connection into the conv that produces h. */
+    const void* w2;
+    int in_stride2;       /* 1: stride-2 conv (openaimodel.py:150-152, model.py:76-89, res_blk.py:15-25): a is the
+                             [a_n, 2 a_h, 2 a_w] input, [a_n, a_h, a_w] the output grid; taps 1 or 9 */
+    int pad_lo;           /* with in_stride2 and taps = 9: 1 = padding 1 all round, 0 = bottom/right only (model.py:82-84) */
 } rdeic_conv_params;
 
 /* 1 if rdeic_conv_gemm should emit stats_out for an [a_n, a_h, a_w] pixel grid, n_out columns and

@@ -47,6 +47,7 @@ class ConvParams(C.Structure):
         ("act_param", f32),
         ("a_ld", i32), ("a2_ld", i32),
         ("stats_out", vp),
+        ("up2", i32), ("a2_center", i32), ("w2", vp), ("in_stride2", i32), ("pad_lo", i32),
     ]
 
 

@@ -50,7 +50,16 @@ struct ConvDev {
     int kb_per_split;              // k-blocks per k-split slice (= all of them without split-K)
     int splits, n_tiles;
     int64_t m_total;
+    // ABI 5
+    int up2;                       // nearest x2 upsample folded in: 4 parity classes x 2x2 taps (z = parity), output grid 2H x 2W
+    int a2_center;                 // second K segment contributes the centre tap only (fused zero-conv injection / 1x1 skip)
+    int in_stride;                 // 1, or 2: stride-2 conv, A is the [a_n, 2 a_h, 2 a_w] input read through a tensor map with element strides 2
+    int tap_lo;                    // first tap offset of a 3x3 filter: -1 (pad 1) or 0 (pad bottom/right only)
 };
+
+__device__ __forceinline__ int conv_total_kb(const ConvDev& p) {
+    return p.a2_center ? p.taps * p.cblk1 + p.cblk2 : p.taps * (p.cblk1 + p.cblk2);
+}
 
 // Epilogue math shared by the GEMM kernel (phase B) and the split-K reduce kernel: 4 consecutive
 // output columns of one row.  v already holds act(acc + bias + row_bias).
@@ -248,7 +257,7 @@ struct TileCfg {
 template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
-                 const __grid_constant__ CUtensorMap tm_b, const ConvDev p) {
+                 const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2, const ConvDev p) {
     pdl_trigger();
     using Cfg = TileCfg<BN, kEW, kMT>;
     constexpr int kStages = Cfg::kStages;
@@ -273,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
     const int cbt = p.cblk1 + p.cblk2;
-    const int total_kb = p.taps * cbt;
+    const int total_kb = conv_total_kb(p);
     const int m_tiles = (p.tiles_w * p.tiles_h * p.tiles_n + kMT - 1) / kMT;   // work items along M
     const int mn_tiles = m_tiles * p.n_tiles;
     const int num_items = mn_tiles * p.splits;
@@ -282,6 +291,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
         if (p.cblk2) tma_prefetch_desc(&tm_a2);
+        if (p.a2_center) tma_prefetch_desc(&tm_b2);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -321,25 +331,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     n0[u] = mt * (kBlockM >> (p.tw_log2 + p.th_log2));
                 }
                 const int col0 = nt * BN;
-                const int wz = p.w_batched ? n0[0] : 0;
-                const int kb_begin = z * p.kb_per_split;
+                // up2: z is the output parity class (py, px), not a k slice; it also selects the weight matrix
+                const int par = p.up2 ? z : 0;
+                const int wz = p.up2 ? par : (p.w_batched ? n0[0] : 0);
+                const int kb_begin = p.up2 ? 0 : z * p.kb_per_split;
                 const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
+                const int kb_seg1 = p.taps * p.cblk1;
+                const int cs = p.in_stride;               // input coordinates = cs * output coordinates + tap offset
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                    const int tap = kb / cbt, cb = kb - tap * cbt;
+                    int tap, cb;
+                    bool seg2;
+                    if (p.a2_center) {
+                        seg2 = kb >= kb_seg1;
+                        if (seg2) { tap = -1; cb = kb - kb_seg1; }
+                        else { tap = kb / p.cblk1; cb = kb - tap * p.cblk1; }
+                    } else {
+                        tap = kb / cbt; cb = kb - tap * cbt;
+                        seg2 = cb >= p.cblk1;
+                        if (seg2) cb -= p.cblk1;
+                    }
                     int dy = 0, dx = 0;
-                    if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-                    else if (p.taps == 25) { dy = tap / 5 - 2; dx = tap % 5 - 2; }
+                    if (tap >= 0) {
+                        if (p.up2) { dy = (tap >> 1) - 1 + (par >> 1); dx = (tap & 1) - 1 + (par & 1); }
+                        else if (p.taps == 9) { dy = tap / 3 + p.tap_lo; dx = tap % 3 + p.tap_lo; }
+                        else if (p.taps == 25) { dy = tap / 5 - 2; dx = tap % 5 - 2; }
+                    }
 #pragma unroll
                     for (int u = 0; u < kMT; ++u) {
                         uint8_t* dst = smem_a + (s * kMT + u) * kATileBytes;
-                        if (cb < p.cblk1)
-                            tma_load_4d(&tm_a, dst, &full_bar[s], cb * kBlockK, w0[u] + dx, h0[u] + dy, n0[u]);
+                        if (seg2 && p.a2_center)        // the injected tensor lives on the output grid, whatever the conv's stride
+                            tma_load_4d(&tm_a2, dst, &full_bar[s], cb * kBlockK, w0[u], h0[u], n0[u]);
                         else
-                            tma_load_4d(&tm_a2, dst, &full_bar[s], (cb - p.cblk1) * kBlockK, w0[u] + dx, h0[u] + dy, n0[u]);
+                            tma_load_4d(seg2 ? &tm_a2 : &tm_a, dst, &full_bar[s], cb * kBlockK, w0[u] * cs + dx, h0[u] * cs + dy, n0[u]);
+                    }
+                    if (seg2 && p.a2_center) {        // centre-tap segment: its own weight matrix [n_out][cpad2]
+                        tma_load_3d(&tm_b2, smem_b + s * Cfg::kBBytes, &full_bar[s], cb * kBlockK, col0, 0);
+                        continue;
                     }
                     tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
                 }
@@ -352,7 +383,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             uint32_t it = 0, t = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
                 const int z = item / mn_tiles;
-                const int kb_begin = z * p.kb_per_split;
+                const int kb_begin = p.up2 ? 0 : z * p.kb_per_split;
                 const int num_kb = min(total_kb, kb_begin + p.kb_per_split) - kb_begin;
                 const uint32_t buf = t & 1, aph = (t >> 1) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator
@@ -506,13 +537,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int gn = mt * (kBlockM >> (p.tw_log2 + p.th_log2)) + rn;
             const int col0 = nt * BN;
             const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
-            const int m_own = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
+            const int m_in = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
+            // row of the output tensor this accumulator row is written to: the same pixel, or with the
+            // upsample folded in (up2) pixel (2 gh + py, 2 gw + px) of the 2H x 2W grid, z = 2 py + px
+            const int m_own = p.up2 ? (int)(((int64_t)gn * 2 * p.a_h + 2 * gh + (z >> 1)) * (2 * p.a_w) + 2 * gw + (z & 1)) : m_in;
+            const int rstep = p.up2 ? 2 : 1;          // output rows between two consecutive accumulator rows of a slab
             // Common case: the whole tile is in bounds and the 32 rows of this warp's slab are
             // consecutive output rows -> phase B needs no shuffles, predicates or divergence.
             const int tn_ = kBlockM >> (p.tw_log2 + p.th_log2);
             const bool tile_full = (tiw * tw + tw <= p.a_w) && (tih * th + th <= p.a_h) && (mt * tn_ + tn_ <= p.a_n);
-            const bool affine = tile_full && (tw >= 32 || (tw == p.a_w && (tw * th >= 32 || th == p.a_h)));
+            const bool affine = tile_full && (tw >= 32 || (!p.up2 && tw == p.a_w && (tw * th >= 32 || th == p.a_h)));
             const int m_slab = __shfl_sync(0xffffffffu, m_own, 0);
+
             EpiOut eo;
             eo.resid = partial ? nullptr : p.resid; eo.resid_is_f32 = p.resid_is_f32; eo.ld_resid = p.ld_resid;
             eo.alpha = partial ? 1.0f : p.alpha;
@@ -672,21 +708,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         // GroupNorm statistics of the tensor being written are fused here (kStats) so the
                         // consumer's statistics pass (a full re-read of the tensor) disappears
                         const int q = lane & 7;
-                        const int64_t m0 = (int64_t)m_slab + (lane >> 3);
+                        const int64_t m0 = (int64_t)m_slab + (lane >> 3) * rstep;
                         const int64_t o_off = m0 * eo.ldo + nbase + 4 * q;
                         float* of = eo.out_f32 ? eo.out_f32 + o_off : nullptr;
                         __nv_bfloat16* ob = eo.out_bf16 ? eo.out_bf16 + o_off : nullptr;
-                        float* sd = kStats ? p.stats_out + (((int64_t)(m_slab >> 5)) * p.n_out + nbase + 4 * q) * 2 : nullptr;
+                        float* sd = nullptr;
+                        if (kStats) {
+                            // statistics slab of this warp's 32 rows; up2 orders the slabs [sample][parity][h][w] so
+                            // that a sample's slabs stay contiguous for the fold
+                            int64_t st_slab = __shfl_sync(0xffffffffu, m_in, 0) >> 5;
+                            if (p.up2) st_slab += ((int64_t)__shfl_sync(0xffffffffu, gn, 0) * 3 + z) * (((int64_t)p.a_h * p.a_w) >> 5);
+                            sd = p.stats_out + (st_slab * p.n_out + nbase + 4 * q) * 2;
+                        }
                         const int64_t r_off = m0 * eo.ld_resid + nbase + 4 * q;
+                        const int64_t ldo_s = (int64_t)eo.ldo * rstep, ldr_s = (int64_t)eo.ld_resid * rstep;
                         if (!eo.resid)
-                            store_slab_out<0, kStats>(stg, lane, eo.alpha, nullptr, 0, of, ob, eo.ldo, sd);
+                            store_slab_out<0, kStats>(stg, lane, eo.alpha, nullptr, 0, of, ob, ldo_s, sd);
                         else if (eo.resid_is_f32)
                             store_slab_out<1, kStats>(stg, lane, eo.alpha, reinterpret_cast<const float*>(eo.resid) + r_off,
-                                                      eo.ld_resid, of, ob, eo.ldo, sd);
+                                                      ldr_s, of, ob, ldo_s, sd);
                         else
                             store_slab_out<2, kStats>(stg, lane, eo.alpha,
                                                       reinterpret_cast<const __nv_bfloat16*>(eo.resid) + r_off,
-                                                      eo.ld_resid, of, ob, eo.ldo, sd);
+                                                      ldr_s, of, ob, ldo_s, sd);
                     } else if (fast_chunk(ci)) {
                         int mr[8], okr[8];
                         float4 rv[8];
@@ -742,7 +786,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
                         }
                     }
-                } else if (affine && vec_io && eo.out_bf16 && !eo.out_f32 && (nbase >> 1) + 16 <= eo.n_cols) {
+                } else if (affine && !p.up2 && vec_io && eo.out_bf16 && !eo.out_f32 && (nbase >> 1) + 16 <= eo.n_cols) {
                     // GEGLU fast path: full in-bounds tile, consecutive rows, bf16 output only
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -871,8 +915,12 @@ static bool stats_tiling_ok(int N, int H, int W, bool force_tn1) {
     return tw >= 32 || (tw == W && (tw * th >= 32 || th == H));
 }
 
+static inline int host_total_kb(const ConvDev& d) {
+    return d.a2_center ? d.taps * d.cblk1 + d.cblk2 : d.taps * (d.cblk1 + d.cblk2);
+}
+
 template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false>
-static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN, kEW, kMT>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
@@ -884,13 +932,13 @@ static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUt
     }
     const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
 
 template <int BN>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb,
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
     // kept for experiments only: with the affine fast path both measured slower than loading the
@@ -898,34 +946,34 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
     // N <= 128 with a long reduction and many tiles: two M tiles per item share each weight stage
     if constexpr (BN == 128) {
         static const bool dual_m = !(getenv("RDEIC_DUAL_M") && atoi(getenv("RDEIC_DUAL_M")) == 0);
-        if (dual_m && splits == 1 && !d.w_batched && d.taps * (d.cblk1 + d.cblk2) >= 9 &&
+        if (dual_m && splits == 1 && !d.w_batched && !d.a2_center && d.in_stride == 1 && host_total_kb(d) >= 9 &&
             (int64_t)m_tiles * d.n_tiles >= 8 * kNumSMs) {
             // exchanged operand roles when the epilogue's fast path covers the whole problem
             static const bool swap_ok = !(getenv("RDEIC_SWAP") && atoi(getenv("RDEIC_SWAP")) == 0);
             const bool vec_io = (d.ldo & 3) == 0 && (!d.resid || (d.ld_resid & 3) == 0);
             if (swap_ok && d.n_tiles == 1 && !d.row_bias && d.act != 2 && d.n_out % 32 == 0 && vec_io &&
                 (d.resid || d.alpha == 1.0f) && stats_tiling_ok(d.a_n, d.a_h, d.a_w, false)) {
-                if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, true>(ta, ta2, tb, d, m_tiles, splits, s);
-                return launch_conv3<BN, 0, 8, false, 2, true>(ta, ta2, tb, d, m_tiles, splits, s);
+                if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+                return launch_conv3<BN, 0, 8, false, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
             }
-            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, d, m_tiles, splits, s);
-            return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, d, m_tiles, splits, s);
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
         }
     }
     if (d.stats_out) {
         static const int epi12_kb_s = getenv("RDEIC_EPI12_KB") ? atoi(getenv("RDEIC_EPI12_KB")) : 10;
-        if (d.taps * (d.cblk1 + d.cblk2) <= epi12_kb_s) return launch_conv3<BN, 0, 12, true>(ta, ta2, tb, d, m_tiles, splits, s);
-        return launch_conv3<BN, 0, 8, true>(ta, ta2, tb, d, m_tiles, splits, s);
+        if (host_total_kb(d) <= epi12_kb_s) return launch_conv3<BN, 0, 12, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+        return launch_conv3<BN, 0, 8, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
     }
     static const bool pre16 = getenv("RDEIC_RESID_PREFETCH") != nullptr;
-    if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv3<BN, 1, 8>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (pre16 && d.resid && !d.resid_is_f32 && !d.partial) return launch_conv3<BN, 1, 8>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
     static const bool ahead = getenv("RDEIC_RESID_AHEAD") != nullptr;
-    if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv3<BN, 2, 8>(ta, ta2, tb, d, m_tiles, splits, s);
+    if (ahead && d.resid && d.resid_is_f32 && !d.partial) return launch_conv3<BN, 2, 8>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
     // few k-blocks per tile -> the epilogue, not the tensor pipe, sets the pace: use 12 epilogue warps
     static const int epi12_kb = getenv("RDEIC_EPI12_KB") ? atoi(getenv("RDEIC_EPI12_KB")) : 10;
-    const int total_kb = d.taps * (d.cblk1 + d.cblk2);
-    if (total_kb <= epi12_kb) return launch_conv3<BN, 0, 12>(ta, ta2, tb, d, m_tiles, splits, s);
-    return launch_conv3<BN, 0, 8>(ta, ta2, tb, d, m_tiles, splits, s);
+    const int total_kb = host_total_kb(d);
+    if (total_kb <= epi12_kb) return launch_conv3<BN, 0, 12>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+    return launch_conv3<BN, 0, 8>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
 }
 
 // Tile width: cost ~ tiles per SM * per-tile time, per-tile time ~ bn (MMA N) + a fixed overhead (pipeline
@@ -976,8 +1024,8 @@ int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, in
                            int kw, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(w_oihw && dst, "rdeic_pack_conv_weight: null pointer");
     RDEIC_CHECK_ARG(n_out > 0 && c1 > 0 && c2 >= 0, "rdeic_pack_conv_weight: bad channel counts");
-    RDEIC_CHECK_ARG((kh == 1 && kw == 1) || (kh == 3 && kw == 3) || (kh == 5 && kw == 5),
-                    "rdeic_pack_conv_weight: only 1x1, 3x3 and 5x5 kernels are supported (got %dx%d)", kh, kw);
+    RDEIC_CHECK_ARG((kh == 1 && kw == 1) || (kh == 2 && kw == 2) || (kh == 3 && kw == 3) || (kh == 5 && kw == 5),
+                    "rdeic_pack_conv_weight: only 1x1, 2x2 (folded upsample), 3x3 and 5x5 kernels are supported (got %dx%d)", kh, kw);
     const int taps = kh * kw;
     const int cp1 = (c1 + 63) / 64 * 64, cp2 = (c2 + 63) / 64 * 64;
     const int64_t total = (int64_t)n_out * taps * (cp1 + cp2);
@@ -996,7 +1044,15 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
                     "rdeic_conv_gemm: channel counts (%d, %d) must be multiples of 8 (TMA 16-byte strides)",
                     p->a_c, p->a2_c);
     RDEIC_CHECK_ARG(p->a2_c == 0 || p->a2, "rdeic_conv_gemm: a2_c > 0 needs a2");
-    RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9 || p->taps == 25, "rdeic_conv_gemm: taps must be 1, 9 or 25");
+    RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9 || p->taps == 25 || (p->taps == 4 && p->up2),
+                    "rdeic_conv_gemm: taps must be 1, 9 or 25 (4 with up2)");
+    RDEIC_CHECK_ARG(p->up2 == 0 || (p->up2 == 1 && p->taps == 4 && p->w_batch_stride > 0 && p->a2_c == 0 && p->act != 2 &&
+                                    p->w_k == 0 && p->in_stride2 == 0),
+                    "rdeic_conv_gemm: up2 needs taps = 4, the four parity weight matrices w_batch_stride apart, one source, no GEGLU");
+    RDEIC_CHECK_ARG(p->a2_center == 0 || (p->a2_c > 0 && p->w2 && (uintptr_t)p->w2 % 16 == 0 && p->w_k == 0 && p->w_batch_stride == 0),
+                    "rdeic_conv_gemm: a2_center needs a second source, its packed weights w2 and a packed w");
+    RDEIC_CHECK_ARG(p->in_stride2 == 0 || ((p->taps == 1 || p->taps == 9) && p->w_batch_stride == 0 && (p->pad_lo == 0 || p->pad_lo == 1)),
+                    "rdeic_conv_gemm: in_stride2 needs a 1x1 or 3x3 filter and pad_lo in {0, 1}");
     const int a_ld = p->a_ld ? p->a_ld : p->a_c, a2_ld = p->a2_ld ? p->a2_ld : p->a2_c;
     RDEIC_CHECK_ARG(a_ld >= p->a_c && a2_ld >= p->a2_c && a_ld % 8 == 0 && a2_ld % 8 == 0,
                     "rdeic_conv_gemm: a_ld/a2_ld (%d, %d) must be multiples of 8 and >= the channel counts", a_ld, a2_ld);
@@ -1018,7 +1074,8 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     ConvDev d;
     d.a_n = p->a_n; d.a_h = p->a_h; d.a_w = p->a_w;
     int tw_eff, th_eff, tn;
-    pick_m_tile(p->a_n, p->a_h, p->a_w, p->w_batch_stride != 0, &tw_eff, &th_eff, &tn);
+    const bool w_batched = p->w_batch_stride != 0 && !p->up2;
+    pick_m_tile(p->a_n, p->a_h, p->a_w, w_batched, &tw_eff, &th_eff, &tn);
     d.tw_log2 = ilog2(tw_eff); d.th_log2 = ilog2(th_eff);
     d.tiles_w = (p->a_w + tw_eff - 1) / tw_eff;
     d.tiles_h = (p->a_h + th_eff - 1) / th_eff;
@@ -1030,7 +1087,9 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.cblk2 = (p->a2_c + 63) / 64;
     d.taps = p->taps;
     d.n_out = p->n_out;
-    d.w_batched = p->w_batch_stride != 0;
+    d.w_batched = w_batched;
+    d.up2 = p->up2; d.a2_center = p->a2_center; d.in_stride = p->in_stride2 ? 2 : 1;
+    d.tap_lo = (p->in_stride2 && p->pad_lo == 0) ? 0 : -1;
     d.bias = p->bias; d.row_bias = p->row_bias; d.row_bias_ld = p->row_bias_ld;
     d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
     d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param;
@@ -1044,6 +1103,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         RDEIC_CHECK_ARG(stats_tiling_ok(p->a_n, p->a_h, p->a_w, false),
                         "rdeic_conv_gemm: stats_out is not supported for a %dx%dx%d pixel grid "
                         "(ask rdeic_conv_stats_supported first)", p->a_n, p->a_h, p->a_w);
+        RDEIC_CHECK_ARG(!p->up2 || tw_eff >= 32, "rdeic_conv_gemm: stats_out with up2 needs an input width that is a multiple of 32");
     }
     d.m_total = (int64_t)p->a_n * p->a_h * p->a_w;
     if (p->act == 2) {
@@ -1053,40 +1113,60 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         RDEIC_CHECK_ARG(p->ldo >= p->n_out, "rdeic_conv_gemm: bad n_out/ldo");
     }
 
-    const int bn = pick_block_n(p->n_out, m_tiles, p->tile_n_hint, p->taps * (d.cblk1 + d.cblk2));
+    const int bn = pick_block_n(p->n_out, p->up2 ? 4 * m_tiles : m_tiles, p->tile_n_hint, host_total_kb(d));
 
-    CUtensorMap ta, ta2, tb;
+    CUtensorMap ta, ta2, tb, tb2;
     {
-        uint64_t dims[4] = {(uint64_t)p->a_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
-        uint64_t str[3] = {(uint64_t)a_ld * 2, (uint64_t)a_ld * 2 * p->a_w, (uint64_t)a_ld * 2 * p->a_w * p->a_h};
-        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)tw_eff, (uint32_t)th_eff, (uint32_t)tn};
-        if (int e = encode_map(&ta, p->a, 4, dims, str, box, "A")) return e;
+        // stride-2 conv: the map describes the [a_n, 2 a_h, 2 a_w] input and is walked with element strides 2 along
+        // W and H (a box of 2 TW x 2 TH elements delivers TW x TH pixels); the tap offset moves the box origin
+        const uint64_t cs = (uint64_t)d.in_stride;
+        const uint64_t iw = (uint64_t)p->a_w * cs, ih = (uint64_t)p->a_h * cs;
+        uint64_t dims[4] = {(uint64_t)p->a_c, iw, ih, (uint64_t)p->a_n};
+        uint64_t str[3] = {(uint64_t)a_ld * 2, (uint64_t)a_ld * 2 * iw, (uint64_t)a_ld * 2 * iw * ih};
+        uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(tw_eff * cs), (uint32_t)(th_eff * cs), (uint32_t)tn};
+        uint32_t estr[4] = {1, (uint32_t)cs, (uint32_t)cs, 1};
+        if (int e = encode_map(&ta, p->a, 4, dims, str, box, "A", estr)) return e;
         ta2 = ta;
         if (p->a2_c) {
-            uint64_t dims2[4] = {(uint64_t)p->a2_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
-            uint64_t str2[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * p->a_w, (uint64_t)a2_ld * 2 * p->a_w * p->a_h};
-            if (int e = encode_map(&ta2, p->a2, 4, dims2, str2, box, "A2")) return e;
+            uint64_t dims2[4] = {(uint64_t)p->a2_c, iw, ih, (uint64_t)p->a_n};
+            uint64_t str2[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * iw, (uint64_t)a2_ld * 2 * iw * ih};
+            if (d.a2_center) {           // always on the output grid, unit element strides
+                uint64_t dims2c[4] = {(uint64_t)p->a2_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
+                uint64_t str2c[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * p->a_w, (uint64_t)a2_ld * 2 * p->a_w * p->a_h};
+                uint32_t box2c[4] = {(uint32_t)kBlockK, (uint32_t)tw_eff, (uint32_t)th_eff, (uint32_t)tn};
+                if (int e = encode_map(&ta2, p->a2, 4, dims2c, str2c, box2c, "A2")) return e;
+            } else if (int e = encode_map(&ta2, p->a2, 4, dims2, str2, box, "A2", estr)) return e;
         }
-        const uint64_t kp = (uint64_t)p->taps * (d.cblk1 + d.cblk2) * kBlockK;
-        const uint64_t nb = d.w_batched ? (uint64_t)p->a_n : 1;
+        const uint64_t kp = (uint64_t)(d.a2_center ? d.taps * d.cblk1 : host_total_kb(d)) * kBlockK;
+        const uint64_t nb = d.up2 ? 4 : (d.w_batched ? (uint64_t)p->a_n : 1);
         const uint64_t wk = p->w_k > 0 ? (uint64_t)p->w_k : kp;      // true K extent (OOB -> 0)
         const uint64_t wld = p->w_ld > 0 ? (uint64_t)p->w_ld : kp;
         uint64_t dimsb[3] = {wk, (uint64_t)p->n_out, nb};
-        uint64_t strb[2] = {wld * 2, d.w_batched ? (uint64_t)p->w_batch_stride * 2 : wld * 2 * (uint64_t)p->n_out};
+        uint64_t strb[2] = {wld * 2, nb > 1 ? (uint64_t)p->w_batch_stride * 2 : wld * 2 * (uint64_t)p->n_out};
         uint32_t boxb[3] = {(uint32_t)kBlockK, (uint32_t)bn, 1};
         if (int e = encode_map(&tb, p->w, 3, dimsb, strb, boxb, "W")) return e;
+        tb2 = tb;
+        if (d.a2_center) {
+            const uint64_t kp2 = (uint64_t)d.cblk2 * kBlockK;
+            uint64_t dimsb2[3] = {kp2, (uint64_t)p->n_out, 1};
+            uint64_t strb2[2] = {kp2 * 2, kp2 * 2 * (uint64_t)p->n_out};
+            if (int e = encode_map(&tb2, p->w2, 3, dimsb2, strb2, boxb, "W2")) return e;
+        }
     }
     cudaStream_t s = as_stream(stream);
     // split-K: layers with few output tiles but a long reduction (UNet levels 2/3: M = 512..2048,
     // K up to 23040) would leave most of the 148 SMs idle; slice K across blockIdx.z, write fp32
     // partials to the caller's workspace and finish with a deterministic reduce + epilogue pass.
     int splits = 1;
-    const int total_kb = p->taps * (d.cblk1 + d.cblk2);
+    const int total_kb = host_total_kb(d);
     const int n_tiles = (p->n_out + bn - 1) / bn;
     d.n_tiles = n_tiles;
     d.kb_per_split = total_kb;
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
-    if (p->act != 2 && !p->stats_out && p->workspace && tiles <= kNumSMs / 2 && total_kb >= 8) {
+    if (d.up2) {
+        splits = 4;                    // the z index of a work item is the output parity class, not a k slice
+        d.splits = 4;
+    } else if (p->act != 2 && !p->stats_out && p->workspace && tiles <= kNumSMs / 2 && total_kb >= 8) {
         int want = (int)(kNumSMs / tiles);
         if (want > total_kb / 4) want = total_kb / 4;
         if (want > 16) want = 16;
@@ -1101,15 +1181,15 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     }
     int rc;
     switch (bn) {
-        case 32: rc = launch_conv<32>(ta, ta2, tb, d, m_tiles, splits, s); break;
-        case 64: rc = launch_conv<64>(ta, ta2, tb, d, m_tiles, splits, s); break;
-        case 128: rc = launch_conv<128>(ta, ta2, tb, d, m_tiles, splits, s); break;
-        case 160: rc = launch_conv<160>(ta, ta2, tb, d, m_tiles, splits, s); break;
-        case 256: rc = launch_conv<256>(ta, ta2, tb, d, m_tiles, splits, s); break;
+        case 32: rc = launch_conv<32>(ta, ta2, tb, tb2, d, m_tiles, splits, s); break;
+        case 64: rc = launch_conv<64>(ta, ta2, tb, tb2, d, m_tiles, splits, s); break;
+        case 128: rc = launch_conv<128>(ta, ta2, tb, tb2, d, m_tiles, splits, s); break;
+        case 160: rc = launch_conv<160>(ta, ta2, tb, tb2, d, m_tiles, splits, s); break;
+        case 256: rc = launch_conv<256>(ta, ta2, tb, tb2, d, m_tiles, splits, s); break;
         default: return set_error("rdeic_conv_gemm: unsupported BLOCK_N %d", bn);
     }
     if (rc) return rc;
-    if (splits > 1) {
+    if (splits > 1 && !d.up2) {
         EpiOut eo;
         eo.resid = p->resid; eo.resid_is_f32 = p->resid_is_f32; eo.ld_resid = p->ld_resid; eo.alpha = p->alpha;
         eo.out_bf16 = (__nv_bfloat16*)p->out_bf16; eo.out_f32 = p->out_f32; eo.ldo = p->ldo; eo.n_cols = p->n_out;

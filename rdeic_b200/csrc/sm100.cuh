@@ -169,10 +169,13 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 inline int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const char* what,
+                      const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims),
                     reinterpret_cast<const cuuint64_t*>(strides_bytes),

@@ -29,6 +29,7 @@ from . import ops
 
 BF16 = torch.bfloat16
 SD = Dict[str, torch.Tensor]
+S2_IM2COL = os.environ.get("RDEIC_S2_IM2COL") is not None      # bring-up switch of the strided-tensor-map stride-2 conv
 
 
 def find_denominator(number: int, start: int) -> int:
@@ -76,6 +77,14 @@ class Conv:
                     w.shape[0], taps)
 
     @staticmethod
+    def load_up2(sd: SD, name: str, dev) -> "Conv":
+        """The conv3x3 behind a nearest x2 upsample (openaimodel.py:106-113, model.py:63-67) as four 2x2 parity
+        kernels (`ops.pack_up2_weight`): `w` is [4, n_out, 4 * cpad], taps = 4."""
+        w = sd[name + ".weight"].to(dev, torch.float32)
+        b = sd.get(name + ".bias")
+        return Conv(ops.pack_up2_weight(w), None if b is None else b.to(dev, torch.float32).contiguous(), w.shape[0], 4)
+
+    @staticmethod
     def fused(sd: SD, names: Sequence[str], dev) -> "Conv":
         """Concatenate several Linear/1x1 weights along the output dim (one GEMM)."""
         ws = [sd[n + ".weight"].to(dev, torch.float32) for n in names]
@@ -87,6 +96,38 @@ class Conv:
             b = torch.cat([torch.zeros(wi.shape[0]) if bi is None else bi.float().cpu() for wi, bi in zip(ws, bs)])
             b = b.to(dev).contiguous()
         return Conv(ops.pack_conv_weight(w), b, w.shape[0], 1)
+
+
+@dataclass
+class Inject:
+    """`h_base = h_base + zero_conv(h_ctr) * scale` (model/rdeic.py:194,203,207) folded into the GEMM that produces
+    h_base: the control tensor is a centre-tap-only second K segment of that conv (`conv_gemm(..., a2=h_ctr, w2=...)`),
+    so the injection costs a few extra k-blocks instead of a kernel that re-reads and re-writes both copies of h_base."""
+    w2: torch.Tensor                # packed bf16 [n_out, 64-padded c_ctr], scale folded in
+    bias: torch.Tensor              # bias of the producing conv + scale * zero-conv bias
+
+    @staticmethod
+    def load(sd: SD, name: str, dev, scale: float, last: "Conv") -> "Inject":
+        z = Conv.load(sd, name, dev, scale=scale)
+        zb = sd[name + ".bias"].to(dev, torch.float32) * scale
+        base_b = last.b if last.b is not None else torch.zeros(last.n_out, device=dev)
+        return Inject(z.w, (base_b + zb).contiguous())
+
+
+class _Inj:
+    """One injection at run time: fused weights, the control tensor, and the event that says it is ready."""
+
+    __slots__ = ("inj", "h", "ev")
+
+    def __init__(self, inj: Inject, h: torch.Tensor, ev=None):
+        self.inj, self.h, self.ev = inj, h, ev
+
+    def kw(self) -> dict:
+        """Called right before the launch that consumes the control tensor: join the control stream, then hand
+        the extra operands to conv_gemm."""
+        if self.ev is not None:
+            torch.cuda.current_stream().wait_event(self.ev)
+        return dict(a2=self.h, w2=self.inj.w2, bias=self.inj.bias)
 
 
 @dataclass
@@ -237,7 +278,7 @@ def _load_unet(sd: SD, prefix: str, dev, *, model_channels: int, width: int, in_
                     blk.append(attn(f"{P}.output_blocks.{oi}.{j}", ch, num_head_channels))
                     j += 1
                 if level and i == num_res_blocks[level]:
-                    blk.append(Layer("up", Conv.load(sd, f"{P}.output_blocks.{oi}.{j}.conv", dev)))
+                    blk.append(Layer("up", Conv.load_up2(sd, f"{P}.output_blocks.{oi}.{j}.conv", dev)))
                     ds //= 2
                 ob.append(blk)
                 oi += 1
@@ -303,6 +344,25 @@ class NoiseEstimatorEngine:
         # rdeic.py:164-165,185: scale_list buffer (already * control_scale) times control_scale again
         sl = sd["control_model.scale_list"].float().cpu() * self.control_scale
         self.scales = [float(v) for v in sl]
+        # Every injection whose target tensor is written by a GEMM on the same pixel grid rides in that GEMM
+        # (`Inject`): the 12 encoder ones, the middle one, and the decoder ones that follow a block not ending in an
+        # upsample.  dec_zero[0] (a second injection into the middle output) and the three after an upsample stay
+        # separate 1x1 GEMMs with the residual epilogue (`_inject`).
+        def last_conv(layers: List[Layer]) -> Optional[Conv]:
+            L = layers[-1]
+            return {"res": lambda: L.w.conv2, "attn": lambda: L.w.proj_out, "down": lambda: L.w,
+                    "conv_in": lambda: L.w, "up": lambda: None}[L.kind]()
+
+        self.fuse_inject = os.environ.get("RDEIC_NO_FUSED_INJECT") is None
+        self.enc_inj = [Inject.load(sd, f"control_model.enc_zero_convs_out.{i}.0", dev, self.scales[i], last_conv(blk))
+                        for i, blk in enumerate(self.base.input_blocks)]
+        self.mid_inj = Inject.load(sd, "control_model.middle_block_out.0", dev, self.scales[n_enc], last_conv(self.base.middle))
+        n_dec = len(self.base.output_blocks)
+        self.dec_inj: List[Optional[Inject]] = []
+        for j, blk in enumerate(self.base.output_blocks):
+            lc = last_conv(blk)
+            self.dec_inj.append(None if (j + 1 >= n_dec or lc is None) else
+                                Inject.load(sd, f"control_model.dec_zero_convs_out.{j + 1}.0", dev, self.scales[n_enc + 2 + j], lc))
         # run the control adapter on a second stream, concurrently with the base UNet (its kernels are
         # small: 64-256 channels, grids that leave most SMs idle); joined at every zero-conv injection
         self.overlap_control = os.environ.get("RDEIC_NO_OVERLAP") is None
@@ -355,7 +415,7 @@ class NoiseEstimatorEngine:
     # fp32 removes ~100 sequential bf16 roundings of the stream per step (measured: per-step rel-L2
     # vs the fp32 reference 1.2e-2 -> see profiles/), at ~1.5x the bytes of block-boundary tensors.
     @staticmethod
-    def _res(w: ResBlockW, x: "Act", x2: Optional["Act"], c: _Ctx) -> "Act":
+    def _res(w: ResBlockW, x: "Act", x2: Optional["Act"], c: _Ctx, ij: Optional[_Inj] = None) -> "Act":
         h = ops.groupnorm(x.f, w.n_in.g, w.n_in.b, w.groups_in, 1e-5, True, x2=None if x2 is None else x2.f,
                           stats1=x.st, stats2=None if x2 is None else x2.st)
         rb = c.emb_rows[:, w.emb_off:w.emb_off + w.cout]
@@ -364,10 +424,11 @@ class NoiseEstimatorEngine:
         xs = x.f
         if w.skip is not None:
             xs = ops.conv_gemm(x.h, w.skip.w, w.cout, 1, a2=None if x2 is None else x2.h, bias=w.skip.b, out_f32=True)
-        return Act(*ops.conv_gemm(h, w.conv2.w, w.cout, 9, bias=w.conv2.b, resid=xs, dual=True, stats=True))
+        kw = ij.kw() if ij is not None else dict(bias=w.conv2.b)
+        return Act(*ops.conv_gemm(h, w.conv2.w, w.cout, 9, resid=xs, dual=True, stats=True, **kw))
 
     @staticmethod
-    def _attn(w: TransformerW, x: "Act", c: _Ctx) -> "Act":
+    def _attn(w: TransformerW, x: "Act", c: _Ctx, ij: Optional[_Inj] = None) -> "Act":
         B, H, W, C = x.f.shape
         scale = w.d_head ** -0.5
         hn = ops.groupnorm(x.f, w.norm.g, w.norm.b, w.groups, 1e-6, False, stats1=x.st)
@@ -384,27 +445,42 @@ class NoiseEstimatorEngine:
         n3 = ops.layernorm(h, w.ln3.g, w.ln3.b)
         f = ops.linear(n3, w.ff1.w, w.ff1.n_out, bias=w.ff1.b, act=2)       # GEGLU fused in the epilogue
         hb = ops.linear(f, w.ff2.w, C, bias=w.ff2.b, resid=h)                 # only consumer is proj_out's A operand
-        of, oh, st = ops.conv_gemm(hb.view(B, H, W, -1), w.proj_out.w, C, 1, bias=w.proj_out.b, resid=x.f, dual=True,
-                                   stats=True)
+        kw = ij.kw() if ij is not None else dict(bias=w.proj_out.b)
+        of, oh, st = ops.conv_gemm(hb.view(B, H, W, -1), w.proj_out.w, C, 1, resid=x.f, dual=True, stats=True, **kw)
         return Act(of, oh, st)
 
-    def _run_block(self, layers: List[Layer], x: "Act", x2: Optional["Act"], c: _Ctx, x_in2=None) -> "Act":
-        for L in layers:
+    def _run_block(self, layers: List[Layer], x: "Act", x2: Optional["Act"], c: _Ctx, x_in2=None,
+                   inj: Optional[_Inj] = None) -> "Act":
+        """One TimestepEmbedSequential (openaimodel.py:79-88).  `inj`: the zero-conv injection the reference applies
+        to this block's output, fused into the block's last GEMM."""
+        for li, L in enumerate(layers):
+            ij = inj if li == len(layers) - 1 else None
             if L.kind == "res":
-                x = self._res(L.w, x, x2, c)
+                x = self._res(L.w, x, x2, c, ij)
                 x2 = None
             elif L.kind == "attn":
-                x = self._attn(L.w, x, c)
+                x = self._attn(L.w, x, c, ij)
             elif L.kind == "down":
-                B, H, W, C = x.h.shape
-                col = ops.im2col_3x3_s2(x.h)
-                of, oh, st = ops.conv_gemm(col.view(B, H // 2, W // 2, -1), L.w.w, L.w.n_out, 1, bias=L.w.b, dual=True,
-                                           stats=True)
-                x = Act(of, oh, st)
+                # stride-2 conv3x3 (openaimodel.py:150-152) read straight from the input through a tensor map with
+                # element strides 2: no im2col gather
+                kw = ij.kw() if ij is not None else dict(bias=L.w.b)
+                if S2_IM2COL:      # bring-up fallback: materialised gather + 1-tap GEMM
+                    B, H, W, C = x.h.shape
+                    col = ops.im2col_3x3_s2(x.h).view(B, H // 2, W // 2, -1)
+                    x = Act(*ops.conv_gemm(col, L.w.w, L.w.n_out, 1, dual=True, stats=True, **kw))
+                else:
+                    x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, dual=True, stats=True, stride2=True, **kw))
             elif L.kind == "up":
-                x = Act(*ops.conv_gemm(ops.upsample2x(x.h), L.w.w, L.w.n_out, 9, bias=L.w.b, dual=True, stats=True))
+                # nearest x2 + conv3x3 (openaimodel.py:106-113) as four 2x2 parity convs on the input grid
+                assert ij is None
+                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 4, bias=L.w.b, dual=True, stats=True, up2=True,
+                                       w_batch_stride=L.w.w.stride(0)))
             elif L.kind == "conv_in":
-                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, a2=x_in2, bias=L.w.b, dual=True, stats=True))
+                if ij is not None:                  # base conv_in has a single source: a2 is free for the injection
+                    assert x_in2 is None
+                    x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, dual=True, stats=True, **ij.kw()))
+                else:
+                    x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, a2=x_in2, bias=L.w.b, dual=True, stats=True))
             else:
                 raise RuntimeError(L.kind)
         return x
@@ -473,32 +549,44 @@ class NoiseEstimatorEngine:
                 cc = _Ctx(self._time_rows(self.ctrl, t_emb), kv_ctrl)
             hc = x8
             hs_ctr: List[Act] = []
-            si = 0
+            fuse = self.fuse_inject
+            n_enc = len(self.base.input_blocks)
             for i, (bb, bc) in enumerate(zip(self.base.input_blocks, self.ctrl.input_blocks)):
                 with on_side():
                     hc = self._run_block(bc, hc, None, cc, x_in2=hint if i == 0 else None)
                     ev = side.record_event() if overlap else None
-                hb = self._run_block(bb, hb, None, cb)
-                if overlap:
-                    main.wait_event(ev)           # join: the injection reads h_ctr
-                hb = self._inject(self.enc_zero[i], hb, hc, self.scales[si])
-                si += 1
+                if fuse:                              # the join happens right before the GEMM that reads h_ctr
+                    hb = self._run_block(bb, hb, None, cb, inj=_Inj(self.enc_inj[i], hc.h, ev))
+                else:
+                    hb = self._run_block(bb, hb, None, cb)
+                    if overlap:
+                        main.wait_event(ev)
+                    hb = self._inject(self.enc_zero[i], hb, hc, self.scales[i])
                 hs_base.append(hb)
                 hs_ctr.append(hc)
                 keep.extend((hb, hc))
             with on_side():
                 hc = self._run_block(self.ctrl.middle, hc, None, cc)
                 ev = side.record_event() if overlap else None
-            hb = self._run_block(self.base.middle, hb, None, cb)
-            if overlap:
-                main.wait_event(ev)
-            hb = self._inject(self.mid_zero, hb, hc, self.scales[si])
-            si += 1
+            if fuse:
+                hb = self._run_block(self.base.middle, hb, None, cb, inj=_Inj(self.mid_inj, hc.h, ev))
+            else:
+                hb = self._run_block(self.base.middle, hb, None, cb)
+                if overlap:
+                    main.wait_event(ev)
+                hb = self._inject(self.mid_zero, hb, hc, self.scales[n_enc])
             keep.extend((hb, hc, cc))
-            for i, blk in enumerate(self.base.output_blocks):
-                hb = self._inject(self.dec_zero[i], hb, hs_ctr.pop(), self.scales[si])
-                si += 1
-                hb = self._run_block(blk, hb, hs_base.pop(), cb)
+            # decoder: the reference injects dec_zero[i](hs_ctr.pop()) BEFORE output block i, i.e. into the output of
+            # block i-1: fused there when that block ends in a GEMM on the same grid
+            hb = self._inject(self.dec_zero[0], hb, hs_ctr.pop(), self.scales[n_enc + 1])
+            n_dec = len(self.base.output_blocks)
+            for j, blk in enumerate(self.base.output_blocks):
+                nxt = self.dec_inj[j] if fuse else None
+                hb = self._run_block(blk, hb, hs_base.pop(), cb, inj=None if nxt is None else _Inj(nxt, hs_ctr[-1].h))
+                if j + 1 < n_dec:
+                    hcj = hs_ctr.pop()
+                    if nxt is None:
+                        hb = self._inject(self.dec_zero[j + 1], hb, hcj, self.scales[n_enc + 2 + j])
         hn = ops.groupnorm(hb.f, self.base.out_norm.g, self.base.out_norm.b, find_denominator(hb.f.shape[-1], 32), 1e-5, True,
                            stats1=hb.st)
         o = ops.conv_gemm(hn, self.base.out_conv.w, self.out_channels, 9, bias=self.base.out_conv.b, out_f32=True)
@@ -609,10 +697,12 @@ class VAEEncoderEngine(_VaeMid):
                 a = self._res32(b, a)
             if down is not None:
                 # model.py:82-84: pad (0,1,0,1) then a stride-2 conv without padding
-                B, H, W, C = a.h.shape
-                col = ops.im2col_3x3_s2(a.h, pad_lo=0)
-                of, oh = ops.linear(col, down.w, down.n_out, bias=down.b, dual=True)
-                a = Act(of.view(B, H // 2, W // 2, down.n_out), oh.view(B, H // 2, W // 2, down.n_out))
+                if S2_IM2COL:
+                    B, H, W, C = a.h.shape
+                    col = ops.im2col_3x3_s2(a.h, pad_lo=0).view(B, H // 2, W // 2, -1)
+                    a = Act(*ops.conv_gemm(col, down.w, down.n_out, 1, bias=down.b, dual=True))
+                else:
+                    a = Act(*ops.conv_gemm(a.h, down.w, down.n_out, 9, bias=down.b, dual=True, stride2=True, pad_lo=0))
         a = self._res32(self.mid1, a)
         a = self._res32(self.mid2, Act(None, self._attn(a.h)[0]))
         return ops.groupnorm(a.f, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
@@ -650,7 +740,7 @@ class VAEDecoderEngine(_VaeMid):
             while (f"{D}.up.{lvl}.block.{i}.conv1.weight") in sd:
                 blocks.append(rb(f"{D}.up.{lvl}.block.{i}"))
                 i += 1
-            up = Conv.load(sd, f"{D}.up.{lvl}.upsample.conv", dev) if (f"{D}.up.{lvl}.upsample.conv.weight") in sd else None
+            up = Conv.load_up2(sd, f"{D}.up.{lvl}.upsample.conv", dev) if (f"{D}.up.{lvl}.upsample.conv.weight") in sd else None
             self.levels.append((blocks, up))
             lvl += 1
         self.norm_out = Norm.load(sd, D + ".norm_out", dev)
@@ -692,7 +782,8 @@ class VAEDecoderEngine(_VaeMid):
             for b in blocks:
                 x, st = self._res(b, x, st)
             if up is not None:
-                x, st = ops.conv_gemm(ops.upsample2x(x), up.w, up.n_out, 9, bias=up.b, stats=True)
+                # nearest x2 + conv3x3 (model.py:63-67) as four 2x2 parity convs: 4/9 of the MACs, no upsampled tensor
+                x, st = ops.conv_gemm(x, up.w, up.n_out, 4, bias=up.b, stats=True, up2=True, w_batch_stride=up.w.stride(0))
         return self._tail(x, st, as_uint8)
 
     @torch.no_grad()

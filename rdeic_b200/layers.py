@@ -5,8 +5,8 @@ Every block consumes the reference's state_dict entries unchanged and runs on NH
 activations through the tcgen05 implicit-GEMM kernel (`ops.conv_gemm`): bias, LeakyReLU / GELU and
 the residual add are fused into the GEMM epilogue, 5x5 convolutions are 25 shifted TMA box loads,
 the sub-pixel convolutions' PixelShuffle is a weight-row permutation at load plus one copy kernel,
-and stride-2 convolutions gather once (`im2col_3x3_s2`) and then run as plain GEMMs (the 1x1
-stride-2 shortcut reads the centre-tap columns of that same gather).
+and stride-2 convolutions (3x3 and the 1x1 shortcut) read the input through a tensor map with element
+strides 2 — no im2col gather.
 
 Channel counts that are not multiples of 8 (the 5/3- and 4/3-width hidden layers of
 EntropyParametersEX, compression_modules.py:91-104) are padded with zero weight rows / columns, so
@@ -54,10 +54,11 @@ def load_conv(sd: SD, name: str, dev, shuffle: bool = False, c1: Optional[int] =
 
 
 def conv(x: torch.Tensor, c: Conv, act: int = ACT_NONE, slope: float = 0.0, resid: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, out_f32: bool = False, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, out_f32: bool = False, x2: Optional[torch.Tensor] = None,
+         stride2: bool = False) -> torch.Tensor:
     """act(conv(cat(x, x2)) + bias) [+ resid] on NHWC bf16 (x / x2 may be channel slices of wider buffers)."""
     return ops.conv_gemm(x, c.w, c.n_out, c.taps, a2=x2, bias=c.b, act=act, act_param=slope, resid=resid, out=out,
-                         out_f32=out_f32)
+                         out_f32=out_f32, stride2=stride2)
 
 
 @dataclass
@@ -108,15 +109,18 @@ class ResidualBlockWithStride:
 
     @staticmethod
     def load(sd: SD, p: str, dev) -> "ResidualBlockWithStride":
-        c1 = load_conv(sd, p + ".conv1", dev)
-        c1.taps = 1                                   # runs as a GEMM over the gathered [M, 9*Cp] matrix
-        return ResidualBlockWithStride(c1, load_conv(sd, p + ".conv2", dev), load_conv(sd, p + ".downsample", dev),
-                                       sd[p + ".conv1.weight"].shape[1])
+        return ResidualBlockWithStride(load_conv(sd, p + ".conv1", dev), load_conv(sd, p + ".conv2", dev),
+                                       load_conv(sd, p + ".downsample", dev), sd[p + ".conv1.weight"].shape[1])
 
     def __call__(self, x: torch.Tensor, out_f32: bool = False) -> torch.Tensor:
-        B, H, W, C = x.shape
-        cp = (C + 63) // 64 * 64
-        col = ops.im2col_3x3_s2(x).view(B, H // 2, W // 2, 9 * cp)
-        h = conv(col, self.conv1, ACT_LRELU, 0.01)
-        identity = conv(col[..., 4 * cp:4 * cp + C], self.downsample)       # centre tap = the stride-2 samples
+        from .engine import S2_IM2COL
+        if S2_IM2COL:                                                       # bring-up fallback
+            B, H, W, C = x.shape
+            cp = (C + 63) // 64 * 64
+            col = ops.im2col_3x3_s2(x).view(B, H // 2, W // 2, 9 * cp)
+            h = ops.conv_gemm(col, self.conv1.w, self.conv1.n_out, 1, bias=self.conv1.b, act=ACT_LRELU, act_param=0.01)
+            identity = conv(col[..., 4 * cp:4 * cp + C], self.downsample)
+            return conv(h, self.conv2, ACT_LRELU, 0.1, resid=identity, out_f32=out_f32)
+        h = conv(x, self.conv1, ACT_LRELU, 0.01, stride2=True)
+        identity = conv(x, self.downsample, stride2=True)                   # 1x1, stride 2: the even-even samples
         return conv(h, self.conv2, ACT_LRELU, 0.1, resid=identity, out_f32=out_f32)

@@ -462,33 +462,43 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
               bias: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
               resid: Optional[torch.Tensor] = None, alpha: float = 1.0, act: int = 0, out_f32: bool = False,
               dual: bool = False, out=None, w_batch_stride: int = 0, w_k: int = 0, w_ld: int = 0, tile_n: int = 0,
-              split_k: bool = True, act_param: float = 0.0, stats: bool = False):
-    """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,H,W,n_out].
+              split_k: bool = True, act_param: float = 0.0, stats: bool = False, up2: bool = False,
+              w2: Optional[torch.Tensor] = None, stride2: bool = False, pad_lo: int = 1):
+    """a: NHWC bf16 [N,H,W,C] (a Linear passes [1,1,M,K]); returns [N,OH,OW,n_out].
 
     Output selection: bf16 by default, fp32 with `out_f32`, both with `dual` (returns the pair
     (fp32, bf16): the fp32 master of a residual stream plus its bf16 tensor-core operand copy).
     `out` may pre-allocate the destination (a tensor, or an (fp32, bf16) pair for `dual`).
     `stats`: also return the per-32-row-slab (sum, sumsq) of every output column ([M/32, n_out, 2]
     fp32) for `groupnorm(..., stats1=...)`; returned as the last element of the result tuple, or
-    None when the pixel grid does not tile cleanly (`conv_stats_supported`)."""
+    None when the pixel grid does not tile cleanly (`conv_stats_supported`).
+    `up2`: nearest x2 upsample folded into the conv (taps = 4, `w_packed` = the four parity matrices of
+    `pack_up2_weight`, output grid 2H x 2W).  `stride2`: stride-2 conv read through a strided tensor map (output grid
+    H/2 x W/2; `pad_lo` 1 = padding 1 all round, 0 = bottom/right only).  `w2`: `a2` is not a concat source but an
+    injected tensor on the output grid with its own 1x1 weights (the fused zero-conv injection)."""
     N, H, W, Cc = a.shape
     if a.dtype != BF16 or not _is_nhwc_slice(a):
         raise TypeError("conv_gemm: A must be bf16 NHWC, dense or a channel slice of a dense NHWC tensor")
-    if a2 is not None and (a2.dtype != BF16 or not _is_nhwc_slice(a2) or a2.shape[:3] != a.shape[:3]):
-        raise TypeError("conv_gemm: a2 must be bf16 NHWC with the pixel grid of A")
+    if stride2 and (H % 2 or W % 2):
+        raise ValueError("conv_gemm: stride2 needs even H and W")
+    gh, gw = (H // 2, W // 2) if stride2 else (H, W)                 # the M grid the kernel tiles
+    OH, OW = (2 * H, 2 * W) if up2 else (gh, gw)                       # the output grid
+    if a2 is not None and (a2.dtype != BF16 or not _is_nhwc_slice(a2) or
+                           tuple(a2.shape[:3]) != ((N, gh, gw) if w2 is not None else (N, H, W))):
+        raise TypeError("conv_gemm: a2 must be bf16 NHWC with the pixel grid of A (of the output when it is injected)")
     n_cols = n_out // 2 if act == 2 else n_out
     of = oh = None
     if dual:
-        of, oh = out if out is not None else (torch.empty((N, H, W, n_cols), dtype=torch.float32, device=a.device),
-                                              torch.empty((N, H, W, n_cols), dtype=BF16, device=a.device))
+        of, oh = out if out is not None else (torch.empty((N, OH, OW, n_cols), dtype=torch.float32, device=a.device),
+                                              torch.empty((N, OH, OW, n_cols), dtype=BF16, device=a.device))
     elif out is not None:
         of, oh = (out, None) if out.dtype == torch.float32 else (None, out)
     elif out_f32:
-        of = torch.empty((N, H, W, n_cols), dtype=torch.float32, device=a.device)
+        of = torch.empty((N, OH, OW, n_cols), dtype=torch.float32, device=a.device)
     else:
-        oh = torch.empty((N, H, W, n_cols), dtype=BF16, device=a.device)
+        oh = torch.empty((N, OH, OW, n_cols), dtype=BF16, device=a.device)
     p = ConvParams()
-    p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, H, W, Cc
+    p.a, p.a_n, p.a_h, p.a_w, p.a_c = _ptr(a), N, gh, gw, Cc
     p.a2, p.a2_c = (_ptr(a2), a2.shape[-1]) if a2 is not None else (None, 0)
     p.a_ld = a.stride(-2)
     p.a2_ld = a2.stride(-2) if a2 is not None else 0
@@ -511,10 +521,18 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         raise ValueError("conv_gemm: dual outputs must share the row stride")
     p.ldo = ref.stride(-2)
     p.tile_n_hint = tile_n
+    p.up2 = int(up2)
+    p.in_stride2, p.pad_lo = int(stride2), pad_lo
+    if w2 is not None:
+        if a2 is None:
+            raise ValueError("conv_gemm: w2 needs a2")
+        p.a2_center, p.w2 = 1, _ptr(w2)
     st = None
-    kb = taps * ((Cc + 63) // 64 + ((a2.shape[-1] + 63) // 64 if a2 is not None else 0))
-    if stats and act != 2 and w_batch_stride == 0 and conv_stats_supported(N, H, W, n_out, kb):
-        st = torch.empty(((N * H * W + 31) // 32, n_out, 2), dtype=torch.float32, device=a.device)
+    cb1, cb2 = (Cc + 63) // 64, ((a2.shape[-1] + 63) // 64 if a2 is not None else 0)
+    kb = taps * cb1 + cb2 if w2 is not None else taps * (cb1 + cb2)
+    if stats and act != 2 and (w_batch_stride == 0 or up2) and conv_stats_supported(N, gh, gw, n_out, kb) and \
+            (not up2 or gw % 32 == 0):
+        st = torch.empty(((N * OH * OW + 31) // 32, n_out, 2), dtype=torch.float32, device=a.device)
         p.stats_out = _ptr(st)
     if split_k:
         ws = _splitk_workspace(a.device)
@@ -524,8 +542,15 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
         e0.record()
         check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
         e1.record()
-        k_true = taps * (Cc + (a2.shape[-1] if a2 is not None else 0))
-        GEMM_PROFILE.append((e0, e1, 2.0 * N * H * W * n_out * k_true))
+        # algorithmic FLOPs of the reference op: an upsample + 3x3 conv counts its 9 taps on the 2H x 2W
+        # grid although the folded form executes 4 taps per output pixel
+        if up2:
+            fl = 2.0 * N * OH * OW * n_out * 9 * Cc
+        elif w2 is not None:
+            fl = 2.0 * N * gh * gw * n_out * (taps * Cc + a2.shape[-1])
+        else:
+            fl = 2.0 * N * gh * gw * n_out * taps * (Cc + (a2.shape[-1] if a2 is not None else 0))
+        GEMM_PROFILE.append((e0, e1, fl))
     else:
         check(_lib.load().rdeic_conv_gemm(C.byref(p), _stream()), "rdeic_conv_gemm")
     if stats:
@@ -533,6 +558,24 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     if dual:
         return of, oh
     return ref
+
+
+def pack_up2_weight(w: torch.Tensor) -> torch.Tensor:
+    """conv3x3 weights OIHW fp32 that follow a nearest x2 upsample (openaimodel.py:106-113, model.py:63-67) ->
+    bf16 [4, n_out, 4 * cpad]: one 2x2 kernel per output parity class (py, px).  Output pixel (2y+py, 2x+px) reads
+    upsampled rows 2y+py-1 .. 2y+py+1, i.e. input rows y-1, y, y (py = 0) or y, y, y+1 (py = 1): taps that land on
+    the same input pixel are summed in fp32 before the bf16 rounding.  The padding survives unchanged: the only
+    out-of-range input row is y-1 = -1 (py = 0) or y+1 = H (py = 1), exactly the zero rows of the padded 2H grid."""
+    w = _need(w, torch.float32, "pack_up2_weight")
+    if w.dim() != 4 or tuple(w.shape[2:]) != (3, 3):
+        raise ValueError("pack_up2_weight: expected OIHW weights of a 3x3 kernel")
+
+    def fold(t: torch.Tensor, axis: int, par: int) -> torch.Tensor:
+        a, b, c = t.unbind(axis)
+        return torch.stack([a, b + c], axis) if par == 0 else torch.stack([a + b, c], axis)
+
+    mats = [pack_conv_weight(fold(fold(w, 2, py), 3, px).contiguous()) for py in (0, 1) for px in (0, 1)]
+    return torch.stack(mats).contiguous()
 
 
 _stats_ok = {}

@@ -774,3 +774,100 @@ def test_conv3x3_exchanged_roles_epilogues(cuda, variant):
         # alpha != 1 without a residual is outside the exchanged form's fast path: the library must fall back
         out = ops.conv_gemm(a, wp, Cout, 9, bias=b, act=4, alpha=0.25, out_f32=True)
         assert _rel(out.cpu(), (0.25 * F.gelu(conv)).cpu()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: upsample / stride-2 / zero-conv injection folded into the implicit GEMM
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 64, 96), (1, 64, 64, 128, 256), (2, 16, 16, 128, 64), (1, 8, 8, 72, 320),
+                                            (1, 8, 40, 64, 32), (3, 12, 20, 16, 48)])
+def test_conv3x3_after_upsample_folded(cuda, B, H, W, Cin, Cout):
+    """nearest x2 + conv3x3 (openaimodel.py:106-113, model.py:63-67) as four 2x2 parity convs.  The folded
+    weights are sums of bf16-exact taps rounded to bf16 once, so the tolerance is bf16 operand rounding."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(61)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1).permute(0, 2, 3, 1)
+    wp = ops.pack_up2_weight(w.to(cuda))
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    of, oh, st = ops.conv_gemm(a, wp, Cout, 4, bias=b.to(cuda), dual=True, stats=True, up2=True, w_batch_stride=wp.stride(0))
+    assert tuple(of.shape) == (B, 2 * H, 2 * W, Cout)
+    assert _rel(of.cpu(), ref) < 4e-3, _rel(of.cpu(), ref)
+    assert torch.equal(oh, of.bfloat16())
+    assert (st is not None) == (W % 32 == 0 and Cout % 32 == 0 and ops.conv_stats_supported(B, H, W, Cout, 4 * ((Cin + 63) // 64)))
+    if st is not None:
+        # the slab table is ordered [sample][parity][h][w]; a consumer only needs per-sample sums
+        gamma, beta = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+        gn = ops.groupnorm(of, gamma.to(cuda), beta.to(cuda), 32, 1e-5, True, stats1=st).float().cpu()
+        gref = F.silu(F.group_norm(of.cpu().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+        assert torch.allclose(gn, gref, atol=4e-2, rtol=2e-2)
+        tot = st.view(B, -1, Cout, 2).sum(1).cpu()
+        assert torch.allclose(tot[..., 0], of.cpu().sum((1, 2)), rtol=1e-3, atol=1e-2)
+    # bf16-only output, no stats (the VAE form)
+    o2 = ops.conv_gemm(a, wp, Cout, 4, bias=b.to(cuda), up2=True, w_batch_stride=wp.stride(0))
+    assert torch.equal(o2, oh)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,pad_lo", [(2, 32, 32, 64, 96, 3, 1), (1, 64, 64, 320, 320, 3, 1), (2, 16, 16, 128, 64, 3, 0),
+                                                     (1, 8, 8, 72, 320, 3, 1), (1, 12, 40, 64, 32, 3, 0), (2, 16, 24, 128, 64, 1, 1),
+                                                     (8, 64, 64, 64, 64, 3, 1)])
+def test_conv_stride2_strided_tensor_map(cuda, B, H, W, Cin, Cout, k, pad_lo):
+    """Stride-2 conv (openaimodel.py:150-152; model.py:82-84 pads bottom/right only; res_blk.py:15-25 incl. the
+    1x1 shortcut) read through a tensor map with element strides 2, against torch."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(62)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin))
+    b = torch.randn(Cout, generator=g)
+    if k == 1:
+        ref = F.conv2d(x, w, b, stride=2)
+    elif pad_lo:
+        ref = F.conv2d(x, w, b, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    ref = ref.permute(0, 2, 3, 1)
+    wp = ops.pack_conv_weight(w.to(cuda))
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    of, oh, st = ops.conv_gemm(a, wp, Cout, k * k, bias=b.to(cuda), dual=True, stats=True, stride2=True, pad_lo=pad_lo)
+    assert tuple(of.shape) == (B, H // 2, W // 2, Cout)
+    assert _rel(of.cpu(), ref) < 1e-3, _rel(of.cpu(), ref)
+    if st is not None:
+        tot = st.view(B, -1, Cout, 2).sum(1).cpu()
+        assert torch.allclose(tot[..., 0], of.cpu().sum((1, 2)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cc,Cout,taps,stride2", [(2, 16, 16, 320, 64, 320, 9, False), (1, 32, 32, 64, 128, 96, 9, False),
+                                                           (2, 8, 8, 1280, 256, 1280, 1, False), (1, 64, 64, 8, 64, 320, 9, False),
+                                                           (2, 32, 32, 128, 64, 128, 9, True), (8, 8, 8, 1280, 256, 1280, 9, False)])
+def test_conv_fused_zero_conv_injection(cuda, B, H, W, Cin, Cc, Cout, taps, stride2):
+    """`h = conv(x) + resid; h = h + zero_conv(h_ctr) * scale` (rdeic.py:194,203,207) in one GEMM: the control
+    tensor is a centre-tap-only second K segment with its own (pre-scaled) weights."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(63)
+    k = 3 if taps == 9 else 1
+    scale = 0.37
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    oh_, ow_ = (H // 2, W // 2) if stride2 else (H, W)
+    hc = _bf(torch.randn(B, Cc, oh_, ow_, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin))
+    wz = _bf(torch.randn(Cout, Cc, 1, 1, generator=g) / math.sqrt(Cc))
+    b, bz = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    resid = torch.randn(B, oh_, ow_, Cout, generator=g)
+    ref = F.conv2d(x, w, b, stride=2 if stride2 else 1, padding=k // 2) + F.conv2d(hc, wz, bz)
+    ref = ref.permute(0, 2, 3, 1) + resid
+    wp, w2 = ops.pack_conv_weight(w.to(cuda)), ops.pack_conv_weight(wz.to(cuda))
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    of, oh, st = ops.conv_gemm(nhwc(x), wp, Cout, taps, a2=nhwc(hc), w2=w2, bias=(b + bz).to(cuda), resid=resid.to(cuda),
+                               dual=True, stats=True, stride2=stride2)
+    assert _rel(of.cpu(), ref) < 1e-3, _rel(of.cpu(), ref)
+    # the scale is folded into w2 / the bias by the caller: check that route too (bf16 rounding of the scaled weights)
+    w2s = ops.pack_conv_weight((wz * scale).to(cuda))
+    of2 = ops.conv_gemm(nhwc(x), wp, Cout, taps, a2=nhwc(hc), w2=w2s, bias=(b + scale * bz).to(cuda), resid=resid.to(cuda),
+                        out_f32=True, stride2=stride2)
+    ref2 = (F.conv2d(x, w, b, stride=2 if stride2 else 1, padding=k // 2) + scale * F.conv2d(hc, wz, bz)).permute(0, 2, 3, 1) + resid
+    assert _rel(of2.cpu(), ref2) < 3e-3, _rel(of2.cpu(), ref2)
