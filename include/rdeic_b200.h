@@ -300,6 +300,8 @@ typedef struct rdeic_conv_f32_params {
     float act_param;      /* LeakyReLU negative slope */
     int a_ld, a2_ld;      /* pixel stride (elements) of a / a2 when they are channel windows of a wider NHWC
                              buffer; 0 = c1 / c2 */
+    void* workspace;      /* optional split-K scratch (fp64 partials, summed in a fixed order); NULL disables it */
+    int64_t workspace_bytes;
 } rdeic_conv_f32_params;
 int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream);
 /* attention.py:171-203 in fp32: q [B,Nq,*], k/v [B,Nk,*] fp32, heads as consecutive d-wide column groups, d <= 512

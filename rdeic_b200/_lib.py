@@ -68,6 +68,7 @@ class ConvF32Params(C.Structure):
         ("out", vp), ("ldo", i32),
         ("act_param", f32),
         ("a_ld", i32), ("a2_ld", i32),
+        ("workspace", vp), ("workspace_bytes", i64),
     ]
 
 

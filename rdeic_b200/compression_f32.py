@@ -39,6 +39,32 @@ def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def _pix_stride(t: torch.Tensor) -> int:
+    """Elements between two pixels of an NHWC tensor (dense, or a channel window of a wider one).  The stride of
+    a size-1 dimension is arbitrary in PyTorch (a [B,C,1,1] -> [B,1,1,C] permute reports 1), so take it from the
+    innermost pixel dimension that actually has more than one entry."""
+    N, H, W, C = t.shape
+    if W > 1:
+        return t.stride(2)
+    if H > 1:
+        return t.stride(1)
+    if N > 1:
+        return t.stride(0)
+    return C
+
+
+_ws: Dict[str, torch.Tensor] = {}
+
+
+def _workspace(dev) -> torch.Tensor:
+    """Caller-owned split-K scratch of the fp32 conv (the library never allocates): 32 MB per device."""
+    ws = _ws.get(str(dev))
+    if ws is None:
+        ws = torch.empty(32 << 20, dtype=torch.uint8, device=dev)
+        _ws[str(dev)] = ws
+    return ws
+
+
 class CompressionNetsF32:
     def __init__(self, sd: SD, prefix: str, device):
         self.sd, self.P, self.dev = sd, prefix, torch.device(device)
@@ -83,15 +109,17 @@ class CompressionNetsF32:
         if out is None:
             out = torch.empty((B, OH, OW, n_out), dtype=F32, device=self.dev)
         q = ConvF32Params()
-        q.a, q.a_n, q.a_h, q.a_w, q.c1, q.a_ld = _p(x), B, H, W, C1, x.stride(-2)
+        q.a, q.a_n, q.a_h, q.a_w, q.c1, q.a_ld = _p(x), B, H, W, C1, _pix_stride(x)
         if x2 is not None:
-            q.a2, q.c2, q.a2_ld = _p(x2), C2, x2.stride(-2)
+            q.a2, q.c2, q.a2_ld = _p(x2), C2, _pix_stride(x2)
         q.ksize, q.stride, q.up = k, stride, 0
         q.w, q.n_out, q.bias = _p(w), n_out, _p(b)
         if resid is not None:
-            q.resid, q.ld_resid = _p(resid), resid.stride(-2)
+            q.resid, q.ld_resid = _p(resid), _pix_stride(resid)
         q.alpha, q.act, q.act_param = 1.0, act, slope
-        q.out, q.ldo = _p(out), out.stride(-2)
+        q.out, q.ldo = _p(out), _pix_stride(out)
+        ws = _workspace(self.dev)
+        q.workspace, q.workspace_bytes = _p(ws), ws.numel()
         ops.check(_lib.load().rdeic_conv_f32(C.byref(q), torch.cuda.current_stream().cuda_stream), "rdeic_conv_f32")
         return out
 

@@ -1097,7 +1097,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0;
     d.stats_out = p->stats_out;
     if (p->stats_out) {
-        RDEIC_CHECK_ARG(p->act != 2 && p->w_batch_stride == 0 && p->n_out % 32 == 0 && p->ldo % 4 == 0 &&
+        RDEIC_CHECK_ARG(p->act != 2 && (p->w_batch_stride == 0 || p->up2) && p->n_out % 32 == 0 && p->ldo % 4 == 0 &&
                             (!p->resid || p->ld_resid % 4 == 0) && (uintptr_t)p->stats_out % 16 == 0,
                         "rdeic_conv_gemm: stats_out needs a plain conv/linear with n_out %% 32 == 0 and 16-byte rows");
         RDEIC_CHECK_ARG(stats_tiling_ok(p->a_n, p->a_h, p->a_w, false),

@@ -28,7 +28,22 @@ struct ConvF32Dev {
     const float* bias; const float* row_bias; int row_bias_ld;
     const float* resid; int ld_resid; float alpha; int act; float act_param;
     float* out; int ldo;
+    double* partial;                // split-K: fp64 partial sums [split][M][n_out]; null = single pass
+    int k_per_split;                // k extent of one split (a multiple of 64), = K without split-K
 };
+
+// bias, per-sample bias, activation, residual for one output element whose reduction is complete
+__device__ __forceinline__ void conv_f32_finish(const ConvF32Dev& p, int64_t m, int n, double v) {
+    if (p.bias) v += (double)p.bias[n];
+    if (p.row_bias) v += (double)p.row_bias[(m / ((int64_t)p.oh * p.ow)) * p.row_bias_ld + n];
+    float f = (float)v;
+    if (p.act == 1) f = f / (1.0f + expf(-f));
+    else if (p.act == 3) f = f > 0.f ? f : f * p.act_param;                        // LeakyReLU
+    else if (p.act == 4) f = 0.5f * f * (1.0f + erff(f * 0.70710678118654752f));  // exact GELU (F.gelu default)
+    if (p.resid) f = fmaf(p.alpha, f, p.resid[m * p.ld_resid + n]);
+    else f *= p.alpha;
+    p.out[m * p.ldo + n] = f;
+}
 
 __global__ void __launch_bounds__(256)
 conv_f32_kernel(const ConvF32Dev p) {
@@ -86,13 +101,15 @@ conv_f32_kernel(const ConvF32Dev p) {
     };
     int since_flush = 0;
     float4 av, bv;
-    fetch(0, av, bv);
-    for (int k0 = 0; k0 < K; k0 += kFK) {
+    const int k_begin = blockIdx.z * p.k_per_split;
+    const int k_end = min(K, k_begin + p.k_per_split);
+    fetch(k_begin, av, bv);
+    for (int k0 = k_begin; k0 < k_end; k0 += kFK) {
         __syncthreads();
         As[lk][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
         Bs[lk][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
         __syncthreads();
-        if (k0 + kFK < K) fetch(k0 + kFK, av, bv);
+        if (k0 + kFK < k_end) fetch(k0 + kFK, av, bv);
 #pragma unroll
         for (int kk = 0; kk < kFK; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -111,27 +128,32 @@ conv_f32_kernel(const ConvF32Dev p) {
                 for (int j = 0; j < 4; ++j) { dacc[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
         }
     }
-    // ---- epilogue: bias, per-sample bias, activation, residual ----
+    // ---- epilogue: bias, per-sample bias, activation, residual (or the fp64 partial of this k split) ----
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t m = m0 + ty * 4 + i;
         if (m >= M) continue;
-        const int64_t b = m / ((int64_t)p.oh * p.ow);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n >= p.n_out) continue;
-            double v = dacc[i][j] + (double)acc[i][j];
-            if (p.bias) v += (double)p.bias[n];
-            if (p.row_bias) v += (double)p.row_bias[b * p.row_bias_ld + n];
-            float f = (float)v;
-            if (p.act == 1) f = f / (1.0f + expf(-f));
-            else if (p.act == 3) f = f > 0.f ? f : f * p.act_param;                        // LeakyReLU
-            else if (p.act == 4) f = 0.5f * f * (1.0f + erff(f * 0.70710678118654752f));  // exact GELU (F.gelu default)
-            if (p.resid) f = fmaf(p.alpha, f, p.resid[m * p.ld_resid + n]);
-            else f *= p.alpha;
-            p.out[m * p.ldo + n] = f;
+            const double v = dacc[i][j] + (double)acc[i][j];
+            if (p.partial) p.partial[((int64_t)blockIdx.z * M + m) * p.n_out + n] = v;
+            else conv_f32_finish(p, m, n, v);
         }
+    }
+}
+
+// split-K second pass: the k slices are summed in a fixed order (deterministic: the CDF indexes built while
+// compressing and while decompressing must be identical), then the same epilogue
+__global__ void __launch_bounds__(256)
+conv_f32_reduce_kernel(const ConvF32Dev p, int splits) {
+    const int64_t M = (int64_t)p.n * p.oh * p.ow;
+    const int64_t total = M * p.n_out;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int z = 0; z < splits; ++z) v += p.partial[(int64_t)z * total + i];
+        conv_f32_finish(p, i / p.n_out, (int)(i % p.n_out), v);
     }
 }
 
@@ -236,7 +258,8 @@ int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream) {
     const int a_ld = p->a_ld ? p->a_ld : p->c1, a2_ld = p->a2_ld ? p->a2_ld : p->c2;
     RDEIC_CHECK_ARG(a_ld >= p->c1 && a2_ld >= p->c2 && a_ld % 4 == 0 && a2_ld % 4 == 0,
                     "rdeic_conv_f32: a_ld/a2_ld (%d, %d) must be multiples of 4 and >= the channel counts", a_ld, a2_ld);
-    RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w) % 16 == 0, "rdeic_conv_f32: operands must be 16-byte aligned");
+    RDEIC_CHECK_ARG(((uintptr_t)p->a | (uintptr_t)p->a2 | (uintptr_t)p->w | (uintptr_t)p->workspace) % 16 == 0,
+                    "rdeic_conv_f32: operands must be 16-byte aligned");
     ConvF32Dev d;
     d.a = p->a; d.a2 = p->a2; d.n = p->a_n; d.h = p->a_h; d.w = p->a_w; d.c1 = p->c1; d.c2 = p->c2;
     d.a_ld = a_ld; d.a2_ld = a2_ld;
@@ -248,9 +271,32 @@ int rdeic_conv_f32(const rdeic_conv_f32_params* p, rdeic_stream_t stream) {
     d.resid = p->resid; d.ld_resid = p->ld_resid; d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param; d.out = p->out; d.ldo = p->ldo;
     RDEIC_CHECK_ARG(p->ldo >= p->n_out && (!p->resid || p->ld_resid >= p->n_out), "rdeic_conv_f32: bad ldo / ld_resid");
     const int64_t M = (int64_t)d.n * d.oh * d.ow;
+    const int K = p->ksize * p->ksize * (p->c1 + p->c2);
     dim3 grid((unsigned)ceil_div64(M, kFM), (unsigned)((p->n_out + kFN - 1) / kFN));
+    // few output tiles and a long reduction (the compressor's 5x5 context nets: M = a few thousand pixels, K up to
+    // 6000): slice K across blockIdx.z so the chip is not left to a handful of CTAs walking hundreds of k chunks
+    int splits = 1;
+    d.partial = nullptr;
+    d.k_per_split = (K + 63) / 64 * 64;
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    if (p->workspace && tiles * 2 <= kNumSMs && K >= 1024) {
+        int want = (int)(2 * kNumSMs / tiles);
+        if (want > K / 256) want = K / 256;
+        if (want > 16) want = 16;
+        while (want > 1 && (int64_t)want * M * p->n_out * (int64_t)sizeof(double) > p->workspace_bytes) --want;
+        if (want >= 2) {
+            d.k_per_split = ((K + want - 1) / want + 63) / 64 * 64;
+            splits = (K + d.k_per_split - 1) / d.k_per_split;
+            d.partial = reinterpret_cast<double*>(p->workspace);
+        }
+    }
+    grid.z = (unsigned)splits;
     conv_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(d);
     RDEIC_LAUNCH_CHECK();
+    if (splits > 1) {
+        conv_f32_reduce_kernel<<<grid_for(M * p->n_out, 256), 256, 0, as_stream(stream)>>>(d, splits);
+        RDEIC_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -16,6 +16,6 @@ RDEIC_NO_FUSED_INJECT=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cp
 cat gpurun_out/s1_bench_noinj.json
 timeout 600 python scripts/tile_sweep.py unet 8 > gpurun_out/s1_tile_sweep_unet.txt 2>&1
 head -30 gpurun_out/s1_tile_sweep_unet.txt
-timeout 300 python bench.py --compressor 1 > gpurun_out/s1_compressor_b1.json 2> gpurun_out/s1_compressor.err
+timeout 300 python bench.py --compressor 1 > gpurun_out/s1_compressor_b1.json 2> gpurun_out/s1_compressor.err; timeout 300 python bench.py --compressor 1 --compressor-precision bf16 >> gpurun_out/s1_compressor_b1.json 2>> gpurun_out/s1_compressor.err; timeout 300 python bench.py --compressor 8 >> gpurun_out/s1_compressor_b1.json 2>> gpurun_out/s1_compressor.err
 cat gpurun_out/s1_compressor_b1.json
 exit $rc

@@ -10,7 +10,9 @@ Files written
   state_dict_keys.json     decode-path keys + shapes of the reference model (full rdeic.yaml)
   full_unet_step.npz       reference apply_model / apply_model_unconditional, full width, 256x256
   full_vae_decode.npz      reference decode_first_stage, full width, 16x16 latent
-  full_sampler.npz         reference SpacedSampler.sample (2 steps) and DDIMSampler.sample (2 steps)
+  full_sampler.npz         reference SpacedSampler.sample (2, 3, 5 steps, CFG) and DDIMSampler.sample (2, 5 steps)
+  full_unet_step_64x64.npz, full_unet_step_64x96.npz   one full-width relay step at the latent shapes of BASELINE
+                           configs 2/5 and 3
   small_*.npz              the same on the reduced-width config (fast CPU tests of the oracle)
   full_c1_decode.npz       BASELINE config[0] end to end: the reference's q_sample -> SpacedSampler.sample (2 relay
                            steps) -> decode_first_stage on one 256x256 image, full width (latent fp32, image fp16)
@@ -109,7 +111,7 @@ def run_config(tag, overrides, unet_hw, vae_hw, samp_hw):
         orig_randn_like = torch.randn_like
         torch.randn_like = lambda t_, **k: pool.pop(0)
         try:
-            for steps in (2, 3):
+            for steps in (2, 3, 5):
                 pool[:] = [n.clone() for n in noises[1:1 + steps]]
                 s = mods["spaced"].SpacedSampler(model, var_type="fixed_small")
                 out[f"spaced_{steps}"] = s.sample(steps, (B, 4, h, w), cond, x_T=x_T.clone()).numpy()
@@ -126,8 +128,32 @@ def run_config(tag, overrides, unet_hw, vae_hw, samp_hw):
         samples, _ = d.sample(S=2, batch_size=B, shape=(4, h, w), conditioning=cond, x_T=x_T.clone(), eta=0.0,
                               verbose=False)
         out["ddim_2"] = samples.numpy()
+        pool[:] = [n.clone() for n in noises[1:6]]
+        samples, _ = d.sample(S=5, batch_size=B, shape=(4, h, w), conditioning=cond, x_T=x_T.clone(), eta=0.0,
+                              verbose=False)
+        out["ddim_5"] = samples.numpy()
         np.savez_compressed(HERE / f"{tag}_sampler.npz", **out)
         print(tag, "samplers", {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
+def run_big_steps():
+    """One full-width relay step at the latent shapes of BASELINE configs 2/5 (64x64) and 3 (64x96) from the
+    reference itself (full-width goldens existed only at 32x32 / 16x16)."""
+    model, mods = rh.build_reference_model(None)
+    params = rh.load_config(None)["params"]
+    load_synthetic_into_reference(model, params)
+    hint_c = params["control_stage_config"]["params"]["hint_channels"]
+    ctx_dim = params["unet_config"]["params"]["context_dim"]
+    with torch.no_grad():
+        for h, w in ((64, 64), (64, 96)):
+            c_latent, hint, ctx, noises = inputs(1, h, w, hint_c, ctx_dim, 1)
+            x = model.q_sample(c_latent, torch.full((1,), 299, dtype=torch.long), noises[0])
+            cond = {"c_latent": [c_latent], "c_crossattn": [ctx], "guide_hint": hint}
+            t = torch.full((1,), 224, dtype=torch.long)
+            eps = model.apply_model(x, t, cond)
+            np.savez_compressed(HERE / f"full_unet_step_{h}x{w}.npz", x=x.numpy(), t=t.numpy(), eps=eps.numpy(),
+                                hw=np.array([h, w]))
+            print("full unet step", h, w, float(eps.abs().max()))
 
 
 def run_c1():
@@ -321,7 +347,9 @@ def run_bitstream():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["entropy", "bitstream", "vae_encode", "compression", "small", "full", "c1"]
+    which = sys.argv[1:] or ["entropy", "bitstream", "vae_encode", "compression", "small", "full", "c1", "big"]
+    if "big" in which:
+        run_big_steps()
     if "entropy" in which:
         run_entropy()
     if "bitstream" in which:
