@@ -154,6 +154,13 @@ int rdeic_transpose_bf16(const void* in, void* out, int batch, int R, int C,
 int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
                       rdeic_stream_t stream);
 
+/* ABI 5.  Blend T overlapping decoded uint8 HWC tiles [T, th, tw, 3] (tile t's top-left pixel at origin_yx[2t],
+ * origin_yx[2t+1]) into one uint8 image [H, W, 3]: weighted mean with a separable linear ramp over `overlap` pixels
+ * at every tile edge.  Tiling large frames is this framework's own behaviour (BASELINE config 4; the reference has
+ * only the dead fold/unfold helpers of ldm/models/diffusion/ddpm.py:724); 2 * overlap <= th, tw. */
+int rdeic_blend_tiles_u8(const uint8_t* tiles, const int32_t* origin_yx, int T, int th, int tw, int overlap,
+                         uint8_t* out, int H, int W, rdeic_stream_t stream);
+
 /* ---- normalisation (HBM-bound) --------------------------------------------------------- */
 
 /* GroupNorm(+SiLU) over NHWC bf16 (or, with in_is_f32, the fp32 master copy of a residual

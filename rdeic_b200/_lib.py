@@ -104,6 +104,7 @@ SIGNATURES = {
     "rdeic_softmax_rows": [vp, i32, vp, i64, i32, f32, vp],
     "rdeic_transpose_bf16": [vp, vp, i32, i32, i32, vp],
     "rdeic_image_to_u8": [vp, vp, i64, i32, vp],
+    "rdeic_blend_tiles_u8": [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "rdeic_groupnorm_workspace_bytes": [i32, i64, i32],
     "rdeic_groupnorm_nhwc": [vp, i32, vp, i32, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "rdeic_groupnorm_from_stats": [vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],

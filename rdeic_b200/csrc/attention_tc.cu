@@ -276,6 +276,12 @@ constexpr int kA2Q = 256;
 constexpr int kA2Threads = 64 + 32 * 8;
 constexpr int kA2Smem = 2 * kATile /*Q*/ + 2 * kAStages * kATile /*K,V*/ + 2 * kAPBytes /*P_A,P_B*/ + 1024 + 256;
 constexpr uint32_t kA2ColS = 0, kA2ColO = 256;    // S_A 0, S_B 128 ; O_A 256, O_B 320
+// kLazy keeps the probabilities in tensor memory (P_A 384, P_B 448: 128 keys = 64 packed columns each) and feeds
+// them to the PV MMAs as a TMEM A operand: no P round trip through shared memory, and the shared memory that
+// held P buys two more K/V stages
+constexpr uint32_t kA2ColP = 384;
+constexpr int kA2LazyStages = 5;
+constexpr int kA2LazySmem = 2 * kATile /*Q*/ + 2 * kA2LazyStages * kATile /*K,V*/ + 1024 + 256;
 
 // kLazy: O stays in TMEM for the whole key loop (the PV MMAs accumulate in place) and is rescaled only
 // when a row's running maximum has grown by more than 2^8 since the reference maximum its exponents use
@@ -287,13 +293,14 @@ __global__ void __launch_bounds__(kA2Threads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
     pdl_trigger();
+    constexpr int kAStages = kLazy ? kA2LazyStages : rdeic::kAStages;      // shadows the 3-stage ring of the other kernels
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     uint8_t* s_q = smem;                                   // 2 tiles: rows 0-127 | 128-255
     uint8_t* s_k = s_q + 2 * kATile;
     uint8_t* s_v = s_k + kAStages * kATile;
-    uint8_t* s_p = s_v + kAStages * kATile;                // P_A | P_B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kAPBytes);
+    uint8_t* s_p = s_v + kAStages * kATile;                // P_A | P_B (not kLazy: there P lives in tensor memory)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + (kLazy ? 0 : 2 * kAPBytes));
     uint64_t* q_full = bars;                  // [1]
     uint64_t* kv_full = bars + 1;             // [kAStages]
     uint64_t* kv_empty = kv_full + kAStages;  // [kAStages]
@@ -363,9 +370,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const uint64_t dv = make_smem_desc_mn(smem_u32(s_v + (i % kAStages) * kATile));
 #pragma unroll
                 for (int ks = 0; ks < kAK / 16; ++ks) {
-                    const uint64_t dp = make_smem_desc(pb + (ks >> 2) * (kAQ * 128) + (ks & 3) * 32);
-                    umma_bf16(tmem_base + kA2ColO + g * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o,
-                              kLazy ? (i | ks) != 0 : ks != 0);
+                    if constexpr (kLazy) {
+                        umma_bf16_ts(tmem_base + kA2ColO + g * kAD, tmem_base + kA2ColP + g * (kAK / 2) + ks * 8,
+                                     dv + (uint64_t)ks * (2048 >> 4), idesc_o, (i | ks) != 0);
+                    } else {
+                        const uint64_t dp = make_smem_desc(pb + (ks >> 2) * (kAQ * 128) + (ks & 3) * 32);
+                        umma_bf16(tmem_base + kA2ColO + g * kAD, dp, dv + (uint64_t)ks * (2048 >> 4), idesc_o, ks != 0);
+                    }
                 }
                 umma_commit(&o_full[g]);
             };
@@ -392,7 +403,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             float m_ref = -INFINITY, l_run = 0.f;
             const uint32_t ts = tmem_base + lane_addr + kA2ColS + g * kAK;
             const uint32_t to = tmem_base + lane_addr + kA2ColO + g * kAD;
-            uint8_t* prow0 = s_p + g * kAPBytes + row * 128;
+            const uint32_t tp = tmem_base + lane_addr + kA2ColP + g * (kAK / 2);
             for (int j = 0; j < T; ++j) {
                 mbar_wait(&s_full[g], j & 1);
                 tc_fence_after();
@@ -433,21 +444,20 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
                 float rowsum = 0.f, rowsum2 = 0.f;
 #pragma unroll
-                for (int c8 = 0; c8 < 16; ++c8) {                    // 8 keys -> one 16-byte chunk of P (S dies as we go)
-                    uint32_t pk[4];
+                for (int c32 = 0; c32 < 4; ++c32) {                  // 32 keys -> 16 packed columns of P (S dies as we go)
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * c]), sc, -m_ref));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + 2 * c + 1]), sc, -m_ref));
+                    for (int c = 0; c < 16; ++c) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c]), sc, -m_ref));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 1]), sc, -m_ref));
                         rowsum += p0; rowsum2 += p1;
                         pk[c] = pack_bf16x2(p0, p1);
                     }
-                    uint8_t* prow = prow0 + (c8 >> 3) * (kAQ * 128);      // 64-key panel
-                    *reinterpret_cast<uint4*>(prow + (((c8 & 7) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    tmem_st16(tp + c32 * 16, pk);
                 }
                 l_run += rowsum + rowsum2;
-                tc_fence_before();                  // the rescale's TMEM stores precede the PV the arrive releases
-                fence_proxy_async();
+                tmem_st_wait();                     // P (and the rescaled O) are in tensor memory ...
+                tc_fence_before();                  // ... before the PV the arrive releases
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g]);
             }
@@ -611,12 +621,12 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
         static bool attr2_set = false;
         if (!attr2_set) {
             RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
-            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
+            RDEIC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2LazySmem));
             attr2_set = true;
         }
         dim3 grid2(Nq / kA2Q, heads, B);
         static const bool lazy = !(getenv("RDEIC_ATTN_LAZY") && atoi(getenv("RDEIC_ATTN_LAZY")) == 0);
-        if (lazy) launch_k(attention_tc2_kernel<true>, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
+        if (lazy) launch_k(attention_tc2_kernel<true>, grid2, kA2Threads, kA2LazySmem, stream, tq, tk, tv, d);
         else launch_k(attention_tc2_kernel<false>, grid2, kA2Threads, kA2Smem, stream, tq, tk, tv, d);
         RDEIC_LAUNCH_CHECK();
         return 0;

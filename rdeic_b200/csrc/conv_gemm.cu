@@ -315,7 +315,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            uint32_t it = 0;
+            // One thread feeds the whole pipeline, and with N <= 160 tiles a k-block is only ~450 tensor clocks:
+            // the per-k-block instruction count of this loop is on the critical path.  So no division or modulo
+            // per k-block: (segment, tap, channel block) and (stage, phase) advance as counters.
+            uint32_t s = 0, ph = 0;
+            const int kw = p.up2 ? 2 : (p.taps == 9 ? 3 : (p.taps == 25 ? 5 : 1));     // filter width
+            const int cs = p.in_stride;               // input coordinates = cs * output coordinates + tap offset
+            const int kb_seg1 = p.taps * p.cblk1;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const int z = item / mn_tiles;
                 int rem = item - z * mn_tiles;
@@ -336,43 +342,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int wz = p.up2 ? par : (p.w_batched ? n0[0] : 0);
                 const int kb_begin = p.up2 ? 0 : z * p.kb_per_split;
                 const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
-                const int kb_seg1 = p.taps * p.cblk1;
-                const int cs = p.in_stride;               // input coordinates = cs * output coordinates + tap offset
-                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (it / kStages) & 1;
+                // offset of tap (0, 0): -1 for a padded 3x3, -2 for 5x5, (py - 1, px - 1) for the folded upsample
+                const int oy = p.up2 ? (par >> 1) - 1 : (kw == 3 ? p.tap_lo : (kw == 5 ? -2 : 0));
+                const int ox = p.up2 ? (par & 1) - 1 : oy;
+                // position of the first k-block of this item (a division only for split-K slices past the first)
+                int tap = 0, cb = 0, seg = 0;
+                if (kb_begin != 0) {
+                    if (p.a2_center) {
+                        seg = kb_begin >= kb_seg1;
+                        if (seg) { tap = p.taps; cb = kb_begin - kb_seg1; }
+                        else { tap = kb_begin / p.cblk1; cb = kb_begin - tap * p.cblk1; }
+                    } else {
+                        tap = kb_begin / cbt; cb = kb_begin - tap * cbt;
+                        seg = cb >= p.cblk1;
+                        if (seg) cb -= p.cblk1;
+                    }
+                }
+                int ty = tap / kw, tx = tap - ty * kw;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-                    int tap, cb;
-                    bool seg2;
-                    if (p.a2_center) {
-                        seg2 = kb >= kb_seg1;
-                        if (seg2) { tap = -1; cb = kb - kb_seg1; }
-                        else { tap = kb / p.cblk1; cb = kb - tap * p.cblk1; }
-                    } else {
-                        tap = kb / cbt; cb = kb - tap * cbt;
-                        seg2 = cb >= p.cblk1;
-                        if (seg2) cb -= p.cblk1;
-                    }
-                    int dy = 0, dx = 0;
-                    if (tap >= 0) {
-                        if (p.up2) { dy = (tap >> 1) - 1 + (par >> 1); dx = (tap & 1) - 1 + (par & 1); }
-                        else if (p.taps == 9) { dy = tap / 3 + p.tap_lo; dx = tap % 3 + p.tap_lo; }
-                        else if (p.taps == 25) { dy = tap / 5 - 2; dx = tap % 5 - 2; }
-                    }
+                    // the injected tensor (centre-tap segment) lives on the output grid, whatever the conv's stride
+                    const bool ctr = seg && p.a2_center;
+                    const int dy = ctr ? 0 : oy + ty, dx = ctr ? 0 : ox + tx;
+                    const int mul = ctr ? 1 : cs;
+                    const CUtensorMap* ma = seg ? &tm_a2 : &tm_a;
 #pragma unroll
-                    for (int u = 0; u < kMT; ++u) {
-                        uint8_t* dst = smem_a + (s * kMT + u) * kATileBytes;
-                        if (seg2 && p.a2_center)        // the injected tensor lives on the output grid, whatever the conv's stride
-                            tma_load_4d(&tm_a2, dst, &full_bar[s], cb * kBlockK, w0[u], h0[u], n0[u]);
-                        else
-                            tma_load_4d(seg2 ? &tm_a2 : &tm_a, dst, &full_bar[s], cb * kBlockK, w0[u] * cs + dx, h0[u] * cs + dy, n0[u]);
+                    for (int u = 0; u < kMT; ++u)
+                        tma_load_4d(ma, smem_a + (s * kMT + u) * kATileBytes, &full_bar[s], cb * kBlockK, w0[u] * mul + dx,
+                                    h0[u] * mul + dy, n0[u]);
+                    if (ctr) tma_load_3d(&tm_b2, smem_b + s * Cfg::kBBytes, &full_bar[s], cb * kBlockK, col0, 0);
+                    else tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+                    // advance (segment, tap, channel block)
+                    if (++cb == (seg ? p.cblk2 : p.cblk1)) {
+                        cb = 0;
+                        bool next_tap = true;
+                        if (p.a2_center) { if (++tap == p.taps) { seg = 1; next_tap = false; } }
+                        else if (!seg && p.cblk2) { seg = 1; next_tap = false; }
+                        else seg = 0;
+                        if (next_tap && ++tx == kw) { tx = 0; ++ty; }
                     }
-                    if (seg2 && p.a2_center) {        // centre-tap segment: its own weight matrix [n_out][cpad2]
-                        tma_load_3d(&tm_b2, smem_b + s * Cfg::kBBytes, &full_bar[s], cb * kBlockK, col0, 0);
-                        continue;
-                    }
-                    tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -380,7 +390,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (lane == 0) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc(BN);
-            uint32_t it = 0, t = 0;
+            uint32_t s = 0, ph = 0, t = 0;
+            const uint64_t da0 = make_smem_desc(smem_u32(smem_a)), db0 = make_smem_desc(smem_u32(smem_b));
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
                 const int z = item / mn_tiles;
                 const int kb_begin = p.up2 ? 0 : z * p.kb_per_split;
@@ -389,22 +400,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * Cfg::kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (it / kStages) & 1;
+                for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint64_t db = make_smem_desc(smem_u32(smem_b + s * Cfg::kBBytes));
+                    // descriptors advance by whole stages: (bytes >> 4) added to the 14-bit start-address field
+                    const uint64_t db = db0 + (uint64_t)(s * (Cfg::kBBytes >> 4));
+                    const uint64_t dst = da0 + (uint64_t)(s * (Cfg::kABytes >> 4));
                     if constexpr (kSwap) {
                         // weights (BN = 128 rows) as the M operand, both pixel tiles (256 rows, contiguous) as N
-                        const uint64_t dpix = make_smem_desc(smem_u32(smem_a + s * Cfg::kABytes));
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                            umma_bf16(tmem_d, db + 2 * k, dpix + 2 * k, make_idesc(kMT * kBlockM), (kb | k) != 0);
+                            umma_bf16(tmem_d, db + 2 * k, dst + 2 * k, make_idesc(kMT * kBlockM), (kb | k) != 0);
                     } else
 #pragma unroll
                     for (int u = 0; u < kMT; ++u) {
-                        const uint64_t da = make_smem_desc(smem_u32(smem_a + (s * kMT + u) * kATileBytes));
+                        const uint64_t da = dst + (uint64_t)(u * (kATileBytes >> 4));
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
@@ -412,6 +422,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         }
                     }
                     umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);      // accumulator complete
             }

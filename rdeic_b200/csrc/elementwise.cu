@@ -394,6 +394,40 @@ image_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int6
     }
 }
 
+// Blend overlapping decoded tiles of one large image (BASELINE config 4; rdeic_b200/parallel.py).  One thread per
+// output pixel: every tile that covers it contributes with a separable linear ramp over the overlap band
+// (weight (i+1)/(ov+1) for the first ov pixels of a tile axis, mirrored at the far end, 1 in between), the
+// weighted mean is rounded to uint8.  Tiles are uint8 HWC as the fused VAE tail wrote them.
+__device__ __forceinline__ float ramp_w(int i, int n, int ov) {
+    if (i < ov) return (float)(i + 1) / (float)(ov + 1);
+    if (i >= n - ov) return (float)(n - i) / (float)(ov + 1);
+    return 1.0f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+blend_tiles_u8_kernel(const uint8_t* __restrict__ tiles, const int* __restrict__ origin, int T, int th, int tw, int ov,
+                      uint8_t* __restrict__ out, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t total = (int64_t)H * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, ws = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const int ly = y - origin[2 * t], lx = x - origin[2 * t + 1];
+            if (ly < 0 || ly >= th || lx < 0 || lx >= tw) continue;
+            const float w = ramp_w(ly, th, ov) * ramp_w(lx, tw, ov);
+            const uint8_t* px = tiles + (((int64_t)t * th + ly) * tw + lx) * 3;
+            acc0 = fmaf(w, (float)px[0], acc0); acc1 = fmaf(w, (float)px[1], acc1); acc2 = fmaf(w, (float)px[2], acc2);
+            ws += w;
+        }
+        const float inv = ws > 0.f ? 1.0f / ws : 0.f;
+        uint8_t* o = out + i * 3;
+        o[0] = (uint8_t)fminf(255.f, rintf(acc0 * inv)); o[1] = (uint8_t)fminf(255.f, rintf(acc1 * inv));
+        o[2] = (uint8_t)fminf(255.f, rintf(acc2 * inv));
+    }
+}
+
 }  // namespace rdeic
 
 using namespace rdeic;
@@ -567,6 +601,17 @@ int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
     RDEIC_CHECK_ARG(in && out && pixels >= 0 && ldc >= 3, "rdeic_image_to_u8: bad args");
     if (pixels == 0) return 0;
     launch_k(image_to_u8_kernel, grid_for(pixels * 3, kThreads), kThreads, 0, as_stream(stream), in, out, pixels, ldc);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_blend_tiles_u8(const uint8_t* tiles, const int32_t* origin_yx, int T, int th, int tw, int overlap,
+                         uint8_t* out, int H, int W, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(tiles && origin_yx && out, "rdeic_blend_tiles_u8: null pointer");
+    RDEIC_CHECK_ARG(T > 0 && th > 0 && tw > 0 && H > 0 && W > 0 && overlap >= 0 && 2 * overlap <= th && 2 * overlap <= tw,
+                    "rdeic_blend_tiles_u8: bad dims (the overlap band must not exceed half a tile)");
+    launch_k(blend_tiles_u8_kernel, grid_for((int64_t)H * W, kThreads), kThreads, 0, as_stream(stream), tiles,
+             (const int*)origin_yx, T, th, tw, overlap, out, H, W);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

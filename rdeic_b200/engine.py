@@ -29,6 +29,7 @@ from . import ops
 
 BF16 = torch.bfloat16
 SD = Dict[str, torch.Tensor]
+RES_F32 = os.environ.get("RDEIC_RES_F32", "0") != "0"            # ResBlock conv1 -> GroupNorm hand-off in fp32
 S2_IM2COL = os.environ.get("RDEIC_S2_IM2COL") is not None      # bring-up switch of the strided-tensor-map stride-2 conv
 
 
@@ -419,7 +420,9 @@ class NoiseEstimatorEngine:
         h = ops.groupnorm(x.f, w.n_in.g, w.n_in.b, w.groups_in, 1e-5, True, x2=None if x2 is None else x2.f,
                           stats1=x.st, stats2=None if x2 is None else x2.st)
         rb = c.emb_rows[:, w.emb_off:w.emb_off + w.cout]
-        h, st = ops.conv_gemm(h, w.conv1.w, w.cout, 9, bias=w.conv1.b, row_bias=rb, stats=True)
+        # conv1's output is consumed by GroupNorm only: written in fp32 it is rounded to bf16 once (after the
+        # normalisation) instead of twice
+        h, st = ops.conv_gemm(h, w.conv1.w, w.cout, 9, bias=w.conv1.b, row_bias=rb, stats=True, out_f32=RES_F32)
         h = ops.groupnorm(h, w.n_out_norm.g, w.n_out_norm.b, w.groups_out, 1e-5, True, stats1=st)
         xs = x.f
         if w.skip is not None:

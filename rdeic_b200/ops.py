@@ -344,6 +344,19 @@ def image_to_u8(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def blend_tiles_u8(tiles: torch.Tensor, origins: torch.Tensor, overlap: int, H: int, W: int) -> torch.Tensor:
+    """tiles uint8 [T,th,tw,3], origins int32 [T,2] (y0, x0 in pixels) -> uint8 [H,W,3]."""
+    tiles = _need(tiles, torch.uint8, "blend_tiles_u8")
+    origins = _need(origins, torch.int32, "blend_tiles_u8")
+    T, th, tw, c = tiles.shape
+    if c != 3 or tuple(origins.shape) != (T, 2):
+        raise ValueError("blend_tiles_u8: expected tiles [T,th,tw,3] and origins [T,2]")
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=tiles.device)
+    check(_lib.load().rdeic_blend_tiles_u8(_ptr(tiles), _ptr(origins), T, th, tw, overlap, _ptr(out), H, W, _stream()),
+          "rdeic_blend_tiles_u8")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # normalisation
 # ---------------------------------------------------------------------------------------------

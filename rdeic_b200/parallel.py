@@ -76,18 +76,24 @@ def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], spec: Sequence[T
 
 
 def gather_images(local: torch.Tensor, counts: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
-    """Gather per-rank uint8 image batches [b_r,H,W,3] to rank `dst` in rank order.  Chunks may
-    differ by one image (shard_range), so every rank pads to the largest chunk first."""
+    """Gather per-rank uint8 image batches [b_r,H,W,3] to rank `dst` in rank order: a real gather (only `dst`
+    receives; every other rank just sends its chunk).  Chunks may differ by one image (shard_range), so every
+    rank pads to the largest chunk first."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()
     m = max(counts)
-    pad = torch.zeros((m, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[:local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
+    if local.shape[0] == m:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((m, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
     if rank != dst:
         return None
+    if all(c == m for c in counts):
+        return torch.cat(bufs, 0)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
 
 
@@ -103,6 +109,42 @@ def plan_tiles(h: int, w: int, tile: int = 96, overlap: int = 16) -> List[Tuple[
         return sorted(set(s))
     th, tw = min(tile, h), min(tile, w)
     return [(y, x, th, tw) for y in starts(h) for x in starts(w)]
+
+
+def plan_tiles_balanced(h: int, w: int, world_size: int, overlap: int = 16, max_tile_area: int = 96 * 96,
+                        align: int = 8) -> List[Tuple[int, int, int, int]]:
+    """Cover an h x w latent with ny x nx equal tiles whose COUNT is a multiple of `world_size`, so every rank
+    decodes the same number of tiles (20 tiles on 8 GPUs keep four ranks idle for a third of the time).  Among
+    the grids with ny * nx % world_size == 0 and tile area <= `max_tile_area` (self-attention is quadratic in the
+    tile's token count) pick the one with the least work per rank; tile sides are multiples of `align` (three
+    stride-2 levels), neighbours overlap by >= `overlap`.  Returns (y0, x0, th, tw) like plan_tiles."""
+    def side(n: int, k: int) -> int:              # smallest aligned tile side so that k tiles cover n with the overlap
+        t = -(-(n + (k - 1) * overlap) // k)
+        t = -(-t // align) * align
+        return min(t, n)
+
+    def starts(n: int, k: int, t: int) -> List[int]:
+        if k == 1 or t >= n:
+            return [0]
+        return [round(i * (n - t) / (k - 1)) for i in range(k)]
+
+    best = None
+    for ny in range(1, h // align + 1):
+        for nx in range(1, w // align + 1):
+            if (ny * nx) % world_size:
+                continue
+            th, tw = side(h, ny), side(w, nx)
+            if th * tw > max_tile_area or (ny > 1 and 2 * overlap > th) or (nx > 1 and 2 * overlap > tw):
+                continue
+            if ny > 1 and (h - th) / (ny - 1) > th - overlap or nx > 1 and (w - tw) / (nx - 1) > tw - overlap:
+                continue
+            cost = (ny * nx // world_size) * th * tw
+            if best is None or cost < best[0]:
+                best = (cost, ny, nx, th, tw)
+    if best is None:
+        raise ValueError(f"plan_tiles_balanced: no {world_size}-way balanced tiling of {h}x{w} with tiles <= {max_tile_area}")
+    _, ny, nx, th, tw = best
+    return [(y, x, th, tw) for y in starts(h, ny, th) for x in starts(w, nx, tw)]
 
 
 def tile_weights(th: int, tw: int, overlap: int, scale: int, device) -> torch.Tensor:
@@ -183,3 +225,49 @@ def decode_tiled(decode_fn, cond: Dict, tile: int = 96, overlap: int = 16, scale
         for j, i in enumerate(range(r, len(plan), world_size)):
             tiles[i] = gathered[r][j]
     return blend_tiles(tiles, plan, h, w, overlap, scale)
+
+
+def decode_tiled_u8(decode_fn, cond: Dict, plan: Sequence[Tuple[int, int, int, int]], overlap: int = 16, scale: int = 8,
+                    rank: Optional[int] = None, world_size: Optional[int] = None, dst: int = 0, blend=None):
+    """The serving form of `decode_tiled`: tiles leave the VAE as uint8 HWC (the fused tail kernel), a rank's tiles
+    are one batch, the gather moves uint8 (a quarter of the fp32 bytes) to `dst` only, and the blend is ONE kernel
+    (`ops.blend_tiles_u8`: weighted mean of the covering tiles with the linear ramp of `tile_weights`, rounded to
+    uint8).  `plan` comes from plan_tiles / plan_tiles_balanced (equal tile shapes); tiles are dealt round-robin.
+    `decode_fn(cond_tiles, indices) -> uint8 [n, th*scale, tw*scale, 3]`.  Returns uint8 [H*scale, W*scale, 3] on
+    `dst`, None elsewhere."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    lat = cond["c_latent"][0]
+    assert lat.shape[0] == 1, "decode_tiled_u8 handles one image at a time"
+    h, w = lat.shape[-2:]
+    th, tw = plan[0][2], plan[0][3]
+    assert all(p[2] == th and p[3] == tw for p in plan), "decode_tiled_u8 needs equal tile shapes"
+    mine = list(range(rank, len(plan), world_size))
+    per = -(-len(plan) // world_size)
+    dev = lat.device
+    buf = torch.zeros((per, th * scale, tw * scale, 3), dtype=torch.uint8, device=dev)
+    if mine:
+        crops = [crop_cond(cond, *plan[i]) for i in mine]
+        ctx = cond["c_crossattn"][0]
+        stacked = {"c_latent": [torch.cat([c["c_latent"][0] for c in crops], 0)],
+                   "c_crossattn": [ctx.expand(len(mine), -1, -1).contiguous()],
+                   "guide_hint": torch.cat([c["guide_hint"] for c in crops], 0)}
+        out = decode_fn(stacked, mine)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == (len(mine), th * scale, tw * scale, 3)
+        buf[:len(mine)] = out
+    if world_size > 1:
+        bufs = [torch.empty_like(buf) for _ in range(world_size)] if rank == dst else None
+        dist.gather(buf, bufs, dst=dst)
+        if rank != dst:
+            return None
+        order = [i for r in range(world_size) for i in range(r, len(plan), world_size)]
+        tiles = torch.cat([b[:len(range(r, len(plan), world_size))] for r, b in enumerate(bufs)], 0)
+    else:
+        order, tiles = mine, buf
+    origins = torch.tensor([[plan[i][0] * scale, plan[i][1] * scale] for i in order], dtype=torch.int32, device=dev)
+    if blend is None:
+        from . import ops
+        blend = ops.blend_tiles_u8
+    return blend(tiles, origins, overlap * scale, h * scale, w * scale)

@@ -22,7 +22,7 @@ sd = synthetic.make_state_dict(params, seed=seed, device=dev)
 e16 = NoiseEstimatorEngine(sd, up, cp, device=dev)
 e32 = NoiseEstimatorF32(sd, up, cp, device=dev)
 g = torch.Generator(device=dev).manual_seed(seed + 100)
-B, h = 1, 32
+B, h = 1, (int(sys.argv[2]) if len(sys.argv) > 2 else 32)
 x = torch.randn(B, 4, h, h, generator=g, device=dev)
 ctx = torch.randn(B, 77, 1024, generator=g, device=dev)
 t = torch.full((B,), 224, dtype=torch.long, device=dev)
