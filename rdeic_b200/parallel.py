@@ -115,9 +115,10 @@ def plan_tiles_balanced(h: int, w: int, world_size: int, overlap: int = 16, max_
                         align: int = 8) -> List[Tuple[int, int, int, int]]:
     """Cover an h x w latent with ny x nx equal tiles whose COUNT is a multiple of `world_size`, so every rank
     decodes the same number of tiles (20 tiles on 8 GPUs keep four ranks idle for a third of the time).  Among
-    the grids with ny * nx % world_size == 0 and tile area <= `max_tile_area` (self-attention is quadratic in the
-    tile's token count) pick the one with the least work per rank; tile sides are multiples of `align` (three
-    stride-2 levels), neighbours overlap by >= `overlap`.  Returns (y0, x0, th, tw) like plan_tiles."""
+    the grids with ny * nx % world_size == 0, tile area <= `max_tile_area` and a token count that is a multiple of
+    128 (the tcgen05 attention tile) pick the one with the least work per rank — convolutions / linears are linear
+    in the tile area, self-attention (about a fifth of a 64x64 tile's FLOPs) quadratic; tile sides are multiples of
+    `align` (three stride-2 levels), neighbours overlap by >= `overlap`.  Returns (y0, x0, th, tw) like plan_tiles."""
     def side(n: int, k: int) -> int:              # smallest aligned tile side so that k tiles cover n with the overlap
         t = -(-(n + (k - 1) * overlap) // k)
         t = -(-t // align) * align
@@ -138,7 +139,12 @@ def plan_tiles_balanced(h: int, w: int, world_size: int, overlap: int = 16, max_
                 continue
             if ny > 1 and (h - th) / (ny - 1) > th - overlap or nx > 1 and (w - tw) / (nx - 1) > tw - overlap:
                 continue
-            cost = (ny * nx // world_size) * th * tw
+            area = th * tw
+            if area % 128 and (ny * nx > 1):
+                continue
+            cost = (ny * nx // world_size) * area * (1.0 + 0.2 * area / 4096.0)
+            if area % 2048:                           # levels 1 / 2 leave the tcgen05 attention tile too
+                cost *= 1.05
             if best is None or cost < best[0]:
                 best = (cost, ny, nx, th, tw)
     if best is None:

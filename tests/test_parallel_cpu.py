@@ -38,6 +38,41 @@ def test_plan_tiles_cover_and_overlap():
             assert a + min(96, h) - b >= 16          # neighbouring rows of tiles overlap by >= 16
 
 
+def test_plan_tiles_balanced():
+    """Tile counts are multiples of the world size, tiles are equal, aligned, cover the latent and overlap."""
+    for h, w in ((176, 256), (64, 64), (96, 200), (128, 128)):
+        for world in (1, 2, 4, 8):
+            plan = parallel.plan_tiles_balanced(h, w, world, overlap=16)
+            assert len(plan) % world == 0
+            th, tw = plan[0][2], plan[0][3]
+            assert all(p[2] == th and p[3] == tw for p in plan) and th % 8 == 0 and tw % 8 == 0 and th * tw <= 96 * 96
+            cover = np.zeros((h, w), int)
+            for y0, x0, _, _ in plan:
+                assert 0 <= y0 and y0 + th <= h and 0 <= x0 and x0 + tw <= w
+                cover[y0:y0 + th, x0:x0 + tw] += 1
+            assert cover.min() >= 1
+            ys, xs = sorted({p[0] for p in plan}), sorted({p[1] for p in plan})
+            assert all(a + th - b >= 16 for a, b in zip(ys, ys[1:])) and all(a + tw - b >= 16 for a, b in zip(xs, xs[1:]))
+    # BASELINE config 4 on 8 GPUs: two tiles per rank instead of the 3/3/3/3/2/2/2/2 deal of 20 tiles
+    plan = parallel.plan_tiles_balanced(176, 256, 8, overlap=16)
+    assert len(plan) in (8, 16) and (plan[0][2] * plan[0][3]) % 128 == 0
+    assert len(parallel.plan_tiles_balanced(176, 256, 8, overlap=16, max_tile_area=80 * 80)) == 16
+
+
+def _torch_blend_u8(tiles, origins, ov, H, W):
+    """CPU stand-in for ops.blend_tiles_u8 (same ramp, same rounding) for the gloo plumbing test."""
+    T, th, tw, _ = tiles.shape
+    ramp = lambda n: torch.tensor([(i + 1) / (ov + 1) if i < ov else ((n - i) / (ov + 1) if i >= n - ov else 1.0)
+                                   for i in range(n)])
+    wgt = ramp(th)[:, None] * ramp(tw)[None, :]
+    acc, ws = torch.zeros(H, W, 3), torch.zeros(H, W, 1)
+    for t in range(T):
+        y0, x0 = int(origins[t, 0]), int(origins[t, 1])
+        acc[y0:y0 + th, x0:x0 + tw] += tiles[t].float() * wgt[..., None]
+        ws[y0:y0 + th, x0:x0 + tw] += wgt[..., None]
+    return torch.clamp(torch.round(acc / ws), 0, 255).to(torch.uint8)
+
+
 def test_blend_of_consistent_tiles_is_identity():
     h, w, s = 40, 56, 2
     full = torch.randn(3, h * s, w * s)
@@ -97,6 +132,16 @@ def _worker(rank, world, port, ret):
 
         img_b = parallel.decode_tiled(fake_decode_batched, big, tile=24, overlap=8, scale=s, batched=True)
         ok_tiles = ok_tiles and ((img_b is None) if rank != 0 else torch.allclose(img_b, ref, atol=1e-5))
+        # the serving form: balanced plan, uint8 tiles, gather to rank 0 only, one blend call
+        plan = parallel.plan_tiles_balanced(h, w, world, overlap=8, max_tile_area=24 * 32)
+        full_u8 = (torch.rand(h * s, w * s, 3, generator=torch.Generator().manual_seed(2)) * 255).to(torch.uint8)
+
+        def fake_decode_u8(c, idx):           # every tile is the matching crop of one consistent image
+            return torch.stack([full_u8[plan[i][0] * s:(plan[i][0] + plan[i][2]) * s,
+                                        plan[i][1] * s:(plan[i][1] + plan[i][3]) * s] for i in idx])
+
+        img_u8 = parallel.decode_tiled_u8(fake_decode_u8, big, plan, overlap=8, scale=s, blend=_torch_blend_u8)
+        ok_tiles = ok_tiles and ((img_u8 is None) if rank != 0 else torch.equal(img_u8, full_u8))
         ret[rank] = (ok_bcast, ok_shard, ok_gather, ok_tiles, ok_deal)
     finally:
         dist.destroy_process_group()
