@@ -154,6 +154,14 @@ int rdeic_transpose_bf16(const void* in, void* out, int batch, int R, int C,
 int rdeic_image_to_u8(const float* in, uint8_t* out, int64_t pixels, int ldc,
                       rdeic_stream_t stream);
 
+/* ABI 5.  src fp32 [rows, C] (row stride ld_src) -> two bf16 channel windows of dst (row stride ld_dst):
+ * hi = bf16(x) at column off_hi, lo = bf16(x - hi) at off_lo.  A GEMM over [hi | lo] with duplicated weight columns
+ * reads x to ~16 mantissa bits: used for the tensors entering the network (x of rdeic.py:176, guide_hint :180,
+ * context :172, timestep_embedding util.py:161), whose rounding would otherwise reach the output through every
+ * skip connection. */
+int rdeic_split_bf16_hilo(const float* src, int64_t rows, int C, int64_t ld_src, void* dst, int64_t ld_dst,
+                          int off_hi, int off_lo, rdeic_stream_t stream);
+
 /* ABI 5.  Blend T overlapping decoded uint8 HWC tiles [T, th, tw, 3] (tile t's top-left pixel at origin_yx[2t],
  * origin_yx[2t+1]) into one uint8 image [H, W, 3]: weighted mean with a separable linear ramp over `overlap` pixels
  * at every tile edge.  Tiling large frames is this framework's own behaviour (BASELINE config 4; the reference has

@@ -104,6 +104,7 @@ SIGNATURES = {
     "rdeic_softmax_rows": [vp, i32, vp, i64, i32, f32, vp],
     "rdeic_transpose_bf16": [vp, vp, i32, i32, i32, vp],
     "rdeic_image_to_u8": [vp, vp, i64, i32, vp],
+    "rdeic_split_bf16_hilo": [vp, i64, i32, i64, vp, i64, i32, i32, vp],
     "rdeic_blend_tiles_u8": [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "rdeic_groupnorm_workspace_bytes": [i32, i64, i32],
     "rdeic_groupnorm_nhwc": [vp, i32, vp, i32, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
@@ -141,7 +142,10 @@ def load() -> C.CDLL:
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path."
         )
     lib = C.CDLL(str(LIB_PATH))
+    partial = _os.environ.get("RDEIC_B200_LIB_PARTIAL") is not None    # A/B runs against an older build (scripts/ab_gemm.py)
     for name, argtypes in SIGNATURES.items():
+        if partial and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)

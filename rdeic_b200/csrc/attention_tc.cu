@@ -414,9 +414,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 tc_fence_before();                  // the only read of S_g: the MMA thread may overwrite it
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_free[g]);
-                float mx = -INFINITY;
+                // four independent chains: one serial chain of 128 dependent FMNMX is ~500 clocks of pure latency
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < kAK; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                for (int c = 0; c < kAK; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sv[c]));     mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 const float m_new = mx * sc;
                 // PV(j-1) must have retired before P_g is overwritten (and before O_g is rescaled)
                 if (j > 0) {
@@ -442,20 +447,23 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                     m_ref = m_to;
                 }
-                float rowsum = 0.f, rowsum2 = 0.f;
+                float rowsum = 0.f, rowsum2 = 0.f, rowsum3 = 0.f, rowsum4 = 0.f;
 #pragma unroll
                 for (int c32 = 0; c32 < 4; ++c32) {                  // 32 keys -> 16 packed columns of P (S dies as we go)
                     uint32_t pk[16];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
+                    for (int c = 0; c < 16; c += 2) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c]), sc, -m_ref));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 1]), sc, -m_ref));
-                        rowsum += p0; rowsum2 += p1;
+                        const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), sc, -m_ref));
+                        const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 3]), sc, -m_ref));
+                        rowsum += p0; rowsum2 += p1; rowsum3 += p2; rowsum4 += p3;
                         pk[c] = pack_bf16x2(p0, p1);
+                        pk[c + 1] = pack_bf16x2(p2, p3);
                     }
                     tmem_st16(tp + c32 * 16, pk);
                 }
-                l_run += rowsum + rowsum2;
+                l_run += (rowsum + rowsum2) + (rowsum3 + rowsum4);
                 tmem_st_wait();                     // P (and the rescaled O) are in tensor memory ...
                 tc_fence_before();                  // ... before the PV the arrive releases
                 __syncwarp();

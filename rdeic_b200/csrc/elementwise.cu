@@ -394,6 +394,26 @@ image_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int6
     }
 }
 
+// x (fp32) -> hi = bf16(x), lo = bf16(x - hi), written as two channel windows of one bf16 row: a GEMM over [hi | lo]
+// with the weight columns duplicated sees x to ~16 mantissa bits.  Used for the tensors that ENTER the network
+// (latent, hint, text context, timestep embedding): their bf16 rounding error would otherwise ride along every
+// skip connection to the output.
+__global__ void __launch_bounds__(kThreads)
+split_bf16_hilo_kernel(const float* __restrict__ src, int64_t rows, int C, int64_t ld_src,
+                       __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int off_hi, int off_lo) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t total = rows * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const float x = src[r * ld_src + c];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        dst[r * ld_dst + off_hi + c] = hi;
+        dst[r * ld_dst + off_lo + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
+    }
+}
+
 // Blend overlapping decoded tiles of one large image (BASELINE config 4; rdeic_b200/parallel.py).  One thread per
 // output pixel: every tile that covers it contributes with a separable linear ramp over the overlap band
 // (weight (i+1)/(ov+1) for the first ov pixels of a tile axis, mirrored at the far end, 1 in between), the
@@ -612,6 +632,19 @@ int rdeic_blend_tiles_u8(const uint8_t* tiles, const int32_t* origin_yx, int T, 
                     "rdeic_blend_tiles_u8: bad dims (the overlap band must not exceed half a tile)");
     launch_k(blend_tiles_u8_kernel, grid_for((int64_t)H * W, kThreads), kThreads, 0, as_stream(stream), tiles,
              (const int*)origin_yx, T, th, tw, overlap, out, H, W);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+int rdeic_split_bf16_hilo(const float* src, int64_t rows, int C, int64_t ld_src, void* dst, int64_t ld_dst,
+                          int off_hi, int off_lo, rdeic_stream_t stream) {
+    RDEIC_CHECK_ARG(src && dst && rows >= 0 && C > 0, "rdeic_split_bf16_hilo: bad args");
+    RDEIC_CHECK_ARG(ld_src >= C && off_hi >= 0 && off_lo >= 0 && off_hi + C <= ld_dst && off_lo + C <= ld_dst &&
+                        (off_hi + C <= off_lo || off_lo + C <= off_hi),
+                    "rdeic_split_bf16_hilo: the two windows must be disjoint and inside a row");
+    if (rows == 0) return 0;
+    launch_k(split_bf16_hilo_kernel, grid_for(rows * C, kThreads), kThreads, 0, as_stream(stream), src, rows, C, ld_src,
+             (__nv_bfloat16*)dst, ld_dst, off_hi, off_lo);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

@@ -270,6 +270,30 @@ def f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split_hilo(src: torch.Tensor, dst: Optional[torch.Tensor] = None, off_hi: int = 0, off_lo: Optional[int] = None):
+    """src fp32 [..., C] (dense rows) -> bf16 [..., ld] holding hi = bf16(src) in columns [off_hi, off_hi + C) and
+    lo = bf16(src - hi) in [off_lo, off_lo + C) (default: right behind hi)."""
+    src = _need(src, torch.float32, "split_hilo")
+    Cc = src.shape[-1]
+    rows = src.numel() // Cc
+    off_lo = off_hi + Cc if off_lo is None else off_lo
+    if dst is None:
+        dst = torch.zeros((*src.shape[:-1], max(off_hi, off_lo) + Cc), dtype=BF16, device=src.device)
+    if dst.dtype != BF16 or not dst.is_contiguous() or dst.numel() // dst.shape[-1] != rows:
+        raise TypeError("split_hilo: dst must be a contiguous bf16 tensor with the rows of src")
+    check(_lib.load().rdeic_split_bf16_hilo(_ptr(src), rows, Cc, Cc, _ptr(dst), dst.shape[-1], off_hi, off_lo, _stream()),
+          "rdeic_split_bf16_hilo")
+    return dst
+
+
+def timestep_embedding_f32(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    t = _need(t, torch.int64, "timestep_embedding_f32")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    check(_lib.load().rdeic_timestep_embedding_f32(_ptr(t), _ptr(out), t.shape[0], dim, max_period, _stream()),
+          "rdeic_timestep_embedding_f32")
+    return out
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     t = _need(t, torch.int64, "timestep_embedding")
     out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)

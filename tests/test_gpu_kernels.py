@@ -871,3 +871,41 @@ def test_conv_fused_zero_conv_injection(cuda, B, H, W, Cin, Cc, Cout, taps, stri
                         out_f32=True, stride2=stride2)
     ref2 = (F.conv2d(x, w, b, stride=2 if stride2 else 1, padding=k // 2) + scale * F.conv2d(hc, wz, bz)).permute(0, 2, 3, 1) + resid
     assert _rel(of2.cpu(), ref2) < 3e-3, _rel(of2.cpu(), ref2)
+
+
+def test_split_hilo(cuda):
+    """hi = bf16(x), lo = bf16(x - hi): hi + lo reproduces x to ~2^-17 relative, hi is torch's own rounding."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(37, 5, 12, generator=g) * 3
+    out = ops.split_hilo(x.to(cuda)).cpu()
+    assert tuple(out.shape) == (37, 5, 24)
+    hi, lo = out[..., :12].float(), out[..., 12:].float()
+    assert torch.equal(hi, x.bfloat16().float())
+    assert torch.equal(lo, (x - hi).bfloat16().float())
+    assert ((hi + lo - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+    # windows inside a wider, pre-zeroed row
+    dst = torch.zeros(37 * 5, 40, dtype=torch.bfloat16, device=cuda)
+    ops.split_hilo(x.view(-1, 12).to(cuda), dst, off_hi=16, off_lo=4)
+    assert torch.equal(dst[:, 16:28].float().cpu(), hi.view(-1, 12)) and torch.equal(dst[:, 4:16].float().cpu(), lo.view(-1, 12))
+    assert float(dst[:, :4].abs().sum()) == 0 and float(dst[:, 28:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("h,w,tile,ov,s", [(40, 56, 24, 8, 2), (24, 24, 24, 4, 8), (64, 96, 32, 16, 4)])
+def test_blend_tiles_u8(cuda, h, w, tile, ov, s):
+    """One-kernel uint8 tile blend against the float blend of rdeic_b200.parallel (same ramp), +-1 LSB for the
+    uint8 rounding; tiles cut from one image blend back to exactly that image."""
+    from rdeic_b200 import ops, parallel
+
+    g = torch.Generator().manual_seed(72)
+    plan = parallel.plan_tiles(h, w, tile, ov)
+    th, tw = plan[0][2], plan[0][3]
+    tiles = torch.randint(0, 256, (len(plan), th * s, tw * s, 3), generator=g, dtype=torch.uint8)
+    origins = torch.tensor([[p[0] * s, p[1] * s] for p in plan], dtype=torch.int32)
+    out = ops.blend_tiles_u8(tiles.to(cuda), origins.to(cuda), ov * s, h * s, w * s).cpu()
+    ref = parallel.blend_tiles([t.permute(2, 0, 1).float() for t in tiles], plan, h, w, ov, s).permute(1, 2, 0)
+    assert (out.float() - ref).abs().max() <= 0.5 + 1e-3
+    full = torch.randint(0, 256, (h * s, w * s, 3), generator=g, dtype=torch.uint8)
+    cut = torch.stack([full[p[0] * s:(p[0] + th) * s, p[1] * s:(p[1] + tw) * s] for p in plan])
+    assert torch.equal(ops.blend_tiles_u8(cut.to(cuda), origins.to(cuda), ov * s, h * s, w * s).cpu(), full)

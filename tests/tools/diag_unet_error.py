@@ -29,9 +29,8 @@ t = torch.full((B,), 224, dtype=torch.long, device=dev)
 with torch.no_grad():
     # bf16 engine pieces
     kvb, kvc, _ = e16.prepare_cond(ctx, None)
-    t_emb = ops.timestep_embedding(t, e16.model_channels)
+    hb, t_emb = e16._step_inputs(x, t)
     cb = _Ctx(e16._time_rows(e16.base, t_emb), kvb)
-    hb = Act(None, ops.nchw_to_nhwc_bf16(x, ldc=8))
     # fp32 pieces
     B_ = "model.diffusion_model"
     h32 = x.permute(0, 2, 3, 1).contiguous()
@@ -39,7 +38,6 @@ with torch.no_grad():
     ops.check(ops._lib.load().rdeic_timestep_embedding_f32(t.data_ptr(), te.data_ptr(), B, e32.model_channels, 10000.0,
                                                            torch.cuda.current_stream().cuda_stream), "te")
     eb = e32._emb(B_, te)
-    print("t_emb", rel_l2(t_emb.float().cpu(), te.cpu()))
     hs16, hs32 = [], []
     cmp = lambda name, a, b: print(f"{name:22s} {rel_l2(a.f.cpu() if a.f is not None else a.h.float().cpu(), b.cpu()):.3e}")
     for i, blk in enumerate(e16.base.input_blocks):
