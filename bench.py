@@ -145,8 +145,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_image"] * 1e3 * BATCH,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference modules (the reference is pure "
-                                                     "Python and cannot travel to the GPU box); bounded sample"},
+            "config": {"workload": WORKLOAD.replace("bf16", "fp32 (CPU)"),
+                       "note": "CPU oracle port of the reference modules (the reference is pure Python and cannot travel to "
+                               "the GPU box); bounded sample: see cpu_baseline.sample"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -317,10 +318,11 @@ def run_b200(args):
         peaks = json.loads(pk.read_text())
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # DRAM bytes per launch of the same kernel: only from an ncu capture of THIS command (`--traffic-from file`, the
+    # kernel summary scripts/kernel_summary.py writes from `ncu ... python bench.py --profile-range`); null otherwise
     traffic = None
-    ks = ROOT / "profiles" / "r01_decode_kernel_summary.json"
-    if ks.exists():     # per-launch DRAM bytes of the same kernel from the committed ncu capture of this workload
-        traffic = json.loads(ks.read_text()).get("conv_gemm_dram_bytes_per_launch")
+    if args.traffic_from and Path(args.traffic_from).exists():
+        traffic = json.loads(Path(args.traffic_from).read_text()).get("conv_gemm_dram_bytes_per_launch")
     roofline = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv3x3/conv1x1/linear)", "bound": "tensor",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "traffic": traffic, "launches_per_step": len(prof),
@@ -347,6 +349,197 @@ def run_b200(args):
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline}
         if sd_cpu is not None:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(sd_cpu, 1, 0).items() if k != "s_per_image"}
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (strong scaling; not the headline line the driver records)
+# ---------------------------------------------------------------------------------------------
+def _entropy_frontend_bitexact(dev) -> bool:
+    """BASELINE config 5's check: checkerboard split / merge / squeeze and the VQ look-up on the GPU against the
+    outputs of the reference's own utils/ckbd.py and VectorQuantiser (tests/golden/entropy_ref.npz), bit for bit."""
+    from rdeic_b200 import ckbd, ops
+
+    g = np.load(ROOT / "tests" / "golden" / "entropy_ref.npz")
+    # the seeded inputs the goldens were made from (tests/golden/make_golden.py::entropy_inputs)
+    gen = torch.Generator().manual_seed(41)
+    y = torch.randn(2, 8, 6, 10, generator=gen) * 6
+    y.view(-1)[3] = -0.0
+    K, D = 512, 256
+    cb = (torch.rand(K, D, generator=gen) * 2 - 1) / K
+    cb[7] = cb[300]
+    pick = torch.randint(0, K, (2 * 3 * 5,), generator=gen)
+    pick[0] = 300
+    z = cb[pick] + 1e-5 * torch.randn(pick.numel(), D, generator=gen)
+    z[0] = cb[300]
+    z = z.reshape(2, 3, 5, D).permute(0, 3, 1, 2).contiguous()
+    bits = lambda t: t.cpu().numpy().view(np.uint32)
+    yc = y.to(dev)
+    a, n = ckbd.ckbd_split(yc)
+    ok = np.array_equal(bits(a), g["anchor"].view(np.uint32)) and np.array_equal(bits(n), g["nonanchor"].view(np.uint32))
+    ok &= np.array_equal(bits(ckbd.ckbd_merge(a, n)), g["merge"].view(np.uint32))
+    sa, sn = ckbd.ckbd_anchor_sequeeze(yc), ckbd.ckbd_nonanchor_sequeeze(yc)
+    ok &= np.array_equal(bits(sa), g["anchor_sq"].view(np.uint32)) and np.array_equal(bits(sn), g["nonanchor_sq"].view(np.uint32))
+    ok &= np.array_equal(bits(ckbd.ckbd_anchor_unsequeeze(sa)), g["anchor_unsq"].view(np.uint32))
+    zq, idx = ops.vq_quant(z.to(dev), cb.to(dev))
+    ok &= np.array_equal(idx.cpu().numpy(), g["vq_idx"]) and np.array_equal(bits(zq), g["vq_zq"].view(np.uint32))
+    # quantise / dequantise round trip on a large tensor: symbols are integers, x_hat - means is integral
+    x = torch.randn(1 << 20, generator=gen).to(dev) * 6
+    mu = torch.randn(1 << 20, generator=gen).to(dev) * 2
+    sym = ops.quantize_symbols(x, mu)
+    ok &= bool(torch.equal(sym, torch.round(x - mu).to(torch.int32)))
+    ok &= bool(torch.equal(ops.dequantize(sym, mu), sym.float() + mu))
+    return bool(ok)
+
+
+def run_other_config(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    real_stdout = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=dev)
+    from rdeic_b200 import RDEIC, build, configs, ops, parallel, synthetic
+    from rdeic_b200.pipeline import relay_decode
+
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    params = configs.default_params()
+    spec = [(k, s) for k, s, _ in synthetic.state_dict_spec(params)]
+    sd = synthetic.make_state_dict(params, seed=WEIGHT_SEED, device=dev) if rank == 0 else None
+    sd = parallel.broadcast_state_dict(sd, spec, dev, src=0)
+    model = RDEIC.from_config({"params": params}, device=dev).load_state_dict(sd)
+    del sd
+    torch.cuda.empty_cache()
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.LAUNCHES
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ops.LAUNCHES - n0
+
+    cfg = args.config
+    extra = {}
+    if cfg in ("c3", "c5"):
+        Hh, Ww, GB = (512, 768, 64) if cfg == "c3" else (512, 512, 32)
+        lo, hi = parallel.shard_range(GB, rank, world)
+        counts = [parallel.shard_range(GB, r, world)[1] - parallel.shard_range(GB, r, world)[0] for r in range(world)]
+        c_latent, hint, ctx, noises = make_inputs(GB, Hh // 8, Ww // 8)
+        while len(noises) < 11:                                   # the 10-step sweep of c5
+            noises = noises + noises[1:]
+        sl = lambda t: t[lo:hi].contiguous()
+        host = {"c_latent": sl(c_latent).pin_memory(), "hint": sl(hint).pin_memory(), "ctx": sl(ctx).pin_memory(),
+                "noises": [sl(n).pin_memory() for n in noises[:11]]}
+        d = {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in host.items()}
+        out_host = torch.empty((GB, Hh, Ww, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def decode(src, steps, to_host=False):
+            if src is host:                                       # e2e: this step's inputs cross PCIe first
+                b = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True))
+                     for k, v in host.items() if k != "noises"}
+                b["noises"] = [t.to(dev, non_blocking=True) for t in host["noises"][:steps + 1]]
+            else:
+                b = src
+            cond = {"c_latent": [b["c_latent"]], "c_crossattn": [b["ctx"]], "guide_hint": b["hint"]}
+            imgs = relay_decode(model, cond, steps, sampler="ddpm", start_noise=b["noises"][0], step_noises=b["noises"][1:steps + 1])
+            allimg = parallel.gather_images(imgs, counts, dst=0)          # NCCL gather of the uint8 images, inside the timed region
+            if to_host and rank == 0:
+                out_host.copy_(allimg, non_blocking=True)
+            return allimg
+
+        for _ in range(max(args.warmup, 3)):
+            decode(d, RELAY_STEPS)
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        ms_dev, launches = timed(lambda: decode(d, RELAY_STEPS), args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        ms_e2e, _ = timed(lambda: decode(host, RELAY_STEPS, to_host=True), args.steps)
+        h2d = sum(t.numel() * 4 for t in [host["c_latent"], host["hint"], host["ctx"], *host["noises"][:RELAY_STEPS + 1]])
+        if cfg == "c5":
+            sweep = {}
+            for st in (2, 5, 10):
+                decode(d, st)
+                ms, _ = timed(lambda: decode(d, st), max(2, args.steps // 2))
+                sweep[str(st)] = GB * max(2, args.steps // 2) / (ms * 1e-3)
+            extra = {"images_per_s_by_relay_steps": sweep, "entropy_frontend_bitexact": _entropy_frontend_bitexact(dev)}
+        value, e2e_v, unit_imgs = GB * args.steps / (ms_dev * 1e-3), GB * args.steps / (ms_e2e * 1e-3), GB
+        workload = (f"{Ww}x{Hh} global batch {GB} split over {world} GPU(s) ({hi - lo} per GPU), 5 relay steps (SpacedSampler), bf16, "
+                    "UNet+control+VAE decode to uint8, NCCL gather of the uint8 images to rank 0 inside the timed region")
+        metric = f"decoded images/s @{Ww}x{Hh} (5 relay steps)"
+        d2h = GB * Hh * Ww * 3
+    else:   # c4: one 2048x1365 image (padded to 2048x1408 -> latent 176x256) as overlapping latent tiles
+        Hl, Wl, OV = 1408 // 8, 2048 // 8, 16
+        g = torch.Generator().manual_seed(4)
+        host = {"c_latent": torch.randn(1, 4, Hl, Wl, generator=g).pin_memory(), "ctx": torch.randn(1, 77, CTX_DIM, generator=g).pin_memory(),
+                "hint": torch.randn(1, HINT_C, Hl, Wl, generator=g).pin_memory()}
+        d = {k: v.to(dev) for k, v in host.items()}
+        plan = parallel.plan_tiles_balanced(Hl, Wl, world, overlap=OV, max_tile_area=args.c4_max_tile_area)
+        out_host = torch.empty((Hl * 8, Wl * 8, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def decode(src, to_host=False):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if src is host else src
+            cond = {"c_latent": [b["c_latent"]], "c_crossattn": [b["ctx"]], "guide_hint": b["hint"]}
+            img = parallel.decode_tiled_u8(lambda c, idx: relay_decode(model, c, RELAY_STEPS), cond, plan, overlap=OV)
+            if to_host and rank == 0:
+                out_host.copy_(img, non_blocking=True)
+            return img
+
+        for _ in range(max(args.warmup, 3)):
+            img = decode(d)
+        if rank == 0:
+            assert tuple(img.shape) == (Hl * 8, Wl * 8, 3)
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        ms_dev, launches = timed(lambda: decode(d), args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        ms_e2e, _ = timed(lambda: decode(host, to_host=True), args.steps)
+        h2d = sum(t.numel() * 4 for t in host.values())
+        value, e2e_v, unit_imgs = args.steps / (ms_dev * 1e-3), args.steps / (ms_e2e * 1e-3), 1
+        th, tw = plan[0][2], plan[0][3]
+        extra = {"tiles": len(plan), "tile_latent": [th, tw], "overlap_latent": OV, "tiles_per_gpu": len(plan) // world,
+                 "mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30}
+        workload = (f"one 2048x1365 image (padded 2048x1408, latent {Hl}x{Wl}) as {len(plan)} overlapping {th}x{tw} latent tiles dealt "
+                    f"over {world} GPU(s), 5 relay steps, uint8 tiles gathered to rank 0 and blended by one kernel")
+        metric = "decoded images/s @2048x1365 tiled (5 relay steps)"
+        d2h = Hl * 8 * Wl * 8 * 3
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload, "baseline_config": cfg, "global_batch": unit_imgs, "parallelism": f"dp{world}",
+                           "l2": "no flush needed: per-step working set exceeds the 126 MB L2"},
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, **extra}
         if real_stdout is not None:
             sys.stdout.flush()
             os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -462,8 +655,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed device region (for ncu --profile-from-start off)")
+    ap.add_argument("--traffic-from", default=None, metavar="JSON",
+                    help="kernel summary of an ncu capture of this same command: fills roofline.traffic (else null)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config: c2 (default, the headline: 512^2 batch 8 per GPU, weak scaling), c3 (768x512 "
+                         "global batch 64 split over the GPUs, strong scaling, uint8 gather timed), c4 (one 2048x1365 image as "
+                         "latent tiles dealt over the GPUs), c5 (512^2 global batch 32, relay steps 2/5/10 + entropy front-end "
+                         "bit-exactness against the reference goldens)")
     ap.add_argument("--compressor", type=int, default=0, metavar="B",
                     help="measure the learned compressor (SURVEY 8f rows) on B 512x512 images instead of the decode")
+    ap.add_argument("--c4-max-tile-area", type=int, default=96 * 96, help="config c4: largest latent tile area the planner may pick")
     ap.add_argument("--compressor-precision", default="mixed", choices=["mixed", "bf16", "fp32"],
                     help="mixed (default): entropy-parameter nets on the fp32 kernels (streams exchangeable with the reference)")
     args = ap.parse_args()
@@ -471,6 +672,8 @@ def main():
         run_compressor(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.config != "c2":
+        run_other_config(args)
     else:
         run_b200(args)
 

@@ -254,7 +254,9 @@ struct TileCfg {
 // two pixel tiles as one N = 256 operand, the same FLOPs take half the MMA slots.  The accumulator is
 // then transposed (TMEM lane = output channel, column = pixel); phase A parks it in the staging buffer
 // already transposed back, so phase B (residual, stores, statistics) is unchanged.
-template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false>
+// kUp: compile-time copy of p.up2 for the epilogue (strided output rows, parity-ordered statistics slabs): the
+// plain instantiations carry none of that state (the 12-warp ones sit at their 128-register cap).
+template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false>
 __global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2, const ConvDev p) {
@@ -551,13 +553,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int m_in = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
             // row of the output tensor this accumulator row is written to: the same pixel, or with the
             // upsample folded in (up2) pixel (2 gh + py, 2 gw + px) of the 2H x 2W grid, z = 2 py + px
-            const int m_own = p.up2 ? (int)(((int64_t)gn * 2 * p.a_h + 2 * gh + (z >> 1)) * (2 * p.a_w) + 2 * gw + (z & 1)) : m_in;
-            const int rstep = p.up2 ? 2 : 1;          // output rows between two consecutive accumulator rows of a slab
+            const int m_own = kUp ? (int)(((int64_t)gn * 2 * p.a_h + 2 * gh + (z >> 1)) * (2 * p.a_w) + 2 * gw + (z & 1)) : m_in;
+            const int rstep = kUp ? 2 : 1;          // output rows between two consecutive accumulator rows of a slab
             // Common case: the whole tile is in bounds and the 32 rows of this warp's slab are
             // consecutive output rows -> phase B needs no shuffles, predicates or divergence.
             const int tn_ = kBlockM >> (p.tw_log2 + p.th_log2);
             const bool tile_full = (tiw * tw + tw <= p.a_w) && (tih * th + th <= p.a_h) && (mt * tn_ + tn_ <= p.a_n);
-            const bool affine = tile_full && (tw >= 32 || (!p.up2 && tw == p.a_w && (tw * th >= 32 || th == p.a_h)));
+            const bool affine = tile_full && (tw >= 32 || (!kUp && tw == p.a_w && (tw * th >= 32 || th == p.a_h)));
             const int m_slab = __shfl_sync(0xffffffffu, m_own, 0);
 
             EpiOut eo;
@@ -728,7 +730,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             // statistics slab of this warp's 32 rows; up2 orders the slabs [sample][parity][h][w] so
                             // that a sample's slabs stay contiguous for the fold
                             int64_t st_slab = __shfl_sync(0xffffffffu, m_in, 0) >> 5;
-                            if (p.up2) st_slab += ((int64_t)__shfl_sync(0xffffffffu, gn, 0) * 3 + z) * (((int64_t)p.a_h * p.a_w) >> 5);
+                            if (kUp) st_slab += ((int64_t)__shfl_sync(0xffffffffu, gn, 0) * 3 + z) * (((int64_t)p.a_h * p.a_w) >> 5);
                             sd = p.stats_out + (st_slab * p.n_out + nbase + 4 * q) * 2;
                         }
                         const int64_t r_off = m0 * eo.ld_resid + nbase + 4 * q;
@@ -797,7 +799,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             if (ok && n < eo.n_cols) epi_store4(eo, (int64_t)m_row, n, val);
                         }
                     }
-                } else if (affine && !p.up2 && vec_io && eo.out_bf16 && !eo.out_f32 && (nbase >> 1) + 16 <= eo.n_cols) {
+                } else if (affine && !kUp && vec_io && eo.out_bf16 && !eo.out_f32 && (nbase >> 1) + 16 <= eo.n_cols) {
                     // GEGLU fast path: full in-bounds tile, consecutive rows, bf16 output only
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -930,20 +932,20 @@ static inline int host_total_kb(const ConvDev& d) {
     return d.a2_center ? d.taps * d.cblk1 + d.cblk2 : d.taps * (d.cblk1 + d.cblk2);
 }
 
-template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false>
+template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false, bool kUp = false>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
     using Cfg = TileCfg<BN, kEW, kMT>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -951,6 +953,10 @@ static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUt
 template <int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                        const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
+    if (d.up2) {              // nearest-upsample folded in: its own instantiations (8 epilogue warps)
+        if (d.stats_out) return launch_conv3<BN, 0, 8, true, 1, false, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+        return launch_conv3<BN, 0, 8, false, 1, false, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+    }
     // Residual prefetch-ahead instantiations (1: bf16 two chunks deep, 2: fp32 one phase ahead) are
     // kept for experiments only: with the affine fast path both measured slower than loading the
     // residual at the top of phase B (VAE 128-ch conv + bf16 residual: 1335 us vs 681 us).
