@@ -57,6 +57,7 @@ class RDEIC:
         self.first_stage_config = dict(first_stage_config)
         self.preprocess_config = dict(preprocess_config) if preprocess_config else None
         self.preprocess_model = None                     # rdeic.py:641 instantiate_from_config(preprocess_config)
+        self.first_stage_encoder = None                  # assigned by load_state_dict when the checkpoint has the VAE encoder
         self.device = torch.device(device)
         self.scale_factor = float(scale_factor)
         if precision not in ("bf16", "fp32"):
@@ -111,8 +112,11 @@ class RDEIC:
 
     def load_state_dict(self, state_dict: Mapping[str, torch.Tensor], strict: bool = True):
         """Consume the reference checkpoint layout and repack it for the
-        tensor-core kernels.  Only decode-path tensors are read; with strict=True their absence
-        raises KeyError like torch's load_state_dict."""
+        tensor-core kernels.  The decode-path tensors (UNet, control adapter, VAE decoder) are always required: a
+        missing one raises KeyError whatever `strict` says.  The optional parts — `first_stage_model.encoder.*`
+        (sender side) and `preprocess_model.*` (learned compressor) — are loaded when present and skipped otherwise
+        (the reference merges two checkpoint files with strict=False, utils/common.py:34-51); the entry points that
+        need them raise RuntimeError when they are absent."""
         sd = normalise_state_dict(state_dict)
         up = dict(self.unet_config.get("params", self.unet_config))
         cp = dict(self.control_stage_config.get("params", self.control_stage_config))
@@ -130,16 +134,19 @@ class RDEIC:
             else:
                 self.first_stage_model = VAEDecoderEngine(sd, self.scale_factor, device=self.device)
         except KeyError as e:
-            if strict:
-                raise KeyError(f"Missing key(s) in state_dict: {e}") from e
-            raise
+            # decode-path tensors are always required (there is nothing to run without them): `strict` only governs
+            # the optional parts below (VAE encoder, learned compressor), like torch's strict=False for extra modules
+            raise KeyError(f"Missing decode-path key(s) in state_dict: {e}") from e
         self._graphs.clear()
         self.first_stage_encoder = None                  # sender side (optional in a decode-only checkpoint)
         if "first_stage_model.encoder.conv_in.weight" in sd:
             self.first_stage_encoder = VAEEncoderEngine(sd, device=self.device)
         # the learned compressor (decompress side of the relay decode: c_latent and guide_hint)
         pp = self.preprocess_config and dict(self.preprocess_config.get("params", self.preprocess_config))
-        if pp and "in_nc" in pp and any(k.startswith("preprocess_model.") for k in sd):
+        has_pm = any(k.startswith("preprocess_model.") for k in sd)
+        if pp and "in_nc" not in pp:
+            raise ValueError("RDEIC: preprocess_config.params lacks in_nc (configs/model/rdeic.yaml preprocess_config)")
+        if pp and has_pm:
             from .compression import Compression
 
             self.preprocess_model = Compression(device=self.device, **pp).load_state_dict(sd, strict=False)
@@ -197,6 +204,30 @@ class RDEIC:
         if self.control_model is None:
             raise RuntimeError("RDEIC: call load_state_dict() before running the model")
 
+    def invalidate_cond(self):
+        """Forget which conditioning the static graph buffers and the K/V / hint caches hold.  Conditioning changes
+        are detected by (tensor identity, torch in-place version); a write that does not bump the version
+        (`tensor.data.copy_`, a DLPack / foreign view, an out-of-band kernel) must be followed by this call."""
+        for g in self._graphs.values():
+            g["cond_id"] = None
+        if self.control_model is not None and hasattr(self.control_model, "_ctx_cache"):
+            self.control_model._ctx_cache.clear()
+            self.control_model._hint_cache.clear()
+        self._cat_cache = None
+
+    def _cond_text(self, cond):
+        """torch.cat(c_crossattn, 1) of rdeic.py:692, built once per set of list elements (a new tensor on every step
+        would re-derive the text K/V and refresh the graph's static buffers on every step)."""
+        cs = cond["c_crossattn"]
+        if len(cs) == 1:
+            return cs[0]
+        key = tuple((id(c), c._version) for c in cs)
+        ent = getattr(self, "_cat_cache", None)
+        if ent is None or ent[0] != key:
+            ent = (key, torch.cat(cs, 1), list(cs))           # the list keeps the ids alive
+            self._cat_cache = ent
+        return ent[1]
+
     def _graphed_step(self, x, t, context, hint, unconditional: bool):
         """Replay one UNet+control step from a CUDA graph.  The graph is keyed by shapes only: the
         step-invariant conditioning (cross-attention K/V of both networks, NHWC bf16 hint) lives in
@@ -244,7 +275,7 @@ class RDEIC:
         """rdeic.py:688-698."""
         assert isinstance(cond, dict)
         self._need_weights()
-        cond_txt = torch.cat(cond["c_crossattn"], 1) if len(cond["c_crossattn"]) > 1 else cond["c_crossattn"][0]
+        cond_txt = self._cond_text(cond)
         guide_hint = cond["guide_hint"]
         x = x_noisy.to(self.device, torch.float32).contiguous()
         t = t.to(self.device, torch.int64).contiguous()
@@ -257,7 +288,7 @@ class RDEIC:
         """rdeic.py:700-709: base UNet without the control branch, same text context."""
         assert isinstance(cond, dict)
         self._need_weights()
-        cond_txt = torch.cat(cond["c_crossattn"], 1) if len(cond["c_crossattn"]) > 1 else cond["c_crossattn"][0]
+        cond_txt = self._cond_text(cond)
         x = x_noisy.to(self.device, torch.float32).contiguous()
         t = t.to(self.device, torch.int64).contiguous()
         if self.use_cuda_graph:

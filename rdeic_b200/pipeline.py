@@ -20,11 +20,17 @@ def relay_decode(model, cond: Dict, steps: int, sampler: str = "ddpm", guidance_
                  as_uint8: bool = True) -> torch.Tensor:
     """inference.py:63-87.  `start_noise` / `step_noises` replace the reference's device-side
     torch.randn draws (inference.py:65, spaced_sampler_relay.py:378) when reproducibility across
-    devices is needed; by default noise is drawn on the GPU exactly where the reference draws it."""
+    devices is needed.  By default noise is drawn on the GPU in the reference's order: process() first draws an
+    `x_T = randn(shape)` it never uses (inference.py:64) and only then the start noise (:65), so one draw of the
+    same shape is made and discarded here to keep the generator stream aligned with the reference's."""
     c_latent = cond["c_latent"][0].to(model.device, torch.float32)
     n, _, h, w = c_latent.shape
     shape = (n, 4, h, w)
-    noise = torch.randn(shape, device=model.device, dtype=torch.float32) if start_noise is None else start_noise
+    if start_noise is None:
+        torch.randn(shape, device=model.device, dtype=torch.float32)          # the reference's dead x_T draw
+        noise = torch.randn(shape, device=model.device, dtype=torch.float32)
+    else:
+        noise = start_noise
     # inference.py:66-67: t = used_timesteps - 1 for every sample (host list: no device round trip)
     x_T = model.q_sample(x_start=c_latent, t=[model.used_timesteps - 1] * n, noise=noise)
     noise_fn: Optional[Callable] = None
@@ -115,6 +121,9 @@ def decode_host_batches(model, batches: Iterable[Dict], steps: int, sampler: str
         buf = slots[s]
         if buf is None or buf.keys() != src.keys() or any(buf[k].shape != v.shape for k, v in src.items()):
             buf = slots[s] = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in src.items()}
+            # fresh buffers come from the current stream's pool: whatever the caller still has queued there (and the
+            # previous owner of that memory) must be ordered before the copy stream writes them
+            s_in.wait_stream(cur)
         with torch.cuda.stream(s_in):
             s_in.wait_event(slot_free[s])                       # the decode two batches back has consumed the slot
             for k, v in src.items():
