@@ -468,8 +468,16 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     for (int c = 0; c < 16; c += 2) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c]), sc, -m_ref));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 1]), sc, -m_ref));
+#if defined(RDEIC_ATTN_POLY2)
+                        const float p2 = ex2_poly(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), sc, -m_ref));
+#else
                         const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), sc, -m_ref));
+#endif
+#if defined(RDEIC_ATTN_NO_POLY)
+                        const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 3]), sc, -m_ref));
+#else
                         const float p3 = ex2_poly(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 3]), sc, -m_ref));
+#endif
                         rowsum += p0; rowsum2 += p1; rowsum3 += p2; rowsum4 += p3;
                         pk[c] = pack_bf16x2(p0, p1);
                         pk[c + 1] = pack_bf16x2(p2, p3);
