@@ -216,6 +216,13 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
                         int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
                         int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream);
 
+bool attention_x_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                           int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, const void* q, const void* k, const void* v,
+                           const void* out);
+int launch_attention_x(const void* q, const void* k, const void* v, void* out, int B, int heads, int Nq, int Nk,
+                       int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
+                       int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream);
+
 }  // namespace rdeic
 
 using namespace rdeic;
@@ -238,6 +245,11 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
         !getenv("RDEIC_ATTN_MMA_SYNC"))
         return launch_attention_tc(q, k, v, out, B, heads, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs,
                                    scale, as_stream(stream));
+    // one KV tile (the 77 text keys of cross-attention): tcgen05 kernel without a key loop
+    if (attention_x_supported(d, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, q, k, v, out) &&
+        !getenv("RDEIC_ATTN_MMA_SYNC"))
+        return launch_attention_x(q, k, v, out, B, heads, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, scale,
+                                  as_stream(stream));
     const float scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Nq + kQTile - 1) / kQTile, heads, B);
     if (d == 64)

@@ -54,19 +54,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// 2^x on the FMA / integer pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative
-// error 7.5e-5, far below the bf16 rounding of P).  The softmax of the two-tile kernel is MUFU bound (ncu: XU pipe
-// 70 % busy, FMA 19 %, ALU 25 %, issue slots 46 %): every fourth exponential takes this route instead of ex2.approx.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float xm = x + 12582912.0f;             // 1.5 * 2^23: the nearest integer n lands in the low mantissa bits
-    const float f = x - (xm - 12582912.0f);       // x - n, in [-0.5, 0.5]
-    float p = fmaf(0.0551711656f, f, 0.2426110804f);
-    p = fmaf(p, f, 0.6932610869f);
-    p = fmaf(p, f, 0.9999280572f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(xm) << 23));    // p * 2^n through the exponent field
-}
-
 __global__ void __launch_bounds__(kAThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttDev p) {
@@ -460,31 +447,29 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                     m_ref = m_to;
                 }
-                float rowsum = 0.f, rowsum2 = 0.f, rowsum3 = 0.f, rowsum4 = 0.f;
+                // Packed fp32x2 arithmetic (FFMA2 / FADD2): the exponent argument s * scale - m and the row sum cost one
+                // instruction per PAIR of keys.  The softmax warps are bound by the MUFU pipe plus whatever of their
+                // other instructions does not overlap it (measured: routing a quarter of the exponentials through an
+                // FMA-pipe polynomial made the kernel 5 % SLOWER, half of them 17 %), so fewer instructions is the lever.
+                const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_ref, -m_ref);
+                float2 rs_a = make_float2(0.f, 0.f), rs_b = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int c32 = 0; c32 < 4; ++c32) {                  // 32 keys -> 16 packed columns of P (S dies as we go)
                     uint32_t pk[16];
 #pragma unroll
                     for (int c = 0; c < 16; c += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c]), sc, -m_ref));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 1]), sc, -m_ref));
-#if defined(RDEIC_ATTN_POLY2)
-                        const float p2 = ex2_poly(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), sc, -m_ref));
-#else
-                        const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), sc, -m_ref));
-#endif
-#if defined(RDEIC_ATTN_NO_POLY)
-                        const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 3]), sc, -m_ref));
-#else
-                        const float p3 = ex2_poly(fmaf(__uint_as_float(sv[c32 * 32 + 2 * c + 3]), sc, -m_ref));
-#endif
-                        rowsum += p0; rowsum2 += p1; rowsum3 += p2; rowsum4 += p3;
-                        pk[c] = pack_bf16x2(p0, p1);
-                        pk[c + 1] = pack_bf16x2(p2, p3);
+                        const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(sv[c32 * 32 + 2 * c]), __uint_as_float(sv[c32 * 32 + 2 * c + 1])), sc2, nm2);
+                        const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(sv[c32 * 32 + 2 * c + 2]), __uint_as_float(sv[c32 * 32 + 2 * c + 3])), sc2, nm2);
+                        const float2 e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+                        const float2 e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+                        rs_a = __fadd2_rn(rs_a, e0);
+                        rs_b = __fadd2_rn(rs_b, e1);
+                        pk[c] = pack_bf16x2(e0.x, e0.y);
+                        pk[c + 1] = pack_bf16x2(e1.x, e1.y);
                     }
                     tmem_st16(tp + c32 * 16, pk);
                 }
-                l_run += (rowsum + rowsum2) + (rowsum3 + rowsum4);
+                l_run += (rs_a.x + rs_a.y) + (rs_b.x + rs_b.y);
                 tmem_st_wait();                     // P (and the rescaled O) are in tensor memory ...
                 tc_fence_before();                  // ... before the PV the arrive releases
                 __syncwarp();
@@ -662,6 +647,194 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
     }
     dim3 grid(Nq / kAQ, heads, B);
     launch_k(attention_tc_kernel, grid, kAThreads, kASmem, stream, tq, tk, tv, d);
+    RDEIC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One KV tile (Nk <= 128: the 77 text keys of every cross-attention, attention.py:171-203 with context = the
+// [B,77,1024] prompt embedding): no key loop, no rescaling.  Small CTAs so that two fit an SM (48 KB of tiles,
+// 256 TMEM columns, 160 threads) and hide each other's TMA -> MMA -> softmax -> MMA -> store latency chain:
+//   warp 4: TMA (Q, K, V tiles; rows past Nq / Nk are zero-filled by the hardware), then the S and PV MMAs
+//   warps 0-3: one query row per thread; S row from TMEM, masked past Nk, softmax, P back into the SAME TMEM
+//              columns as bf16 pairs (each thread only ever touches its own lane), O row out, scaled, stored.
+// The PV MMAs read P from tensor memory (A operand) and V as an MN-major operand from its row-major tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAXThreads = 160;
+constexpr int kAXSmem = 3 * kATile + 1024 + 128;
+constexpr uint32_t kAXColS = 0, kAXColO = 128;       // S / P at 0, O at 128 (256 columns allocated)
+
+struct AttXDev {
+    int Nq, Nk;
+    float scale_log2;
+    __nv_bfloat16* out;
+    int64_t ldo, o_bs;
+};
+
+__global__ void __launch_bounds__(kAXThreads)
+attention_x_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const AttXDev p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* s_q = smem;
+    uint8_t* s_k = s_q + kATile;
+    uint8_t* s_v = s_k + kATile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + kATile);
+    uint64_t* ld_full = bars;          // Q, K, V landed
+    uint64_t* s_full = bars + 1;       // S ready
+    uint64_t* p_full = bars + 2;       // P written (4 warps)
+    uint64_t* o_full = bars + 3;       // O ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int nk16 = (p.Nk + 15) & ~15;             // keys the MMAs see (zero rows past Nk)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_k);
+        tma_prefetch_desc(&tm_v);
+        mbar_init(ld_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 4) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(ld_full, 3 * kATile);
+            tma_load_3d(&tm_q, s_q, ld_full, head * kAD, qt * kAQ, b);
+            tma_load_3d(&tm_k, s_k, ld_full, head * kAD, 0, b);
+            tma_load_3d(&tm_v, s_v, ld_full, head * kAD, 0, b);
+            mbar_wait(ld_full, 0);
+            tc_fence_after();
+            const uint32_t idesc_s = make_idesc_mn(kAQ, nk16, false);
+            const uint64_t dq = make_smem_desc(smem_u32(s_q)), dk = make_smem_desc(smem_u32(s_k));
+#pragma unroll
+            for (int k = 0; k < kAD / 16; ++k) umma_bf16(tmem_base + kAXColS, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+            umma_commit(s_full);
+            mbar_wait(p_full, 0);
+            tc_fence_after();
+            constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);
+            const uint64_t dv = make_smem_desc_mn(smem_u32(s_v));
+            for (int ks = 0; ks < nk16 / 16; ++ks)
+                umma_bf16_ts(tmem_base + kAXColO, tmem_base + kAXColS + ks * 8, dv + (uint64_t)ks * (2048 >> 4), idesc_o, ks != 0);
+            umma_commit(o_full);
+        }
+    } else {
+        const int row = warp * 32 + lane;                       // warp w owns TMEM lanes 32w .. 32w+31
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        const uint32_t ts = tmem_base + lane_addr + kAXColS, to = tmem_base + lane_addr + kAXColO;
+        const float sc = p.scale_log2;
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        uint32_t sv[kAK];
+#pragma unroll
+        for (int c = 0; c < kAK; c += 16)
+            if (c < nk16) tmem_ld16(ts + c, sv + c);
+        tmem_ld_wait();
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kAK; c += 2) {
+            if (c < p.Nk) mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+            if (c + 1 < p.Nk) mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+        }
+        const float m = fmaxf(mx0, mx1) * sc;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c16 = 0; c16 < kAK; c16 += 32) {               // 32 keys -> 16 packed columns
+            if (c16 < nk16) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int k0 = c16 + 2 * c;
+                    const float p0 = k0 < p.Nk ? ex2_approx(fmaf(__uint_as_float(sv[k0]), sc, -m)) : 0.f;
+                    const float p1 = k0 + 1 < p.Nk ? ex2_approx(fmaf(__uint_as_float(sv[k0 + 1]), sc, -m)) : 0.f;
+                    l0 += p0; l1 += p1;
+                    pk[c] = pack_bf16x2(p0, p1);
+                }
+                tmem_st16(ts + (c16 >> 1), pk);                 // P overwrites the S columns this thread has already read
+            }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        const float inv = 1.0f / (l0 + l1);
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const int64_t qrow = (int64_t)qt * kAQ + row;
+        __nv_bfloat16* dst = p.out + (int64_t)b * p.o_bs + qrow * p.ldo + head * kAD;
+#pragma unroll
+        for (int c2 = 0; c2 < kAD; c2 += 32) {
+            uint32_t r[32];
+            tmem_ld16(to + c2, r);
+            tmem_ld16(to + c2 + 16, r + 16);
+            tmem_ld_wait();
+            if (qrow < p.Nq) {
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(r[8 * v8]) * inv, __uint_as_float(r[8 * v8 + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(r[8 * v8 + 2]) * inv, __uint_as_float(r[8 * v8 + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(r[8 * v8 + 4]) * inv, __uint_as_float(r[8 * v8 + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(r[8 * v8 + 6]) * inv, __uint_as_float(r[8 * v8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c2 + 8 * v8) = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// host: single-KV-tile tcgen05 kernel (cross-attention): d = 64, Nk <= 128, any Nq
+bool attention_x_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                           int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, const void* q, const void* k, const void* v,
+                           const void* out) {
+    return d == kAD && Nk <= kAK && Nk >= 1 && Nq >= 1 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 &&
+           q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0 &&
+           (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0;
+}
+
+int launch_attention_x(const void* q, const void* k, const void* v, void* out, int B, int heads, int Nq, int Nk,
+                       int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
+                       int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream) {
+    CUtensorMap tq, tk, tv;
+    const uint32_t box[3] = {(uint32_t)kAD, (uint32_t)kAQ, 1};
+    auto mk = [&](CUtensorMap* m, const void* ptr, int N, int64_t ld, int64_t bs, const char* what) -> int {
+        const uint64_t bstride = (B > 1 ? (uint64_t)bs : (uint64_t)ld * N) * 2;
+        uint64_t dims[3] = {(uint64_t)heads * kAD, (uint64_t)N, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)ld * 2, bstride};
+        return encode_map(m, ptr, 3, dims, str, box, what);
+    };
+    if (int e = mk(&tq, q, Nq, ldq, q_bs, "xattn Q")) return e;
+    if (int e = mk(&tk, k, Nk, ldk, k_bs, "xattn K")) return e;
+    if (int e = mk(&tv, v, Nk, ldv, v_bs, "xattn V")) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RDEIC_CUDA(cudaFuncSetAttribute(attention_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAXSmem));
+        attr_set = true;
+    }
+    AttXDev d;
+    d.Nq = Nq; d.Nk = Nk;
+    d.scale_log2 = scale * 1.4426950408889634f;
+    d.out = (__nv_bfloat16*)out;
+    d.ldo = ldo; d.o_bs = o_bs;
+    dim3 grid((Nq + kAQ - 1) / kAQ, heads, B);
+    launch_k(attention_x_kernel, grid, kAXThreads, kAXSmem, stream, tq, tk, tv, d);
     RDEIC_LAUNCH_CHECK();
     return 0;
 }

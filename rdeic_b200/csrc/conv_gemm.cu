@@ -227,6 +227,24 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     return __ffma2_rn(ahx, erf_abs, hx);                         // 0.5 x + 0.5 |x| erf(|x|/sqrt2)
 }
 
+// GELU in its tanh form for the GEGLU gate (attention.py:54-56) of the bf16 throughput mode:
+//   0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))),  one MUFU (tanh.approx) + 5 packed fp32x2 operations per PAIR
+// against two MUFU (rcp, ex2) and ~12 packed operations for the erf form above.  The GEGLU GEMMs are bound by this
+// epilogue arithmetic (K = 320..1280 against N = 2560..10240 gate/value columns), not by the tensor pipe.  The tanh form
+// differs from F.gelu's exact erf by at most 4.8e-4 absolute (1.8e-4 rms for gates ~ N(0, 1.5)), a ninth of the bf16
+// rounding (1.7e-3 rms) the product takes on its way to the next GEMM.  Exact-GELU users (act = 4: the compressor's
+// entropy-parameter nets) keep the erf form.
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+    const float2 x2 = __fmul2_rn(x, x);
+    const float2 t0 = __ffma2_rn(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
+    const float2 u = __fmul2_rn(x, t0);
+    float2 th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(u.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(u.y));
+    const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    return __ffma2_rn(hx, th, hx);
+}
+
 template <int BN, int kEW, int kMT = 1>
 struct TileCfg {
     static_assert(kMT * BN <= 256, "two accumulator buffers must fit the 512 TMEM columns");
@@ -704,7 +722,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         // interleaved that way at load): attention.py:54-56  x * gelu(gate)
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
+#ifdef RDEIC_GEGLU_ERF
                             const float2 o2 = __fmul2_rn(make_float2(v[j], v[j + 1]), gelu_erf2(make_float2(v[16 + j], v[17 + j])));
+#else
+                            const float2 o2 = __fmul2_rn(make_float2(v[j], v[j + 1]), gelu_tanh2(make_float2(v[16 + j], v[17 + j])));
+#endif
                             v[j] = o2.x; v[j + 1] = o2.y;
                         }
                     }

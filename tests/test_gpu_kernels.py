@@ -481,7 +481,10 @@ def test_split_k_matches_single_pass(cuda, M, K, N):
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", [(2, 5, 256, 256, 64), (1, 10, 100, 77, 64), (1, 4, 1024, 1024, 16),
                                              (2, 16, 64, 77, 16), (1, 20, 64, 64, 64), (1, 2, 4096, 4096, 64),
-                                             (1, 3, 70, 130, 16), (8, 10, 1024, 1024, 64), (5, 15, 1024, 384, 64)])
+                                             (1, 3, 70, 130, 16), (8, 10, 1024, 1024, 64), (5, 15, 1024, 384, 64),
+                                             # one KV tile (cross-attention on the text keys): tcgen05 kernel without a key loop
+                                             (8, 5, 4096, 77, 64), (2, 20, 64, 77, 64), (1, 3, 200, 128, 64), (2, 2, 130, 1, 64),
+                                             (1, 4, 256, 16, 64), (3, 1, 5, 100, 64)])
 def test_attention(cuda, B, heads, Nq, Nk, d):
     from rdeic_b200 import ops
 
