@@ -196,6 +196,10 @@ int rdeic_gn_silu_conv3x3_tail(const void* x, const float* stats, const float* g
                                const void* w_packed, const float* bias, int n_out, float* out_f32, int ldo,
                                uint8_t* out_u8, int B, int H, int W, int C, int groups, float eps,
                                void* workspace, rdeic_stream_t stream);
+/* ABI 5.  1 when rdeic_groupnorm_nhwc runs this problem as ONE kernel (one CTA per sample and group, no workspace
+ * traffic): tensors of at most 4 M elements with an even number of channels per group.  Callers holding fused
+ * statistics skip rdeic_groupnorm_from_stats for such tensors: two launches cost more than the statistics save. */
+int rdeic_groupnorm_is_small(int B, int64_t HW, int C1, int C2, int groups);
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
                          const float* gamma, const float* beta, void* out, int B, int64_t HW,
                          int groups, float eps, int silu, void* workspace,

@@ -107,6 +107,7 @@ SIGNATURES = {
     "rdeic_split_bf16_hilo": [vp, i64, i32, i64, vp, i64, i32, i32, vp],
     "rdeic_blend_tiles_u8": [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp],
     "rdeic_groupnorm_workspace_bytes": [i32, i64, i32],
+    "rdeic_groupnorm_is_small": [i32, i64, i32, i32, i32],
     "rdeic_groupnorm_nhwc": [vp, i32, vp, i32, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "rdeic_groupnorm_from_stats": [vp, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "rdeic_gn_silu_conv3x3_tail": [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, f32, vp, vp],

@@ -385,12 +385,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     // the injected tensor (centre-tap segment) lives on the output grid, whatever the conv's stride
                     const bool ctr = seg && p.a2_center;
                     const int dy = ctr ? 0 : oy + ty, dx = ctr ? 0 : ox + tx;
-                    const int mul = ctr ? 1 : cs;
+                    // ... and with the upsample folded in (up2) that grid is 2H x 2W: this parity class's pixels are every
+                    // other one of it (the a2 map has element strides 2), starting at (py, px)
+                    const int mul = ctr ? (p.up2 ? 2 : 1) : cs;
+                    const int ey = (ctr && p.up2) ? (par >> 1) : dy, ex = (ctr && p.up2) ? (par & 1) : dx;
                     const CUtensorMap* ma = seg ? &tm_a2 : &tm_a;
 #pragma unroll
                     for (int u = 0; u < kMT; ++u)
-                        tma_load_4d(ma, smem_a + (s * kMT + u) * kATileBytes, &full_bar[s], cb * kBlockK, w0[u] * mul + dx,
-                                    h0[u] * mul + dy, n0[u]);
+                        tma_load_4d(ma, smem_a + (s * kMT + u) * kATileBytes, &full_bar[s], cb * kBlockK, w0[u] * mul + ex,
+                                    h0[u] * mul + ey, n0[u]);
                     if (ctr) tma_load_3d(&tm_b2, smem_b + s * Cfg::kBBytes, &full_bar[s], cb * kBlockK, col0, 0);
                     else tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
                     // advance (segment, tap, channel block)
@@ -1085,10 +1088,11 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(p->a2_c == 0 || p->a2, "rdeic_conv_gemm: a2_c > 0 needs a2");
     RDEIC_CHECK_ARG(p->taps == 1 || p->taps == 9 || p->taps == 25 || (p->taps == 4 && p->up2),
                     "rdeic_conv_gemm: taps must be 1, 9 or 25 (4 with up2)");
-    RDEIC_CHECK_ARG(p->up2 == 0 || (p->up2 == 1 && p->taps == 4 && p->w_batch_stride > 0 && p->a2_c == 0 && p->act != 2 &&
-                                    p->w_k == 0 && p->in_stride2 == 0),
-                    "rdeic_conv_gemm: up2 needs taps = 4, the four parity weight matrices w_batch_stride apart, one source, no GEGLU");
-    RDEIC_CHECK_ARG(p->a2_center == 0 || (p->a2_c > 0 && p->w2 && (uintptr_t)p->w2 % 16 == 0 && p->w_k == 0 && p->w_batch_stride == 0),
+    RDEIC_CHECK_ARG(p->up2 == 0 || (p->up2 == 1 && p->taps == 4 && p->w_batch_stride > 0 && (p->a2_c == 0 || p->a2_center) &&
+                                    p->act != 2 && p->w_k == 0 && p->in_stride2 == 0),
+                    "rdeic_conv_gemm: up2 needs taps = 4, the four parity weight matrices w_batch_stride apart, no concat source, no GEGLU");
+    RDEIC_CHECK_ARG(p->a2_center == 0 || (p->a2_c > 0 && p->w2 && (uintptr_t)p->w2 % 16 == 0 && p->w_k == 0 &&
+                                          (p->w_batch_stride == 0 || p->up2)),
                     "rdeic_conv_gemm: a2_center needs a second source, its packed weights w2 and a packed w");
     RDEIC_CHECK_ARG(p->in_stride2 == 0 || ((p->taps == 1 || p->taps == 9) && p->w_batch_stride == 0 && (p->pad_lo == 0 || p->pad_lo == 1)),
                     "rdeic_conv_gemm: in_stride2 needs a 1x1 or 3x3 filter and pad_lo in {0, 1}");
@@ -1169,11 +1173,14 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
         if (p->a2_c) {
             uint64_t dims2[4] = {(uint64_t)p->a2_c, iw, ih, (uint64_t)p->a_n};
             uint64_t str2[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * iw, (uint64_t)a2_ld * 2 * iw * ih};
-            if (d.a2_center) {           // always on the output grid, unit element strides
-                uint64_t dims2c[4] = {(uint64_t)p->a2_c, (uint64_t)p->a_w, (uint64_t)p->a_h, (uint64_t)p->a_n};
-                uint64_t str2c[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * p->a_w, (uint64_t)a2_ld * 2 * p->a_w * p->a_h};
-                uint32_t box2c[4] = {(uint32_t)kBlockK, (uint32_t)tw_eff, (uint32_t)th_eff, (uint32_t)tn};
-                if (int e = encode_map(&ta2, p->a2, 4, dims2c, str2c, box2c, "A2")) return e;
+            if (d.a2_center) {           // always on the output grid: unit element strides, or (up2) every other pixel of 2H x 2W
+                const uint64_t us = d.up2 ? 2 : 1;
+                const uint64_t ow = (uint64_t)p->a_w * us, oh = (uint64_t)p->a_h * us;
+                uint64_t dims2c[4] = {(uint64_t)p->a2_c, ow, oh, (uint64_t)p->a_n};
+                uint64_t str2c[3] = {(uint64_t)a2_ld * 2, (uint64_t)a2_ld * 2 * ow, (uint64_t)a2_ld * 2 * ow * oh};
+                uint32_t box2c[4] = {(uint32_t)kBlockK, (uint32_t)(tw_eff * us), (uint32_t)(th_eff * us), (uint32_t)tn};
+                uint32_t estr2c[4] = {1, (uint32_t)us, (uint32_t)us, 1};
+                if (int e = encode_map(&ta2, p->a2, 4, dims2c, str2c, box2c, "A2", estr2c)) return e;
             } else if (int e = encode_map(&ta2, p->a2, 4, dims2, str2, box, "A2", estr)) return e;
         }
         const uint64_t kp = (uint64_t)(d.a2_center ? d.taps * d.cblk1 : host_total_kb(d)) * kBlockK;

@@ -189,6 +189,74 @@ gn_fold_stats_kernel(const float2* __restrict__ st1, int C1, const float2* __res
     }
 }
 
+// Small tensors (UNet levels 2-3, the control adapter: <= 4 M elements): GroupNorm(+SiLU) in ONE kernel, one CTA per
+// (sample, group).  At that size the statistics + apply pair (or fold + apply) is two launch latencies around a few
+// microseconds of work; here the group's HW x C/G elements are read twice by the same CTA (second time from L1/L2),
+// statistics are reduced in a fixed order (fp32 per thread, fp64 across the CTA: deterministic) and nothing goes
+// through a workspace.  Two channels per access (C/G is even for every GroupNorm on the path).
+constexpr int kGnSmallMaxElems = 1 << 22;
+
+template <bool kF32>
+__global__ void __launch_bounds__(kGnThreads)
+gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
+                const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                int HW, int G, float eps, int silu, FastDiv div_pairs) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ double s_red[2][kGnThreads / 32];
+    __shared__ float s_stat[2];
+    const int C = C1 + C2, cg = C / G, pairs = cg >> 1;
+    const int b = blockIdx.y, c0 = blockIdx.x * cg;
+    const int total = HW * pairs;
+    auto load2 = [&](int p, int c) -> float2 {
+        const bool first = c < C1;
+        const int64_t off = first ? ((int64_t)b * HW + p) * C1 + c : ((int64_t)b * HW + p) * C2 + (c - C1);
+        const void* src = first ? x1 : x2;
+        if (kF32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(src) + off);
+        float2 v;
+        unpack_bf16x2(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(src) + off), v.x, v.y);
+        return v;
+    };
+    float s = 0.f, q = 0.f;
+    for (int i = threadIdx.x; i < total; i += kGnThreads) {
+        uint32_t p, j;
+        div_pairs.divmod((uint32_t)i, p, j);
+        const float2 v = load2((int)p, c0 + 2 * (int)j);
+        s += v.x + v.y;
+        q = fmaf(v.x, v.x, fmaf(v.y, v.y, q));
+    }
+    double ds = (double)s, dq = (double)q;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = ds; s_red[1][threadIdx.x >> 5] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < kGnThreads / 32; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+        const double n = (double)HW * cg;
+        const double mean = a / n;
+        double var = c / n - mean * mean;        // biased variance, as nn.GroupNorm
+        if (var < 0.0) var = 0.0;
+        s_stat[0] = (float)mean;
+        s_stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_stat[0], rstd = s_stat[1];
+    for (int i = threadIdx.x; i < total; i += kGnThreads) {
+        uint32_t p, j;
+        div_pairs.divmod((uint32_t)i, p, j);
+        const int c = c0 + 2 * (int)j;
+        const float2 v = load2((int)p, c);
+        const float2 ga = *reinterpret_cast<const float2*>(gamma + c), be = *reinterpret_cast<const float2*>(beta + c);
+        float y0 = fmaf((v.x - mean) * rstd, ga.x, be.x), y1 = fmaf((v.y - mean) * rstd, ga.y, be.y);
+        if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        *reinterpret_cast<uint32_t*>(out + ((int64_t)b * HW + p) * C + c) = pack_bf16x2(y0, y1);
+    }
+}
+
 template <bool kF32, bool kOutF32 = false>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
@@ -642,6 +710,14 @@ int64_t rdeic_groupnorm_workspace_bytes(int B, int64_t HW, int C) {
     return (int64_t)B * kGnMaxChunks * kGnMaxGroups * (int64_t)sizeof(float2);
 }
 
+int rdeic_groupnorm_is_small(int B, int64_t HW, int C1, int C2, int groups) {
+    const int C = C1 + C2;
+    if (B <= 0 || HW <= 0 || groups <= 0 || C % groups) return 0;
+    const int cg = C / groups;
+    // pairs of channels must not straddle the two sources, and a group's pairs are 8-byte aligned fp32 / 4-byte bf16
+    return (int64_t)B * HW * C <= kGnSmallMaxElems && HW * (int64_t)cg < (1ll << 30) && cg % 2 == 0 && C1 % 2 == 0;
+}
+
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
                          const float* gamma, const float* beta, void* out, int B, int64_t HW,
                          int groups, float eps, int silu, void* workspace,
@@ -660,6 +736,17 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     RDEIC_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0,
                     "rdeic_groupnorm_nhwc: tensors must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
+    if (rdeic_groupnorm_is_small(B, HW, C1, C2, groups)) {
+        const FastDiv div_pairs((uint32_t)((C / groups) >> 1));
+        if (in_is_f32)
+            launch_k(gn_small_kernel<true>, dim3((unsigned)groups, B), kGnThreads, 0, s, x1, C1, x2, C2, gamma, beta,
+                     (__nv_bfloat16*)out, (int)HW, groups, eps, silu, div_pairs);
+        else
+            launch_k(gn_small_kernel<false>, dim3((unsigned)groups, B), kGnThreads, 0, s, x1, C1, x2, C2, gamma, beta,
+                     (__nv_bfloat16*)out, (int)HW, groups, eps, silu, div_pairs);
+        RDEIC_LAUNCH_CHECK();
+        return 0;
+    }
     const int nchunk = gn_num_chunks(B, HW);
     if (in_is_f32)
         launch_k(gn_stats_kernel<true>, dim3(nchunk, B), kGnThreads, 0, s, x1, C1, x2, C2, HW, groups, (float2*)workspace);

@@ -365,13 +365,13 @@ class NoiseEstimatorEngine:
         sl = sd["control_model.scale_list"].float().cpu() * self.control_scale
         self.scales = [float(v) for v in sl]
         # Every injection whose target tensor is written by a GEMM on the same pixel grid rides in that GEMM
-        # (`Inject`): the 12 encoder ones, the middle one, and the decoder ones that follow a block not ending in an
-        # upsample.  dec_zero[0] (a second injection into the middle output) and the three after an upsample stay
-        # separate 1x1 GEMMs with the residual epilogue (`_inject`).
+        # (`Inject`): the 12 encoder ones, the middle one, and the decoder ones (after an upsample the control tensor
+        # lives on the 2H x 2W output grid: each parity class of the folded conv reads every other pixel of it).
+        # Only dec_zero[0], a second injection into the middle output, stays a separate 1x1 GEMM (`_inject`).
         def last_conv(layers: List[Layer]) -> Optional[Conv]:
             L = layers[-1]
             return {"res": lambda: L.w.conv2, "attn": lambda: L.w.proj_out, "down": lambda: L.w,
-                    "conv_in": lambda: L.w, "up": lambda: None}[L.kind]()
+                    "conv_in": lambda: L.w, "up": lambda: L.w}[L.kind]()
 
         self.fuse_inject = os.environ.get("RDEIC_NO_FUSED_INJECT") is None
         self.enc_inj = [Inject.load(sd, f"control_model.enc_zero_convs_out.{i}.0", dev, self.scales[i], last_conv(blk))
@@ -497,9 +497,9 @@ class NoiseEstimatorEngine:
                     x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 9, dual=True, stats=True, stride2=True, **kw))
             elif L.kind == "up":
                 # nearest x2 + conv3x3 (openaimodel.py:106-113) as four 2x2 parity convs on the input grid
-                assert ij is None
-                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 4, bias=L.w.b, dual=True, stats=True, up2=True,
-                                       w_batch_stride=L.w.w.stride(0)))
+                kw = ij.kw() if ij is not None else dict(bias=L.w.b)
+                x = Act(*ops.conv_gemm(x.h, L.w.w, L.w.n_out, 4, dual=True, stats=True, up2=True,
+                                       w_batch_stride=L.w.w.stride(0), **kw))
             elif L.kind == "conv_in":
                 if ij is not None:                  # base conv_in has a single source: a2 is free for the injection
                     assert x_in2 is None

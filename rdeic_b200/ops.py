@@ -22,7 +22,7 @@ GEMM_PROFILE = None   # when a list: conv_gemm appends (start_event, end_event, 
 
 
 _KERNELS_PER_CALL = {"rdeic_groupnorm_nhwc": 2, "rdeic_groupnorm_from_stats": 2, "rdeic_vq_quant": 3,
-                     "rdeic_gn_silu_conv3x3_tail": 2}
+                     "rdeic_gn_silu_conv3x3_tail": 2, "rdeic_groupnorm_nhwc(small)": 1}
 
 
 def check(status: int, what: str) -> None:
@@ -411,6 +411,13 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
         raise TypeError("groupnorm: both sources must share a dtype")
     out = torch.empty((B, H, W, C1 + C2), dtype=BF16, device=x1.device)
     ws = workspace if workspace is not None else _gn_workspace(B, x1.device)
+    if _lib.load().rdeic_groupnorm_is_small(B, H * W, C1, C2, groups):
+        # one kernel per GroupNorm for the small tensors of UNet levels 2-3 / the control adapter (fused statistics,
+        # if any, are ignored: fold + apply would be two launch latencies)
+        check(_lib.load().rdeic_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, int(x1.dtype == torch.float32), _ptr(gamma),
+                                               _ptr(beta), _ptr(out), B, H * W, groups, eps, 1 if silu else 0, _ptr(ws),
+                                               _stream()), "rdeic_groupnorm_nhwc(small)")
+        return out
     if stats1 is not None and (x2 is None or stats2 is not None):
         check(_lib.load().rdeic_groupnorm_from_stats(_ptr(x1), C1, _ptr(stats1), _ptr(x2), C2, _ptr(stats2),
                                                      int(x1.dtype == torch.float32), _ptr(gamma), _ptr(beta), _ptr(out),
@@ -521,7 +528,7 @@ def conv_gemm(a: torch.Tensor, w_packed: torch.Tensor, n_out: int, taps: int, *,
     gh, gw = (H // 2, W // 2) if stride2 else (H, W)                 # the M grid the kernel tiles
     OH, OW = (2 * H, 2 * W) if up2 else (gh, gw)                       # the output grid
     if a2 is not None and (a2.dtype != BF16 or not _is_nhwc_slice(a2) or
-                           tuple(a2.shape[:3]) != ((N, gh, gw) if w2 is not None else (N, H, W))):
+                           tuple(a2.shape[:3]) != ((N, OH, OW) if w2 is not None else (N, H, W))):
         raise TypeError("conv_gemm: a2 must be bf16 NHWC with the pixel grid of A (of the output when it is injected)")
     n_cols = n_out // 2 if act == 2 else n_out
     of = oh = None

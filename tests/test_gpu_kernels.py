@@ -297,7 +297,9 @@ def test_image_to_u8(cuda):
 @pytest.mark.parametrize("B,H,W,C1,C2,silu,eps", [
     (2, 16, 16, 320, 0, True, 1e-5), (1, 8, 8, 1280, 1280, True, 1e-5), (2, 32, 32, 640, 320, True, 1e-5),
     (1, 12, 20, 64, 0, False, 1e-6), (1, 64, 64, 128, 0, True, 1e-6), (3, 4, 4, 256, 0, False, 1e-6),
-    (1, 5, 3, 960, 0, True, 1e-5)])
+    (1, 5, 3, 960, 0, True, 1e-5),
+    # > 4 M elements: the statistics + apply pair (smaller ones run as one kernel, one CTA per sample and group)
+    (2, 128, 128, 320, 0, True, 1e-5), (1, 96, 96, 320, 320, True, 1e-5), (5, 64, 64, 256, 0, False, 1e-6)])
 def test_groupnorm(cuda, B, H, W, C1, C2, silu, eps):
     from rdeic_b200 import ops
 
@@ -912,3 +914,25 @@ def test_blend_tiles_u8(cuda, h, w, tile, ov, s):
     full = torch.randint(0, 256, (h * s, w * s, 3), generator=g, dtype=torch.uint8)
     cut = torch.stack([full[p[0] * s:(p[0] + th) * s, p[1] * s:(p[1] + tw) * s] for p in plan])
     assert torch.equal(ops.blend_tiles_u8(cut.to(cuda), origins.to(cuda), ov * s, h * s, w * s).cpu(), full)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cc,Cout", [(2, 32, 32, 64, 64, 96), (1, 16, 16, 128, 256, 320), (8, 8, 8, 1280, 256, 1280)])
+def test_conv_upsample_folded_with_injection(cuda, B, H, W, Cin, Cc, Cout):
+    """The decoder's `h = Upsample.conv(nearest2x(h)); h = h + zero_conv(h_ctr) * scale` (openaimodel.py:106-113 then
+    rdeic.py:207 before the next block) in one GEMM: the control tensor lives on the 2H x 2W output grid and every
+    parity class of the folded conv reads every other pixel of it."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(64)
+    x = _bf(torch.randn(B, Cin, H, W, generator=g))
+    hc = _bf(torch.randn(B, Cc, 2 * H, 2 * W, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    wz = _bf(torch.randn(Cout, Cc, 1, 1, generator=g) / math.sqrt(Cc))
+    b, bz = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = (F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1) + F.conv2d(hc, wz, bz)).permute(0, 2, 3, 1)
+    wp, w2 = ops.pack_up2_weight(w.to(cuda)), ops.pack_conv_weight(wz.to(cuda))
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    of, oh, st = ops.conv_gemm(nhwc(x), wp, Cout, 4, a2=nhwc(hc), w2=w2, bias=(b + bz).to(cuda), dual=True, stats=True, up2=True,
+                               w_batch_stride=wp.stride(0))
+    assert tuple(of.shape) == (B, 2 * H, 2 * W, Cout)
+    assert _rel(of.cpu(), ref) < 4e-3, _rel(of.cpu(), ref)
