@@ -218,6 +218,7 @@ gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         return v;
     };
     float s = 0.f, q = 0.f;
+#pragma unroll 4
     for (int i = threadIdx.x; i < total; i += kGnThreads) {
         uint32_t p, j;
         div_pairs.divmod((uint32_t)i, p, j);
@@ -245,6 +246,7 @@ gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
     __syncthreads();
     const float mean = s_stat[0], rstd = s_stat[1];
+#pragma unroll 4
     for (int i = threadIdx.x; i < total; i += kGnThreads) {
         uint32_t p, j;
         div_pairs.divmod((uint32_t)i, p, j);
@@ -714,8 +716,11 @@ int rdeic_groupnorm_is_small(int B, int64_t HW, int C1, int C2, int groups) {
     const int C = C1 + C2;
     if (B <= 0 || HW <= 0 || groups <= 0 || C % groups) return 0;
     const int cg = C / groups;
-    // pairs of channels must not straddle the two sources, and a group's pairs are 8-byte aligned fp32 / 4-byte bf16
-    return (int64_t)B * HW * C <= kGnSmallMaxElems && HW * (int64_t)cg < (1ll << 30) && cg % 2 == 0 && C1 % 2 == 0;
+    // pairs of channels must not straddle the two sources, and a group's pairs are 8-byte aligned fp32 / 4-byte bf16.
+    // One CTA walks a whole group: worth it only while that is a couple of dozen iterations per thread and a pixel's
+    // slice of the group fills at least one 32-byte sector (the control adapter's 64- and 128-channel levels at 64^2 /
+    // 32^2 have 2 or 4 channels per group and thousands of pixels: measured 84 us here against ~15 us for fold + apply).
+    return (int64_t)B * HW * C <= kGnSmallMaxElems && HW * (int64_t)cg <= 12288 && cg >= 8 && cg % 2 == 0 && C1 % 2 == 0;
 }
 
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,

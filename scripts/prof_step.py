@@ -1,5 +1,8 @@
-"""Per-kernel device time of one CUDA-graph UNet+control step and one VAE decode, from CUPTI through torch.profiler
-(no kernel replay, so the graph's two-stream overlap and PDL stay as in production): where the step goes now.
+"""Where one CUDA-graph UNet+control step goes, kernel by kernel, from CUPTI through torch.profiler (no kernel replay, so
+the graph's two-stream overlap and PDL stay as in production).  With programmatic dependent launch a kernel's recorded
+duration includes the time it sits at griddepcontrol.wait behind its predecessor, so durations are not additive; what is
+additive along a stream is each kernel's END-TO-END increment end(i) - end(i-1).  The script prints, per kernel class on
+the stream that carries the critical path, the sum of those increments (= that class's share of the step).
 A breakdown tool; bench numbers never come from a profiled run.  Usage: python scripts/prof_step.py [batch]"""
 import re
 import sys
@@ -29,25 +32,62 @@ for _ in range(3):
 torch.cuda.synchronize()
 
 
-def run(fn, n, title):
+def short(name):
+    name = re.sub(r"^void ", "", name).replace("rdeic::", "")
+    return re.sub(r"\(.*", "", name)
+
+
+def run(fn, title):
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(n):
-            fn()
+        fn()
         torch.cuda.synchronize()
-    agg = defaultdict(lambda: [0.0, 0])
-    t0, t1 = 1e30, 0.0
-    for e in prof.events():
-        if e.device_type is not None and "cuda" in str(e.device_type).lower() and e.device_time_total > 0:
-            name = re.sub(r"^void ", "", e.name).replace("rdeic::", "")
-            name = re.sub(r"\(.*", "", name)
-            agg[name][0] += e.device_time_total
-            agg[name][1] += 1
-            t0, t1 = min(t0, e.time_range.start), max(t1, e.time_range.end)
-    tot = sum(v[0] for v in agg.values())
-    print(f"== {title}: {n} x; sum of kernel time {tot / n / 1e3:.3f} ms per call, span {(t1 - t0) / n / 1e3:.3f} ms per call")
-    for name, (us, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-        print(f"  {us / n / 1e3:8.3f} ms {100 * us / tot:5.1f}%  n={cnt // n:4d}  avg {us / cnt:8.1f} us  {name[:110]}")
+    evs = [e for e in prof.profiler.kineto_results.events() if str(e.device_type()).lower().endswith("cuda") and e.duration_ns() > 0]
+    streams = defaultdict(list)
+    for e in evs:
+        streams[e.device_resource_id()].append((e.start_ns(), e.start_ns() + e.duration_ns(), short(e.name())))
+    t0 = min(s for v in streams.values() for s, _, _ in v)
+    t1 = max(t for v in streams.values() for _, t, _ in v)
+    print(f"== {title}: span {(t1 - t0) / 1e6:.3f} ms, {len(evs)} kernels on {len(streams)} stream(s)")
+    # A CUDA graph spreads its branches over internal streams, so per-stream gaps mean nothing.  Sweep the union
+    # timeline instead: time with 0 / 1 / >= 2 kernels in flight, and for every instant with exactly one kernel in
+    # flight charge it to that kernel (the serial part of the step); overlapped time is charged to "(overlap)".
+    pts = []
+    allk = [k for v in streams.values() for k in v]
+    for i, (s_, t_, name) in enumerate(allk):
+        pts.append((s_, 1, i))
+        pts.append((t_, -1, i))
+    pts.sort()
+    live = set()
+    last = pts[0][0]
+    excl = defaultdict(float)
+    hist = defaultdict(float)
+    for t_, kind, i in pts:
+        dt = t_ - last
+        if dt > 0:
+            n = len(live)
+            hist[min(n, 3)] += dt
+            if n == 0:
+                excl["(no kernel in flight)"] += dt
+            elif n == 1:
+                excl[allk[next(iter(live))][2]] += dt
+            else:
+                # PDL: a successor is resident (waiting at griddepcontrol.wait) while its predecessor runs: charge the
+                # kernel that started FIRST (the one doing the work)
+                first = min(live, key=lambda j: allk[j][0])
+                excl[allk[first][2]] += dt
+        last = t_
+        if kind == 1:
+            live.add(i)
+        else:
+            live.discard(i)
+    tot = sum(excl.values())
+    print(f"  in flight: 0 kernels {hist[0] / 1e6:.3f} ms, 1 kernel {hist[1] / 1e6:.3f} ms, 2 {hist[2] / 1e6:.3f} ms, >= 3 {hist[3] / 1e6:.3f} ms")
+    cnt = defaultdict(int)
+    for _, _, name in allk:
+        cnt[name] += 1
+    for name, ns in sorted(excl.items(), key=lambda kv: -kv[1])[:34]:
+        print(f"    {ns / 1e6:7.3f} ms {100 * ns / tot:5.1f}%  n={cnt.get(name, 0):4d}  {name[:110]}")
 
 
-run(lambda: model.apply_model(x, tt, cond), 5, f"UNet+control step, batch {batch} (graph replay)")
-run(lambda: model.decode_first_stage_u8(z), 3, f"VAE decode to uint8, batch {batch}")
+run(lambda: model.apply_model(x, tt, cond), f"UNet+control step, batch {batch} (graph replay)")
+run(lambda: model.decode_first_stage_u8(z), f"VAE decode to uint8, batch {batch}")
