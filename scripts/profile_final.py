@@ -3,7 +3,11 @@
 2 linear K=320 N=320 + fp32 residual   3 GEGLU linear K=320 N=2560   4 tcgen05 attention N=4096 h=5 d=64
 5 GroupNorm+SiLU [8,512,512,128] (stats + apply)   6 LayerNorm [32768,320]   7 relay_update   8 ckbd encode phase
 9 conv3x3 128->128 @512^2 (VAE) emitting GroupNorm statistics   10 GroupNorm from those statistics (fold + apply)
-11 conv5x5 8->224 @32^2 batch 8 (compressor channel context)"""
+11 conv5x5 8->224 @32^2 batch 8 (compressor channel context)
+round 2:  12 nearest-x2 + conv3x3 640->640 folded into four 2x2 parity convs @32^2->64^2   13 stride-2 conv3x3 320->320 through an
+element-strided tensor map   14 conv3x3 320->320 with the zero-conv injection as a centre-tap K segment   15 cross-attention
+(77 text keys, single-KV-tile tcgen05 kernel)   16 GroupNorm [8,16,16,1280] as one kernel   17 fp32 conv5x5 224->128 @32^2 batch 8
+(entropy-parameter path, CUDA cores, split-K)   18 uint8 tile blend 2048x1408"""
 import sys
 from pathlib import Path
 import torch
@@ -27,6 +31,17 @@ sc = torch.exp(torch.rand(8, 64, 128, 128, generator=g, device=dev) * 8 - 3); ta
 w128 = ops.pack_conv_weight(rnd(128, 128, 3, 3) / 34)
 _, st128 = ops.conv_gemm(gn, w128, 128, 9, bias=gam, resid=gn, stats=True)
 x8 = rnd(8, 32, 32, 8).bfloat16(); w5 = ops.pack_conv_weight(rnd(224, 8, 5, 5) / 14); b224 = rnd(224)
+x640 = rnd(8, 32, 32, 640).bfloat16(); wup = ops.pack_up2_weight(rnd(640, 640, 3, 3) / 76); b640 = rnd(640)
+hc = rnd(8, 64, 64, 64).bfloat16(); wz = ops.pack_conv_weight(rnd(320, 64, 1, 1) / 8)
+kv77 = rnd(8, 77, 640).bfloat16(); q77 = rnd(8, 4096, 320).bfloat16()
+gs = rnd(8, 16, 16, 1280); g1280, b1280 = torch.ones(1280, device=dev), torch.zeros(1280, device=dev)
+from rdeic_b200.compression_f32 import CompressionNetsF32  # noqa: E402
+nets = CompressionNetsF32({"c.weight": rnd(128, 224, 5, 5).cpu() / 75, "c.bias": rnd(128).cpu()}, "", dev)
+xf = rnd(8, 32, 32, 224)
+from rdeic_b200 import parallel  # noqa: E402
+plan = parallel.plan_tiles_balanced(176, 256, 8, 16)
+tiles = torch.randint(0, 255, (len(plan), plan[0][2] * 8, plan[0][3] * 8, 3), device=dev, dtype=torch.uint8)
+org = torch.tensor([[p_[0] * 8, p_[1] * 8] for p_ in plan], dtype=torch.int32, device=dev)
 fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True),
        lambda: ops.conv_gemm(x512, w512, 512, 9, bias=b512),
        lambda: ops.linear(xl, wl, 320, bias=b320, resid=rl, out_f32=True),
@@ -38,7 +53,14 @@ fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True
        lambda: ops.ckbd_encode_phase(y, sc, mu, tab, 0.11, 0),
        lambda: ops.conv_gemm(gn, w128, 128, 9, bias=gam, resid=gn, stats=True),
        lambda: ops.groupnorm(gn, gam, bet, 32, 1e-6, True, stats1=st128),
-       lambda: ops.conv_gemm(x8, w5, 224, 25, bias=b224, act=4)]
+       lambda: ops.conv_gemm(x8, w5, 224, 25, bias=b224, act=4),
+       lambda: ops.conv_gemm(x640, wup, 640, 4, bias=b640, dual=True, stats=True, up2=True, w_batch_stride=wup.stride(0)),
+       lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, dual=True, stats=True, stride2=True),
+       lambda: ops.conv_gemm(x320, w320, 320, 9, a2=hc, w2=wz, bias=b320, resid=r32, dual=True, stats=True),
+       lambda: ops.attention(q77, kv77[..., :320], kv77[..., 320:], 5, 64, 0.125),
+       lambda: ops.groupnorm(gs, g1280, b1280, 32, 1e-5, True),
+       lambda: nets.conv(xf, "c", act=4),
+       lambda: ops.blend_tiles_u8(tiles, org, 128, 1408, 2048)]
 for _ in range(2):
     for f in fns:
         f()
