@@ -285,7 +285,9 @@ int rdeic_pack_conv_weight(const float* w_oihw, void* dst, int n_out, int c1, in
 
 /* Fused softmax(Q K^T * scale) V (attention.py:171-203).  q [B, Nq, *] with row stride ldq
  * (elements), heads laid out as consecutive d-wide column groups; k, v [B, Nk, *] likewise;
- * batch strides in elements.  d in {16, 64}.  out [B, Nq, heads*d] row stride ldo.
+ * batch strides in elements.  d in {16, 64}, or {256, 512} with Nq and Nk multiples of 128: the VAE mid-block
+ * attention of ldm/modules/diffusionmodules/model.py:181-205 (one head, d = C = 512) as a flash kernel -- the [B, N, N]
+ * score tensor of the reference's bmm / softmax / bmm is never materialised.  out [B, Nq, heads*d] row stride ldo.
  * scale > 0 (the reference passes dim_head ** -0.5, attention.py:163): row maxima are taken on the raw
  * logits and the scale is folded into the multiply-add that feeds the exponential. */
 int rdeic_attention(const void* q, const void* k, const void* v, void* out, int B, int heads,

@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 BUILD = HERE / "_build"
 LIB = HERE / "librdeic_b200.so"
-SOURCES = ["api.cu", "entropy.cu", "elementwise.cu", "norm.cu", "conv_gemm.cu", "attention.cu", "attention_tc.cu",
+SOURCES = ["api.cu", "entropy.cu", "elementwise.cu", "norm.cu", "conv_gemm.cu", "attention.cu", "attention_tc.cu", "attention_wide.cu",
            "fp32_mode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -223,6 +223,13 @@ int launch_attention_x(const void* q, const void* k, const void* v, void* out, i
                        int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs,
                        int64_t v_bs, int64_t o_bs, float scale, cudaStream_t stream);
 
+bool attention_wide_supported(int d, int Nq, int Nk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs,
+                              int64_t k_bs, int64_t v_bs, int64_t o_bs, const void* q, const void* k, const void* v,
+                              const void* out);
+int launch_attention_wide(const void* q, const void* k, const void* v, void* out, int B, int heads, int Nq, int Nk, int d,
+                          int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs,
+                          int64_t o_bs, float scale, cudaStream_t stream);
+
 }  // namespace rdeic
 
 using namespace rdeic;
@@ -233,7 +240,7 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
                                int64_t v_bs, int64_t o_bs, float scale, rdeic_stream_t stream) {
     RDEIC_CHECK_ARG(q && k && v && out, "rdeic_attention: null pointer");
     RDEIC_CHECK_ARG(B > 0 && heads > 0 && Nq > 0 && Nk > 0, "rdeic_attention: empty problem");
-    RDEIC_CHECK_ARG(d == 16 || d == 64, "rdeic_attention: head dim %d not instantiated (16, 64)", d);
+    RDEIC_CHECK_ARG(d == 16 || d == 64 || d == 256 || d == 512, "rdeic_attention: head dim %d not instantiated (16, 64, 256, 512)", d);
     RDEIC_CHECK_ARG(scale > 0.f, "rdeic_attention: scale must be positive (got %g)", (double)scale);
     RDEIC_CHECK_ARG(B <= 65535 && heads <= 65535, "rdeic_attention: grid too large");
     RDEIC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 &&
@@ -241,6 +248,14 @@ extern "C" int rdeic_attention(const void* q, const void* k, const void* v, void
                     "rdeic_attention: strides must keep 16-byte row alignment");
     RDEIC_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) % 16 == 0 && (uintptr_t)out % 4 == 0,
                     "rdeic_attention: pointers must be 16-byte aligned");
+    // wide heads (the VAE mid-block attention, d = C = 512): flash kernel with the value dimension split over two CTAs
+    if (d >= 256) {
+        RDEIC_CHECK_ARG((int64_t)B * heads <= 65535, "rdeic_attention: grid too large");
+        RDEIC_CHECK_ARG(attention_wide_supported(d, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, q, k, v, out),
+                        "rdeic_attention: d = %d needs Nq and Nk to be multiples of 128 (got %d, %d) and 16-byte aligned rows", d, Nq, Nk);
+        return launch_attention_wide(q, k, v, out, B, heads, Nq, Nk, d, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs, scale,
+                                     as_stream(stream));
+    }
     if (attention_tc_supported(d, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, q, k, v, out) &&
         !getenv("RDEIC_ATTN_MMA_SYNC"))
         return launch_attention_tc(q, k, v, out, B, heads, Nq, Nk, ldq, ldk, ldv, ldo, q_bs, k_bs, v_bs, o_bs,

@@ -273,7 +273,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 // order inside a group already guarantees the hand-offs (P(j+1) and PV(j+1) come after add_o(j)).
 // ---------------------------------------------------------------------------------------------
 constexpr int kA2Q = 256;
-constexpr int kA2Threads = 64 + 32 * 8;
+// warp 0 = TMA producer, warps 1 / 2 = MMA issuers of group A / B, warp 3 idle, warps 4-7 / 8-11 = softmax group A / B.
+// One issuing thread sustains one tcgen05.mma per ~100 clocks whatever the shape (scripts/micro/ubench.cu: N = 16 .. 160, A in
+// shared or tensor memory, all 100 clocks; two issuing warps: 52 per SM, four: 26), and a 128-key step of the two groups is
+// 8 S + 16 PV instructions: 2400 clocks from one thread against 2048 clocks of MUFU work.  With one issuer per group the
+// instruction stream is 1200 clocks per step and the exponentials are the only bound left.
+// Warps 0-3 form one warp group so that setmaxnreg can hand their registers to the softmax groups.
+constexpr int kA2Threads = 128 + 32 * 8;
+constexpr int kA2RegsCtl = 56, kA2RegsSoft = 216;         // 128 * 56 + 256 * 216 = 62464 <= 384 * 168
 constexpr int kA2Smem = 2 * kATile /*Q*/ + 2 * kAStages * kATile /*K,V*/ + 2 * kAPBytes /*P_A,P_B*/ + 1024 + 256;
 constexpr uint32_t kA2ColS = 0, kA2ColO = 256;    // S_A 0, S_B 128 ; O_A 256, O_B 320
 // kLazy keeps the probabilities in tensor memory (P_A 384, P_B 448: 128 keys = 64 packed columns each) and feeds
@@ -288,6 +295,9 @@ constexpr int kA2LazySmem = 2 * kATile /*Q*/ + 2 * kA2LazyStages * kATile /*K,V*
 // (exact: l and O carry the same factor, which cancels in O / l; P <= 256 is harmless in bf16).  The
 // per-step fold-in of PV (TMEM load + 64 adds + 64 multiplies per thread) disappears, and with the 64
 // accumulator registers gone the S tile is read from TMEM once (128 registers) instead of twice.
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 template <bool kLazy>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -319,7 +329,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tma_prefetch_desc(&tm_k);
         tma_prefetch_desc(&tm_v);
         mbar_init(q_full, 1);
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }   // both issuers release a stage
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1);
             mbar_init(&s_free[g], 4);
@@ -336,7 +346,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
 
+    // (setmaxnreg sits inside each role's branch: ptxas bounds the registers of the code that FOLLOWS one, path-insensitively)
     if (warp == 0) {
+        setmaxnreg_dec<kA2RegsCtl>();
         if (lane == 0) {
             mbar_expect_tx(q_full, 2 * kATile);
             tma_load_3d(&tm_q, s_q, q_full, head * kAD, qt * kA2Q, b);
@@ -349,8 +361,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 tma_load_3d(&tm_v, s_v + s * kATile, &kv_full[s], head * kAD, j * kAK, b);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
+        setmaxnreg_dec<kA2RegsCtl>();
         if (lane == 0) {
+            const int grp = warp - 1;                                    // this thread issues group grp's S and PV MMAs
             constexpr uint32_t idesc_s = make_idesc_mn(kAQ, kAK, false);
             constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);
             auto issue_s = [&](int g, int j) {
@@ -383,18 +397,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(q_full, 0);
             for (int j = 0; j < T; ++j) {
                 mbar_wait(&kv_full[j % kAStages], (j / kAStages) & 1);
-                // steady-state arrival order of the waits: A frees S, A finishes P, then B half a period later
-                issue_s(0, j);
-                if (j > 0) issue_pv(0, j - 1);
-                issue_s(1, j);
-                if (j > 0) { issue_pv(1, j - 1); umma_commit(&kv_empty[(j - 1) % kAStages]); }
+                issue_s(grp, j);
+                if (j > 0) { issue_pv(grp, j - 1); umma_commit(&kv_empty[(j - 1) % kAStages]); }
             }
-            issue_pv(0, T - 1);
-            issue_pv(1, T - 1);
+            issue_pv(grp, T - 1);
             umma_commit(&kv_empty[(T - 1) % kAStages]);
         }
+    } else if (warp == 3) {
+        setmaxnreg_dec<kA2RegsCtl>();
     } else {
-        const int g = (warp - 2) >> 2;              // softmax group: 0 = A, 1 = B
+        setmaxnreg_inc<kA2RegsSoft>();
+        const int g = (warp - 4) >> 2;              // softmax group: 0 = A, 1 = B
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;           // row inside the group's 128-row tile
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;

@@ -55,6 +55,11 @@ struct ConvDev {
     int a2_center;                 // second K segment contributes the centre tap only (fused zero-conv injection / 1x1 skip)
     int in_stride;                 // 1, or 2: stride-2 conv, A is the [a_n, 2 a_h, 2 a_w] input read through a tensor map with element strides 2
     int tap_lo;                    // first tap offset of a 3x3 filter: -1 (pad 1) or 0 (pad bottom/right only)
+    // work-item order inside a k-split / parity class: 0 = all M tiles of N tile 0, then N tile 1, ... (CTAs running at the
+    // same time read the same weight tile); 1 = the N tiles of one M tile are consecutive items, so neighbouring CTAs fetch
+    // the SAME activation boxes at the same time and the L2 serves them once (the activation side is what saturates the
+    // L2 -> SM path of the N = 160 tiles: 16 KB per 320 tensor clocks per SM)
+    int m_major;
 };
 
 __device__ __forceinline__ int conv_total_kb(const ConvDev& p) {
@@ -245,10 +250,12 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
     return __ffma2_rn(hx, th, hx);
 }
 
-template <int BN, int kEW, int kMT = 1>
+template <int BN, int kEW, int kMT = 1, int kIss = 1>
 struct TileCfg {
-    static_assert(kMT * BN <= 256, "two accumulator buffers must fit the 512 TMEM columns");
-    static constexpr int kThreads = 64 + 32 * kEW;
+    static_assert(kMT * BN <= 512, "the accumulators of one work item must fit the 512 TMEM columns");
+    static_assert(kIss == 1 || (kIss == 2 && kMT == 2), "two issuing warps: one per M tile of the item");
+    static constexpr int kThreads = 64 + 32 * (kIss - 1) + 32 * kEW;   // TMA warp, kIss MMA warps, kEW epilogue warps
+    static constexpr int kFirstEpiWarp = 1 + kIss;
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kABytes = kMT * kATileBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -257,8 +264,11 @@ struct TileCfg {
     static constexpr int kStagesRaw = (kMaxSmem - kStagingBytes - 1024 - 256) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kAccCols = kMT * BN;
-    static constexpr int kAccStride = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : 256;   // TMEM columns per buffer
-    static constexpr int kTmemCols = 2 * kAccStride;                   // double-buffered accumulator
+    // two accumulator buffers (the epilogue of item i overlaps the main loop of item i+1) when they fit; one otherwise
+    // (2 x 160 columns: the epilogue is exposed, 2-3 thousand clocks against a main loop of tens of thousands)
+    static constexpr int kAccBufs = kAccCols <= 256 ? 2 : 1;
+    static constexpr int kAccStride = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;   // TMEM columns per buffer
+    static constexpr int kTmemCols = kAccBufs * kAccStride;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -274,13 +284,19 @@ struct TileCfg {
 // already transposed back, so phase B (residual, stores, statistics) is unchanged.
 // kUp: compile-time copy of p.up2 for the epilogue (strided output rows, parity-ordered statistics slabs): the
 // plain instantiations carry none of that state (the 12-warp ones sit at their 128-register cap).
-template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false>
-__global__ void __launch_bounds__(64 + 32 * kEW, 1)
+// kIss: warps issuing tcgen05.mma.  ONE thread sustains one instruction per ~100 clocks whatever the shape (measured,
+// scripts/micro/ubench.cu: N = 16 .. 128 all 100 clocks, N = 160 113, N = 256 136-161; two issuing warps 52 per SM, four 26), so
+// an N = 160 tile runs the tensor pipe at 80 / 113 of its rate and N = 128 at 64 / 100.  With kIss == 2 (and kMT == 2) each
+// M tile of the item has its own issuing warp and accumulator: both streams are in order, so the result is bit-identical
+// to the one-issuer kernel, and the pipe sees an instruction every ~56 clocks.
+template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1>
+__global__ void __launch_bounds__(64 + 32 * (kIss - 1) + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2, const ConvDev p) {
     pdl_trigger();
-    using Cfg = TileCfg<BN, kEW, kMT>;
+    using Cfg = TileCfg<BN, kEW, kMT, kIss>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kAccBufs = Cfg::kAccBufs;
     constexpr int kCStride = kEW / 4;            // epilogue warps per TMEM lane quadrant = chunk stride
     // residual handling in the epilogue: 0 = loaded at the top of phase B, 1 = bf16 residual
     // prefetched two chunks deep, 2 = fp32 residual prefetched one phase ahead (single buffer)
@@ -314,10 +330,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (p.a2_center) tma_prefetch_desc(&tm_b2);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], kIss);          // every issuing warp releases the stage
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_full[b], kIss);
             mbar_init(&acc_empty[b], kEW);
         }
         fence_barrier_init();
@@ -345,8 +361,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const int z = item / mn_tiles;
                 int rem = item - z * mn_tiles;
-                const int nt = rem / m_tiles;
-                const int mi = rem - nt * m_tiles;
+                const int nt = p.m_major ? rem % p.n_tiles : rem / m_tiles;
+                const int mi = p.m_major ? rem / p.n_tiles : rem - nt * m_tiles;
                 int w0[kMT], h0[kMT], n0[kMT];
 #pragma unroll
                 for (int u = 0; u < kMT; ++u) {
@@ -409,17 +425,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (kIss == 2 && warp == 2)) {
         if (lane == 0) {
-            // ===== MMA issuer =====
+            // ===== MMA issuer (kIss == 2: warp 1 owns M tile 0 of every item, warp 2 M tile 1) =====
             constexpr uint32_t idesc = make_idesc(BN);
+            const int u_lo = kIss == 2 ? warp - 1 : 0, u_hi = kIss == 2 ? warp : kMT;
             uint32_t s = 0, ph = 0, t = 0;
             const uint64_t da0 = make_smem_desc(smem_u32(smem_a)), db0 = make_smem_desc(smem_u32(smem_b));
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
                 const int z = item / mn_tiles;
                 const int kb_begin = p.up2 ? 0 : z * p.kb_per_split;
                 const int num_kb = min(total_kb, kb_begin + p.kb_per_split) - kb_begin;
-                const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+                const uint32_t buf = t % kAccBufs, aph = (t / kAccBufs) & 1;
                 mbar_wait(&acc_empty[buf], aph ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * Cfg::kAccStride;
@@ -437,6 +454,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     } else
 #pragma unroll
                     for (int u = 0; u < kMT; ++u) {
+                        if (u < u_lo || u >= u_hi) continue;
                         const uint64_t da = dst + (uint64_t)(u * (kATileBytes >> 4));
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -454,7 +472,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===== epilogue, exchanged operands: TMEM lane = output channel, column = pixel =====
         // Host guarantees: every real tile is full and affine, n_out % 32 == 0, no per-sample bias, no GEGLU,
         // one k-split, vector-aligned rows, alpha == 1 unless there is a residual.
-        const int ew = warp - 2;
+        const int ew = warp - Cfg::kFirstEpiWarp;
         const int quad = warp & 3;                    // channels col0 + 32 * quad + lane
         const int half = ew >> 2;
         float4* stg = reinterpret_cast<float4*>(smem_stg) + ew * 256;
@@ -470,7 +488,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int cbase = col0 + 32 * quad;
             const bool ch_ok = cbase < p.n_out;
             const float bias_c = (ch_ok && p.bias) ? p.bias[cbase + lane] : 0.f;
-            const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+            const uint32_t buf = t % kAccBufs, aph = (t / kAccBufs) & 1;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + ((uint32_t)(quad * 32) << 16);
@@ -546,7 +564,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // its 32x32 sub-tile so that 8 lanes cover 128 contiguous bytes of one output row, adds
         // the residual (prefetched with the same coalesced mapping) and writes fp32 and/or bf16.
         // Two warps share each TMEM lane quadrant and take alternate 32-column chunks.
-        const int ew = warp - 2;                      // 0..7
+        const int ew = warp - Cfg::kFirstEpiWarp;     // 0..kEW-1
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int half = ew >> 2;                     // which chunks of the tile: half, half + kCStride, ...
         const int r = quad * 32 + lane;               // row inside the M tile
@@ -560,8 +578,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
             const int z = item / mn_tiles;
             int rem = item - z * mn_tiles;
-            const int nt = rem / m_tiles;
-            const int mi = rem - nt * m_tiles;
+            const int nt = p.m_major ? rem % p.n_tiles : rem / m_tiles;
+            const int mi = p.m_major ? rem / p.n_tiles : rem - nt * m_tiles;
 #pragma unroll 1
             for (int u = 0; u < kMT; ++u) {           // the item's M tiles share one accumulator buffer
             int mt = mi * kMT + u;
@@ -591,7 +609,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             eo.ldo = partial ? p.n_out : p.ldo;
             eo.n_cols = geglu ? (p.n_out >> 1) : p.n_out;
             const bool vec_io = (eo.ldo & 3) == 0 && (!eo.resid || (eo.ld_resid & 3) == 0);
-            const uint32_t buf = t & 1, aph = (t >> 1) & 1;
+            const uint32_t buf = t % kAccBufs, aph = (t / kAccBufs) & 1;
             constexpr int kChunks = BN / 32;
             // chunks this warp owns: half, half+2, ...
             int last_c = -1;
@@ -957,20 +975,20 @@ static inline int host_total_kb(const ConvDev& d) {
     return d.a2_center ? d.taps * d.cblk1 + d.cblk2 : d.taps * (d.cblk1 + d.cblk2);
 }
 
-template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false, bool kUp = false>
+template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
-    using Cfg = TileCfg<BN, kEW, kMT>;
+    using Cfg = TileCfg<BN, kEW, kMT, kIss>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -998,8 +1016,22 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                 if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
                 return launch_conv3<BN, 0, 8, false, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
             }
-            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
-            return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+        }
+    }
+    // N = 160 tiles (UNet levels 0 / 1: 320 and 640 output channels) with a long reduction: two M tiles per item, one
+    // issuing warp each.  Per k-block the pipe then needs 8 x 80 = 640 clocks for two tiles where one issuer took 452 per tile.
+    // Items are twice as large, so it pays when the one-tile schedule needs at least two rounds of CTAs:
+    //   rounds(units / 2) * 640 < rounds(units) * 452
+    if constexpr (BN == 160) {
+        static const int dual160 = getenv("RDEIC_DUAL160") ? atoi(getenv("RDEIC_DUAL160")) : 1;
+        const int64_t units = (int64_t)m_tiles * d.n_tiles;
+        const int64_t r1 = (units + kNumSMs - 1) / kNumSMs, r2 = ((int64_t)((m_tiles + 1) / 2) * d.n_tiles + kNumSMs - 1) / kNumSMs;
+        if (dual160 && splits == 1 && !d.w_batched && !d.a2_center && d.in_stride == 1 && host_total_kb(d) >= 18 &&
+            m_tiles >= 2 && r2 * 640 < r1 * 452) {
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
         }
     }
     if (d.stats_out) {
@@ -1137,7 +1169,7 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
     d.resid = p->resid; d.resid_is_f32 = p->resid_is_f32; d.ld_resid = p->ld_resid;
     d.alpha = p->alpha; d.act = p->act; d.act_param = p->act_param;
     d.out_bf16 = (__nv_bfloat16*)p->out_bf16; d.out_f32 = p->out_f32; d.ldo = p->ldo;
-    d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0;
+    d.partial = nullptr; d.kb_per_split = 0; d.splits = 1; d.n_tiles = 0; d.m_major = 0;
     d.stats_out = p->stats_out;
     if (p->stats_out) {
         RDEIC_CHECK_ARG(p->act != 2 && (p->w_batch_stride == 0 || p->up2) && p->n_out % 32 == 0 && p->ldo % 4 == 0 &&
@@ -1224,6 +1256,11 @@ int rdeic_conv_gemm(const rdeic_conv_params* p, rdeic_stream_t stream) {
             d.partial = reinterpret_cast<float*>(p->workspace);
             d.splits = splits;
         }
+    }
+    {
+        static const int m_major_env = getenv("RDEIC_M_MAJOR") ? atoi(getenv("RDEIC_M_MAJOR")) : 0;
+        // 1: whenever there are several N tiles and several waves of items; 2: only when the N tiles divide the grid evenly
+        if (m_major_env && n_tiles > 1 && tiles > kNumSMs && (m_major_env == 1 || kNumSMs % n_tiles == 0)) d.m_major = 1;
     }
     int rc;
     switch (bn) {

@@ -682,10 +682,15 @@ class _VaeMid:
         q = ops.linear(hn, self.attn_q.w, C, bias=self.attn_q.b)
         k = ops.linear(hn, self.attn_k.w, C, bias=self.attn_k.b)
         v = ops.linear(hn, self.attn_v.w, C, bias=self.attn_v.b)
-        s = ops.conv_gemm(q.view(B, 1, N, C), k, N, 1, w_batch_stride=N * C, w_k=C, w_ld=C, out_f32=True)
-        p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
-        vt = ops.transpose_bf16(v)                                   # [B, C, N]: K-major B operand for P V
-        o = ops.conv_gemm(p.view(B, 1, N, N), vt, C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
+        if N % 128 == 0 and C in (256, 512):
+            # flash kernel for wide heads (csrc/attention_wide.cu): S tiles live in tensor memory, the [B, N, N]
+            # score tensor of model.py:192-200 (9.7 GB of fp32 at 768x512, batch 64) is never written
+            o = ops.attention(q, k, v, 1, C, float(C) ** -0.5)
+        else:
+            s = ops.conv_gemm(q.view(B, 1, N, C), k, N, 1, w_batch_stride=N * C, w_k=C, w_ld=C, out_f32=True)
+            p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
+            vt = ops.transpose_bf16(v)                               # [B, C, N]: K-major B operand for P V
+            o = ops.conv_gemm(p.view(B, 1, N, N), vt, C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
         out, st_o = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.view(B, N, C),
                                stats=True)
         return out.view(B, H, W, C), st_o

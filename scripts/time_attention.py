@@ -14,7 +14,8 @@ B = 8
 for name, heads, d, Nq, Nk in [("self L0", 5, 64, 4096, 4096), ("self L1", 10, 64, 1024, 1024), ("self L2", 20, 64, 256, 256),
                                ("self mid", 20, 64, 64, 64), ("cross L0", 5, 64, 4096, 77), ("cross L1", 10, 64, 1024, 77),
                                ("cross L2", 20, 64, 256, 77), ("ctrl self L0", 4, 16, 4096, 4096), ("ctrl self L1", 8, 16, 1024, 1024),
-                               ("ctrl cross L0", 4, 16, 4096, 77)]:
+                               ("ctrl cross L0", 4, 16, 4096, 77), ("vae mid 512^2", 1, 512, 4096, 4096),
+                               ("vae mid 768x512", 1, 512, 6144, 6144)]:
     C = heads * d
     qkv = torch.randn(B, Nq, 3 * C, generator=g, device=dev).bfloat16()
     kv = torch.randn(B, Nk, 2 * C, generator=g, device=dev).bfloat16()

@@ -525,6 +525,43 @@ def test_attention_growing_logits(cuda, B, heads, N):
     assert (out - ref).abs().max() < 6e-2 and _rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,heads,Nq,Nk,d,grow", [(2, 1, 256, 384, 512, False), (1, 1, 1024, 1024, 512, False),
+                                                  (2, 2, 128, 256, 256, False), (1, 1, 384, 4096, 512, True),
+                                                  (3, 1, 128, 128, 512, False)])
+def test_attention_wide_heads(cuda, B, heads, Nq, Nk, d, grow):
+    """The VAE mid-block attention (ldm/modules/diffusionmodules/model.py:181-205: one head, d = C = 512) as a flash
+    kernel: value dimension split over two CTAs, O resident in tensor memory with lazy rescaling (grow = logits that
+    keep rising along the key axis, so every row rescales several times)."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(35)
+    q = _bf(torch.randn(B, Nq, heads * d, generator=g))
+    k = _bf(torch.randn(B, Nk, heads * d, generator=g))
+    if grow:
+        q = _bf(q * (0.5 + 2.0 * torch.rand(B, Nq, 1, generator=g)))
+        k = _bf(k * torch.linspace(0.3, 4.0, Nk)[None, :, None])
+    v = _bf(torch.randn(B, Nk, heads * d, generator=g))
+    sp = lambda t: t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3)
+    sim = torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * d ** -0.5
+    if grow:
+        assert float(sim.max()) > 30.0
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), sp(v)).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    out = ops.attention(q.to(cuda).bfloat16(), k.to(cuda).bfloat16(), v.to(cuda).bfloat16(), heads, d,
+                        d ** -0.5).float().cpu()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < (6e-2 if grow else 2e-2)
+    assert _rel(out, ref) < 1e-2
+
+
+def test_attention_wide_rejects_ragged(cuda):
+    from rdeic_b200 import ops
+    from rdeic_b200._lib import RdeicLibraryError
+
+    t = torch.zeros(1, 100, 512, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(RdeicLibraryError):
+        ops.attention(t, t, t, 1, 512, 512 ** -0.5)
+
+
 def test_attention_fused_qkv_slices(cuda):
     from rdeic_b200 import ops
 
@@ -706,6 +743,45 @@ def test_conv3x3_two_m_tiles_per_item(cuda, B, H, W, C1, C2, Cout, stats):
         assert _rel(y.float().cpu(), ref.cpu()) < 4e-3            # bf16 output rounding
     else:
         assert _rel(res.cpu(), ref.cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,stats", [(8, 64, 64, 128, 0, 320, True), (5, 64, 64, 128, 0, 320, False),
+                                                     (3, 64, 96, 64, 64, 640, True), (1, 129, 128, 192, 0, 320, False),
+                                                     (8, 32, 32, 128, 0, 640, True)])
+def test_conv3x3_two_issuers_n160(cuda, B, H, W, C1, C2, Cout, stats):
+    """N = 160 tiles with a long reduction and >= 2 rounds of tiles run two M tiles per item with one MMA-issuing warp
+    and one accumulator each (UNet levels 0 / 1: openaimodel.py:203,229 at 320 / 640 channels): even and odd tile
+    counts, two K segments, fused statistics, fp32 + bf16 outputs.  Each accumulator sees its own in-order instruction
+    stream, so the result must be bit-identical run to run."""
+    from rdeic_b200 import ops
+
+    g = torch.Generator().manual_seed(92)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = _bf(torch.randn(B, C1 + C2, H, W, generator=g)).to(cuda)
+        w = _bf(torch.randn(Cout, C1 + C2, 3, 3, generator=g) / math.sqrt(9 * (C1 + C2))).to(cuda)
+        b = torch.randn(Cout, generator=g).to(cuda)
+        resid = torch.randn(B, H, W, Cout, generator=g).to(cuda)
+        ref = resid + F.conv2d(x, w, b, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    a = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    a1 = a[..., :C1].contiguous()
+    a2 = a[..., C1:].contiguous() if C2 else None
+    wp = ops.pack_conv_weight(w, c1=C1) if C2 else ops.pack_conv_weight(w)
+    run = lambda: ops.conv_gemm(a1, wp, Cout, 9, a2=a2, bias=b, resid=resid, dual=True, stats=stats)
+    res = run()
+    yf, yb = res[0], res[1]
+    assert _rel(yf.cpu(), ref.cpu()) < 1e-3
+    assert torch.equal(yb.float(), yf.bfloat16().float())
+    if stats:
+        st = res[2]
+        assert st is not None
+        ref_b = yf.view(B * H * W // 32, 32, Cout)
+        assert _rel(st[..., 0].cpu(), ref_b.sum(1).cpu()) < 1e-3 and _rel(st[..., 1].cpu(), (ref_b * ref_b).sum(1).cpu()) < 1e-3
+    res2 = run()
+    assert torch.equal(res2[0], yf)
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 40, 48), (1, 8, 100)])
