@@ -103,7 +103,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     pdl_wait();   // prologue above overlapped the previous kernel's tail
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== TMA producer =====
             mbar_expect_tx(q_full, kATile);
             tma_load_3d(&tm_q, s_q, q_full, head * kAD, qt * kAQ, b);
@@ -116,7 +116,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== MMA issuer =====
             constexpr uint32_t idesc_s = make_idesc_mn(kAQ, kAK, false);   // S  = Q K^T : N = 128 keys
             constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);    // O  = P V   : N = 64, V MN-major
@@ -349,7 +349,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // (setmaxnreg sits inside each role's branch: ptxas bounds the registers of the code that FOLLOWS one, path-insensitively)
     if (warp == 0) {
         setmaxnreg_dec<kA2RegsCtl>();
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(q_full, 2 * kATile);
             tma_load_3d(&tm_q, s_q, q_full, head * kAD, qt * kA2Q, b);
             tma_load_3d(&tm_q, s_q + kATile, q_full, head * kAD, qt * kA2Q + kAQ, b);
@@ -363,7 +363,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
     } else if (warp == 1 || warp == 2) {
         setmaxnreg_dec<kA2RegsCtl>();
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const int grp = warp - 1;                                    // this thread issues group grp's S and PV MMAs
             constexpr uint32_t idesc_s = make_idesc_mn(kAQ, kAK, false);
             constexpr uint32_t idesc_o = make_idesc_mn(kAQ, kAD, true);
@@ -722,7 +722,7 @@ attention_x_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     pdl_wait();
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(ld_full, 3 * kATile);
             tma_load_3d(&tm_q, s_q, ld_full, head * kAD, qt * kAQ, b);
             tma_load_3d(&tm_k, s_k, ld_full, head * kAD, 0, b);

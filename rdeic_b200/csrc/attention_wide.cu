@@ -111,7 +111,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== TMA producer: Q once, then stages in exactly the order the MMA thread consumes them =====
             mbar_expect_tx(q_full, kPanels * kWPanel);
             for (int pn = 0; pn < kPanels; ++pn) tma_load_3d(&tm_q, s_q + pn * kWPanel, q_full, c_head + pn * 64, qt * kWQ, b);
@@ -137,7 +137,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== issuer of S(j) = Q K(j)^T into S buffer j & 1 =====
             constexpr uint32_t idesc_s = make_idesc_mn(kWQ, kWK, false);
             uint32_t s = 0, ph = 0;
@@ -163,7 +163,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== issuer of O += P(j) V(j) =====
             constexpr uint32_t idesc_o = make_idesc_mn(kWQ, 64, true);
             uint32_t s = 0, ph = 0;

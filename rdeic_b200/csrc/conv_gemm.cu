@@ -250,20 +250,22 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
     return __ffma2_rn(hx, th, hx);
 }
 
-template <int BN, int kEW, int kMT = 1, int kIss = 1>
+template <int BN, int kEW, int kMT = 1, int kIss = 1, int kNT = 1>
 struct TileCfg {
-    static_assert(kMT * BN <= 512, "the accumulators of one work item must fit the 512 TMEM columns");
+    static_assert(kMT * kNT * BN <= 512, "the accumulators of one work item must fit the 512 TMEM columns");
+    static_assert(kNT == 1 || (kNT == 2 && kMT == 1 && kIss == 1), "two N tiles per item: one M tile, one issuing warp");
     static_assert(kIss == 1 || (kIss == 2 && kMT == 2), "two issuing warps: one per M tile of the item");
     static constexpr int kThreads = 64 + 32 * (kIss - 1) + 32 * kEW;   // TMA warp, kIss MMA warps, kEW epilogue warps
     static constexpr int kFirstEpiWarp = 1 + kIss;
-    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kBTileBytes = BN * kBlockK * 2;
+    static constexpr int kBBytes = kNT * kBTileBytes;
     static constexpr int kABytes = kMT * kATileBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStagingBytes = kEW * 4096;                   // 32 rows x 128 B per epilogue warp
     static constexpr int kMaxSmem = 227 * 1024;
     static constexpr int kStagesRaw = (kMaxSmem - kStagingBytes - 1024 - 256) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kAccCols = kMT * BN;
+    static constexpr int kAccCols = kMT * kNT * BN;
     // two accumulator buffers (the epilogue of item i overlaps the main loop of item i+1) when they fit; one otherwise
     // (2 x 160 columns: the epilogue is exposed, 2-3 thousand clocks against a main loop of tens of thousands)
     static constexpr int kAccBufs = kAccCols <= 256 ? 2 : 1;
@@ -289,12 +291,18 @@ struct TileCfg {
 // an N = 160 tile runs the tensor pipe at 80 / 113 of its rate and N = 128 at 64 / 100.  With kIss == 2 (and kMT == 2) each
 // M tile of the item has its own issuing warp and accumulator: both streams are in order, so the result is bit-identical
 // to the one-issuer kernel, and the pipe sees an instruction every ~56 clocks.
-template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1>
+// kNT = 2: two N tiles per work item against ONE activation stage (accumulators side by side in tensor memory).  What bounds
+// an N = 160 tile with a long reduction is the L2 -> SM path, not the tensor pipe: 16 KB of activations per 320 tensor clocks
+// is 51 B/clk per SM against ~43 B/clk the L2 delivers chip-wide (the weight tile is the same for every CTA at a given
+// moment and is largely served once).  With both N tiles of a 320-channel layer in one item the activation box crosses
+// L2 -> SM once per 640 tensor clocks.  2 x 160 columns leave no room for a second accumulator buffer: the epilogue of an
+// item is exposed (a few thousand clocks against a main loop of 45+ k-blocks x 640).
+template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1, int kNT = 1>
 __global__ void __launch_bounds__(64 + 32 * (kIss - 1) + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2, const ConvDev p) {
     pdl_trigger();
-    using Cfg = TileCfg<BN, kEW, kMT, kIss>;
+    using Cfg = TileCfg<BN, kEW, kMT, kIss, kNT>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kAccBufs = Cfg::kAccBufs;
     constexpr int kCStride = kEW / 4;            // epilogue warps per TMEM lane quadrant = chunk stride
@@ -349,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== TMA producer =====
             // One thread feeds the whole pipeline, and with N <= 160 tiles a k-block is only ~450 tensor clocks:
             // the per-k-block instruction count of this loop is on the critical path.  So no division or modulo
@@ -372,7 +380,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     w0[u] = tiw * tw; h0[u] = tih * th;
                     n0[u] = mt * (kBlockM >> (p.tw_log2 + p.th_log2));
                 }
-                const int col0 = nt * BN;
+                const int col0 = nt * (kNT * BN);
                 // up2: z is the output parity class (py, px), not a k slice; it also selects the weight matrix
                 const int par = p.up2 ? z : 0;
                 const int wz = p.up2 ? par : (p.w_batched ? n0[0] : 0);
@@ -410,8 +418,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     for (int u = 0; u < kMT; ++u)
                         tma_load_4d(ma, smem_a + (s * kMT + u) * kATileBytes, &full_bar[s], cb * kBlockK, w0[u] * mul + ex,
                                     h0[u] * mul + ey, n0[u]);
-                    if (ctr) tma_load_3d(&tm_b2, smem_b + s * Cfg::kBBytes, &full_bar[s], cb * kBlockK, col0, 0);
-                    else tma_load_3d(&tm_b, smem_b + s * Cfg::kBBytes, &full_bar[s], kb * kBlockK, col0, wz);
+#pragma unroll
+                    for (int v = 0; v < kNT; ++v) {      // weight rows past n_out are zero-filled by the hardware
+                        uint8_t* dstb = smem_b + s * Cfg::kBBytes + v * Cfg::kBTileBytes;
+                        if (ctr) tma_load_3d(&tm_b2, dstb, &full_bar[s], cb * kBlockK, col0 + v * BN, 0);
+                        else tma_load_3d(&tm_b, dstb, &full_bar[s], kb * kBlockK, col0 + v * BN, wz);
+                    }
                     // advance (segment, tap, channel block)
                     if (++cb == (seg ? p.cblk2 : p.cblk1)) {
                         cb = 0;
@@ -426,7 +438,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else if (warp == 1 || (kIss == 2 && warp == 2)) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // ===== MMA issuer (kIss == 2: warp 1 owns M tile 0 of every item, warp 2 M tile 1) =====
             constexpr uint32_t idesc = make_idesc(BN);
             const int u_lo = kIss == 2 ? warp - 1 : 0, u_hi = kIss == 2 ? warp : kMT;
@@ -459,7 +471,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // advance 16 elements = 32 bytes along K inside the swizzle row: +2 (>>4)
-                            umma_bf16(tmem_d + u * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                            for (int v = 0; v < kNT; ++v)
+                                umma_bf16(tmem_d + (u * kNT + v) * BN, da + 2 * k, db + (uint64_t)(v * (Cfg::kBTileBytes >> 4)) + 2 * k, idesc,
+                                          (kb | k) != 0);
                         }
                     }
                     umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
@@ -581,13 +596,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int nt = p.m_major ? rem % p.n_tiles : rem / m_tiles;
             const int mi = p.m_major ? rem / p.n_tiles : rem - nt * m_tiles;
 #pragma unroll 1
-            for (int u = 0; u < kMT; ++u) {           // the item's M tiles share one accumulator buffer
+            for (int sub = 0; sub < kMT * kNT; ++sub) {   // the item's M (or N) tiles share one accumulator buffer
+            const int u = kNT == 2 ? 0 : sub;
             int mt = mi * kMT + u;
             const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
             const int tih = mt % p.tiles_h; mt /= p.tiles_h;
             const int gw = tiw * tw + rw, gh = tih * th + rh;
             const int gn = mt * (kBlockM >> (p.tw_log2 + p.th_log2)) + rn;
-            const int col0 = nt * BN;
+            const int col0 = (nt * kNT + (kNT == 2 ? sub : 0)) * BN;
             const int row_ok = (gw < p.a_w && gh < p.a_h && gn < p.a_n) ? 1 : 0;
             const int m_in = (int)(((int64_t)gn * p.a_h + gh) * p.a_w + gw);
             // row of the output tensor this accumulator row is written to: the same pixel, or with the
@@ -661,12 +677,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
             };
             if (kAheadF32) prefetch_f32(half);
-            if (u == 0) {
+            if (sub == 0) {
                 mbar_wait(&acc_full[buf], aph);
                 tc_fence_after();
             }
-            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + u * BN + ((uint32_t)(quad * 32) << 16);
-            if (last_c < 0 && u == kMT - 1) {       // nothing to read: release the buffer right away
+            const uint32_t tmem_acc = tmem_base + buf * Cfg::kAccStride + sub * BN + ((uint32_t)(quad * 32) << 16);
+            if (last_c < 0 && sub == kMT * kNT - 1) {       // nothing to read: release the buffer right away
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
@@ -681,7 +697,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
                 const bool full32 = nbase + 32 <= p.n_out;
                 tmem_ld_wait();
-                if (ci == last_c && u == kMT - 1) {  // all TMEM reads of this item by this warp are done
+                if (ci == last_c && sub == kMT * kNT - 1) {  // all TMEM reads of this item by this warp are done
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
@@ -869,7 +885,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (kAheadF32) prefetch_f32(ci + kCStride);     // in flight during the next chunk's TMEM load + phase A
                 __syncwarp();
             }
-            }   // u
+            }   // sub
         }
     }
     tc_fence_before();
@@ -975,20 +991,20 @@ static inline int host_total_kb(const ConvDev& d) {
     return d.a2_center ? d.taps * d.cblk1 + d.cblk2 : d.taps * (d.cblk1 + d.cblk2);
 }
 
-template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1>
+template <int BN, int kPre, int kEW, bool kStats = false, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1, int kNT = 1>
 static int launch_conv3(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const CUtensorMap& tb2,
                         const ConvDev& d, int m_tiles, int splits, cudaStream_t s) {
-    using Cfg = TileCfg<BN, kEW, kMT, kIss>;
+    using Cfg = TileCfg<BN, kEW, kMT, kIss, kNT>;
     static_assert(Cfg::kStages >= 2, "pipeline needs at least two stages");
     static bool attr_set = false;
     if (!attr_set) {
-        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss>,
+        RDEIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss, kNT>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_set = true;
     }
     const int64_t items = (int64_t)((m_tiles + kMT - 1) / kMT) * d.n_tiles * splits;
     dim3 grid((unsigned)(items < kNumSMs ? items : kNumSMs));
-    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
+    RDEIC_CUDA(launch_k(conv_gemm_kernel<BN, kPre, kEW, kStats, kMT, kSwap, kUp, kIss, kNT>, grid, Cfg::kThreads, Cfg::kSmemBytes, s, ta, ta2, tb, tb2, d));
     RDEIC_LAUNCH_CHECK();
     return 0;
 }
@@ -1016,16 +1032,33 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
                 if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
                 return launch_conv3<BN, 0, 8, false, 2, true>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
             }
-            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
-            return launch_conv3<BN, 0, 8, false, 2, false, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 2>(ta, ta2, tb, tb2, d, m_tiles, splits, s);
         }
     }
     // N = 160 tiles (UNet levels 0 / 1: 320 and 640 output channels) with a long reduction: two M tiles per item, one
     // issuing warp each.  Per k-block the pipe then needs 8 x 80 = 640 clocks for two tiles where one issuer took 452 per tile.
     // Items are twice as large, so it pays when the one-tile schedule needs at least two rounds of CTAs:
     //   rounds(units / 2) * 640 < rounds(units) * 452
+    // N = 160 tiles with a long reduction and at least two rounds of tiles: both N tiles of a pair in one item (kNT = 2)
     if constexpr (BN == 160) {
-        static const int dual160 = getenv("RDEIC_DUAL160") ? atoi(getenv("RDEIC_DUAL160")) : 1;
+        static const int pair160 = getenv("RDEIC_PAIR160") ? atoi(getenv("RDEIC_PAIR160")) : 0;   // off: measured 63.6 -> 74.9 us at UNet level 0 (single accumulator buffer, three stages)
+        const int64_t units = (int64_t)m_tiles * d.n_tiles;
+        const int64_t rounds1 = (units + kNumSMs - 1) / kNumSMs;
+        const int64_t rounds2 = ((int64_t)m_tiles * ((d.n_tiles + 1) / 2) + kNumSMs - 1) / kNumSMs;
+        if (pair160 && splits == 1 && !d.w_batched && d.n_tiles >= 2 && host_total_kb(d) >= 18 && rounds2 < rounds1) {
+            ConvDev d2 = d;
+            d2.n_tiles = (d.n_tiles + 1) / 2;
+            d2.m_major = 0;
+            if (d.stats_out) return launch_conv3<BN, 0, 8, true, 1, false, false, 1, 2>(ta, ta2, tb, tb2, d2, m_tiles, splits, s);
+            return launch_conv3<BN, 0, 8, false, 1, false, false, 1, 2>(ta, ta2, tb, tb2, d2, m_tiles, splits, s);
+        }
+    }
+    if constexpr (BN == 160) {
+        // (off by default: built when one thread was believed to issue at most one tcgen05.mma per ~100 clocks; that was the
+        // ELECT / BRA.U.ANY wrapper of a `lane == 0` branch -- see elect_one_sync() -- and with it gone one issuer keeps the
+        // pipe full, while this variant pays a single-buffered accumulator and three smem stages: 64 -> 76 us at level 0)
+        static const int dual160 = getenv("RDEIC_DUAL160") ? atoi(getenv("RDEIC_DUAL160")) : 0;
         const int64_t units = (int64_t)m_tiles * d.n_tiles;
         const int64_t r1 = (units + kNumSMs - 1) / kNumSMs, r2 = ((int64_t)((m_tiles + 1) / 2) * d.n_tiles + kNumSMs - 1) / kNumSMs;
         if (dual160 && splits == 1 && !d.w_batched && !d.a2_center && d.in_stride == 1 && host_total_kb(d) >= 18 &&

@@ -28,6 +28,28 @@ static inline int gn_num_chunks(int B, int64_t HW) {
 
 // Fold width for statistics that arrive as a slab table: kFoldSlabs slabs per fold CTA (the apply kernel's
 // prologue sums the nfold partials of its sample, 8 threads per group, four loads in flight).
+// Pixel chunks of the apply pass: ONE resident wave of CTAs (the kernel's prologue and its load latency chain are paid once
+// per CTA; with 8 * 148 / B chunks and 3-4 resident CTAs per SM the UNet level-0 pass ran 2.3 waves of 32-pixel CTAs).
+// Tensors far larger than the L2 (the VAE's 512^2 / 256^2 levels) keep the finer 8 * 148 / B chunking: there the prologue is
+// noise and the shorter tail of many small CTAs wins (A/B on one box: 217.6 vs 224.1 us on [8,512,512,128], 38.8 vs 34.8 us
+// on the UNet's [8,64,64,320] fp32 stream, fold + apply).
+template <typename K>
+static inline int gn_apply_chunks(K kernel, int B, int64_t HW, int C) {
+    if ((int64_t)B * HW * C > (int64_t)1 << 25) return gn_num_chunks(B, HW);
+    static int per_sm = 0;              // one static per kernel instantiation
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kGnThreads, 0) != cudaSuccess || n < 1) n = 2;
+        per_sm = n;
+    }
+    int64_t want = ((int64_t)per_sm * kNumSMs) / B;
+    const int64_t max_by_rows = HW / 32 > 0 ? HW / 32 : 1;
+    if (want > max_by_rows) want = max_by_rows;
+    if (want > 65535) want = 65535;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
 static inline int gn_num_fold(int B, int64_t HW) {
     static const int per = getenv("RDEIC_GN_FOLD_SLABS") ? atoi(getenv("RDEIC_GN_FOLD_SLABS")) : 1;
     const int64_t slabs = HW / 32;
@@ -51,6 +73,30 @@ __device__ __forceinline__ void load8(const void* base, int64_t vec_index, float
         f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
     } else {
         const uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(base) + vec_index);
+        unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
+        unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
+    }
+}
+
+// the same in two steps: the raw 16 / 32 bytes now, the fp32 values later (keeps a prefetched bf16 row in 4 registers)
+template <bool kF32> struct Raw8 { uint4 v[kF32 ? 2 : 1]; };
+template <bool kF32>
+__device__ __forceinline__ void load8_raw(const void* base, int64_t vec_index, Raw8<kF32>& r) {
+    if (kF32) {
+        r.v[0] = ld_stream_u4(reinterpret_cast<const uint4*>(base) + 2 * vec_index);
+        r.v[kF32 ? 1 : 0] = ld_stream_u4(reinterpret_cast<const uint4*>(base) + 2 * vec_index + 1);
+    } else {
+        r.v[0] = ld_stream_u4(reinterpret_cast<const uint4*>(base) + vec_index);
+    }
+}
+template <bool kF32>
+__device__ __forceinline__ void unpack8(const Raw8<kF32>& r, float* f) {
+    if (kF32) {
+        const uint4 a = r.v[0], b = r.v[kF32 ? 1 : 0];
+        f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+        f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    } else {
+        const uint4 v = r.v[0];
         unpack_bf16x2(v.x, f[0], f[1]); unpack_bf16x2(v.y, f[2], f[3]);
         unpack_bf16x2(v.z, f[4], f[5]); unpack_bf16x2(v.w, f[6], f[7]);
     }
@@ -259,8 +305,9 @@ gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
 }
 
+// (bf16 input: 4 resident CTAs per SM, i.e. at most 64 registers -- the VAE's 537 MB tensors want the bytes in flight)
 template <bool kF32, bool kOutF32 = false>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, kF32 ? 3 : 4)
 gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
@@ -275,6 +322,31 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     const int VL = C >> 3, VL1 = C1 >> 3, VL2 = C2 >> 3;
     const int b = blockIdx.y;
     const int cg = C / G;
+    // Each thread keeps ONE 8-channel lane for the whole pass, so its scale/shift live in registers
+    // (reading them from shared memory per element made the kernel smem-bandwidth bound: 4 LDS.128
+    // per 16 bytes of payload) and the loop has no index division.
+    const int64_t o1 = (int64_t)b * HW * VL1, o2 = (int64_t)b * HW * VL2;
+    uint4* bo = out + (int64_t)b * HW * VL * (kOutF32 ? 2 : 1);
+    const int nchunk_a = gridDim.x;
+    const int64_t per = (HW + nchunk_a - 1) / nchunk_a;
+    const int64_t p0 = blockIdx.x * per;
+    const int64_t p1 = (p0 + per < HW) ? p0 + per : HW;
+    const int lanes_per_pass = VL < kGnThreads ? VL : kGnThreads;
+    const int rows_per_iter = kGnThreads / lanes_per_pass;
+    const int row = threadIdx.x / lanes_per_pass, lane_in = threadIdx.x - row * lanes_per_pass;
+    // The first four rows of this thread's lane are requested BEFORE the statistics are finalised: the loads do not depend
+    // on them, and the prologue below (a chain of L2 round trips, an fp64 reduction and two CTA barriers) is then hidden
+    // behind the HBM latency instead of preceding it (UNet level 0: a CTA's whole share is 12 rows per thread).
+    Raw8<kF32> f4[4];
+    const bool pre_ok = row < rows_per_iter && lane_in < VL && p0 + row + 3 * (int64_t)rows_per_iter < p1;
+    if (pre_ok) {
+        const bool first = lane_in < VL1;
+        const void* src = first ? x1 : x2;
+        const int64_t stride = first ? VL1 : VL2;
+        const int64_t off = (first ? o1 + lane_in : o2 + (lane_in - VL1));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8_raw<kF32>(src, off + (p0 + row + u * (int64_t)rows_per_iter) * stride, f4[u]);
+    }
     {   // finalise the statistics: 8 threads per group split the chunk partials (fixed order ->
         // deterministic), fp64 combine; a single thread per group would serialise nchunk L2 round trips
         const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
@@ -318,18 +390,6 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         s_shift[c] = beta[c] - s_mean[g] * sc;
     }
     __syncthreads();
-    // Each thread keeps ONE 8-channel lane for the whole pass, so its scale/shift live in registers
-    // (reading them from shared memory per element made the kernel smem-bandwidth bound: 4 LDS.128
-    // per 16 bytes of payload) and the loop has no index division.
-    const int64_t o1 = (int64_t)b * HW * VL1, o2 = (int64_t)b * HW * VL2;
-    uint4* bo = out + (int64_t)b * HW * VL * (kOutF32 ? 2 : 1);
-    const int nchunk_a = gridDim.x;
-    const int64_t per = (HW + nchunk_a - 1) / nchunk_a;
-    const int64_t p0 = blockIdx.x * per;
-    const int64_t p1 = (p0 + per < HW) ? p0 + per : HW;
-    const int lanes_per_pass = VL < kGnThreads ? VL : kGnThreads;
-    const int rows_per_iter = kGnThreads / lanes_per_pass;
-    const int row = threadIdx.x / lanes_per_pass, lane_in = threadIdx.x - row * lanes_per_pass;
     for (int lane_base = 0; lane_base < VL; lane_base += lanes_per_pass) {
         const int l = lane_base + lane_in;
         if (row >= rows_per_iter || l >= VL) continue;
@@ -340,7 +400,9 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         const void* src = first ? x1 : x2;
         const int64_t stride = first ? VL1 : VL2;
         const int64_t off = (first ? o1 + l : o2 + (l - VL1));
-        auto finish = [&](float* f, int64_t p) {
+        auto finish = [&](const Raw8<kF32>& raw, int64_t p) {
+            float f[8];
+            unpack8<kF32>(raw, f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
             if (kOutF32) {               // fp32 kernel mode: exact exp / division, fp32 result
@@ -365,18 +427,24 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
             st_stream_u4(bo + p * VL + l, o);
         };
         int64_t p = p0 + row;
+        if (lane_base == 0 && pre_ok) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) finish(f4[u], p + u * (int64_t)rows_per_iter);
+            p += 4 * (int64_t)rows_per_iter;
+        }
         for (; p + 3 * (int64_t)rows_per_iter < p1; p += 4 * (int64_t)rows_per_iter) {
-            float f[4][8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) load8<kF32>(src, off + (p + u * (int64_t)rows_per_iter) * stride, f[u]);
+            for (int u = 0; u < 4; ++u) load8_raw<kF32>(src, off + (p + u * (int64_t)rows_per_iter) * stride, f4[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) finish(f[u], p + u * (int64_t)rows_per_iter);
+            for (int u = 0; u < 4; ++u) finish(f4[u], p + u * (int64_t)rows_per_iter);
         }
-        for (; p < p1; p += rows_per_iter) {
-            float f[8];
-            load8<kF32>(src, off + p * stride, f);
-            finish(f, p);
-        }
+        // tail: up to three rows, requested together
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (p + u * (int64_t)rows_per_iter < p1) load8_raw<kF32>(src, off + (p + u * (int64_t)rows_per_iter) * stride, f4[u]);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (p + u * (int64_t)rows_per_iter < p1) finish(f4[u], p + u * (int64_t)rows_per_iter);
     }
 }
 
@@ -759,12 +827,11 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
         launch_k(gn_stats_kernel<false>, dim3(nchunk, B), kGnThreads, 0, s, x1, C1, x2, C2, HW, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
-    int64_t blocks = nchunk;          // same pixel chunking as the statistics pass
     if (in_is_f32)
-        launch_k(gn_apply_kernel<true>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     else
-        launch_k(gn_apply_kernel<false>, dim3((unsigned)blocks, B), kGnThreads, 0, s, 
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -792,12 +859,11 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
              (const float2*)stats2, C2, HW / 32, groups, (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
-    const int nchunk = gn_num_chunks(B, HW);
     if (in_is_f32)
-        launch_k(gn_apply_kernel<true>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
     else
-        launch_k(gn_apply_kernel<false>, dim3((unsigned)nchunk, B), kGnThreads, 0, s,
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -857,7 +923,7 @@ int rdeic_groupnorm_nhwc_f32(const float* x1, int C1, const float* x2, int C2, c
              (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
-    launch_k(gn_apply_kernel<true, true>, dim3((unsigned)nchunk, B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2,
+    launch_k(gn_apply_kernel<true, true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true, true>, B, HW, C), B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2,
              C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;

@@ -13,6 +13,23 @@ namespace rdeic {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
+// One thread of a converged warp, chosen by the hardware (PTX elect.sync).  The single-thread roles (TMA producer,
+// tcgen05.mma issuer) MUST be entered through this and not through `lane == 0`: tcgen05.mma / cp.async.bulk.tensor are
+// warp-uniform instructions, and behind a plain lane test ptxas cannot prove that one thread is active, so it wraps EVERY
+// one of them in an ELECT / BRA.U.ANY loop (serving the active threads one at a time).  Measured (scripts/micro/ubench.cu,
+// profiles/r02_ubench.txt): ~100 clocks per tcgen05.mma whatever its shape behind `lane == 0` (N = 256: 161), against
+// 64 / 80 / 128 clocks for N = 128 / 160 / 256 behind elect.sync -- exactly N / 2, the rate of the tensor pipe.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -223,6 +223,67 @@ static int run_mma_multi() {
     return 0;
 }
 
+// same loop as mma_rate_kernel (SS), but the issuing thread is chosen by elect.sync inside a warp-uniform branch (CUTLASS's
+// elect_one_sync) instead of `threadIdx.x == 0`: does ptxas then drop the ELECT / BRA.U.ANY wrapper around every UTCHMMA?
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__global__ void __launch_bounds__(128) mma_elect_kernel(int n, int count, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* s_a = smem;
+    uint8_t* s_b = smem + 16384;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_proxy_async();
+    if (threadIdx.x < 32) tmem_alloc<512>(&slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_mn(128, n, false);
+            const uint64_t da = make_smem_desc(smem_u32(s_a));
+            const uint64_t db = make_smem_desc(smem_u32(s_b));
+            const long long t0 = clock64();
+            for (int i = 0; i < count; ++i) {
+                const uint32_t d = tm + ((n <= 128) ? (i & 1) * 128 : 0);
+                const int k = i & 3;
+                umma_bf16(d, da + 2 * k, db + 2 * k, idesc, 1);
+            }
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t1 = clock64();
+            if (blockIdx.x == 0) cycles[0] = t1 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(tm); }
+}
+
+static int run_mma_elect() {
+    long long* d;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaFuncSetAttribute(mma_elect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 1024));
+    const int count = 4096;
+    const int ns[6] = {16, 64, 128, 160, 192, 256};
+    for (int i = 0; i < 6; ++i) {
+        mma_elect_kernel<<<148, 128, 16384 + 32768 + 1024>>>(ns[i], count, d);
+        CK(cudaDeviceSynchronize());
+        long long c;
+        CK(cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost));
+        printf("mma-elect SS N=%3d: %6.1f clk per MMA (ideal N/2 = %d)\n", ns[i], (double)c / count, ns[i] / 2);
+    }
+    cudaFree(d);
+    return 0;
+}
+
 static int run_mma() {
     long long* d;
     CK(cudaMalloc(&d, 8));
@@ -318,6 +379,7 @@ int main(int argc, char** argv) {
     }
     if (!strcmp(what, "mma") || !strcmp(what, "all")) if (run_mma()) return 1;
     if (!strcmp(what, "mmaw") || !strcmp(what, "all")) if (run_mma_multi()) return 1;
+    if (!strcmp(what, "elect") || !strcmp(what, "all")) if (run_mma_elect()) return 1;
     if (!strcmp(what, "mixed")) if (run_mixed()) return 1;
     return 0;
 }
