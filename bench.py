@@ -30,7 +30,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "decoded images/s @512^2 (5 relay steps)"
 UNIT = "images/s"
-WORKLOAD = "512x512 batch 8 per GPU, 5 relay steps (SpacedSampler), bf16, UNet+control+VAE decode to uint8"
+WORKLOAD = "512x512 batch 8 per GPU, 5 relay steps (SpacedSampler), UNet+control+VAE decode to uint8 (arithmetic type: see dtype)"
 H = W = 512
 BATCH = 8
 RELAY_STEPS = 5
@@ -103,33 +103,45 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(sd_cpu, steps_to_time: int, warmup: int):
-    """Time the oracle (plain PyTorch fp32 restatement of the reference modules) on ONE 512x512
-    image: `steps_to_time` UNet+control relay steps and one VAE decode; the 5-step decode time is
-    composed as 5 x mean(step) + VAE (every relay step runs the identical network)."""
-    from oracle import nn as onn
+def bench_config(world: int) -> dict:
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+            "l2": "no flush needed: per-step working set (1.9 GB bf16 weights + >1 GB activations) exceeds the 126 MB L2"}
 
+
+def cpu_decode_one_image(sd_cpu, c_latent, hint, ctx, noises):
+    """One image through the oracle (plain PyTorch fp32 restatement of the reference modules): q_sample at t = 299,
+    RELAY_STEPS SpacedSampler steps over UNet + control adapter, VAE decode, uint8 -- the whole path of one unit."""
+    from oracle import nn as onn
+    from oracle import sampler as osamp
+
+    kw = dict(model_channels=320, base_d_head=64, ctrl_d_head=16)
+    x_T = osamp.q_sample(c_latent, 299, noises[0])
+    apply_model = lambda x, t: onn.noise_estimator_forward(sd_cpu, x, hint, t, ctx, **kw)
+    z = osamp.spaced_sample(apply_model, x_T, RELAY_STEPS, noises[1:])
+    return onn.to_uint8(onn.vae_decode(sd_cpu, z))
+
+
+def cpu_reference_sample(sd_cpu, steps_to_time: int, warmup: int):
+    """Time the oracle on a BOUNDED sample of the workload: each step decodes ONE 512x512 image of the batch of 8,
+    completely (5 relay steps + VAE decode), on all host cores.  Nothing is extrapolated: `ms_per_step` is the measured
+    mean of the timed steps and `value` = 1 image / that."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c_latent, hint, ctx, noises = make_inputs(1, H // 8, W // 8)
-    t = torch.full((1,), 299, dtype=torch.long)
-    kw = dict(model_channels=320, base_d_head=64, ctrl_d_head=16)
-    step_times = []
+    times = []
     with torch.no_grad():
         for i in range(warmup + steps_to_time):
             t0 = time.perf_counter()
-            onn.noise_estimator_forward(sd_cpu, noises[0], hint, t, ctx, **kw)
+            cpu_decode_one_image(sd_cpu, c_latent, hint, ctx, noises)
             dt = time.perf_counter() - t0
             if i >= warmup:
-                step_times.append(dt)
-        t0 = time.perf_counter()
-        onn.vae_decode(sd_cpu, c_latent)
-        t_vae = time.perf_counter() - t0
-    t_step = float(np.mean(step_times))
-    t_img = RELAY_STEPS * t_step + t_vae
+                times.append(dt)
+    t_img = float(np.mean(times))
     return {"value": 1.0 / t_img, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 image 512x512 fp32 on host cores: {steps_to_time} UNet+control step(s) timed "
-                      f"({t_step:.2f} s each) + 1 VAE decode ({t_vae:.2f} s); 5-step decode = 5*step + VAE",
+            "sample": f"each step = 1 of the batch's 8 images, 512x512, decoded completely (q_sample, {RELAY_STEPS} relay steps "
+                      f"over UNet+control, VAE decode, uint8) by the fp32 oracle port on {cores} host threads; "
+                      f"{steps_to_time} step(s) timed after {warmup} warm-up, mean {t_img:.2f} s per image",
             "s_per_image": t_img}
 
 
@@ -141,13 +153,14 @@ def run_reference(args):
 
     sd = synthetic.make_state_dict(configs.default_params(), seed=WEIGHT_SEED, device="cpu")
     t0 = time.perf_counter()
-    res = cpu_reference_sample(sd, max(1, args.steps), min(args.warmup, 1))
+    res = cpu_reference_sample(sd, max(1, args.steps), max(0, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_image"] * 1e3 * BATCH,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["s_per_image"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.replace("bf16", "fp32 (CPU)"),
-                       "note": "CPU oracle port of the reference modules (the reference is pure Python and cannot travel to "
-                               "the GPU box); bounded sample: see cpu_baseline.sample"},
+            "config": bench_config(max(1, args.gpus)),
+            "reference_note": "CPU oracle port of the reference modules (the reference is pure Python with five absent "
+                              "dependencies and cannot travel to the GPU box); a step is a bounded sample of the workload: "
+                              "see cpu_baseline.sample",
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -337,18 +350,17 @@ def run_b200(args):
         line = {"metric": METRIC, "value": n_img / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                           "l2": "no flush needed: per-step working set (1.9 GB bf16 weights + >1 GB activations) "
-                                 "exceeds the 126 MB L2", "sampler": "SpacedSampler fixed_small, CUDA-graphed UNet step",
-                           "inputs": "two HBM-resident batches alternate step to step: the once-per-batch conditioning work "
-                                     "(text K/V projections, NHWC bf16 hint) is inside every timed step; e2e: "
-                                     "pipeline.decode_host_batches, H2D/D2H double buffered against the decode"},
+                "config": bench_config(world),
+                "arm_notes": {"sampler": "SpacedSampler fixed_small, CUDA-graphed UNet step",
+                              "inputs": "two HBM-resident batches alternate step to step: the once-per-batch conditioning work "
+                                        "(text K/V projections, NHWC bf16 hint) is inside every timed step; e2e: "
+                                        "pipeline.decode_host_batches, H2D/D2H double buffered against the decode"},
                 "unet_step_ms": ms_unet / 10, "vae_decode_ms": ms_vae / 3,
                 "e2e": {"value": n_img / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline}
         if sd_cpu is not None:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(sd_cpu, 1, 0).items() if k != "s_per_image"}
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_sample(sd_cpu, 2, 0).items() if k != "s_per_image"}
         if real_stdout is not None:
             sys.stdout.flush()
             os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -386,7 +386,13 @@ class NoiseEstimatorEngine:
         # run the control adapter on a second stream, concurrently with the base UNet (its kernels are
         # small: 64-256 channels, grids that leave most SMs idle); joined at every zero-conv injection
         self.overlap_control = os.environ.get("RDEIC_NO_OVERLAP") is None
-        self._side: Optional[torch.cuda.Stream] = None
+        self._sides: Dict[int, torch.cuda.Stream] = {}
+        # batch lanes: the step of a batch of B runs as two independent half-batch pipelines on two streams.  Every
+        # kernel then has a partner from the other lane queued behind it, so the CTAs of one kernel's last round and the
+        # launch gap after it are filled by the other lane's kernel instead of idling (persistent kernels hold an SM
+        # each: the partner's CTAs start on an SM the moment this kernel's CTA leaves it).
+        self.lanes = int(os.environ.get("RDEIC_LANES", "1"))
+        self._lane_streams: List[torch.cuda.Stream] = []
         self._ctx_cache: Dict[tuple, tuple] = {}
         self._hint_cache: Dict[tuple, torch.Tensor] = {}
 
@@ -546,6 +552,31 @@ class NoiseEstimatorEngine:
                          hint: Optional[torch.Tensor], unconditional: bool = False) -> torch.Tensor:
         """Same as `forward` with the step-invariant conditioning already derived by `prepare_cond`
         (this is the part that is captured into a CUDA graph)."""
+        B = x.shape[0]
+        if self.lanes < 2 or B < 4 or B % 2:
+            return self._forward_lane(x, t, kv_base, kv_ctrl, hint, unconditional, 0)
+        main = torch.cuda.current_stream()
+        while len(self._lane_streams) < 2:
+            self._lane_streams.append(torch.cuda.Stream(device=self.device))
+        outs = []
+        half = B // 2
+        prev = ops.WS_SLOT
+        try:
+            for lane, s in enumerate(self._lane_streams[:2]):
+                sl = slice(lane * half, (lane + 1) * half)
+                s.wait_stream(main)
+                ops.WS_SLOT = 2 * lane            # each lane (and its control side stream: +1) owns its scratch memory
+                with torch.cuda.stream(s):
+                    outs.append(self._forward_lane(x[sl], t[sl], kv_base[sl], kv_ctrl[sl], None if hint is None else hint[sl],
+                                                   unconditional, lane))
+        finally:
+            ops.WS_SLOT = prev
+        for s in self._lane_streams[:2]:
+            main.wait_stream(s)
+        return torch.cat(outs)
+
+    def _forward_lane(self, x: torch.Tensor, t: torch.Tensor, kv_base: torch.Tensor, kv_ctrl: torch.Tensor,
+                      hint: Optional[torch.Tensor], unconditional: bool, lane: int) -> torch.Tensor:
         B, Cin, h, w = x.shape
         x8, t_emb = self._step_inputs(x, t)
         cb = _Ctx(self._time_rows(self.base, t_emb), kv_base)
@@ -562,9 +593,9 @@ class NoiseEstimatorEngine:
             keep: List[object] = []           # nothing allocated in this step is freed (hence reused) before
             main = torch.cuda.current_stream()  # the step ends: cross-stream reads stay valid without record_stream
             overlap = self.overlap_control
-            if overlap and self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            side = self._side if overlap else main
+            if overlap and lane not in self._sides:
+                self._sides[lane] = torch.cuda.Stream(device=self.device)
+            side = self._sides[lane] if overlap else main
 
             @contextmanager
             def on_side():
@@ -572,7 +603,7 @@ class NoiseEstimatorEngine:
                     yield
                     return
                 prev = ops.WS_SLOT
-                ops.WS_SLOT = 1
+                ops.WS_SLOT = prev + 1
                 try:
                     with torch.cuda.stream(side):
                         yield
