@@ -295,9 +295,6 @@ constexpr int kA2LazySmem = 2 * kATile /*Q*/ + 2 * kA2LazyStages * kATile /*K,V*
 // (exact: l and O carry the same factor, which cancels in O / l; P <= 256 is harmless in bf16).  The
 // per-step fold-in of PV (TMEM load + 64 adds + 64 multiplies per thread) disappears, and with the 64
 // accumulator registers gone the S tile is read from TMEM once (128 registers) instead of twice.
-template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-
 template <bool kLazy>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,

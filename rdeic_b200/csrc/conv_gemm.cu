@@ -255,8 +255,13 @@ struct TileCfg {
     static_assert(kMT * kNT * BN <= 512, "the accumulators of one work item must fit the 512 TMEM columns");
     static_assert(kNT == 1 || (kNT == 2 && kMT == 1 && kIss == 1), "two N tiles per item: one M tile, one issuing warp");
     static_assert(kIss == 1 || (kIss == 2 && kMT == 2), "two issuing warps: one per M tile of the item");
-    static constexpr int kThreads = 64 + 32 * (kIss - 1) + 32 * kEW;   // TMA warp, kIss MMA warps, kEW epilogue warps
-    static constexpr int kFirstEpiWarp = 1 + kIss;
+    // warp 0 TMA, warp 1 (and 2 with kIss == 2) MMA, warp 3 idle: one warp group of control warps, so that setmaxnreg can
+    // hand their registers to the epilogue warp groups (warps 4 ..)
+    static constexpr int kThreads = 128 + 32 * kEW;
+    static constexpr int kFirstEpiWarp = 4;
+    static constexpr int kRegsCtl = 56;
+    static constexpr int kRegsEpi = kEW == 8 ? 224 : 152;               // 128 * 56 + 256 * 224 = 384 * 168 ; 128 * 56 + 384 * 152 = 512 * 128
+    static_assert(kEW == 8 || kEW == 12, "register split is written for 8 or 12 epilogue warps");
     static constexpr int kBTileBytes = BN * kBlockK * 2;
     static constexpr int kBBytes = kNT * kBTileBytes;
     static constexpr int kABytes = kMT * kATileBytes;
@@ -298,7 +303,7 @@ struct TileCfg {
 // L2 -> SM once per 640 tensor clocks.  2 x 160 columns leave no room for a second accumulator buffer: the epilogue of an
 // item is exposed (a few thousand clocks against a main loop of 45+ k-blocks x 640).
 template <int BN, int kResidMode, int kEW, bool kStats, int kMT = 1, bool kSwap = false, bool kUp = false, int kIss = 1, int kNT = 1>
-__global__ void __launch_bounds__(64 + 32 * (kIss - 1) + 32 * kEW, 1)
+__global__ void __launch_bounds__(128 + 32 * kEW, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2, const ConvDev p) {
     pdl_trigger();
@@ -357,6 +362,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     pdl_wait();
 
     if (warp == 0) {
+        setmaxnreg_dec<Cfg::kRegsCtl>();
         if (elect_one_sync()) {
             // ===== TMA producer =====
             // One thread feeds the whole pipeline, and with N <= 160 tiles a k-block is only ~450 tensor clocks:
@@ -438,6 +444,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else if (warp == 1 || (kIss == 2 && warp == 2)) {
+        setmaxnreg_dec<Cfg::kRegsCtl>();
         if (elect_one_sync()) {
             // ===== MMA issuer (kIss == 2: warp 1 owns M tile 0 of every item, warp 2 M tile 1) =====
             constexpr uint32_t idesc = make_idesc(BN);
@@ -483,7 +490,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 umma_commit(&acc_full[buf]);      // accumulator complete
             }
         }
+    } else if (warp < Cfg::kFirstEpiWarp) {
+        setmaxnreg_dec<Cfg::kRegsCtl>();             // idle warps of the control warp group
     } else if constexpr (kSwap) {
+        setmaxnreg_inc<Cfg::kRegsEpi>();
         // ===== epilogue, exchanged operands: TMEM lane = output channel, column = pixel =====
         // Host guarantees: every real tile is full and affine, n_out % 32 == 0, no per-sample bias, no GEGLU,
         // one k-split, vector-aligned rows, alpha == 1 unless there is a residual.
@@ -572,6 +582,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else {
+        setmaxnreg_inc<Cfg::kRegsEpi>();
         // ===== epilogue: TMEM -> registers -> (swizzled smem transpose) -> coalesced global =====
         // Phase A: each thread owns one accumulator row (TMEM lane) and 32 columns per chunk; it
         // adds bias / per-sample bias, applies the activation and parks the row in shared memory

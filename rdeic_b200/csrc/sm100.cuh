@@ -30,6 +30,10 @@ __device__ __forceinline__ bool elect_one_sync() {
         : "=r"(pred));
     return pred != 0;
 }
+// Register reallocation between warp groups (four consecutive warps; every warp of the group executes the same instruction).
+// Put these INSIDE each role's branch: ptxas bounds the registers of the code that follows one path-insensitively.
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -749,10 +749,10 @@ def test_conv3x3_two_m_tiles_per_item(cuda, B, H, W, C1, C2, Cout, stats):
                                                      (3, 64, 96, 64, 64, 640, True), (1, 129, 128, 192, 0, 320, False),
                                                      (8, 32, 32, 128, 0, 640, True)])
 def test_conv3x3_two_issuers_n160(cuda, B, H, W, C1, C2, Cout, stats):
-    """N = 160 tiles with a long reduction and >= 2 rounds of tiles run two M tiles per item with one MMA-issuing warp
-    and one accumulator each (UNet levels 0 / 1: openaimodel.py:203,229 at 320 / 640 channels): even and odd tile
-    counts, two K segments, fused statistics, fp32 + bf16 outputs.  Each accumulator sees its own in-order instruction
-    stream, so the result must be bit-identical run to run."""
+    """N = 160 tiles with a long reduction and >= 2 rounds of tiles (UNet levels 0 / 1: openaimodel.py:203,229 at 320 /
+    640 channels): even and odd tile counts, two K segments, fused statistics, fp32 + bf16 outputs, bit-identical run to
+    run.  These are the shapes the paired-tile variants (kNT = 2 / kIss = 2, `test_conv_variants_behind_switches`) take
+    over when their switch is on; each accumulator there sees its own in-order instruction stream."""
     from rdeic_b200 import ops
 
     g = torch.Generator().manual_seed(92)
@@ -782,6 +782,21 @@ def test_conv3x3_two_issuers_n160(cuda, B, H, W, C1, C2, Cout, stats):
         assert _rel(st[..., 0].cpu(), ref_b.sum(1).cpu()) < 1e-3 and _rel(st[..., 1].cpu(), (ref_b * ref_b).sum(1).cpu()) < 1e-3
     res2 = run()
     assert torch.equal(res2[0], yf)
+
+
+@pytest.mark.parametrize("env", ["RDEIC_PAIR160", "RDEIC_DUAL160", "RDEIC_M_MAJOR"])
+def test_conv_variants_behind_switches(cuda, env):
+    """The conv variants that lost their A/B stay in the library behind environment switches (two N tiles per item sharing
+    the activation stage; two M tiles per item with one issuing warp each; activation-major item order).  The switches are
+    read once per process, so the N = 160 cases above are re-run in a child process with the switch on."""
+    import os
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider", __file__, "-k",
+                        "two_issuers_n160 or conv3x3_tc or conv_two_sources"], env=dict(os.environ, **{env: "1"}),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 40, 48), (1, 8, 100)])
