@@ -7,7 +7,8 @@
 round 2:  12 nearest-x2 + conv3x3 640->640 folded into four 2x2 parity convs @32^2->64^2   13 stride-2 conv3x3 320->320 through an
 element-strided tensor map   14 conv3x3 320->320 with the zero-conv injection as a centre-tap K segment   15 cross-attention
 (77 text keys, single-KV-tile tcgen05 kernel)   16 GroupNorm [8,16,16,1280] as one kernel   17 fp32 conv5x5 224->128 @32^2 batch 8
-(entropy-parameter path, CUDA cores, split-K)   18 uint8 tile blend 2048x1408"""
+(entropy-parameter path, CUDA cores, split-K)   18 uint8 tile blend 2048x1408
+19 VAE mid-block attention N=4096 d=512 (flash kernel for wide heads)   20 control-adapter self-attention N=4096 h=4 d=16 (mma.sync)"""
 import sys
 from pathlib import Path
 import torch
@@ -42,6 +43,7 @@ from rdeic_b200 import parallel  # noqa: E402
 plan = parallel.plan_tiles_balanced(176, 256, 8, 16)
 tiles = torch.randint(0, 255, (len(plan), plan[0][2] * 8, plan[0][3] * 8, 3), device=dev, dtype=torch.uint8)
 org = torch.tensor([[p_[0] * 8, p_[1] * 8] for p_ in plan], dtype=torch.int32, device=dev)
+qw = rnd(8, 4096, 1536).bfloat16(); q16 = rnd(8, 4096, 192).bfloat16()
 fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True),
        lambda: ops.conv_gemm(x512, w512, 512, 9, bias=b512),
        lambda: ops.linear(xl, wl, 320, bias=b320, resid=rl, out_f32=True),
@@ -60,7 +62,9 @@ fns = [lambda: ops.conv_gemm(x320, w320, 320, 9, bias=b320, resid=r32, dual=True
        lambda: ops.attention(q77, kv77[..., :320], kv77[..., 320:], 5, 64, 0.125),
        lambda: ops.groupnorm(gs, g1280, b1280, 32, 1e-5, True),
        lambda: nets.conv(xf, "c", act=4),
-       lambda: ops.blend_tiles_u8(tiles, org, 128, 1408, 2048)]
+       lambda: ops.blend_tiles_u8(tiles, org, 128, 1408, 2048),
+       lambda: ops.attention(qw[..., :512], qw[..., 512:1024], qw[..., 1024:], 1, 512, 512 ** -0.5),
+       lambda: ops.attention(q16[..., :64], q16[..., 64:128], q16[..., 128:], 4, 16, 0.25)]
 for _ in range(2):
     for f in fns:
         f()

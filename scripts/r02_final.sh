@@ -13,8 +13,10 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r
 cut -c1-400 gpurun_out/r02_bench_reference_arm.json
 timeout 300 python scripts/bench_hbm_kernels.py > gpurun_out/r02_hbm_kernels.json 2> gpurun_out/r02_hbm.err || echo "hbm rc=$?"
 timeout 300 python scripts/prof_step.py 8 > gpurun_out/r02_step_timeline.txt 2>&1 || echo "prof rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_kernels_full python scripts/profile_final.py > gpurun_out/r02_ncu_full.log 2>&1 || echo "ncu full rc=$?"
-python scripts/ncu_summary.py gpurun_out/r02_kernels_full.ncu-rep > gpurun_out/r02_kernels_ncu_full_summary.txt 2>/dev/null
+# the report itself (> 64 MiB with source pages) stays on the box: gpurun copies back at most 64 MiB, and a directory over the limit is dropped whole
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -o /tmp/r02_kernels_full python scripts/profile_final.py > gpurun_out/r02_ncu_full.log 2>&1 || echo "ncu full rc=$?"
+python scripts/ncu_summary.py /tmp/r02_kernels_full.ncu-rep > gpurun_out/r02_kernels_ncu_full_summary.txt 2>/dev/null
+ncu -i /tmp/r02_kernels_full.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/r02_kernels_ncu_full_raw.csv.gz
 timeout ${NCU_LIMIT:-1000} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   --cache-control none --profile-from-start off --csv --log-file gpurun_out/r02_bench_launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profile-range > gpurun_out/r02_bench_ncu.log 2>&1 || echo "ncu list rc=$?"
