@@ -85,7 +85,11 @@ struct FastDiv {
 };
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef RDEIC_PDL_NO_TRIGGER      // A/B build: dependents launch when the last CTA exits (implicit trigger) instead of at kernel start
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // x * sigmoid(x); __fdividef = rcp.approx + mul (an IEEE divide costs ~10x more instructions, which made
 // the GroupNorm+SiLU apply pass issue-bound instead of HBM-bound)

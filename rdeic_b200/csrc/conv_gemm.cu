@@ -138,14 +138,37 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // selected by one warp-uniform switch per chunk: the generic form predicates every alternative, which
 // doubled the issued instructions of the epilogue-bound small-K linears.
 //   kRes: 0 none, 1 fp32, 2 bf16.   Pointers arrive offset to (first row of the lane, first column).
-template <int kRes, bool kF32, bool kB16, bool kStats>
+// The residual of a slab (8 row-steps x 4 columns per lane), requested BEFORE the accumulator chunk is read from tensor
+// memory: the loads do not depend on it, and issued at the top of phase B their L2 / HBM latency (~1 us) was the largest
+// single stall of the epilogue-bound small-K linears (ncu source page: 18 % of all samples on the first FFMA after them).
+template <int kRes>
+__device__ __forceinline__ void load_resid8(const void* __restrict__ resid, int64_t ld_resid, float4* rv) {
+    if (kRes == 1) {
+        const float* rp = reinterpret_cast<const float*>(resid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (int64_t)(4 * i) * ld_resid);
+    } else if (kRes == 2) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(resid);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint2 u = *reinterpret_cast<const uint2*>(rp + (int64_t)(4 * i) * ld_resid);
+            unpack_bf16x2(u.x, rv[i].x, rv[i].y);
+            unpack_bf16x2(u.y, rv[i].z, rv[i].w);
+        }
+    }
+}
+
+template <int kRes, bool kF32, bool kB16, bool kStats, bool kPre = false>
 __device__ __forceinline__ void store_slab(const float4* __restrict__ stg, int lane, float alpha,
                                            const void* __restrict__ resid, int64_t ld_resid,
                                            float* __restrict__ of, __nv_bfloat16* __restrict__ ob, int64_t ldo,
-                                           float* __restrict__ stats_dst) {
+                                           float* __restrict__ stats_dst, const float4* rv_pre = nullptr) {
     const int q = lane & 7, r0 = lane >> 3;
     float4 rv[8];
-    if (kRes == 1) {
+    if (kPre && kRes != 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = rv_pre[i];
+    } else if (kRes == 1) {
         const float* rp = reinterpret_cast<const float*>(resid);
 #pragma unroll
         for (int i = 0; i < 8; ++i) rv[i] = *reinterpret_cast<const float4*>(rp + (int64_t)(4 * i) * ld_resid);
@@ -194,13 +217,13 @@ __device__ __forceinline__ void store_slab(const float4* __restrict__ stg, int l
     }
 }
 
-template <int kRes, bool kStats>
+template <int kRes, bool kStats, bool kPre = false>
 __device__ __forceinline__ void store_slab_out(const float4* stg, int lane, float alpha, const void* resid,
                                                int64_t ld_resid, float* of, __nv_bfloat16* ob, int64_t ldo,
-                                               float* stats_dst) {
-    if (of && ob) store_slab<kRes, true, true, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
-    else if (of) store_slab<kRes, true, false, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
-    else store_slab<kRes, false, true, kStats>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst);
+                                               float* stats_dst, const float4* rv_pre = nullptr) {
+    if (of && ob) store_slab<kRes, true, true, kStats, kPre>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst, rv_pre);
+    else if (of) store_slab<kRes, true, false, kStats, kPre>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst, rv_pre);
+    else store_slab<kRes, false, true, kStats, kPre>(stg, lane, alpha, resid, ld_resid, of, ob, ldo, stats_dst, rv_pre);
 }
 
 // kMT = M tiles per work item: with kMT == 2 one CTA walks two adjacent 128-row M tiles against the
@@ -526,10 +549,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
 #pragma unroll 1
             for (int ci = half; ci < kChunks && ch_ok; ci += kCStride) {
-                uint32_t acc[32];
-                tmem_ld16(tmem_acc + (uint32_t)(ci * 32), acc);
-                tmem_ld16(tmem_acc + (uint32_t)(ci * 32) + 16, acc + 16);
-                // coordinates of the chunk's first pixel (lane 0's row) while the load is in flight
+                // coordinates of the chunk's first pixel (lane 0's row)
                 int mt = mi * kMT + (ci >> 2);
                 const bool tile_ok = mt < total_tiles;
                 const int tiw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -538,6 +558,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int gw = tiw * tw + (r0 & (tw - 1)), gh = tih * th + ((r0 >> p.tw_log2) & (th - 1));
                 const int gn = mt * tn_ + (r0 >> (p.tw_log2 + p.th_log2));
                 const int64_t m_slab = ((int64_t)gn * p.a_h + gh) * p.a_w + gw;
+                // (the residual stays at the top of phase B here: requested ahead of the accumulator read it cost 22 % on the
+                // VAE's 128-channel convs with a bf16 residual, 593 -> 725 us)
+                uint32_t acc[32];
+                tmem_ld16(tmem_acc + (uint32_t)(ci * 32), acc);
+                tmem_ld16(tmem_acc + (uint32_t)(ci * 32) + 16, acc + 16);
                 tmem_ld_wait();
                 if (ci == last_c) {
                     tc_fence_before();
@@ -703,6 +728,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int nbase = col0 + c;
                 if (nbase >= p.n_out) break;                                      // warp-uniform
                 if (kPrefetchResid) prefetch(ci + kCStride, rnext);
+                // slab fast path (below): its residual is requested now, ahead of the accumulator chunk it will be added to
+                const bool use_slab = !geglu && affine && fast_chunk(ci) && !(kPrefetchResid && pre_bf16) &&
+                                      !(kAheadF32 && ahead_f32) && (eo.resid || eo.alpha == 1.0f);
+                // (fp32 residuals only -- the UNet's residual stream: 28.8 -> 26.9 us on the K = 320 linears; with bf16 residuals --
+                // the VAE -- the early request measured 7 % slower, 502 -> 536 us, and they stay at the top of phase B)
+                float4 rvp[8];
+                if (use_slab && eo.resid && eo.resid_is_f32) {
+                    const int64_t r_off = ((int64_t)m_slab + (lane >> 3) * rstep) * eo.ld_resid + nbase + 4 * (lane & 7);
+                    load_resid8<1>(reinterpret_cast<const float*>(eo.resid) + r_off, (int64_t)eo.ld_resid * rstep, rvp);
+                }
                 uint32_t acc[32];
                 tmem_ld16(tmem_acc + (uint32_t)c, acc);
                 tmem_ld16(tmem_acc + (uint32_t)c + 16, acc + 16);
@@ -786,8 +821,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         stg[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (!geglu) {
-                    if (affine && fast_chunk(ci) && !(kPrefetchResid && pre_bf16) && !(kAheadF32 && ahead_f32) &&
-                        (eo.resid || eo.alpha == 1.0f)) {
+                    if (use_slab) {
                         // GroupNorm statistics of the tensor being written are fused here (kStats) so the
                         // consumer's statistics pass (a full re-read of the tensor) disappears
                         const int q = lane & 7;
@@ -808,8 +842,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         if (!eo.resid)
                             store_slab_out<0, kStats>(stg, lane, eo.alpha, nullptr, 0, of, ob, ldo_s, sd);
                         else if (eo.resid_is_f32)
-                            store_slab_out<1, kStats>(stg, lane, eo.alpha, reinterpret_cast<const float*>(eo.resid) + r_off,
-                                                      ldr_s, of, ob, ldo_s, sd);
+                            store_slab_out<1, kStats, true>(stg, lane, eo.alpha, reinterpret_cast<const float*>(eo.resid) + r_off,
+                                                            ldr_s, of, ob, ldo_s, sd, rvp);
                         else
                             store_slab_out<2, kStats>(stg, lane, eo.alpha,
                                                       reinterpret_cast<const __nv_bfloat16*>(eo.resid) + r_off,
