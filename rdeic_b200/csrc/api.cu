@@ -10,12 +10,10 @@ char* err_buf() {
     return buf;
 }
 
-// Programmatic dependent launch is OFF by default: inside the CUDA-graph UNet step it measured 4 % SLOWER than plain
-// kernel-to-kernel edges (11.30 -> 10.86 ms at batch 8, scripts/ab_unet.py on one box; neutral on the eager VAE decode):
-// every kernel triggers its dependents on entry, so the next grid's CTAs queue for SMs while the current grid still has
-// waves to run.  RDEIC_PDL=1 turns it back on (RDEIC_NO_PDL is still honoured).
+// Programmatic dependent launch is ON by default, with the implicit trigger (see pdl_trigger() in common.cuh for the
+// measurements behind both choices).  RDEIC_PDL=0 or RDEIC_NO_PDL=1 turns it off.
 bool pdl_enabled() {
-    static const bool on = getenv("RDEIC_PDL") != nullptr && atoi(getenv("RDEIC_PDL")) != 0 && getenv("RDEIC_NO_PDL") == nullptr;
+    static const bool on = !(getenv("RDEIC_PDL") != nullptr && atoi(getenv("RDEIC_PDL")) == 0) && getenv("RDEIC_NO_PDL") == nullptr;
     return on;
 }
 

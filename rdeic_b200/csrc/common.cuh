@@ -28,11 +28,10 @@ int set_error(const char* fmt, ...);
 #define RDEIC_LAUNCH_CHECK() RDEIC_CUDA(cudaPeekAtLastError())
 
 // Programmatic dependent launch (PDL): every kernel of the library is launched with
-// programmaticStreamSerialization, calls pdl_trigger() on entry (the next kernel in the stream may
-// start launching: its launch latency and prologue overlap our execution) and pdl_wait() before
-// its first global-memory access (blocks until the preceding grid has completed and flushed).
-// ~660 dependent launches per UNet step make launch gaps a first-order cost.  RDEIC_NO_PDL=1
-// falls back to plain stream order.
+// programmaticStreamSerialization and calls pdl_wait() before its first global-memory access (blocks until the
+// preceding grid has completed and flushed); the next kernel in the stream is launched as soon as our last CTA has
+// exited instead of after the grid-completion round trip.  ~590 dependent launches per UNet step make launch gaps a
+// first-order cost.  RDEIC_PDL=0 (or RDEIC_NO_PDL=1) falls back to plain stream order.
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
@@ -85,8 +84,22 @@ struct FastDiv {
 };
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pdl_trigger() is a no-op: the dependents of a grid launch when its last CTA EXITS (the implicit trigger).  With
+// griddepcontrol.launch_dependents at kernel entry the next grid's CTAs take an SM each as soon as one frees up and sit
+// there until this grid has finished -- SMs that the kernels of the step's other stream (the control adapter) would have used:
+// UNet+control step 10.61 -> 11.12 ms.  With the implicit trigger programmatic launch still removes the
+// grid-complete -> grid-launch latency of ~590 kernel boundaries: 10.61 -> 10.40 ms (A/B/C on one box, two repetitions).
+// -DRDEIC_PDL_EARLY_TRIGGER restores the entry trigger for A/B builds.
+// Short, many-CTA kernels (LayerNorm, GroupNorm, split-K reduce, elementwise) DO trigger on entry when built with
+// -DRDEIC_PDL_SHORT_EARLY: their dependents are mostly GEMMs, whose prologue (barriers, TMEM allocation, tensor-map
+// prefetch) then overlaps the few microseconds in which the short kernel's last wave drains.
+__device__ __forceinline__ void pdl_trigger_short() {
+#if defined(RDEIC_PDL_EARLY_TRIGGER) || defined(RDEIC_PDL_SHORT_EARLY)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_trigger() {
-#ifndef RDEIC_PDL_NO_TRIGGER      // A/B build: dependents launch when the last CTA exits (implicit trigger) instead of at kernel start
+#ifdef RDEIC_PDL_EARLY_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }

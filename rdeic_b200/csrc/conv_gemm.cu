@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t m_total, int n_out,
                      int rows_per_sample, const float* __restrict__ bias,
                      const float* __restrict__ row_bias, int row_bias_ld, int act, float act_param, EpiOut eo) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int n4 = (n_out + 3) >> 2;
     const int64_t total = m_total * n4;

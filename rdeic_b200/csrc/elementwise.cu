@@ -19,7 +19,7 @@ __device__ __forceinline__ float guided_eps(float e, float eu, float scale, bool
 __global__ void __launch_bounds__(kThreads)
 q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                 float* __restrict__ out, int64_t n, float a, float b) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -31,7 +31,7 @@ relay_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                     const float* __restrict__ eps_u, float gscale,
                     const float* __restrict__ noise, float* __restrict__ out, int64_t n,
                     float r, float rm1, float c1, float c2, float sigma) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -52,7 +52,7 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                    const float* __restrict__ noise, float* __restrict__ out,
                    float* __restrict__ pred_out, int64_t n, float s1m, float sqrt_at,
                    float sqrt_aprev, float dir, float sigma) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -73,7 +73,7 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps,
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C,
                     int64_t HW, int ldc, int c_off) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
@@ -98,7 +98,7 @@ template <bool kF32>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int C, int64_t HW,
                     int ldc) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
@@ -126,7 +126,7 @@ nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int C
 
 __global__ void __launch_bounds__(kThreads)
 f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -137,7 +137,7 @@ f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ ds
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t,
                                           __nv_bfloat16* __restrict__ out, int B, int dim,
                                           float max_period) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,7 +156,7 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t,
 template <bool kF32>
 __global__ void __launch_bounds__(kThreads)
 silu_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -169,7 +169,7 @@ silu_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t
 // attention.py:54-56: x, gate = proj(x).chunk(2); x * gelu(gate)   (exact erf GELU)
 __global__ void __launch_bounds__(kThreads)
 geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows, int F) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int fv = F >> 3;  // vectors of 8 bf16
     const int64_t total = rows * fv;
@@ -200,7 +200,7 @@ geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows
 __global__ void __launch_bounds__(kThreads)
 upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                   int cv) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t total = (int64_t)B * H * W * cv;
     const int64_t orow = (int64_t)2 * W * cv;
@@ -223,7 +223,7 @@ upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, 
 __global__ void __launch_bounds__(kThreads)
 pixel_shuffle2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                       int cv) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t total = (int64_t)B * (2 * H) * (2 * W) * cv;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -242,7 +242,7 @@ pixel_shuffle2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int
 __global__ void __launch_bounds__(kThreads)
 im2col_s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
                  int C, int Cp, int pad_lo) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int Ho = H / 2, Wo = W / 2;
     const int cpv = Cp >> 3, cv = C >> 3;
@@ -268,7 +268,7 @@ template <bool kF32>
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const void* __restrict__ in, __nv_bfloat16* __restrict__ out, int n,
                     float scale) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const float* inf = reinterpret_cast<const float*>(in) + row * n;
@@ -308,7 +308,7 @@ softmax_rows_kernel(const void* __restrict__ in, __nv_bfloat16* __restrict__ out
 template <int kVec>
 __global__ void __launch_bounds__(256)
 softmax_rows_f32_reg_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int n4, float scale) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const float4* src = in + row * n4;
@@ -358,7 +358,7 @@ softmax_rows_f32_reg_kernel(const float4* __restrict__ in, uint2* __restrict__ o
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                       int R, int C) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ __nv_bfloat16 tile[32][34];
     const int64_t base = (int64_t)blockIdx.z * R * C;
@@ -379,7 +379,7 @@ transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __res
 __global__ void __launch_bounds__(kThreads)
 image_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t pixels,
                    int ldc) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t total = pixels * 3;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -401,7 +401,7 @@ image_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int6
 __global__ void __launch_bounds__(kThreads)
 split_bf16_hilo_kernel(const float* __restrict__ src, int64_t rows, int C, int64_t ld_src,
                        __nv_bfloat16* __restrict__ dst, int64_t ld_dst, int off_hi, int off_lo) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t total = rows * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -427,7 +427,7 @@ __device__ __forceinline__ float ramp_w(int i, int n, int ov) {
 __global__ void __launch_bounds__(kThreads)
 blend_tiles_u8_kernel(const uint8_t* __restrict__ tiles, const int* __restrict__ origin, int T, int th, int tw, int ov,
                       uint8_t* __restrict__ out, int H, int W) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int64_t total = (int64_t)H * W;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

@@ -108,7 +108,7 @@ template <bool kF32>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 int64_t HW, int G, float2* __restrict__ partial) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ float s_part[kGnThreads * 16];   // [row][lane][8 sum | 8 sq]
     __shared__ float s_csum[kGnMaxC];
@@ -199,7 +199,7 @@ gn_stats_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
 __global__ void __launch_bounds__(kGnThreads)
 gn_fold_stats_kernel(const float2* __restrict__ st1, int C1, const float2* __restrict__ st2, int C2,
                      int64_t slabs_per_sample, int G, float2* __restrict__ partial) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ float s_csum[kGnMaxC];
     __shared__ float s_csq[kGnMaxC];
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kGnThreads)
 gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                 int HW, int G, float eps, int silu, FastDiv div_pairs) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ double s_red[2][kGnThreads / 32];
     __shared__ float s_stat[2];
@@ -312,7 +312,7 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, int64_t HW, int G, float eps, int silu,
                 const float2* __restrict__ partial, int nchunk, FastDiv div_vl) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     __shared__ float s_scale[kGnMaxC];
     __shared__ float s_shift[kGnMaxC];
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, uint4* __restrict__ out, int64_t rows, int C,
                  float eps) {
-    pdl_trigger();
+    pdl_trigger_short();
     pdl_wait();
     const int VL = C >> 3;
     const int lane = threadIdx.x & (kLanes - 1);
