@@ -197,7 +197,8 @@ int rdeic_gn_silu_conv3x3_tail(const void* x, const float* stats, const float* g
                                uint8_t* out_u8, int B, int H, int W, int C, int groups, float eps,
                                void* workspace, rdeic_stream_t stream);
 /* ABI 5.  1 when rdeic_groupnorm_nhwc runs this problem as ONE kernel (one CTA per sample and group, no workspace
- * traffic): tensors of at most 4 M elements with an even number of channels per group.  Callers holding fused
+ * traffic, the group's elements stay in registers between the statistics and the apply pass): tensors of at most 4 M
+ * elements whose groups have 8 or more (an even number of) channels and at most 12 288 elements.  Callers holding fused
  * statistics skip rdeic_groupnorm_from_stats for such tensors: two launches cost more than the statistics save. */
 int rdeic_groupnorm_is_small(int B, int64_t HW, int C1, int C2, int groups);
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,

@@ -241,8 +241,12 @@ gn_fold_stats_kernel(const float2* __restrict__ st1, int C1, const float2* __res
 // statistics are reduced in a fixed order (fp32 per thread, fp64 across the CTA: deterministic) and nothing goes
 // through a workspace.  Two channels per access (C/G is even for every GroupNorm on the path).
 constexpr int kGnSmallMaxElems = 1 << 22;
+constexpr int kGnSmallGroupElems = 12288;        // elements of one (sample, group): 24 channel pairs per thread
+constexpr int kGnSmallGroupElemsWide = 20480;    // second instantiation, 40 pairs per thread (UNet level 1, [8,32,32,640]: 1024 x 20):
+                                                 // measured 23 us per launch against 18 us for fold + apply, so rdeic_groupnorm_is_small
+                                                 // does not select it; kept for callers without fused statistics
 
-template <bool kF32>
+template <bool kF32, int kGroupElems>
 __global__ void __launch_bounds__(kGnThreads)
 gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2, int C2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
@@ -263,14 +267,26 @@ gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
         unpack_bf16x2(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(src) + off), v.x, v.y);
         return v;
     };
+    // the group's elements stay in registers between the statistics and the apply pass (<= 24 channel pairs per thread:
+    // rdeic_groupnorm_is_small caps a group at 12 288 elements): every load is requested up front, one memory round trip
+    // instead of a dozen dependent ones in a kernel that is nothing but latency (9.7 us per launch before)
+    constexpr int kMaxPairs = kGroupElems / 2 / kGnThreads;
+    float2 v[kMaxPairs];
     float s = 0.f, q = 0.f;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < total; i += kGnThreads) {
-        uint32_t p, j;
-        div_pairs.divmod((uint32_t)i, p, j);
-        const float2 v = load2((int)p, c0 + 2 * (int)j);
-        s += v.x + v.y;
-        q = fmaf(v.x, v.x, fmaf(v.y, v.y, q));
+#pragma unroll
+    for (int k = 0; k < kMaxPairs; ++k) {
+        const int i = threadIdx.x + k * kGnThreads;
+        v[k] = make_float2(0.f, 0.f);
+        if (i < total) {
+            uint32_t p, j;
+            div_pairs.divmod((uint32_t)i, p, j);
+            v[k] = load2((int)p, c0 + 2 * (int)j);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPairs; ++k) {
+        s += v[k].x + v[k].y;
+        q = fmaf(v[k].x, v[k].x, fmaf(v[k].y, v[k].y, q));
     }
     double ds = (double)s, dq = (double)q;
 #pragma unroll
@@ -292,18 +308,21 @@ gn_small_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
     }
     __syncthreads();
     const float mean = s_stat[0], rstd = s_stat[1];
-#pragma unroll 4
-    for (int i = threadIdx.x; i < total; i += kGnThreads) {
-        uint32_t p, j;
-        div_pairs.divmod((uint32_t)i, p, j);
-        const int c = c0 + 2 * (int)j;
-        const float2 v = load2((int)p, c);
-        const float2 ga = *reinterpret_cast<const float2*>(gamma + c), be = *reinterpret_cast<const float2*>(beta + c);
-        float y0 = fmaf((v.x - mean) * rstd, ga.x, be.x), y1 = fmaf((v.y - mean) * rstd, ga.y, be.y);
-        if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-        *reinterpret_cast<uint32_t*>(out + ((int64_t)b * HW + p) * C + c) = pack_bf16x2(y0, y1);
+#pragma unroll
+    for (int k = 0; k < kMaxPairs; ++k) {
+        const int i = threadIdx.x + k * kGnThreads;
+        if (i < total) {
+            uint32_t p, j;
+            div_pairs.divmod((uint32_t)i, p, j);
+            const int c = c0 + 2 * (int)j;
+            const float2 ga = *reinterpret_cast<const float2*>(gamma + c), be = *reinterpret_cast<const float2*>(beta + c);
+            float y0 = fmaf((v[k].x - mean) * rstd, ga.x, be.x), y1 = fmaf((v[k].y - mean) * rstd, ga.y, be.y);
+            if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            *reinterpret_cast<uint32_t*>(out + ((int64_t)b * HW + p) * C + c) = pack_bf16x2(y0, y1);
+        }
     }
 }
+
 
 // (bf16 input: 4 resident CTAs per SM, i.e. at most 64 registers -- the VAE's 537 MB tensors want the bytes in flight)
 template <bool kF32, bool kOutF32 = false>
@@ -788,7 +807,7 @@ int rdeic_groupnorm_is_small(int B, int64_t HW, int C1, int C2, int groups) {
     // One CTA walks a whole group: worth it only while that is a couple of dozen iterations per thread and a pixel's
     // slice of the group fills at least one 32-byte sector (the control adapter's 64- and 128-channel levels at 64^2 /
     // 32^2 have 2 or 4 channels per group and thousands of pixels: measured 84 us here against ~15 us for fold + apply).
-    return (int64_t)B * HW * C <= kGnSmallMaxElems && HW * (int64_t)cg <= 12288 && cg >= 8 && cg % 2 == 0 && C1 % 2 == 0;
+    return (int64_t)B * HW * C <= kGnSmallMaxElems && HW * (int64_t)cg <= kGnSmallGroupElems && cg >= 8 && cg % 2 == 0 && C1 % 2 == 0;
 }
 
 int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_is_f32,
@@ -811,12 +830,13 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     cudaStream_t s = as_stream(stream);
     if (rdeic_groupnorm_is_small(B, HW, C1, C2, groups)) {
         const FastDiv div_pairs((uint32_t)((C / groups) >> 1));
-        if (in_is_f32)
-            launch_k(gn_small_kernel<true>, dim3((unsigned)groups, B), kGnThreads, 0, s, x1, C1, x2, C2, gamma, beta,
-                     (__nv_bfloat16*)out, (int)HW, groups, eps, silu, div_pairs);
-        else
-            launch_k(gn_small_kernel<false>, dim3((unsigned)groups, B), kGnThreads, 0, s, x1, C1, x2, C2, gamma, beta,
-                     (__nv_bfloat16*)out, (int)HW, groups, eps, silu, div_pairs);
+        const bool wide = HW * (int64_t)(C / groups) > kGnSmallGroupElems;
+        auto go = [&](auto kernel) {
+            launch_k(kernel, dim3((unsigned)groups, B), kGnThreads, 0, s, x1, C1, x2, C2, gamma, beta, (__nv_bfloat16*)out, (int)HW,
+                     groups, eps, silu, div_pairs);
+        };
+        if (in_is_f32) { if (wide) go(gn_small_kernel<true, kGnSmallGroupElemsWide>); else go(gn_small_kernel<true, kGnSmallGroupElems>); }
+        else { if (wide) go(gn_small_kernel<false, kGnSmallGroupElemsWide>); else go(gn_small_kernel<false, kGnSmallGroupElems>); }
         RDEIC_LAUNCH_CHECK();
         return 0;
     }

@@ -298,7 +298,9 @@ def test_image_to_u8(cuda):
     (2, 16, 16, 320, 0, True, 1e-5), (1, 8, 8, 1280, 1280, True, 1e-5), (2, 32, 32, 640, 320, True, 1e-5),
     (1, 12, 20, 64, 0, False, 1e-6), (1, 64, 64, 128, 0, True, 1e-6), (3, 4, 4, 256, 0, False, 1e-6),
     (1, 5, 3, 960, 0, True, 1e-5),
-    # > 4 M elements: the statistics + apply pair (smaller ones run as one kernel, one CTA per sample and group)
+    # UNet level-1 sizes (groups of 20 480 elements: fold / statistics + apply)
+    (2, 32, 32, 640, 0, True, 1e-5), (8, 32, 32, 640, 0, False, 1e-5), (1, 32, 32, 320, 320, True, 1e-5),
+    # > 4 M elements or larger groups: the statistics + apply pair (smaller ones run as one kernel, one CTA per sample and group)
     (2, 128, 128, 320, 0, True, 1e-5), (1, 96, 96, 320, 320, True, 1e-5), (5, 64, 64, 256, 0, False, 1e-6)])
 def test_groupnorm(cuda, B, H, W, C1, C2, silu, eps):
     from rdeic_b200 import ops
