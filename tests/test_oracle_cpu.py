@@ -328,3 +328,18 @@ def test_oracle_vae_encoder_matches_reference_golden(tag):
         base = synthetic.make_state_dict(configs.small_params(), seed=231)
         ext = synthetic.make_state_dict(configs.small_params(), seed=231, encoder=True)
         assert all(torch.equal(base[k], ext[k]) for k in base)
+
+
+def test_bench_arms_share_config():
+    """bench.py prints the same `config` object from both arms (the driver compares them) and the reference arm's
+    step is a real bounded sample: one image of the batch decoded completely by the oracle port."""
+    import importlib
+    import inspect
+
+    bench = importlib.import_module("bench")
+    c1, c2 = bench.bench_config(1), bench.bench_config(8)
+    assert set(c1) == {"workload", "global_batch", "parallelism", "l2"} and c1["global_batch"] * 8 == c2["global_batch"]
+    assert "bf16" not in c1["workload"] and "fp32" not in c1["workload"]          # the arithmetic type lives in `dtype`
+    src = inspect.getsource(bench.run_reference) + inspect.getsource(bench.run_b200)
+    assert src.count("bench_config(") == 2
+    assert "s_per_image\"] * 1e3," in inspect.getsource(bench.run_reference)        # measured step time, not x BATCH
