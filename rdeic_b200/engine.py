@@ -60,10 +60,20 @@ class Conv:
 
     @staticmethod
     def load(sd: SD, name: str, dev, c1: Optional[int] = None, scale: float = 1.0, geglu: bool = False,
-             in_idx: Optional[Sequence[int]] = None) -> "Conv":
+             in_idx: Optional[Sequence[int]] = None, split3: bool = False) -> "Conv":
         """`in_idx`: input-channel gather applied to the weight (repeats allowed): the operand layout of an input
-        that arrives as [hi | lo] halves needs every weight column twice."""
+        that arrives as [hi | lo] halves needs every weight column twice.  `split3`: the weight as [w_hi | w_hi | w_lo]
+        along the input channels (zero padded to a multiple of 8), for activations that arrive as `ops.split3` wrote
+        them ([hi | lo | hi]): three bf16 passes with fp32-equivalent products."""
         w = sd[name + ".weight"].to(dev, torch.float32)
+        if split3:
+            assert in_idx is None and c1 is None and not geglu
+            w_hi = w.bfloat16().float()
+            w_lo = (w - w_hi).bfloat16().float()
+            w = torch.cat([w_hi, w_hi, w_lo], 1)
+            pad = (-w.shape[1]) % 8
+            if pad:
+                w = torch.cat([w, torch.zeros((w.shape[0], pad, *w.shape[2:]), device=w.device)], 1)
         if in_idx is not None:
             w = w[:, torch.as_tensor(list(in_idx), device=w.device)].contiguous()
         if scale != 1.0:
@@ -736,12 +746,34 @@ class VAEEncoderEngine(_VaeMid):
     `apply_condition_compress` (model/rdeic.py:660-663) uses only `c`, the 512-channel feature map
     after norm_out + swish, so conv_out / quant_conv / the posterior are not computed."""
 
-    def __init__(self, sd: SD, device="cuda", prefix: str = "first_stage_model"):
+    def __init__(self, sd: SD, device="cuda", prefix: str = "first_stage_model", precision: str = "bf16"):
+        """precision "bf16": one tensor-core pass per conv (the throughput mode: feature map within 1.2e-2 rel-L2 of the
+        reference's fp32 result -- 26 convs of bf16 operand rounding).  "high": every conv3x3 / 1x1 on the residual path
+        as a three-pass split-bf16 product (activations [hi | lo | hi] against weights [w_hi | w_hi | w_lo], still
+        tcgen05, fp32 accumulation, 3x the MACs), GroupNorm in and out in fp32: the verification mode of the sender side."""
         dev = torch.device(device)
         self.device = dev
+        if precision not in ("bf16", "high"):
+            raise ValueError("VAEEncoderEngine: precision must be 'bf16' or 'high'")
+        self.precision = precision
         E = prefix + ".encoder"
         super().__init__(sd, E + ".mid", dev)
-        self.conv_in = Conv.load(sd, E + ".conv_in", dev)
+        if precision == "high":
+            self._hi: Dict[int, Conv] = {}           # id(bf16 Conv) -> its split3 twin
+
+            def twin(c: Optional[Conv], name: str):
+                if c is not None:
+                    self._hi[id(c)] = Conv.load(sd, name, dev, split3=True)
+
+            for blk, nm in ((self.mid1, E + ".mid.block_1"), (self.mid2, E + ".mid.block_2")):
+                twin(blk.c1, nm + ".conv1"); twin(blk.c2, nm + ".conv2"); twin(blk.nin, nm + ".nin_shortcut")
+            for c, nm in ((self.attn_q, ".q"), (self.attn_k, ".k"), (self.attn_v, ".v"), (self.attn_out, ".proj_out")):
+                twin(c, E + ".mid.attn_1" + nm)
+        # the image enters as bf16 [hi | lo] halves against duplicated weight columns (3 + 3 channels in the 8 that TMA's
+        # 16-byte stride needs anyway): ~16 mantissa bits for the 8-bit pixels instead of 8
+        cin = sd[E + ".conv_in.weight"].shape[1]
+        self.in_ch = cin
+        self.conv_in = Conv.load(sd, E + ".conv_in", dev, in_idx=list(range(cin)) * 2 if INPUT_HILO else None)
         self.levels = []
         lvl = 0
         while any(k.startswith(f"{E}.down.{lvl}.") for k in sd):
@@ -751,16 +783,30 @@ class VAEEncoderEngine(_VaeMid):
                 blocks.append(_load_vae_res(sd, f"{E}.down.{lvl}.block.{i}", dev))
                 i += 1
             down = Conv.load(sd, f"{E}.down.{lvl}.downsample.conv", dev) if (f"{E}.down.{lvl}.downsample.conv.weight") in sd else None
+            if precision == "high":
+                for i, b in enumerate(blocks):
+                    nm = f"{E}.down.{lvl}.block.{i}"
+                    twin(b.c1, nm + ".conv1"); twin(b.c2, nm + ".conv2"); twin(b.nin, nm + ".nin_shortcut")
+                twin(down, f"{E}.down.{lvl}.downsample.conv")
             self.levels.append((blocks, down))
             lvl += 1
         self.norm_out = Norm.load(sd, E + ".norm_out", dev)
+        if precision == "high":
+            twin(self.conv_in, E + ".conv_in")
 
     @torch.no_grad()
     def encode_hc_nhwc(self, x: torch.Tensor) -> torch.Tensor:
         """x [B,3,H,W] fp32 NCHW in [-1,1] -> c NHWC bf16 [B,H/8,W/8,512]."""
         if not x.is_cuda:
             raise ops._lib.RdeicLibraryError("VAEEncoderEngine needs CUDA tensors; there is no CPU path")
-        h = ops.nchw_to_nhwc_bf16(x.float().contiguous(), ldc=8)
+        if self.precision == "high":
+            return self._encode_high(x)
+        if INPUT_HILO:
+            B, Cin, H, W = x.shape
+            h = ops.split_hilo(x.float().permute(0, 2, 3, 1).contiguous(),
+                               torch.zeros((B, H, W, (2 * Cin + 7) // 8 * 8), dtype=BF16, device=x.device))
+        else:
+            h = ops.nchw_to_nhwc_bf16(x.float().contiguous(), ldc=8)
         # 13 residual blocks deep: keep an fp32 master of the residual stream next to the bf16 copy the
         # tensor cores read (same scheme as the UNet step), or bf16 re-rounding compounds to 1.5e-2
         a = Act(*ops.conv_gemm(h, self.conv_in.w, self.conv_in.n_out, 9, bias=self.conv_in.b, dual=True))
@@ -776,14 +822,69 @@ class VAEEncoderEngine(_VaeMid):
                 else:
                     a = Act(*ops.conv_gemm(a.h, down.w, down.n_out, 9, bias=down.b, dual=True, stride2=True, pad_lo=0))
         a = self._res32(self.mid1, a)
-        a = self._res32(self.mid2, Act(None, self._attn(a.h)[0]))
+        a = self._res32(self.mid2, self._attn32(a))
         return ops.groupnorm(a.f, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
+
+    # ----- precision = "high": fp32 residual stream, three-pass split-bf16 convs ------------------------------------
+    def _conv3(self, c: Conv, a: torch.Tensor, taps: int, **kw) -> torch.Tensor:
+        """fp32 NHWC in -> fp32 NHWC out: a.w as a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in one tcgen05 GEMM over 3C channels."""
+        t = self._hi[id(c)]
+        return ops.conv_gemm(ops.split3(a), t.w, t.n_out, taps, bias=t.b, out_f32=True, **kw)
+
+    def _res_high(self, w: VaeRes, x: torch.Tensor) -> torch.Tensor:
+        h = ops.groupnorm_f32(x, w.n1.g, w.n1.b, 32, 1e-6, True)
+        h = self._conv3(w.c1, h, 9)
+        h = ops.groupnorm_f32(h, w.n2.g, w.n2.b, 32, 1e-6, True)
+        xs = x if w.nin is None else self._conv3(w.nin, x, 1)
+        return self._conv3(w.c2, h, 9, resid=xs)
+
+    def _attn_high(self, x: torch.Tensor) -> torch.Tensor:
+        B, H, W, C = x.shape
+        N = H * W
+        hn = ops.groupnorm_f32(x, self.attn_norm.g, self.attn_norm.b, 32, 1e-6, False)
+        q, k, v = (ops.f32_to_bf16(self._conv3(c, hn, 1).view(B * N, C)).view(B, N, C) for c in (self.attn_q, self.attn_k, self.attn_v))
+        if N % 128 == 0 and C in (256, 512):
+            o = ops.attention(q, k, v, 1, C, float(C) ** -0.5)
+        else:
+            s = ops.conv_gemm(q.view(B, 1, N, C), k, N, 1, w_batch_stride=N * C, w_k=C, w_ld=C, out_f32=True)
+            p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
+            o = ops.conv_gemm(p.view(B, 1, N, N), ops.transpose_bf16(v), C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
+        return self._conv3(self.attn_out, o.float().view(B, H, W, C), 1, resid=x)
+
+    def _encode_high(self, x: torch.Tensor) -> torch.Tensor:
+        a = self._conv3(self.conv_in, x.float().permute(0, 2, 3, 1).contiguous(), 9)
+        for blocks, down in self.levels:
+            for b in blocks:
+                a = self._res_high(b, a)
+            if down is not None:
+                a = self._conv3(down, a, 9, stride2=True, pad_lo=0)
+        a = self._res_high(self.mid2, self._attn_high(self._res_high(self.mid1, a)))
+        return ops.groupnorm(a, self.norm_out.g, self.norm_out.b, 32, 1e-6, True)
+
+    def _attn32(self, x: Act) -> Act:
+        """The mid-block attention with the fp32 master of the residual stream: GroupNorm reads it, proj_out adds to it
+        and writes both copies (the decoder's `_attn` carries bf16 only: 51 dB there, 1.3e-2 here)."""
+        B, H, W, C = x.h.shape
+        N = H * W
+        hn = ops.groupnorm(x.f, self.attn_norm.g, self.attn_norm.b, 32, 1e-6, False).view(B, N, C)
+        q = ops.linear(hn, self.attn_q.w, C, bias=self.attn_q.b)
+        k = ops.linear(hn, self.attn_k.w, C, bias=self.attn_k.b)
+        v = ops.linear(hn, self.attn_v.w, C, bias=self.attn_v.b)
+        if N % 128 == 0 and C in (256, 512):
+            o = ops.attention(q, k, v, 1, C, float(C) ** -0.5)
+        else:
+            s = ops.conv_gemm(q.view(B, 1, N, C), k, N, 1, w_batch_stride=N * C, w_k=C, w_ld=C, out_f32=True)
+            p = ops.softmax_rows(s.view(B, N, N), float(C) ** -0.5)
+            vt = ops.transpose_bf16(v)
+            o = ops.conv_gemm(p.view(B, 1, N, N), vt, C, 1, w_batch_stride=C * N, w_k=N, w_ld=N)
+        of, oh = ops.linear(o.view(B, N, C), self.attn_out.w, C, bias=self.attn_out.b, resid=x.f.view(B, N, C), dual=True)
+        return Act(of.view(B, H, W, C), oh.view(B, H, W, C))
 
     @staticmethod
     def _res32(w: VaeRes, x: Act) -> Act:
         src = x.f if x.f is not None else x.h
         h = ops.groupnorm(src, w.n1.g, w.n1.b, 32, 1e-6, True)
-        h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b)
+        h = ops.conv_gemm(h, w.c1.w, w.cout, 9, bias=w.c1.b, out_f32=True)      # conv1 -> norm2 hand-off in fp32 (one rounding less per block)
         h = ops.groupnorm(h, w.n2.g, w.n2.b, 32, 1e-6, True)
         xs = src if w.nin is None else ops.conv_gemm(x.h, w.nin.w, w.cout, 1, bias=w.nin.b, out_f32=True)
         return Act(*ops.conv_gemm(h, w.c2.w, w.cout, 9, bias=w.c2.b, resid=xs, dual=True))

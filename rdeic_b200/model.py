@@ -140,7 +140,10 @@ class RDEIC:
         self._graphs.clear()
         self.first_stage_encoder = None                  # sender side (optional in a decode-only checkpoint)
         if "first_stage_model.encoder.conv_in.weight" in sd:
-            self.first_stage_encoder = VAEEncoderEngine(sd, device=self.device)
+            # the verification mode (precision="fp32") takes the sender side's verification mode with it: three-pass
+            # split-bf16 convs and an fp32 residual stream (1.7e-3 of the reference's feature map against 1.1e-2)
+            self.first_stage_encoder = VAEEncoderEngine(sd, device=self.device,
+                                                        precision="high" if self.precision == "fp32" else "bf16")
         # the learned compressor (decompress side of the relay decode: c_latent and guide_hint)
         pp = self.preprocess_config and dict(self.preprocess_config.get("params", self.preprocess_config))
         has_pm = any(k.startswith("preprocess_model.") for k in sd)

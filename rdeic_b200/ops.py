@@ -430,6 +430,30 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups:
     return out
 
 
+def groupnorm_f32(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool) -> torch.Tensor:
+    """fp32 NHWC in -> fp32 NHWC out (exact exp / division in SiLU): the GroupNorm of the fp32 kernel mode, also the
+    producer of the [hi | lo | hi] operands of the split-bf16 convs."""
+    x = _need(x, torch.float32, "groupnorm_f32")
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    ws = _gn_workspace(B, x.device)
+    check(_lib.load().rdeic_groupnorm_nhwc_f32(_ptr(x), C, None, 0, _ptr(gamma), _ptr(beta), _ptr(out), B, H * W, groups, eps,
+                                               1 if silu else 0, _ptr(ws), _stream()), "rdeic_groupnorm_nhwc_f32")
+    return out
+
+
+def split3(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., C] -> bf16 [..., ceil8(3C)] = [hi | lo | hi] (zero padded): the A operand of a three-pass split-bf16
+    product against weights packed as [w_hi | w_hi | w_lo] (`engine.Conv.load(split3=True)`):
+    a.w = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo + O(2^-16), fp32 accumulation on the tensor cores."""
+    src = _need(src, torch.float32, "split3")
+    Cc = src.shape[-1]
+    dst = torch.zeros((*src.shape[:-1], (3 * Cc + 7) // 8 * 8), dtype=BF16, device=src.device)
+    split_hilo(src, dst, 0, Cc)
+    split_hilo(src, dst, 2 * Cc, Cc)
+    return dst
+
+
 def pack_tail_weight(w: torch.Tensor) -> torch.Tensor:
     """conv_out weight OIHW fp32 [n_out <= 4, C, 3, 3] -> bf16 [9 taps, 8 (zero-padded n_out), C] for `gn_silu_conv3x3_tail`."""
     n_out, cin, kh, kw = w.shape

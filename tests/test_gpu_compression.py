@@ -314,9 +314,27 @@ def test_vae_encoder_matches_reference(cuda, tag):
     g = np.load(GOLD / f"{tag}_vae_encode.npz")
     c = VAEEncoderEngine(sd, device=cuda).encode_hc(torch.from_numpy(g["x"]).to(cuda))
     assert tuple(c.shape) == g["c"].shape
-    # 26 convs deep with bf16 operands and random (non-contracting) weights: operand rounding adds up
-    # to 1.3e-2 (full) / 1.5e-2 (small) even with the fp32 residual master (tests/tools/diag_vae_encoder.py)
-    assert rel_l2(c.cpu(), g["c"]) < 2e-2
+    # 26 convs deep with bf16 operands and random (non-contracting) weights: operand rounding adds up to 1.14e-2 (full) /
+    # 1.38e-2 (small) with the fp32 residual master, the fp32 conv1 -> norm2 hand-off and the image as [hi | lo]
+    # (tests/tools/diag_vae_encoder.py prints the growth per block); precision="high" below is the mode that meets 1e-2
+    assert rel_l2(c.cpu(), g["c"]) < 1.5e-2
+
+
+def test_vae_encoder_high_precision_mode(cuda):
+    """precision="high": every conv of the encoder as a three-pass split-bf16 tcgen05 product with an fp32 residual
+    stream -- the sender side's verification mode, an order of magnitude under the 1e-2 bar the bf16 mode sits just above."""
+    from rdeic_b200 import configs, synthetic
+    from rdeic_b200.engine import VAEEncoderEngine
+
+    for tag, params in (("small", configs.small_params()), ("full", configs.default_params())):
+        sd = synthetic.make_state_dict(params, seed=231, encoder=True)
+        g = np.load(GOLD / f"{tag}_vae_encode.npz")
+        x = torch.from_numpy(g["x"]).to(cuda)
+        hi = VAEEncoderEngine(sd, device=cuda, precision="high").encode_hc(x)
+        lo = VAEEncoderEngine(sd, device=cuda).encode_hc(x)
+        e_hi, e_lo = rel_l2(hi.cpu(), g["c"]), rel_l2(lo.cpu(), g["c"])
+        print(f"[{tag}] vae encoder rel-L2 vs reference: high {e_hi:.3e}, bf16 {e_lo:.3e}")
+        assert e_hi < 2.5e-3 and e_hi < e_lo            # measured 1.7e-3: the bf16 rounding of q / k / v and of the result itself
 
 
 def test_sender_to_receiver_through_a_file(cuda, tmp_path):
