@@ -13,9 +13,8 @@
 //   smem   : Q tile resident (128 rows x d, d/64 panels of 16 KB), a ring of 16 KB stages carrying K panels
 //            (128 keys x 64 d, K-major) and V sub-tiles (128 keys x 64 d_v, consumed MN-major: no transpose).
 //   warps  : 0 = TMA producer, 1 = issuer of the S = Q K^T MMAs (+ TMEM allocation), 2 = issuer of the PV MMAs,
-//            4..7 = softmax, one query row per thread.  Two issuing warps because ONE thread sustains only one
-//            tcgen05.mma per ~100 clocks whatever its shape (scripts/micro/ubench.cu, profiles/r02_ubench.txt) and a
-//            step is 32 + 32 instructions that the tensor pipe would finish in ~3100 clocks.
+//            4..7 = softmax, one query row per thread.  Two issuing warps, one per instruction stream (S and PV have
+//            their own operand rings and hand-offs); a step is 32 + 32 instructions, ~3100 tensor clocks.
 //   O stays in tensor memory for the whole key loop and is rescaled only when a row's maximum has grown by more than
 //   2^8 over the reference maximum its exponents use (exact: O and l carry the same factor) -- as attention_tc2_kernel.
 #include "common.cuh"

@@ -303,22 +303,22 @@ struct TileCfg {
 };
 
 // Persistent, warp-specialised kernel: one CTA per SM loops over (m-tile, n-tile, k-split) work
-// items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue.
+// items.  warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-3 idle (control warp group), warps 4.. = epilogue.
 // Three pipelines: smem stages (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so
 // the epilogue of tile i overlaps the main loop of tile i+1), and the static tile schedule.
-// kSwap (with kMT == 2, BN == 128): operand roles exchanged.  One M=128 tcgen05.mma costs >= 128 clocks
-// whatever N is (its A operand is read from shared memory at a fixed rate), so an N = 128 tile runs the
-// tensor pipe at half rate.  With the WEIGHT tile as the M operand (128 output channels) and the item's
-// two pixel tiles as one N = 256 operand, the same FLOPs take half the MMA slots.  The accumulator is
+// kSwap (with kMT == 2, BN == 128): operand roles exchanged.  With the WEIGHT tile as the M operand (128 output
+// channels) and the item's two pixel tiles as one N = 256 operand, the same FLOPs take half the tcgen05.mma instructions
+// and the weight tile is read from shared memory once per 256 pixels.  (Built in round 1, when every instruction cost
+// ~100 clocks behind a `lane == 0` branch -- see elect_one_sync() -- and kept: 793 -> 558 us then, still the faster form.)  The accumulator is
 // then transposed (TMEM lane = output channel, column = pixel); phase A parks it in the staging buffer
 // already transposed back, so phase B (residual, stores, statistics) is unchanged.
 // kUp: compile-time copy of p.up2 for the epilogue (strided output rows, parity-ordered statistics slabs): the
 // plain instantiations carry none of that state (the 12-warp ones sit at their 128-register cap).
-// kIss: warps issuing tcgen05.mma.  ONE thread sustains one instruction per ~100 clocks whatever the shape (measured,
-// scripts/micro/ubench.cu: N = 16 .. 128 all 100 clocks, N = 160 113, N = 256 136-161; two issuing warps 52 per SM, four 26), so
-// an N = 160 tile runs the tensor pipe at 80 / 113 of its rate and N = 128 at 64 / 100.  With kIss == 2 (and kMT == 2) each
-// M tile of the item has its own issuing warp and accumulator: both streams are in order, so the result is bit-identical
-// to the one-issuer kernel, and the pipe sees an instruction every ~56 clocks.
+// kIss: warps issuing tcgen05.mma.  Behind a `lane == 0` branch ONE thread sustained one instruction per ~100 clocks
+// whatever the shape (scripts/micro/ubench.cu: N = 16 .. 128 all 100 clocks, N = 160 113, N = 256 136-161; two issuing warps
+// 52 per SM, four 26).  With kIss == 2 (and kMT == 2) each M tile of the item has its own issuing warp and accumulator: both
+// streams are in order, so the result is bit-identical to the one-issuer kernel.  The cause turned out to be the branch,
+// not the hardware (elect_one_sync(): N / 2 clocks per instruction from one thread), so this variant is off by default.
 // kNT = 2: two N tiles per work item against ONE activation stage (accumulators side by side in tensor memory).  What bounds
 // an N = 160 tile with a long reduction is the L2 -> SM path, not the tensor pipe: 16 KB of activations per 320 tensor clocks
 // is 51 B/clk per SM against ~43 B/clk the L2 delivers chip-wide (the weight tile is the same for every CTA at a given
@@ -1130,8 +1130,8 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
 
 // Tile width: cost ~ tiles per SM * per-tile time, per-tile time ~ bn (MMA N) + a fixed overhead (pipeline
 // fill, epilogue tail: ~96 columns' worth, fitted on the K <= 1280 linears of UNet levels 1-2).  A model that
-// charged the main loop the same for every width (on the theory that an M=128 MMA costs 128 clocks whatever
-// N is) was A/B-tested on one box and lost: UNet step 12.94 -> 13.60 ms, VAE 22.0 -> 23.8 ms.
+// charged the main loop the same for every width was A/B-tested on one box and lost: UNet step 12.94 -> 13.60 ms,
+// VAE 22.0 -> 23.8 ms.  The constants were swept again after the issue-rate fix (scripts/r02_s28.sh): unchanged.
 static int pick_block_n(int n_out, int m_tiles, int hint, int total_kb) {
     (void)total_kb;
     if (hint == 32 || hint == 64 || hint == 128 || hint == 160 || hint == 256) return hint;

@@ -470,10 +470,9 @@ gn_apply_kernel(const void* __restrict__ x1, int C1, const void* __restrict__ x2
 // ------------------------------------------------------------------------------------------------
 // VAE tail: norm_out -> swish -> conv_out (3x3, C -> 3) -> optional uint8 post-process, ONE kernel
 // (model.py:683-686 `h = self.norm_out(h); h = nonlinearity(h); h = self.conv_out(h)`, inference.py:85-87).
-// The tcgen05 implicit GEMM is the wrong tool for 3 output channels: one M=128 tcgen05.mma costs
-// >= 128 clocks whatever N is (the A operand has to be read from shared memory), so an N=32 tile runs
-// the tensor pipe at 1/8 rate and re-reads the activation 9 times from L2 (0.5-0.8 ms at 512^2, batch
-// 8).  Here a CTA stages an (8+2) x (32+2) pixel halo tile ONCE, applying GroupNorm scale/shift and
+// The tcgen05 implicit GEMM is the wrong tool for 3 output channels: an N = 32 tile spends its time
+// reading the M = 128 A operand from shared memory (39-48 clocks per instruction for N <= 64 against N / 2 = 16
+// of tensor work), and re-reads the activation 9 times from L2 (0.5-0.8 ms at 512^2, batch 8).  Here a CTA stages an (8+2) x (32+2) pixel halo tile ONCE, applying GroupNorm scale/shift and
 // SiLU on the way into shared memory (zero outside the image = the conv's padding), and 8 warps run
 // mma.sync m16n8k16 (16 pixels x 8 padded output channels) over the 9 taps from shared memory.
 // The normalised activation never goes back to HBM (saves the gn_apply pass: 2 x 537 MB at 512^2).
