@@ -971,6 +971,42 @@ def test_conv_fused_zero_conv_injection(cuda, B, H, W, Cin, Cc, Cout, taps, stri
     assert _rel(of2.cpu(), ref2) < 3e-3, _rel(of2.cpu(), ref2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride2", [(2, 16, 16, 128, 128, 3, False), (1, 32, 32, 3, 128, 3, False),
+                                                      (1, 32, 32, 128, 256, 1, False), (2, 32, 32, 128, 128, 3, True)])
+def test_conv_three_pass_split_bf16(cuda, B, H, W, Cin, Cout, k, stride2):
+    """fp32-equivalent products on the tensor cores: activations as [hi | lo | hi] (`ops.split3`) against weights packed as
+    [w_hi | w_hi | w_lo] (`Conv.load(split3=True)`) in ONE tcgen05 GEMM over 3C channels -- the convs of the VAE encoder's
+    precision="high" mode (ldm/modules/diffusionmodules/model.py:82-84,128-151 at fp32 fidelity).  The plain bf16 conv of
+    the same fp32 data is two orders of magnitude further from the fp32 result."""
+    from rdeic_b200 import ops
+    from rdeic_b200.engine import Conv
+
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(k * k * Cin)
+    b = torch.randn(Cout, generator=g)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        if stride2:          # model.py:82-84: pad (0,1,0,1), stride 2, no padding
+            ref = F.conv2d(F.pad(x.to(cuda).double(), (0, 1, 0, 1)), w.to(cuda).double(), b.to(cuda).double(), stride=2)
+        else:
+            ref = F.conv2d(x.to(cuda).double(), w.to(cuda).double(), b.to(cuda).double(), padding=k // 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = ref.permute(0, 2, 3, 1).float().cpu()
+    sd = {"c.weight": w, "c.bias": b}
+    a32 = x.to(cuda).permute(0, 2, 3, 1).contiguous()
+    kw = dict(stride2=True, pad_lo=0) if stride2 else {}
+    c3 = Conv.load(sd, "c", cuda, split3=True)
+    out3 = ops.conv_gemm(ops.split3(a32), c3.w, c3.n_out, k * k, bias=c3.b, out_f32=True, **kw).cpu()
+    if Cin % 8 == 0:
+        c1 = Conv.load(sd, "c", cuda)
+        out1 = ops.conv_gemm(ops.f32_to_bf16(a32), c1.w, c1.n_out, k * k, bias=c1.b, out_f32=True, **kw).cpu()
+        assert _rel(out1, ref) > 20 * _rel(out3, ref)
+    assert _rel(out3, ref) < 3e-5, _rel(out3, ref)
+
+
 def test_split_hilo(cuda):
     """hi = bf16(x), lo = bf16(x - hi): hi + lo reproduces x to ~2^-17 relative, hi is torch's own rounding."""
     from rdeic_b200 import ops
