@@ -33,7 +33,7 @@ static inline int gn_num_chunks(int B, int64_t HW) {
 // Tensors far larger than the L2 (the VAE's 512^2 / 256^2 levels) keep the finer 8 * 148 / B chunking: there the prologue is
 // noise and the shorter tail of many small CTAs wins (A/B on one box: 217.6 vs 224.1 us on [8,512,512,128], 38.8 vs 34.8 us
 // on the UNet's [8,64,64,320] fp32 stream, fold + apply).
-template <typename K>
+template <int kTag, typename K>       // kTag: the instantiations share one function-pointer type, so the type alone would share the static
 static inline int gn_apply_chunks(K kernel, int B, int64_t HW, int C) {
     if ((int64_t)B * HW * C > (int64_t)1 << 25) return gn_num_chunks(B, HW);
     static int per_sm = 0;              // one static per kernel instantiation
@@ -847,10 +847,10 @@ int rdeic_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int in_
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
     if (in_is_f32)
-        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s, 
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks<0>(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     else
-        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s, 
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks<1>(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s, 
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -879,10 +879,10 @@ int rdeic_groupnorm_from_stats(const void* x1, int C1, const float* stats1, cons
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
     if (in_is_f32)
-        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s,
+        launch_k(gn_apply_kernel<true>, dim3((unsigned)gn_apply_chunks<0>(gn_apply_kernel<true>, B, HW, C), B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
     else
-        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s,
+        launch_k(gn_apply_kernel<false>, dim3((unsigned)gn_apply_chunks<1>(gn_apply_kernel<false>, B, HW, C), B), kGnThreads, 0, s,
             x1, C1, x2, C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nfold, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
@@ -942,7 +942,7 @@ int rdeic_groupnorm_nhwc_f32(const float* x1, int C1, const float* x2, int C2, c
              (float2*)workspace);
     RDEIC_LAUNCH_CHECK();
     const FastDiv div_vl((uint32_t)(C / 8));
-    launch_k(gn_apply_kernel<true, true>, dim3((unsigned)gn_apply_chunks(gn_apply_kernel<true, true>, B, HW, C), B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2,
+    launch_k(gn_apply_kernel<true, true>, dim3((unsigned)gn_apply_chunks<2>(gn_apply_kernel<true, true>, B, HW, C), B), kGnThreads, 0, s, (const void*)x1, C1, (const void*)x2,
              C2, gamma, beta, (uint4*)out, HW, groups, eps, silu, (const float2*)workspace, nchunk, div_vl);
     RDEIC_LAUNCH_CHECK();
     return 0;
